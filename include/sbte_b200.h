@@ -1,0 +1,166 @@
+/*
+ * include/sbte_b200.h -- C ABI of libsbte_b200.so, the B200 (sm_100a) collision hot path of SpectralBTE.
+ *
+ * Two groups of entry points, all with C linkage, plain pointers and sizes:
+ *
+ *  (1) DROP-IN symbols: byte-for-byte the link interface of the reference's collision, conservation
+ *      and transport modules, so exec/boltz.c and src/initializer.c link against this library in
+ *      place of src/collisions.c, src/conserve.c, src/transportroutines.c and
+ *      src/boundaryConditions.c with no source change.  They take HOST pointers,
+ *      return void and, like the reference, report failure by printing and exit(1).
+ *
+ *  (2) sbte_* extension surface: the device-resident fast path (weights uploaded once, spectra,
+ *      slabs and moments stay in HBM).  They return 0 on success, non-zero on failure with the
+ *      message available from sbte_last_error().  Pointers named d_* are DEVICE pointers.
+ *
+ * There is no CPU fallback: every entry point fails loudly when no CUDA device is usable.
+ * Citations are to the reference tree (/root/reference).
+ */
+#ifndef SBTE_B200_H
+#define SBTE_B200_H
+#include <stddef.h>
+#if defined(__GNUC__)
+#define SBTE_API __attribute__((visibility("default")))
+#else
+#define SBTE_API
+#endif
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ (1) drop-in link interface */
+
+/* ABI mirror of `species` (src/species.h:11-26); only .mass and .name are read by this library. */
+typedef struct sbte_species {
+  size_t id;
+  size_t num_levels;
+  size_t *lev_id;
+  double Rgas, mass, mm, d_ref, T_ref, mu_ref, omega, E0;
+  double *Ei, *gi;
+  char name[80];
+} sbte_species;
+
+/* src/collisions.h:27 (src/collisions.c:33-74). Retains nothing from vel/zeta after returning
+ * (the reference keeps the pointers; the grids are copied to the device here). */
+SBTE_API void initialize_coll(int nodes, double length, double *vel, double *zeta);
+/* src/collisions.h:33 (src/collisions.c:81-89) */
+SBTE_API void dealloc_coll(void);
+/* src/collisions.h:38 (src/collisions.c:212-221). f, g, Q: N^3 host doubles; conv_weights: N^3 row
+ * pointers of N^3 doubles (src/weights.c:61-63). The rows are uploaded once and cached, keyed on
+ * the conv_weights pointer value; they are treated as immutable (BASELINE/SURVEY 8b). */
+SBTE_API void ComputeQ(double *f, double *g, double *Q, double **conv_weights);
+/* src/collisions.h:40 (src/collisions.c:178-210) */
+SBTE_API void ComputeQ_maxPreserve(double *f, double *g, double *Q, double **conv_weights);
+/* src/collisions.h:42 (src/collisions.c:232-283); in/out: N^3 interleaved complex (fftw_complex) */
+SBTE_API void fft3D(double (*in)[2], double (*out)[2], int invert);
+
+/* src/conserve.h:6 (src/conserve.c:17-43); only num_spec == 1 is supported */
+SBTE_API void initialize_conservation(int nodes, double h_v, double *vel, sbte_species *mix, int num_spec);
+/* src/conserve.h:8 (src/conserve.c:45-73) */
+SBTE_API void initialize_conservation_fast(int nodes, double h_v, double *vel);
+/* src/conserve.h:16 (src/conserve.c:207-264): Q[0] -> N^3 host doubles, corrected in place */
+SBTE_API void conserveAllMoments(double **Q);
+/* src/conserve.h:10 (src/conserve.c:76-84) */
+SBTE_API void dealloc_conservation(void);
+
+/* src/transportroutines.h:3 (src/transportroutines.c:27-59) */
+SBTE_API void initialize_transport(int numV, int numX, double lv, double *xnodes, double *dxnodes, double *vel, int IC,
+                          double timestep, double TWall_in, sbte_species *mix);
+/* src/transportroutines.h:20,22 (src/transportroutines.c:473-492): f, f_conv are arrays of
+ * numX + 2*order cell pointers. Single rank per process (the reference's MPI halo is replaced by
+ * sbte_slab_* + the caller's exchange, see section (2)). */
+SBTE_API void advectOne(double **f, double **f_conv, int id);
+SBTE_API void advectTwo(double **f, double **f_conv, int id);
+/* src/transportroutines.h:24 (src/transportroutines.c:494-501) */
+SBTE_API void dealloc_trans(void);
+
+/* ------------------------------------------------------------------ (2) device-resident extension */
+
+typedef struct sbte_ctx sbte_ctx;
+typedef struct sbte_slab sbte_slab;
+
+SBTE_API const char *sbte_last_error(void);
+
+/* One context per (N, L_v) grid and device. v, eta: N host doubles each (src/initializer.c:66-82). */
+SBTE_API int sbte_create(sbte_ctx **out, int N, double L_v, const double *v, const double *eta, int device);
+SBTE_API int sbte_destroy(sbte_ctx *c);
+SBTE_API int sbte_sync(sbte_ctx *c);
+SBTE_API void *sbte_stream(sbte_ctx *c);                      /* the cudaStream_t every kernel is launched on */
+SBTE_API unsigned long long sbte_launch_count(sbte_ctx *c);   /* kernels launched so far through c */
+SBTE_API int sbte_reserve(sbte_ctx *c, int cells);            /* pre-size scratch for a batch of cells */
+/* CUDA-event timing of the convolution kernel (K2) alone, on the context stream: enable, run, then
+ * read the summed device time and the number of K2 launches since the last read. */
+SBTE_API int sbte_k2_profile(sbte_ctx *c, int enable);
+SBTE_API int sbte_k2_profile_read(sbte_ctx *c, double *total_ms, int *launches);
+
+/* raw device memory for C hosts without CUDA headers */
+SBTE_API int sbte_dev_alloc(void **d_ptr, size_t bytes);
+SBTE_API int sbte_dev_free(void *d_ptr);
+SBTE_API int sbte_h2d(sbte_ctx *c, void *d_dst, const void *src, size_t bytes);
+SBTE_API int sbte_d2h(sbte_ctx *c, void *dst, const void *d_src, size_t bytes);
+SBTE_API int sbte_d2d(sbte_ctx *c, void *d_dst, const void *d_src, size_t bytes);   /* async on the context stream */
+
+/* Weights: N^3 x N^3 doubles, row-major [zeta][xi]; file format = src/weights.c:78-88,101-103
+ * (headerless native doubles, name Weights/N%d_isotropic_L_v%g_lambda%g.wts, :68). */
+SBTE_API int sbte_weights_upload_rows(sbte_ctx *c, double *const *rows);
+SBTE_API int sbte_weights_upload(sbte_ctx *c, const double *W);
+SBTE_API int sbte_weights_load_file(sbte_ctx *c, const char *path);
+SBTE_API int sbte_weights_bind_device(sbte_ctx *c, const double *d_W);
+SBTE_API int sbte_weights_fill_synthetic(sbte_ctx *c, unsigned long long seed); /* splitmix64 -> [-0.5,0.5) */
+SBTE_API const double *sbte_weights_device(sbte_ctx *c);
+
+/* kernel selection for the convolution */
+enum { SBTE_K2_AUTO = 0, SBTE_K2_GENERIC = 1, SBTE_K2_STREAM = 2, SBTE_K2_BATCH = 3, SBTE_K2_STREAM_DEEP = 4 };
+
+/* fft3D on device data (src/collisions.c:232-283); batch cells of N^3 interleaved complex */
+SBTE_API int sbte_fft3d(sbte_ctx *c, const double *d_in, double *d_out, int invert, int batch);
+/* Q^ = compute_Qhat before the inverse transform (src/collisions.c:108-165); d_qhat: batch x N^3 complex */
+SBTE_API int sbte_qhat(sbte_ctx *c, const double *d_f, const double *d_g, double *d_qhat, int batch, int k2);
+/* ComputeQ (src/collisions.c:212-221) for `batch` cells laid out [cell][N^3] */
+SBTE_API int sbte_compute_q(sbte_ctx *c, const double *d_f, const double *d_g, double *d_Q, int batch, int k2);
+/* ComputeQ_maxPreserve (src/collisions.c:178-210), one cell; one weight pass for the three products */
+SBTE_API int sbte_compute_q_maxpreserve(sbte_ctx *c, const double *d_f, const double *d_g, double *d_Q, int k2);
+/* conserveAllMoments (src/conserve.c:207-264) on `batch` cells in place */
+SBTE_API int sbte_conserve(sbte_ctx *c, double *d_Q, int batch);
+/* b = C Q, the five conserved functionals per cell (src/conserve.c:217-240); d_b5: batch x 5 */
+SBTE_API int sbte_moment_functionals(sbte_ctx *c, const double *d_Q, double *d_b5, int batch);
+/* per cell: rho, u_x, u_y, u_z, T, E_pos, E_neg, p (src/momentRoutines.c:58-183); d_mom8: batch x 8 */
+SBTE_API int sbte_moments(sbte_ctx *c, const double *d_f, double *d_mom8, int batch);
+/* one 0D time step, order 1 (Euler) or 2 (Heun) (exec/boltz.c:189-241); f stays on the device */
+SBTE_API int sbte_step_0d(sbte_ctx *c, double *d_f, double dt, double Kn, int order, int k2);
+
+/* host-pointer forms used by the drop-in symbols and by end-to-end timing */
+SBTE_API int sbte_compute_q_host(sbte_ctx *c, const double *f, const double *g, double *Q, int k2);
+SBTE_API int sbte_compute_q_maxpreserve_host(sbte_ctx *c, const double *f, const double *g, double *Q, int k2);
+
+/* ---- 1D slabs: cells_local + 2*order cells of N^3 doubles, contiguous, ghosts at both ends ----
+ * rank/nranks describe the block partition of the global mesh (src/mesh_setup.c:46-53); walls and
+ * extrapolation apply only on rank 0 / rank nranks-1 (src/transportroutines.c:107-172,261-404). */
+SBTE_API int sbte_slab_create(sbte_ctx *c, sbte_slab **out, int cells_local, int order, const double *x, const double *dx,
+                     int init_field, double dt, int rank, int nranks);
+SBTE_API int sbte_slab_destroy(sbte_slab *s);
+SBTE_API double *sbte_slab_f(sbte_slab *s);        /* device pointer of the f slab   (exec/boltz.c f_inhom) */
+SBTE_API double *sbte_slab_fconv(sbte_slab *s);    /* device pointer of f_conv */
+SBTE_API int sbte_slab_upload(sbte_slab *s, const double *f_host);      /* (cells_local + 2*order) x N^3 */
+SBTE_API int sbte_slab_download(sbte_slab *s, double *f_host);
+/* transport half of the step: advectOne / advectTwo on the slab (ghost cells must already hold the
+ * neighbours' data when nranks > 1; sbte_slab_halo_* give the send/recv regions). which: 0 f->f_conv, 1 f_conv->f */
+SBTE_API int sbte_slab_advect(sbte_slab *s, int which);
+/* stage = 0,1 for the two upwindTwo passes inside advectTwo (halo needed before each) */
+SBTE_API int sbte_slab_upwind_stage(sbte_slab *s, int which, int stage);
+SBTE_API int sbte_slab_advect_finish(sbte_slab *s, int which);
+/* device pointers + element counts of the boundary cells to send / ghost cells to receive for the
+ * array the next upwind pass reads. side 0 = left neighbour, 1 = right neighbour */
+SBTE_API int sbte_slab_halo_regions(sbte_slab *s, int which, int stage, int side, double **d_send, double **d_recv,
+                           size_t *count);
+/* collision half: per-cell ComputeQ + conserve + Euler / Heun (exec/boltz.c:285-345) */
+SBTE_API int sbte_slab_collide(sbte_slab *s, double Kn, int k2);
+/* whole single-rank step (exec/boltz.c:264-353) */
+SBTE_API int sbte_slab_step(sbte_slab *s, double Kn, int k2);
+/* rho, u_x, u_y, u_z, T, Epos, Eneg, p of every owned cell -> host (cells_local x 8) */
+SBTE_API int sbte_slab_moments(sbte_slab *s, double *mom_host);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

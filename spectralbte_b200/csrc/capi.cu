@@ -1,0 +1,551 @@
+// spectralbte_b200/csrc/capi.cu -- the sbte_* C ABI (include/sbte_b200.h, section 2): context,
+// weights, device-pointer operations and the 0D step.  The drop-in symbols live in dropin.cu, the
+// 1D slab in slab.cu.
+#include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <algorithm>
+#include <string>
+
+#include "../../include/sbte_b200.h"
+#include "common.cuh"
+#include "internal.h"
+
+namespace sbte {
+
+static thread_local std::string g_err;
+void set_error(const std::string& msg) { g_err = msg; }
+
+void k2_mark(sbte_ctx* c) {
+  if (!c->k2_prof) return;
+  if (c->k2_ev_used == c->k2_ev.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->k2_ev.push_back(e);
+  }
+  cudaEventRecord(c->k2_ev[c->k2_ev_used++], c->stream);
+}
+
+#define CK(call)                                                                                      \
+  do {                                                                                                \
+    cudaError_t e_ = (call);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      sbte::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));                            \
+      return 1;                                                                                       \
+    }                                                                                                 \
+  } while (0)
+
+static int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    set_error(std::string(what) + ": " + cudaGetErrorString(e));
+    return 1;
+  }
+  return 0;
+}
+
+// Gram matrix of the moment functionals and its scaled-pivot LU (src/conserve.c:268-317, 89-168).
+// The pivot row is the first row that improves on the diagonal entry (:115-126); row swaps touch
+// only columns >= k (:140-145), which the solve in conserve.cu mirrors.
+static int build_lu(const sbte_ctx* c, ConsLU* out) {
+  const int N = c->N, n = 5;
+  const double* v = c->v.data();
+  const double* wt = c->wt.data();
+  double* A = out->a;
+  double s[5];
+  for (int a = 0; a < n; a++)
+    for (int b = 0; b < n; b++) {
+      double acc = 0.0;
+      for (int i = 0; i < N; i++)
+        for (int j = 0; j < N; j++)
+          for (int k = 0; k < N; k++) {
+            const double pre = wt[i] * wt[j] * wt[k] * c->dv * c->dv * c->dv * 1.0;
+            const double row[5] = {pre, pre * v[i], pre * v[j], pre * v[k],
+                                   pre * 0.5 * (v[i] * v[i] + v[j] * v[j] + v[k] * v[k])};
+            acc += row[a] * row[b];
+          }
+      A[a * n + b] = acc;
+    }
+  for (int i = 0; i < n; i++) {
+    s[i] = fabs(A[i * n]);
+    for (int j = 0; j < n; j++)
+      if (s[i] < fabs(A[i * n + j])) s[i] = fabs(A[i * n + j]);
+  }
+  for (int k = 0; k < n - 1; k++) {
+    double best = fabs(A[k * n + k] / s[k]);
+    int prow = k;
+    bool taken = false;
+    for (int i = k; i < n; i++) {
+      const double cand = fabs(A[i * n + k] / s[i]);
+      if (best < cand) {
+        best = cand;
+        if (!taken) { prow = i; taken = true; }
+      }
+    }
+    out->piv[k] = prow;
+    if (best == 0.0) { set_error("conservation matrix is singular"); return 1; }
+    if (prow != k) {
+      for (int j = k; j < n; j++) { const double t = A[k * n + j]; A[k * n + j] = A[prow * n + j]; A[prow * n + j] = t; }
+      const double t = s[k]; s[k] = s[prow]; s[prow] = t;
+    }
+    for (int i = k + 1; i < n; i++) {
+      const double m = A[i * n + k] / A[k * n + k];
+      A[i * n + k] = m;
+      for (int j = k + 1; j < n; j++) A[i * n + j] -= m * A[k * n + j];
+    }
+  }
+  out->piv[n - 1] = n - 1;
+  return 0;
+}
+
+static void free_scratch(sbte_ctx* c) {
+  cudaFree(c->d_tmp); cudaFree(c->d_specA); cudaFree(c->d_specB); cudaFree(c->d_specC);
+  for (int i = 0; i < 3; i++) cudaFree(c->d_lay[i]);
+  cudaFree(c->d_qhat); cudaFree(c->d_Q); cudaFree(c->d_f); cudaFree(c->d_g); cudaFree(c->d_M); cudaFree(c->d_mom);
+  c->d_tmp = c->d_specA = c->d_specB = c->d_specC = c->d_qhat = nullptr;
+  c->d_lay[0] = c->d_lay[1] = c->d_lay[2] = nullptr;
+  c->d_Q = c->d_f = c->d_g = c->d_M = c->d_mom = nullptr;
+  c->cap = 0;
+}
+
+int ensure_capacity(sbte_ctx* c, int cells) {
+  if (cells <= c->cap) return 0;
+  CK(cudaSetDevice(c->device));
+  CK(cudaStreamSynchronize(c->stream));
+  free_scratch(c);
+  const size_t padded = (size_t)((cells + 31) / 32) * 32;  // cell-minor layout works in groups of 32
+  const size_t cb = padded * (size_t)c->n3 * sizeof(double2);
+  const size_t rb = padded * (size_t)c->n3 * sizeof(double);
+  CK(cudaMalloc(&c->d_tmp, cb));
+  CK(cudaMalloc(&c->d_specA, cb));
+  CK(cudaMalloc(&c->d_lay[0], cb));
+  CK(cudaMemsetAsync(c->d_lay[0], 0, cb, c->stream));  // padding cells of the last group read as zero
+  CK(cudaMalloc(&c->d_qhat, cb));
+  CK(cudaMalloc(&c->d_Q, rb));
+  CK(cudaMalloc(&c->d_f, rb));
+  CK(cudaMalloc(&c->d_g, rb));
+  CK(cudaMalloc(&c->d_mom, padded * 8 * sizeof(double)));
+  // small-batch paths (0D, two-species pairs): second/third spectra and Maxwellian scratch, 32 cells
+  const size_t cb32 = (size_t)32 * (size_t)c->n3 * sizeof(double2);
+  CK(cudaMalloc(&c->d_specB, cb32));
+  CK(cudaMalloc(&c->d_specC, cb32));
+  CK(cudaMalloc(&c->d_lay[1], cb32));
+  CK(cudaMalloc(&c->d_lay[2], cb32));
+  CK(cudaMalloc(&c->d_M, 4 * (size_t)c->n3 * sizeof(double)));
+  c->cap = cells;
+  return 0;
+}
+
+static int make_tensor_map(sbte_ctx* c) {
+  c->tmap_ok = false;
+  if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
+  typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
+  if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return 1; }
+  const int N = c->N;
+  const int cols_per_cta = (N >= 16) ? 8 : 4;  // BatchCfg<N>::COLS
+  cuuint64_t gdim[2] = {(cuuint64_t)c->n3, (cuuint64_t)c->n3};
+  cuuint64_t gstride[1] = {(cuuint64_t)c->n3 * sizeof(double)};
+  cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)(cols_per_cta * N)};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = ((encode_fn)fn)(&c->tmapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)c->d_W, gdim, gstride, box, estr,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return 1; }
+  c->tmap_ok = true;
+  return 0;
+}
+
+static int release_weights(sbte_ctx* c) {
+  if (c->owns_W && c->d_W) cudaFree((void*)c->d_W);
+  c->d_W = nullptr; c->owns_W = false; c->host_key = nullptr; c->tmap_ok = false;
+  return 0;
+}
+
+static int alloc_weights(sbte_ctx* c) {
+  release_weights(c);
+  double* p = nullptr;
+  CK(cudaMalloc(&p, (size_t)c->n3 * c->n3 * sizeof(double)));
+  c->d_W = p; c->owns_W = true;
+  return 0;
+}
+
+__global__ void synth_weights_kernel(double* __restrict__ W, size_t n, unsigned long long seed) {
+  for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+    unsigned long long z = (unsigned long long)(i + 1) * 0x9E3779B97F4A7C15ULL + seed;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ULL;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBULL;
+    z = z ^ (z >> 31);
+    W[i] = (double)(z >> 11) * (1.0 / 9007199254740992.0) - 0.5;
+  }
+}
+
+// ---- convolution dispatch -------------------------------------------------------------------
+// spectra of f (dif side) and g (xi side) -> qhat (natural layout)
+static int resolve_k2(sbte_ctx* c, int batch, int k2) {
+  if (k2 == SBTE_K2_AUTO) {
+    if (batch == 1) return qhat_stream_supported(c->N) ? SBTE_K2_STREAM : SBTE_K2_GENERIC;
+    return qhat_batch_supported(c->N) ? SBTE_K2_BATCH : SBTE_K2_GENERIC;
+  }
+  return k2;
+}
+
+int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d_qhat, int batch, int k2) {
+  if (!c->d_W) { set_error("no weights bound"); return 1; }
+  if (ensure_capacity(c, batch)) return 1;
+  k2 = resolve_k2(c, batch, k2);
+  const bool same = (d_f == d_g);
+  if (k2 == SBTE_K2_BATCH) {
+    if (!same) { set_error("batched convolution requires f == g (single species)"); return 1; }
+    if (!qhat_batch_supported(c->N)) { set_error("batched convolution: unsupported N"); return 1; }
+    launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
+    launch_qhat_batch(c, c->d_lay[0], d_qhat, batch);
+  } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
+    if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
+    launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
+    const double2* gl = c->d_lay[0];
+    if (!same) {
+      launch_fft3d(c, d_g, nullptr, 0, 1, nullptr, c->d_lay[1], LAY_PARITY, nullptr, false);
+      gl = c->d_lay[1];
+    }
+    QhatPair p = {gl, c->d_lay[0]};
+    launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2);
+  } else {
+    if (!same && batch > 4) { set_error("generic convolution with f != g is limited to 4 cells"); return 1; }
+    launch_fft3d(c, d_f, nullptr, 0, batch, c->d_specA, nullptr, 0, nullptr, false);
+    const double2* gs = c->d_specA;
+    if (!same) {
+      launch_fft3d(c, d_g, nullptr, 0, batch, c->d_specB, nullptr, 0, nullptr, false);
+      gs = c->d_specB;
+    }
+    QhatPair p = {gs, c->d_specA};
+    launch_qhat_generic(c, 1, &p, d_qhat, batch);
+  }
+  return check_launch("qhat");
+}
+
+int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
+  if (qhat_from_real(c, d_f, d_g, c->d_qhat, batch, k2)) return 1;
+  launch_fft3d(c, nullptr, c->d_qhat, 1, batch, nullptr, nullptr, 0, d_Q, false);
+  return check_launch("inverse fft");
+}
+
+// ComputeQ_maxPreserve (src/collisions.c:178-210) with the three products folded into one weight pass:
+//   Q^ = sum W ( g_j^[xi] (M_i + g_i)^[zeta-xi] + M_j^[xi] g_i^[zeta-xi] ),  (M_i + g_i)^ = f^.
+int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int k2) {
+  if (!c->d_W) { set_error("no weights bound"); return 1; }
+  if (ensure_capacity(c, 1)) return 1;
+  k2 = resolve_k2(c, 1, k2);
+  const long n3 = c->n3;
+  double* Mi = c->d_M; double* gi = c->d_M + n3; double* Mj = c->d_M + 2 * n3; double* gj = c->d_M + 3 * n3;
+  const bool same = (d_f == d_g);
+  launch_maxwellian_split(c, d_f, nullptr, Mi, gi);
+  if (!same) launch_maxwellian_split(c, d_g, Mi, Mj, gj);
+  else { Mj = Mi; gj = gi; }
+  const bool stream = (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP);
+  if (stream && !qhat_stream_supported(c->N)) { set_error("stream convolution: N must be in {16,24,32}"); return 1; }
+  const int lay = stream ? LAY_PARITY : LAY_NATURAL;
+  // three spectra: f^ (A), g_i^ (B), M_j^ (C); g_j^ == g_i^ for one species (f == g)
+  launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], lay, nullptr, false);
+  launch_fft3d(c, gi, nullptr, 0, 1, nullptr, c->d_lay[1], lay, nullptr, false);
+  launch_fft3d(c, Mj, nullptr, 0, 1, nullptr, c->d_lay[2], lay, nullptr, false);
+  const double2* gjhat = c->d_lay[1];
+  if (!same) {
+    launch_fft3d(c, gj, nullptr, 0, 1, nullptr, c->d_specB, lay, nullptr, false);
+    gjhat = c->d_specB;
+  }
+  QhatPair pairs[2] = {{gjhat, c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]}};
+  if (stream) launch_qhat_stream(c, 2, pairs, c->d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2);
+  else launch_qhat_generic(c, 2, pairs, c->d_qhat, 1);
+  launch_fft3d(c, nullptr, c->d_qhat, 1, 1, nullptr, nullptr, 0, d_Q, false);
+  return check_launch("maxpreserve");
+}
+
+}  // namespace sbte
+
+using namespace sbte;
+
+extern "C" {
+
+const char* sbte_last_error(void) { return g_err.c_str(); }
+
+int sbte_create(sbte_ctx** out, int N, double L_v, const double* v, const double* eta, int device) {
+  *out = nullptr;
+  if (N < 2 || N > 32 || (N % 2) != 0) { set_error("N must be even and in [2, 32]"); return 1; }
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    set_error("no CUDA device available: libsbte_b200 has no CPU fallback");
+    return 1;
+  }
+  CK(cudaSetDevice(device));
+  sbte_ctx* c = new sbte_ctx();
+  c->N = N; c->n3 = (long)N * N * N; c->device = device; c->L_v = L_v;
+  c->v.assign(v, v + N); c->eta.assign(eta, eta + N);
+  c->wt.assign(N, 1.0); c->wt[0] = 0.5; c->wt[N - 1] = 0.5;   // src/collisions.c:48-54
+  c->dv = v[1] - v[0];                                        // src/collisions.c:39-43
+  c->deta = eta[1] - eta[0];
+  c->L_eta = -eta[0];
+  CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+
+  std::vector<double2> tab(N);
+  for (int m = 0; m < N; m++) tab[m] = make_double2(cos(2.0 * M_PI * m / N), sin(2.0 * M_PI * m / N));
+  CK(cudaMalloc(&c->d_dft, N * sizeof(double2)));
+  CK(cudaMemcpy(c->d_dft, tab.data(), N * sizeof(double2), cudaMemcpyHostToDevice));
+  CK(cudaMalloc(&c->d_v, N * sizeof(double)));
+  CK(cudaMalloc(&c->d_wt, N * sizeof(double)));
+  CK(cudaMemcpy(c->d_v, v, N * sizeof(double), cudaMemcpyHostToDevice));
+  CK(cudaMemcpy(c->d_wt, c->wt.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+
+  // twiddle tables with the reference's own expressions (src/collisions.c:238-281), in host libm
+  const double scale3 = pow(1.0 / sqrt(2.0 * M_PI), 3.0);
+  for (int d = 0; d < 2; d++) {
+    const double delta = d ? c->deta : c->dv;
+    const double L_start = d ? c->L_v : c->L_eta;
+    const double L_end = d ? c->L_eta : c->L_v;
+    const double* arr = d ? c->v.data() : c->eta.data();
+    const double sign = d ? -1.0 : 1.0;
+    c->pref[d] = scale3 * delta * delta * delta;
+    std::vector<double2> pre(3 * N - 2), post((size_t)c->n3);
+    for (int s = 0; s < 3 * N - 2; s++) {
+      const double sum = sign * (double)s * L_start * delta;
+      pre[s] = make_double2(cos(sum), sin(sum));
+    }
+    for (int i = 0; i < N; i++)
+      for (int j = 0; j < N; j++)
+        for (int k = 0; k < N; k++) {
+          const double sum = sign * L_end * (arr[i] + arr[j] + arr[k]);
+          post[k + (size_t)N * (j + (size_t)N * i)] = make_double2(cos(sum), sin(sum));
+        }
+    CK(cudaMalloc(&c->d_pre[d], pre.size() * sizeof(double2)));
+    CK(cudaMalloc(&c->d_post[d], post.size() * sizeof(double2)));
+    CK(cudaMemcpy(c->d_pre[d], pre.data(), pre.size() * sizeof(double2), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(c->d_post[d], post.data(), post.size() * sizeof(double2), cudaMemcpyHostToDevice));
+  }
+  if (build_lu(c, &c->lu)) { delete c; return 1; }
+  *out = c;
+  return 0;
+}
+
+int sbte_destroy(sbte_ctx* c) {
+  if (!c) return 0;
+  cudaSetDevice(c->device);
+  cudaStreamSynchronize(c->stream);
+  free_scratch(c);
+  release_weights(c);
+  cudaFree(c->d_v); cudaFree(c->d_wt); cudaFree(c->d_dft);
+  for (int d = 0; d < 2; d++) { cudaFree(c->d_pre[d]); cudaFree(c->d_post[d]); }
+  if (c->h_pin) cudaFreeHost(c->h_pin);
+  for (cudaEvent_t e : c->k2_ev) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+  return 0;
+}
+
+int sbte_sync(sbte_ctx* c) { CK(cudaStreamSynchronize(c->stream)); return check_launch("sync"); }
+void* sbte_stream(sbte_ctx* c) { return (void*)c->stream; }
+unsigned long long sbte_launch_count(sbte_ctx* c) { return c->launches; }
+int sbte_reserve(sbte_ctx* c, int cells) { return ensure_capacity(c, cells); }
+
+int sbte_k2_profile(sbte_ctx* c, int enable) {
+  c->k2_prof = enable != 0;
+  c->k2_ev_used = 0;
+  return 0;
+}
+
+int sbte_k2_profile_read(sbte_ctx* c, double* total_ms, int* launches) {
+  CK(cudaStreamSynchronize(c->stream));
+  double sum = 0.0;
+  const size_t pairs = c->k2_ev_used / 2;
+  for (size_t i = 0; i < pairs; i++) {
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, c->k2_ev[2 * i], c->k2_ev[2 * i + 1]));
+    sum += ms;
+  }
+  *total_ms = sum;
+  *launches = (int)pairs;
+  c->k2_ev_used = 0;
+  return 0;
+}
+
+int sbte_dev_alloc(void** d_ptr, size_t bytes) { CK(cudaMalloc(d_ptr, bytes)); return 0; }
+int sbte_dev_free(void* d_ptr) { CK(cudaFree(d_ptr)); return 0; }
+int sbte_h2d(sbte_ctx* c, void* d_dst, const void* src, size_t bytes) {
+  CK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+int sbte_d2h(sbte_ctx* c, void* dst, const void* d_src, size_t bytes) {
+  CK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return 0;
+}
+
+int sbte_d2d(sbte_ctx* c, void* d_dst, const void* d_src, size_t bytes) {
+  CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->stream));
+  return 0;
+}
+
+// ---- weights
+int sbte_weights_upload_rows(sbte_ctx* c, double* const* rows) {
+  CK(cudaSetDevice(c->device));
+  if (alloc_weights(c)) return 1;
+  // rows are separate host allocations (src/weights.c:61-63): gather through a pinned bounce buffer
+  const size_t row_bytes = (size_t)c->n3 * sizeof(double);
+  const size_t rows_per_chunk = std::max<size_t>(1, (64u << 20) / row_bytes);
+  double* pin[2] = {nullptr, nullptr};
+  CK(cudaMallocHost(&pin[0], rows_per_chunk * row_bytes));
+  CK(cudaMallocHost(&pin[1], rows_per_chunk * row_bytes));
+  cudaEvent_t ev[2];
+  CK(cudaEventCreate(&ev[0])); CK(cudaEventCreate(&ev[1]));
+  int b = 0;
+  for (size_t r0 = 0; r0 < (size_t)c->n3; r0 += rows_per_chunk, b ^= 1) {
+    const size_t nr = std::min(rows_per_chunk, (size_t)c->n3 - r0);
+    CK(cudaEventSynchronize(ev[b]));
+    for (size_t r = 0; r < nr; r++) memcpy(pin[b] + r * c->n3, rows[r0 + r], row_bytes);
+    CK(cudaMemcpyAsync((double*)c->d_W + r0 * c->n3, pin[b], nr * row_bytes, cudaMemcpyHostToDevice, c->stream));
+    CK(cudaEventRecord(ev[b], c->stream));
+  }
+  CK(cudaStreamSynchronize(c->stream));
+  cudaFreeHost(pin[0]); cudaFreeHost(pin[1]);
+  cudaEventDestroy(ev[0]); cudaEventDestroy(ev[1]);
+  c->host_key = (const void*)rows;
+  return make_tensor_map(c);
+}
+
+int sbte_weights_upload(sbte_ctx* c, const double* W) {
+  CK(cudaSetDevice(c->device));
+  if (alloc_weights(c)) return 1;
+  CK(cudaMemcpy((void*)c->d_W, W, (size_t)c->n3 * c->n3 * sizeof(double), cudaMemcpyHostToDevice));
+  return make_tensor_map(c);
+}
+
+int sbte_weights_load_file(sbte_ctx* c, const char* path) {
+  CK(cudaSetDevice(c->device));
+  FILE* fp = fopen(path, "rb");
+  if (!fp) { set_error(std::string("cannot open weight file ") + path); return 1; }
+  if (alloc_weights(c)) { fclose(fp); return 1; }
+  const size_t total = (size_t)c->n3 * c->n3;
+  const size_t chunk = (size_t)(64u << 20) / sizeof(double);
+  double* pin = nullptr;
+  CK(cudaMallocHost(&pin, chunk * sizeof(double)));
+  for (size_t off = 0; off < total; off += chunk) {
+    const size_t n = std::min(chunk, total - off);
+    if (fread(pin, sizeof(double), n, fp) != n) {   // src/weights.c:82-86
+      fclose(fp); cudaFreeHost(pin); release_weights(c);
+      set_error("Error reading weight file");
+      return 1;
+    }
+    CK(cudaMemcpy((double*)c->d_W + off, pin, n * sizeof(double), cudaMemcpyHostToDevice));
+  }
+  fclose(fp);
+  cudaFreeHost(pin);
+  return make_tensor_map(c);
+}
+
+int sbte_weights_bind_device(sbte_ctx* c, const double* d_W) {
+  release_weights(c);
+  c->d_W = d_W; c->owns_W = false;
+  return make_tensor_map(c);
+}
+
+int sbte_weights_fill_synthetic(sbte_ctx* c, unsigned long long seed) {
+  CK(cudaSetDevice(c->device));
+  if (alloc_weights(c)) return 1;
+  synth_weights_kernel<<<148 * 8, 256, 0, c->stream>>>((double*)c->d_W, (size_t)c->n3 * c->n3, seed);
+  c->launches += 1;
+  CK(cudaStreamSynchronize(c->stream));
+  return make_tensor_map(c);
+}
+
+const double* sbte_weights_device(sbte_ctx* c) { return c->d_W; }
+
+// ---- device-pointer operations
+int sbte_fft3d(sbte_ctx* c, const double* d_in, double* d_out, int invert, int batch) {
+  if (ensure_capacity(c, batch)) return 1;
+  launch_fft3d(c, nullptr, (const double2*)d_in, invert, batch, (double2*)d_out, nullptr, 0, nullptr, false);
+  return check_launch("fft3d");
+}
+
+int sbte_qhat(sbte_ctx* c, const double* d_f, const double* d_g, double* d_qhat, int batch, int k2) {
+  return qhat_from_real(c, d_f, d_g, (double2*)d_qhat, batch, k2);
+}
+
+int sbte_compute_q(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
+  return compute_q_dev(c, d_f, d_g, d_Q, batch, k2);
+}
+
+int sbte_compute_q_maxpreserve(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int k2) {
+  return compute_q_maxpreserve_dev(c, d_f, d_g, d_Q, k2);
+}
+
+int sbte_conserve(sbte_ctx* c, double* d_Q, int batch) {
+  launch_conserve(c, d_Q, batch);
+  return check_launch("conserve");
+}
+
+int sbte_moment_functionals(sbte_ctx* c, const double* d_Q, double* d_b5, int batch) {
+  launch_moment_functionals(c, d_Q, d_b5, batch);
+  return check_launch("moment_functionals");
+}
+
+int sbte_moments(sbte_ctx* c, const double* d_f, double* d_mom8, int batch) {
+  launch_moments(c, d_f, d_mom8, batch);
+  return check_launch("moments");
+}
+
+// exec/boltz.c:189-241
+int sbte_step_0d(sbte_ctx* c, double* d_f, double dt, double Kn, int order, int k2) {
+  if (ensure_capacity(c, 1)) return 1;
+  const long n3 = c->n3;
+  double* Q = c->d_Q;
+  if (compute_q_maxpreserve_dev(c, d_f, d_f, Q, k2)) return 1;
+  launch_conserve(c, Q, 1);
+  if (order == 1) {
+    launch_update(c, d_f, 1.0, d_f, 0.0, nullptr, dt, Kn, Q, n3);
+  } else {
+    double* f1 = c->d_g;
+    launch_update(c, f1, 1.0, d_f, 0.0, nullptr, dt, Kn, Q, n3);
+    if (compute_q_maxpreserve_dev(c, f1, f1, Q, k2)) return 1;
+    launch_conserve(c, Q, 1);
+    launch_update(c, d_f, 0.5, d_f, 0.5, f1, 0.5 * dt, Kn, Q, n3);
+  }
+  return check_launch("step_0d");
+}
+
+// ---- host-pointer forms
+int sbte_compute_q_host(sbte_ctx* c, const double* f, const double* g, double* Q, int k2) {
+  if (ensure_capacity(c, 1)) return 1;
+  const size_t bytes = (size_t)c->n3 * sizeof(double);
+  CK(cudaMemcpyAsync(c->d_f, f, bytes, cudaMemcpyHostToDevice, c->stream));
+  const double* dg = c->d_f;
+  if (g != f) {
+    CK(cudaMemcpyAsync(c->d_g, g, bytes, cudaMemcpyHostToDevice, c->stream));
+    dg = c->d_g;
+  }
+  if (compute_q_dev(c, c->d_f, dg, c->d_Q, 1, k2)) return 1;
+  CK(cudaMemcpyAsync(Q, c->d_Q, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return check_launch("compute_q_host");
+}
+
+int sbte_compute_q_maxpreserve_host(sbte_ctx* c, const double* f, const double* g, double* Q, int k2) {
+  if (ensure_capacity(c, 1)) return 1;
+  const size_t bytes = (size_t)c->n3 * sizeof(double);
+  CK(cudaMemcpyAsync(c->d_f, f, bytes, cudaMemcpyHostToDevice, c->stream));
+  const double* dg = c->d_f;
+  if (g != f) {
+    CK(cudaMemcpyAsync(c->d_g, g, bytes, cudaMemcpyHostToDevice, c->stream));
+    dg = c->d_g;
+  }
+  if (compute_q_maxpreserve_dev(c, c->d_f, dg, c->d_Q, k2)) return 1;
+  CK(cudaMemcpyAsync(Q, c->d_Q, bytes, cudaMemcpyDeviceToHost, c->stream));
+  CK(cudaStreamSynchronize(c->stream));
+  return check_launch("compute_q_maxpreserve_host");
+}
+
+}  // extern "C"

@@ -1,0 +1,187 @@
+// spectralbte_b200/csrc/dropin.cu -- the reference's link interface (include/sbte_b200.h, section 1).
+//
+// exec/boltz.c and src/initializer.c of the reference call these exactly as they call
+// src/collisions.c, src/conserve.c and src/transportroutines.c; here each call moves its host
+// arguments to the device, runs the sm_100a kernels and copies the result back.  Like the
+// reference, state is process-global (one grid per process) and errors are fatal (printf + exit),
+// cf. src/conserve.c:130-135, src/weights.c:83-86.
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <vector>
+
+#include "../../include/sbte_b200.h"
+#include "internal.h"
+
+namespace {
+
+sbte_ctx* g_ctx = nullptr;
+bool g_cons_ready = false;
+
+struct TransportState {
+  bool ready = false;
+  int N = 0, nX = 0, ic = 0;
+  double dt = 0;
+  std::vector<double> x, dx;       // as handed to initialize_transport (length unknown: kept as pointers too)
+  const double* xp = nullptr;
+  const double* dxp = nullptr;
+  sbte_slab* slab = nullptr;
+  int slab_order = 0;
+} g_tr;
+
+[[noreturn]] void die(const char* where) {
+  printf("libsbte_b200: %s failed: %s\n", where, sbte_last_error());
+  fflush(stdout);
+  exit(1);
+}
+
+int local_device() {
+  // one process per GPU: honour the launcher's LOCAL_RANK / MPI local rank if present
+  const char* names[] = {"SBTE_DEVICE", "LOCAL_RANK", "OMPI_COMM_WORLD_LOCAL_RANK", "MV2_COMM_WORLD_LOCAL_RANK",
+                         "SLURM_LOCALID"};
+  for (const char* n : names) {
+    const char* v = getenv(n);
+    if (v && *v) {
+      int ndev = 0;
+      if (cudaGetDeviceCount(&ndev) == cudaSuccess && ndev > 0) return atoi(v) % ndev;
+    }
+  }
+  return 0;
+}
+
+void need_ctx(const char* who) {
+  if (!g_ctx) {
+    printf("libsbte_b200: %s called before initialize_coll\n", who);
+    exit(1);
+  }
+}
+
+void sync_weights(double** conv_weights) {
+  if (g_ctx->host_key != (const void*)conv_weights || !g_ctx->d_W) {
+    if (sbte_weights_upload_rows(g_ctx, conv_weights)) die("weight upload");
+  }
+}
+
+sbte_slab* slab_for(int order) {
+  if (!g_tr.ready) {
+    printf("libsbte_b200: advect called before initialize_transport\n");
+    exit(1);
+  }
+  if (g_tr.slab && g_tr.slab_order != order) { sbte_slab_destroy(g_tr.slab); g_tr.slab = nullptr; }
+  if (!g_tr.slab) {
+    // the caller's x/dx arrays have nX + 2*order entries (src/mesh_setup.c:78-79)
+    if (sbte_slab_create(g_ctx, &g_tr.slab, g_tr.nX, order, g_tr.xp, g_tr.dxp, g_tr.ic, g_tr.dt, 0, 1))
+      die("slab creation");
+    g_tr.slab_order = order;
+  }
+  return g_tr.slab;
+}
+
+// advectOne / advectTwo on arrays of host cell pointers: gather -> device slab -> kernels -> scatter.
+void advect_host(double** f, double** f_conv, int order) {
+  need_ctx("advect");
+  sbte_slab* s = slab_for(order);
+  const long n3 = g_ctx->n3;
+  const int ncell = g_tr.nX + 2 * order;
+  std::vector<double> host((size_t)ncell * n3, 0.0);
+  for (int l = order; l < g_tr.nX + order; l++) memcpy(&host[(size_t)l * n3], f[l], n3 * sizeof(double));
+  if (sbte_slab_upload(s, host.data())) die("slab upload");
+  if (sbte_slab_advect(s, 0)) die("advect");
+  // results: owned cells of f_conv
+  std::vector<double> out((size_t)ncell * n3);
+  if (sbte_d2h(g_ctx, out.data(), sbte_slab_fconv(s), out.size() * sizeof(double))) die("slab download");
+  for (int l = order; l < g_tr.nX + order; l++) memcpy(f_conv[l], &out[(size_t)l * n3], n3 * sizeof(double));
+}
+
+}  // namespace
+
+extern "C" {
+
+void initialize_coll(int nodes, double length, double* vel, double* zeta) {
+  if (g_ctx) { sbte_destroy(g_ctx); g_ctx = nullptr; }
+  if (sbte_create(&g_ctx, nodes, length, vel, zeta, local_device())) die("initialize_coll");
+}
+
+void dealloc_coll(void) {
+  if (g_tr.slab) { sbte_slab_destroy(g_tr.slab); g_tr.slab = nullptr; }
+  if (g_ctx) { sbte_destroy(g_ctx); g_ctx = nullptr; }
+}
+
+void ComputeQ(double* f, double* g, double* Q, double** conv_weights) {
+  need_ctx("ComputeQ");
+  sync_weights(conv_weights);
+  if (sbte_compute_q_host(g_ctx, f, g, Q, SBTE_K2_AUTO)) die("ComputeQ");
+}
+
+void ComputeQ_maxPreserve(double* f, double* g, double* Q, double** conv_weights) {
+  need_ctx("ComputeQ_maxPreserve");
+  sync_weights(conv_weights);
+  if (sbte_compute_q_maxpreserve_host(g_ctx, f, g, Q, SBTE_K2_AUTO)) die("ComputeQ_maxPreserve");
+}
+
+void fft3D(double (*in)[2], double (*out)[2], int invert) {
+  need_ctx("fft3D");
+  const size_t bytes = (size_t)g_ctx->n3 * 2 * sizeof(double);
+  if (sbte::ensure_capacity(g_ctx, 1)) die("fft3D");
+  double* din = (double*)g_ctx->d_specB;
+  double* dout = (double*)g_ctx->d_specC;
+  if (sbte_h2d(g_ctx, din, in, bytes)) die("fft3D h2d");
+  if (sbte_fft3d(g_ctx, din, dout, invert, 1)) die("fft3D");
+  if (sbte_d2h(g_ctx, out, dout, bytes)) die("fft3D d2h");
+}
+
+void initialize_conservation(int nodes, double h_v, double* vel, sbte_species* mix, int num_spec) {
+  (void)h_v; (void)vel;
+  need_ctx("initialize_conservation");
+  if (num_spec != 1) {
+    printf("libsbte_b200: only single-species conservation is implemented (num_spec = %d)\n", num_spec);
+    exit(1);
+  }
+  if (mix && mix[0].mass != 1.0) {
+    printf("libsbte_b200: only unit-mass species are implemented (mass = %g)\n", mix[0].mass);
+    exit(1);
+  }
+  if (nodes != g_ctx->N) {
+    printf("libsbte_b200: initialize_conservation grid (%d) differs from initialize_coll (%d)\n", nodes, g_ctx->N);
+    exit(1);
+  }
+  g_cons_ready = true;  // the LU of the moment Gram matrix is built with the context
+}
+
+void initialize_conservation_fast(int nodes, double h_v, double* vel) {
+  initialize_conservation(nodes, h_v, vel, nullptr, 1);
+}
+
+void conserveAllMoments(double** Q) {
+  need_ctx("conserveAllMoments");
+  if (!g_cons_ready) {
+    printf("libsbte_b200: conserveAllMoments called before initialize_conservation\n");
+    exit(1);
+  }
+  const size_t bytes = (size_t)g_ctx->n3 * sizeof(double);
+  if (sbte::ensure_capacity(g_ctx, 1)) die("conserveAllMoments");
+  if (sbte_h2d(g_ctx, g_ctx->d_Q, Q[0], bytes)) die("conserve h2d");
+  if (sbte_conserve(g_ctx, g_ctx->d_Q, 1)) die("conserveAllMoments");
+  if (sbte_d2h(g_ctx, Q[0], g_ctx->d_Q, bytes)) die("conserve d2h");
+}
+
+void dealloc_conservation(void) { g_cons_ready = false; }
+
+void initialize_transport(int numV, int numX, double lv, double* xnodes, double* dxnodes, double* vel, int IC,
+                          double timestep, double TWall_in, sbte_species* mix) {
+  (void)lv; (void)vel; (void)TWall_in; (void)mix;
+  g_tr.ready = true;
+  g_tr.N = numV; g_tr.nX = numX; g_tr.ic = IC; g_tr.dt = timestep;
+  g_tr.xp = xnodes; g_tr.dxp = dxnodes;   // retained like the reference (src/transportroutines.c:31-32)
+  if (g_tr.slab) { sbte_slab_destroy(g_tr.slab); g_tr.slab = nullptr; }
+}
+
+void advectOne(double** f, double** f_conv, int id) { (void)id; advect_host(f, f_conv, 1); }
+void advectTwo(double** f, double** f_conv, int id) { (void)id; advect_host(f, f_conv, 2); }
+
+void dealloc_trans(void) {
+  if (g_tr.slab) { sbte_slab_destroy(g_tr.slab); g_tr.slab = nullptr; }
+  g_tr.ready = false;
+}
+
+}  // extern "C"

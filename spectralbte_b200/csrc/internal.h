@@ -1,0 +1,103 @@
+// spectralbte_b200/csrc/internal.h -- library-internal state and kernel launchers.
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+
+struct sbte_slab;
+
+// Conservation data handed to kernels by value: the factored Gram matrix of the five moment
+// functionals and its pivots (reference: src/conserve.c:89-168,268-317).
+struct ConsLU {
+  double a[25];
+  int piv[5];
+};
+
+struct sbte_ctx {
+  int N = 0;
+  long n3 = 0;
+  int device = 0;
+  double L_v = 0, L_eta = 0, dv = 0, deta = 0;
+  cudaStream_t stream = nullptr;
+  std::vector<double> v, eta, wt;
+
+  // device tables
+  double* d_v = nullptr;         // [N]
+  double* d_wt = nullptr;        // [N] trapezoid weights
+  double2* d_dft = nullptr;      // [N] (cos, sin)(2 pi m / N)
+  double2* d_pre[2] = {nullptr, nullptr};   // [3N-2] pre-twiddle (cos,sin) by i+j+k; 0 = forward, 1 = inverse
+  double2* d_post[2] = {nullptr, nullptr};  // [N^3] post-twiddle (cos,sin)
+  double pref[2] = {0, 0};       // (2 pi)^-3/2 delta^3
+  ConsLU lu;
+
+  // weights
+  const double* d_W = nullptr;   // N^3 x N^3, row-major [zeta][xi]
+  bool owns_W = false;
+  const void* host_key = nullptr;  // identity of the host row-pointer array the cached copy came from
+  CUtensorMap tmapW;
+  bool tmap_ok = false;
+
+  // scratch, sized for `cap` cells
+  int cap = 0;
+  double2* d_tmp = nullptr;      // FFT intermediate           [cap][n3]
+  double2* d_specA = nullptr;    // spectra, natural layout     [cap][n3]  (operand "f": zeta - xi side)
+  double2* d_specB = nullptr;    //                             [cap][n3]  (operand "g": xi side)
+  double2* d_specC = nullptr;    // third spectrum (maxPreserve: Maxwellian)
+  double2* d_lay[3] = {nullptr, nullptr, nullptr};  // kernel-specific operand layouts of A, B, C
+  double2* d_qhat = nullptr;     // [cap][n3]
+  double* d_Q = nullptr;         // [cap][n3]
+  double* d_f = nullptr;         // staging for host-pointer entry points [cap][n3]
+  double* d_g = nullptr;
+  double* d_M = nullptr;         // Maxwellian / perturbation scratch (0D)
+  double* d_mom = nullptr;       // [cap][8] moments
+  double* h_pin = nullptr;       // pinned host staging, 3 * n3 doubles
+  unsigned long long launches = 0;  // kernels launched through this context
+  bool k2_prof = false;             // bracket every K2 launch with CUDA events
+  std::vector<cudaEvent_t> k2_ev;   // [2*i], [2*i+1] = start/stop of launch i
+  size_t k2_ev_used = 0;
+};
+
+namespace sbte {
+
+void set_error(const std::string& msg);
+void k2_mark(sbte_ctx* c);   // records a profiling event on c->stream when K2 profiling is on
+int ensure_capacity(sbte_ctx* c, int cells);
+
+// operand layouts produced by the forward transform's last pass
+enum SpecLayout {
+  LAY_NATURAL = 0,   // [cell][x][y][z]
+  LAY_PARITY = 1,    // [cell][x][y][z&1][z>>1]            (stream kernel: conflict-free 2-column reads)
+  LAY_CELLMINOR = 2  // [cell/32][x][y][z][cell%32]        (batched kernel: lanes = cells)
+};
+
+// fft.cu -- K1 / K3. in_real: N^3 doubles per cell; in_cplx: N^3 double2 per cell (exactly one non-null).
+// out_nat / out_lay / out_real may each be null. batch = number of cells.
+void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,
+                  double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real);
+
+// qhat.cu -- K2
+struct QhatPair {
+  const double2* xi_side;    // g^[xi]
+  const double2* dif_side;   // f^[zeta - xi]
+};
+// generic: natural-layout operands, any N, any batch (one CTA per (zeta, cell))
+void launch_qhat_generic(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int batch);
+// stream kernel (N in {16,24,32}, batch 1): parity-layout operands
+bool qhat_stream_supported(int N);
+void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth);
+// batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32
+bool qhat_batch_supported(int N);
+void launch_qhat_batch(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells);
+
+// conserve.cu -- K4 / K5 / moments
+void launch_conserve(sbte_ctx* c, double* Q, int batch);
+// out = a*x + b*y + s*Q/Kn   (x, y, out may alias; y may be null)   -- time-integration glue
+void launch_update(sbte_ctx* c, double* out, double a, const double* x, double b, const double* y, double s,
+                   double Kn, const double* Q, long n);
+void launch_moments(sbte_ctx* c, const double* f, double* mom8, int batch);   // rho,ux,uy,uz,T,Epos,Eneg,-
+void launch_maxwellian_split(sbte_ctx* c, const double* f, const double* Msub, double* M, double* g);
+void launch_moment_functionals(sbte_ctx* c, const double* Q, double* b5, int batch);
+
+}  // namespace sbte

@@ -1,0 +1,284 @@
+// spectralbte_b200/csrc/qhat.cu -- K2: the weighted spectral convolution
+//     Q^[zeta] = sum_xi W[zeta][xi] * g^[xi] * f^[wrap(zeta + N/2 - xi)]
+// (reference hot loop: /root/reference/src/collisions.c:127-165; wrap once per dimension :141-158).
+//
+// Three kernels:
+//   qhat_generic : any N, any batch.  One CTA per (zeta row, cell); correctness path for sizes the
+//                  tuned kernels do not cover (N = 6, 8, 12, 22, ...).
+//   qhat_stream  : batch 1 (0D).  HBM-bound: every weight is read exactly once with 128-bit
+//                  non-allocating loads, software-pipelined in registers; the operand planes
+//                  g^[xi_x][.][.] and f^[X][.][.] are staged by TMA bulk copies (cp.async.bulk +
+//                  mbarrier) into a double-buffered shared-memory ring; each thread owns a
+//                  4-row x 2-column register tile so the Toeplitz structure in z gives 8 weights per
+//                  7 operand reads.  NP operand pairs can share one weight pass (maxPreserve).
+//   qhat_batch   : many cells share each weight (1D).  FP64-bound: lanes = cells, one warp per
+//                  zeta (x,y) column, the whole N x N (zeta_z, xi_z) Toeplitz tile in registers.
+//                  (qhat_batch.cu)
+#include "common.cuh"
+#include "internal.h"
+
+namespace sbte {
+
+// ------------------------------------------------------------------------------------------
+// generic
+// ------------------------------------------------------------------------------------------
+template <int NP>
+__global__ void __launch_bounds__(256)
+qhat_generic_kernel(const double* __restrict__ W, const double2* __restrict__ xi0, const double2* __restrict__ df0,
+                    const double2* __restrict__ xi1, const double2* __restrict__ df1, double2* __restrict__ qhat,
+                    int N) {
+  __shared__ double red[2 * 32];
+  const long n3 = (long)N * N * N;
+  const int zeta = blockIdx.x;
+  const long cell = blockIdx.y;
+  const int n2 = N / 2;
+  const int zx = zeta / (N * N), zy = (zeta / N) % N, zz = zeta % N;
+  const double* w = W + (long)zeta * n3;
+  const double2* g0 = xi0 + cell * n3;
+  const double2* f0 = df0 + cell * n3;
+  const double2* g1 = NP > 1 ? xi1 + cell * n3 : nullptr;
+  const double2* f1 = NP > 1 ? df1 + cell * n3 : nullptr;
+  double acc[2] = {0.0, 0.0};
+  for (int xi = threadIdx.x; xi < n3; xi += blockDim.x) {
+    const int ex = xi / (N * N), ey = (xi / N) % N, ez = xi % N;
+    int x = zx + n2 - ex, y = zy + n2 - ey, z = zz + n2 - ez;
+    if (x < 0) x += N; else if (x > N - 1) x -= N;
+    if (y < 0) y += N; else if (y > N - 1) y -= N;
+    if (z < 0) z += N; else if (z > N - 1) z -= N;
+    const int idx = z + N * (y + N * x);
+    double2 p = cmul(g0[xi], f0[idx]);
+    if (NP > 1) {
+      const double2 q = cmul(g1[xi], f1[idx]);
+      p.x += q.x; p.y += q.y;
+    }
+    const double wv = w[xi];
+    acc[0] = fma(wv, p.x, acc[0]);
+    acc[1] = fma(wv, p.y, acc[1]);
+  }
+  block_reduce_sum<2>(acc, red);
+  if (threadIdx.x == 0) qhat[cell * n3 + zeta] = make_double2(acc[0], acc[1]);
+}
+
+void launch_qhat_generic(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int batch) {
+  dim3 grid((unsigned)c->n3, batch);
+  k2_mark(c);
+  if (npairs == 1)
+    qhat_generic_kernel<1><<<grid, 256, 0, c->stream>>>(c->d_W, pairs[0].xi_side, pairs[0].dif_side, nullptr, nullptr,
+                                                        qhat, c->N);
+  else
+    qhat_generic_kernel<2><<<grid, 256, 0, c->stream>>>(c->d_W, pairs[0].xi_side, pairs[0].dif_side, pairs[1].xi_side,
+                                                        pairs[1].dif_side, qhat, c->N);
+  k2_mark(c);
+  c->launches += 1;
+}
+
+// ------------------------------------------------------------------------------------------
+// stream kernel
+// ------------------------------------------------------------------------------------------
+template <int N>
+struct StreamCfg {
+  static constexpr int HALF = N / 2;            // 2-column groups per N-long weight row segment
+  static constexpr int RGW = 32 / HALF;         // 4-row groups handled by one warp
+  static constexpr int ROWS_W = RGW * 4;        // rows per warp
+  static constexpr int RB = N / ROWS_W;         // warps that tile the N rows of one zeta (x,y) column
+  static constexpr int PH = (8 / RB) < 1 ? 1 : (8 / RB);  // xi_y phases (warps sharing the same rows)
+  static constexpr int NWARP = RB * PH;
+  static constexpr int THREADS = NWARP * 32;
+  static constexpr int SPC = N / PH;            // steps per xi_x chunk per warp
+  static constexpr int PLANE = N * N;           // complex elements per operand plane
+  static_assert(N % 2 == 0 && 32 % HALF == 0 || N == 24, "unsupported N");
+  static_assert(N % ROWS_W == 0, "rows must tile");
+  static_assert(N % PH == 0, "phases must tile");
+};
+
+template <int N, int NP, int DEPTH>
+__global__ void __launch_bounds__(StreamCfg<N>::THREADS, (N == 32 && NP == 1 && DEPTH <= 2) ? 2 : 1)
+qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
+                   const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat) {
+  using C = StreamCfg<N>;
+  constexpr int HALF = C::HALF, PLANE = C::PLANE;
+  constexpr long n3 = (long)N * N * N;
+  constexpr uint32_t STAGE_ELEMS = 2 * NP * PLANE;  // per stage: NP x (xi-side plane, dif-side plane)
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double2* planes = reinterpret_cast<double2*>(smraw);                       // [2][NP][2][PLANE]
+  uint64_t* full = reinterpret_cast<uint64_t*>(smraw + 2 * STAGE_ELEMS * sizeof(double2));
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int rb = warp % C::RB, ph = warp / C::RB;
+  const int cp = lane % HALF, rgw = lane / HALF;
+  const bool active = rgw < C::RGW;
+  const int zx = blockIdx.x / N, zy = blockIdx.x % N;
+  const int r0 = rb * C::ROWS_W + (active ? rgw : 0) * 4;   // first of this thread's 4 zeta_z rows
+  const int c0 = 2 * cp;                                    // first of its 2 xi_z columns
+
+  // thread-constant operand offsets inside a parity-split line [par][z>>1]
+  int offw[5];
+#pragma unroll
+  for (int k = 0; k < 5; k++) {
+    int z = r0 - c0 - 1 + N / 2 + k;
+    z = ((z % N) + N) % N;
+    offw[k] = (z & 1) * HALF + (z >> 1);
+  }
+  const int offg0 = cp, offg1 = HALF + cp;
+
+  auto issue_chunk = [&](int chunk) {  // one thread: stage the operand planes of xi_x = chunk
+    const int s = chunk & 1;
+    int X = zx + N / 2 - chunk;
+    if (X < 0) X += N; else if (X > N - 1) X -= N;
+    double2* dst = planes + (size_t)s * STAGE_ELEMS;
+    mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * (uint32_t)sizeof(double2));
+    tma_bulk_g2s(dst, xiA + (size_t)chunk * PLANE, PLANE * sizeof(double2), &full[s]);
+    tma_bulk_g2s(dst + PLANE, dfA + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
+    if (NP > 1) {
+      tma_bulk_g2s(dst + 2 * PLANE, xiB + (size_t)chunk * PLANE, PLANE * sizeof(double2), &full[s]);
+      tma_bulk_g2s(dst + 3 * PLANE, dfB + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
+    }
+  };
+
+  if (tid == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_fence_init();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    issue_chunk(0);
+    issue_chunk(1);
+  }
+
+  // weight stream: rows zeta = (zx, zy, r0 + j), j = 0..3; this thread's 16 bytes sit at column c0
+  const double* wrow = W + ((long)blockIdx.x * N + r0) * n3 + c0;
+  constexpr int NIT = N * C::SPC;  // iterations of this warp over (xi_x, xi_y)
+  double2 wb[DEPTH][4];
+  auto load_w = [&](int it, double2 (&dst)[4]) {
+    const int ex = it / C::SPC, ey = ph + (it % C::SPC) * C::PH;
+    const double* p = wrow + ((long)ex * N + ey) * N;
+#pragma unroll
+    for (int j = 0; j < 4; j++) dst[j] = ldg_stream_f64x2(p + (long)j * n3);
+  };
+  if (active) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) load_w(d, wb[d]);
+  }
+
+  double2 acc[4];
+#pragma unroll
+  for (int j = 0; j < 4; j++) acc[j] = make_double2(0.0, 0.0);
+
+  for (int it0 = 0; it0 < NIT; it0 += DEPTH) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; d++) {
+      const int it = it0 + d;
+      const int chunk = it / C::SPC, step = it % C::SPC;
+      const int s = chunk & 1;
+      if (step == 0) mbar_wait(&full[s], (chunk >> 1) & 1);
+      const int ey = ph + step * C::PH;
+      int Y = zy + N / 2 - ey;
+      if (Y < 0) Y += N; else if (Y > N - 1) Y -= N;
+      const double2* st = planes + (size_t)s * STAGE_ELEMS;
+      if (active) {
+        double2 p[4][2];
+        {
+          const double2* gl = st + ey * N;
+          const double2* fl = st + PLANE + Y * N;
+          const double2 g0 = gl[offg0], g1 = gl[offg1];
+          double2 fw[5];
+#pragma unroll
+          for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            p[j][0] = cmul(g0, fw[j + 1]);
+            p[j][1] = cmul(g1, fw[j]);
+          }
+        }
+        if (NP > 1) {
+          const double2* gl = st + 2 * PLANE + ey * N;
+          const double2* fl = st + 3 * PLANE + Y * N;
+          const double2 g0 = gl[offg0], g1 = gl[offg1];
+          double2 fw[5];
+#pragma unroll
+          for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            const double2 a = cmul(g0, fw[j + 1]), b = cmul(g1, fw[j]);
+            p[j][0].x += a.x; p[j][0].y += a.y;
+            p[j][1].x += b.x; p[j][1].y += b.y;
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          cmac(acc[j], wb[d][j].x, p[j][0]);
+          cmac(acc[j], wb[d][j].y, p[j][1]);
+        }
+        if (it + DEPTH < NIT) load_w(it + DEPTH, wb[d]);
+      }
+      if (step == C::SPC - 1) {
+        // every warp is done with stage s: refill it with the planes of chunk + 2
+        __syncthreads();
+        if (tid == 0 && chunk + 2 < N) issue_chunk(chunk + 2);
+      }
+    }
+  }
+
+  // deterministic cross-thread reduction: [thread][4] partial sums -> N rows (reuses the plane ring;
+  // the trailing __syncthreads of the last chunk guarantees nobody still reads it)
+  double2* red = planes;
+#pragma unroll
+  for (int j = 0; j < 4; j++) red[tid * 4 + j] = active ? acc[j] : make_double2(0.0, 0.0);
+  __syncthreads();
+  if (tid < N) {
+    const int r = tid;
+    const int rbr = r / C::ROWS_W, rg = (r % C::ROWS_W) / 4, j = r % 4;
+    double sr = 0.0, si = 0.0;
+    for (int p = 0; p < C::PH; p++) {
+      const int w = p * C::RB + rbr;
+      for (int q = 0; q < HALF; q++) {
+        const double2 v = red[((w * 32) + rg * HALF + q) * 4 + j];
+        sr += v.x; si += v.y;
+      }
+    }
+    qhat[(long)blockIdx.x * N + r] = make_double2(sr, si);
+  }
+}
+
+bool qhat_stream_supported(int N) { return N == 16 || N == 24 || N == 32; }
+
+template <int N, int NP, int DEPTH>
+static void launch_stream_inst(sbte_ctx* c, const QhatPair* pairs, double2* qhat) {
+  using C = StreamCfg<N>;
+  const size_t smem = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2) + 64;
+  auto kern = qhat_stream_kernel<N, NP, DEPTH>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  k2_mark(c);
+  kern<<<N * N, C::THREADS, smem, c->stream>>>(c->d_W, pairs[0].xi_side, pairs[0].dif_side,
+                                               NP > 1 ? pairs[1].xi_side : nullptr,
+                                               NP > 1 ? pairs[1].dif_side : nullptr, qhat);
+  k2_mark(c);
+  c->launches += 1;
+}
+
+template <int N>
+static void launch_stream_n(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth) {
+  if (npairs == 1) {
+    if (depth >= 4) launch_stream_inst<N, 1, 4>(c, pairs, qhat);
+    else launch_stream_inst<N, 1, 2>(c, pairs, qhat);
+  } else {
+    if (depth >= 4) launch_stream_inst<N, 2, 4>(c, pairs, qhat);
+    else launch_stream_inst<N, 2, 2>(c, pairs, qhat);
+  }
+}
+
+void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth) {
+  switch (c->N) {
+    case 16: launch_stream_n<16>(c, npairs, pairs, qhat, depth); break;
+    case 24: launch_stream_n<24>(c, npairs, pairs, qhat, depth); break;
+    case 32: launch_stream_n<32>(c, npairs, pairs, qhat, depth); break;
+    default: set_error("qhat_stream: unsupported N"); break;
+  }
+}
+
+}  // namespace sbte

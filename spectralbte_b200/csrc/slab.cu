@@ -1,0 +1,257 @@
+// spectralbte_b200/csrc/slab.cu -- device-resident 1D-3V state: a slab of cells_local + 2*order
+// cells per rank, the transport half-steps and the batched collision half-step.
+//
+// Mirrors the 1D branch of the reference driver (/root/reference/exec/boltz.c:264-353) and the
+// ghost-cell logic of src/transportroutines.c:107-172 (order 1) and :261-404 (order 2), with the
+// blocking MPI halo replaced by "ghost cells are filled by the caller" (NCCL / peer copies between
+// the regions reported by sbte_slab_halo_regions) so f never leaves the device.
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/sbte_b200.h"
+#include "internal.h"
+#include "transport.h"
+
+namespace sbte {
+int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2);
+}
+
+struct sbte_slab {
+  sbte_ctx* c = nullptr;
+  int nX = 0, order = 1, ic = 0, rank = 0, nranks = 1, ncell = 0;
+  double dt = 0;
+  double *d_x = nullptr, *d_dx = nullptr;
+  double *d_f = nullptr, *d_fc = nullptr, *d_f1 = nullptr, *d_ft = nullptr;  // f, f_conv, f_1, f_tmp
+  double *d_fl = nullptr, *d_fr = nullptr;                                   // wall faces
+  double* d_Q = nullptr;                                                     // nX cells
+  double* d_mom = nullptr;
+};
+
+using namespace sbte;
+
+#define CKS(call)                                                                 \
+  do {                                                                            \
+    cudaError_t e_ = (call);                                                      \
+    if (e_ != cudaSuccess) {                                                      \
+      sbte::set_error(std::string(#call) + ": " + cudaGetErrorString(e_));        \
+      return 1;                                                                   \
+    }                                                                             \
+  } while (0)
+
+static int launch_ok(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) { set_error(std::string(what) + ": " + cudaGetErrorString(e)); return 1; }
+  return 0;
+}
+
+static const double T0_WALL = 1.0, T1_WALL = 2.0;  // src/transportroutines.c:46-47
+static const double TWALL_IN = 1.0;                // src/initializer.c:275
+
+static inline double* cell(double* base, long n3, int l) { return base + (long)l * n3; }
+
+// ghost cells owned by the physical boundaries, order 1 (src/transportroutines.c:116-137,156-172)
+static void fill_ghosts_one(sbte_slab* s, double* f) {
+  sbte_ctx* c = s->c;
+  const long n3 = c->n3;
+  const size_t cb = (size_t)n3 * sizeof(double);
+  const int nX = s->nX, ic = s->ic;
+  cudaStream_t st = c->stream;
+  const bool first = s->rank == 0, last = s->rank == s->nranks - 1;
+  if (first) {
+    if (ic == 3 || ic == 5) { launch_diffuse_bc(st, cell(f, n3, 1), cell(f, n3, 0), c->d_v, c->d_wt, c->N, c->dv, T0_WALL, 0); c->launches++; }
+    else if (ic == 1) { launch_diffuse_bc(st, cell(f, n3, 1), cell(f, n3, 0), c->d_v, c->d_wt, c->N, c->dv, 2.0 * TWALL_IN, 0); c->launches++; }
+    else if (ic != 6) cudaMemcpyAsync(cell(f, n3, 0), cell(f, n3, 1), cb, cudaMemcpyDeviceToDevice, st);
+  }
+  if (last) {
+    if (ic == 3 || ic == 5) { launch_diffuse_bc(st, cell(f, n3, nX), cell(f, n3, nX + 1), c->d_v, c->d_wt, c->N, c->dv, T1_WALL, 1); c->launches++; }
+    else if (ic != 6) cudaMemcpyAsync(cell(f, n3, nX + 1), cell(f, n3, nX), cb, cudaMemcpyDeviceToDevice, st);
+  }
+  if (ic == 6 && s->nranks == 1) {  // periodic wrap inside one rank (:167-170)
+    cudaMemcpyAsync(cell(f, n3, 0), cell(f, n3, nX), cb, cudaMemcpyDeviceToDevice, st);
+    cudaMemcpyAsync(cell(f, n3, nX + 1), cell(f, n3, 1), cb, cudaMemcpyDeviceToDevice, st);
+  }
+}
+
+// one upwindTwo pass src -> dst (src/transportroutines.c:241-470); ghosts from neighbours must be in place
+static void upwind_two_pass(sbte_slab* s, double* src, double* dst) {
+  sbte_ctx* c = s->c;
+  const long n3 = c->n3;
+  const int nX = s->nX, ic = s->ic, N = c->N;
+  cudaStream_t st = c->stream;
+  const bool first = s->rank == 0, last = s->rank == s->nranks - 1;
+  if (first) {
+    launch_extrapolate(st, src, n3, 1, 2, 3); c->launches++;
+    const bool wall = (ic == 3 || ic == 5 || ic == 1);
+    launch_wall_face(st, src, s->d_fl, s->d_x, s->d_dx, N, 2, 0, wall ? 0 : 1); c->launches++;
+    if (wall) {
+      launch_diffuse_bc(st, s->d_fl, s->d_fl, c->d_v, c->d_wt, N, c->dv, (ic == 1) ? 2.0 * TWALL_IN : T0_WALL, 0);
+      c->launches++;
+    }
+  }
+  if (last) {
+    launch_extrapolate(st, src, n3, nX + 2, nX + 1, nX); c->launches++;
+    const bool wall = (ic == 3 || ic == 5);
+    launch_wall_face(st, src, s->d_fr, s->d_x, s->d_dx, N, nX + 1, 1, wall ? 0 : 1); c->launches++;
+    if (wall) { launch_diffuse_bc(st, s->d_fr, s->d_fr, c->d_v, c->d_wt, N, c->dv, T1_WALL, 1); c->launches++; }
+  }
+  launch_upwind_two(st, src, dst, s->d_fl, s->d_fr, c->d_v, s->d_x, s->d_dx, N, nX, s->dt, first ? 1 : 0, last ? 1 : 0);
+  c->launches++;
+}
+
+static void pick(sbte_slab* s, int which, double*& A, double*& B) {
+  if (which == 0) { A = s->d_f; B = s->d_fc; } else { A = s->d_fc; B = s->d_f; }
+}
+
+extern "C" {
+
+int sbte_slab_create(sbte_ctx* c, sbte_slab** out, int cells_local, int order, const double* x, const double* dx,
+                     int init_field, double dt, int rank, int nranks) {
+  *out = nullptr;
+  if (order != 1 && order != 2) { set_error("Space_order must be 1 or 2"); return 1; }
+  if (init_field == 5) { set_error("Init_field 5 (Poiseuille forcing) is not implemented"); return 1; }
+  if (cells_local < 2 * order) { set_error("too few cells per rank"); return 1; }
+  CKS(cudaSetDevice(c->device));
+  sbte_slab* s = new sbte_slab();
+  s->c = c; s->nX = cells_local; s->order = order; s->ic = init_field; s->dt = dt; s->rank = rank; s->nranks = nranks;
+  s->ncell = cells_local + 2 * order;
+  const long n3 = c->n3;
+  const size_t sb = (size_t)s->ncell * n3 * sizeof(double);
+  std::vector<double> hx(x, x + s->ncell), hdx(dx, dx + s->ncell);
+  if (rank == nranks - 1) {
+    // right ghost coordinates by extension, as the last-rank branch of src/mesh_setup.c:165-175 does
+    // (the reference's single-rank branch leaves them uninitialised, :121-146)
+    for (int g = cells_local + order; g < s->ncell; g++) { hdx[g] = hdx[g - 1]; hx[g] = hx[g - 1] + hdx[g - 1]; }
+  }
+  CKS(cudaMalloc(&s->d_x, s->ncell * sizeof(double)));
+  CKS(cudaMalloc(&s->d_dx, s->ncell * sizeof(double)));
+  CKS(cudaMemcpy(s->d_x, hx.data(), s->ncell * sizeof(double), cudaMemcpyHostToDevice));
+  CKS(cudaMemcpy(s->d_dx, hdx.data(), s->ncell * sizeof(double), cudaMemcpyHostToDevice));
+  CKS(cudaMalloc(&s->d_f, sb));
+  CKS(cudaMalloc(&s->d_fc, sb));
+  CKS(cudaMemset(s->d_f, 0, sb));
+  CKS(cudaMemset(s->d_fc, 0, sb));
+  if (order == 2) {
+    CKS(cudaMalloc(&s->d_f1, sb));
+    CKS(cudaMalloc(&s->d_ft, sb));
+    CKS(cudaMemset(s->d_f1, 0, sb));
+    CKS(cudaMemset(s->d_ft, 0, sb));
+    CKS(cudaMalloc(&s->d_fl, n3 * sizeof(double)));
+    CKS(cudaMalloc(&s->d_fr, n3 * sizeof(double)));
+  }
+  CKS(cudaMalloc(&s->d_Q, (size_t)cells_local * n3 * sizeof(double)));
+  CKS(cudaMalloc(&s->d_mom, (size_t)cells_local * 8 * sizeof(double)));
+  if (ensure_capacity(c, cells_local)) { sbte_slab_destroy(s); return 1; }
+  *out = s;
+  return 0;
+}
+
+int sbte_slab_destroy(sbte_slab* s) {
+  if (!s) return 0;
+  cudaStreamSynchronize(s->c->stream);
+  cudaFree(s->d_x); cudaFree(s->d_dx); cudaFree(s->d_f); cudaFree(s->d_fc); cudaFree(s->d_f1); cudaFree(s->d_ft);
+  cudaFree(s->d_fl); cudaFree(s->d_fr); cudaFree(s->d_Q); cudaFree(s->d_mom);
+  delete s;
+  return 0;
+}
+
+double* sbte_slab_f(sbte_slab* s) { return s->d_f; }
+double* sbte_slab_fconv(sbte_slab* s) { return s->d_fc; }
+
+int sbte_slab_upload(sbte_slab* s, const double* f_host) {
+  return sbte_h2d(s->c, s->d_f, f_host, (size_t)s->ncell * s->c->n3 * sizeof(double));
+}
+int sbte_slab_download(sbte_slab* s, double* f_host) {
+  return sbte_d2h(s->c, f_host, s->d_f, (size_t)s->ncell * s->c->n3 * sizeof(double));
+}
+
+int sbte_slab_halo_regions(sbte_slab* s, int which, int stage, int side, double** d_send, double** d_recv,
+                           size_t* count) {
+  double *A, *B;
+  pick(s, which, A, B);
+  double* arr = (s->order == 2 && stage == 1) ? s->d_ft : A;
+  const long n3 = s->c->n3;
+  const int o = s->order, nX = s->nX;
+  *count = (size_t)o * n3;
+  if (side == 0) {  // left neighbour: send my first `o` owned cells, receive into my left ghosts
+    *d_send = cell(arr, n3, o);
+    *d_recv = cell(arr, n3, 0);
+  } else {          // right neighbour: send my last `o` owned cells, receive into my right ghosts
+    *d_send = cell(arr, n3, nX);
+    *d_recv = cell(arr, n3, nX + o);
+  }
+  return 0;
+}
+
+int sbte_slab_upwind_stage(sbte_slab* s, int which, int stage) {
+  double *A, *B;
+  pick(s, which, A, B);
+  sbte_ctx* c = s->c;
+  if (s->order == 1) {
+    fill_ghosts_one(s, A);
+    launch_upwind_one(c->stream, A, B, c->d_v, s->d_dx, c->N, s->nX, s->dt);
+    c->launches++;
+  } else {
+    if (stage == 0) upwind_two_pass(s, A, s->d_ft);
+    else upwind_two_pass(s, s->d_ft, B);
+  }
+  return launch_ok("upwind");
+}
+
+int sbte_slab_advect_finish(sbte_slab* s, int which) {
+  if (s->order == 1) return 0;
+  double *A, *B;
+  pick(s, which, A, B);
+  const long n3 = s->c->n3;
+  launch_average(s->c->stream, cell(A, n3, 2), cell(B, n3, 2), (long)s->nX * n3);
+  s->c->launches++;
+  return launch_ok("advect average");
+}
+
+int sbte_slab_advect(sbte_slab* s, int which) {
+  if (s->nranks != 1) { set_error("sbte_slab_advect is the single-rank form; use the staged calls with halos"); return 1; }
+  if (sbte_slab_upwind_stage(s, which, 0)) return 1;
+  if (s->order == 2) {
+    if (sbte_slab_upwind_stage(s, which, 1)) return 1;
+    if (sbte_slab_advect_finish(s, which)) return 1;
+  }
+  return 0;
+}
+
+// exec/boltz.c:285-345 for all owned cells at once
+int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
+  sbte_ctx* c = s->c;
+  const long n3 = c->n3;
+  const int o = s->order, nX = s->nX;
+  const long n = (long)nX * n3;
+  double* fc = cell(s->d_fc, n3, o);
+  double* f = cell(s->d_f, n3, o);
+  if (compute_q_dev(c, fc, fc, s->d_Q, nX, k2)) return 1;
+  launch_conserve(c, s->d_Q, nX);
+  if (o == 1) {
+    launch_update(c, f, 1.0, fc, 0.0, nullptr, s->dt, Kn, s->d_Q, n);          // f = f_conv + dt Q / Kn
+  } else {
+    double* f1 = cell(s->d_f1, n3, o);
+    launch_update(c, f1, 1.0, fc, 0.0, nullptr, s->dt, Kn, s->d_Q, n);         // f_1 = f_conv + dt Q / Kn
+    if (compute_q_dev(c, f1, f1, s->d_Q, nX, k2)) return 1;
+    launch_conserve(c, s->d_Q, nX);
+    launch_update(c, fc, 0.5, fc, 0.5, f1, 0.5 * s->dt, Kn, s->d_Q, n);        // Heun average
+  }
+  return launch_ok("collide");
+}
+
+int sbte_slab_step(sbte_slab* s, double Kn, int k2) {
+  if (sbte_slab_advect(s, 0)) return 1;
+  if (sbte_slab_collide(s, Kn, k2)) return 1;
+  if (s->order == 2 && sbte_slab_advect(s, 1)) return 1;
+  return 0;
+}
+
+int sbte_slab_moments(sbte_slab* s, double* mom_host) {
+  sbte_ctx* c = s->c;
+  launch_moments(c, cell(s->d_f, c->n3, s->order), s->d_mom, s->nX);
+  if (launch_ok("moments")) return 1;
+  return sbte_d2h(c, mom_host, s->d_mom, (size_t)s->nX * 8 * sizeof(double));
+}
+
+}  // extern "C"

@@ -1,0 +1,173 @@
+// spectralbte_b200/csrc/transport.cu -- K6 / K7: 1D upwind transport and diffuse walls on device slabs.
+//
+// References (relative to /root/reference):
+//   upwindOne   src/transportroutines.c:94-238   (ghost fill :107-172, stencil :203-216)
+//   upwindTwo   src/transportroutines.c:241-470  (extrapolated ghosts :271-297, wall faces :351-404,
+//                                                 minmod MUSCL stencil :406-468)
+//   advectTwo   src/transportroutines.c:477-492  (two upwindTwo passes, then the average)
+//   minmod      src/transportroutines.c:80-90
+//   setDiffuseReflectionBC  src/boundaryConditions.c:39-84
+// Slabs are contiguous [cell][N^3]; threads run along the velocity index (coalesced), the x-stencil
+// strides by whole cells.  v_x index i is the slowest velocity index: i < N/2 moves left.
+#include "common.cuh"
+#include "transport.h"
+
+namespace sbte {
+
+__device__ __forceinline__ double minmod3(double a, double b, double d) {
+  if (a > 0 && b > 0 && d > 0) return fmin(fmin(a, b), d);
+  if (a < 0 && b < 0 && d < 0) return fmax(fmax(a, b), d);
+  return 0.0;
+}
+
+// ---------------------------------------------------------------- diffuse wall (K7)
+// sigma_W from the outgoing half of `in`, Maxwellian at TW into the incoming half of `out`.
+__global__ void __launch_bounds__(512)
+diffuse_bc_kernel(const double* __restrict__ in, double* __restrict__ out, const double* __restrict__ v,
+                  const double* __restrict__ wt, int N, double hv, double TW, int bdry) {
+  __shared__ double scratch[32];
+  const int nn = N * N, half = (N / 2) * nn;
+  const int obeg = (bdry == 0) ? 0 : half, oend = (bdry == 0) ? half : N * nn;   // outgoing
+  const int ibeg = (bdry == 0) ? half : 0, iend = (bdry == 0) ? N * nn : half;   // incoming
+  double s[1] = {0.0};
+  for (int idx = obeg + threadIdx.x; idx < oend; idx += blockDim.x) {
+    const int i = idx / nn, j = (idx / N) % N, k = idx % N;
+    s[0] += v[i] * wt[i] * wt[j] * wt[k] * hv * hv * hv * in[idx];
+  }
+  block_reduce_sum<1>(s, scratch);
+  double sig = s[0];
+  if (bdry == 0) sig *= -sqrt(2.0 * M_PI * 1.0 / (1.0 * TW));
+  else sig *= sqrt(2.0 * M_PI * 1.0 / (1.0 * TW));
+  const double pre = sig * pow(0.5 * 1.0 / (M_PI * 1.0 * TW), 1.5);
+  __syncthreads();  // `in` may alias `out`: all reads of the outgoing half are done (disjoint halves anyway)
+  for (int idx = ibeg + threadIdx.x; idx < iend; idx += blockDim.x) {
+    const int i = idx / nn, j = (idx / N) % N, k = idx % N;
+    out[idx] = pre * exp(-0.5 * 1.0 / (1.0 * TW) * (v[i] * v[i] + v[j] * v[j] + v[k] * v[k]));
+  }
+}
+
+void launch_diffuse_bc(cudaStream_t st, const double* in, double* out, const double* v, const double* wt, int N,
+                       double hv, double TW, int bdry) {
+  diffuse_bc_kernel<<<1, 512, 0, st>>>(in, out, v, wt, N, hv, TW, bdry);
+}
+
+// ---------------------------------------------------------------- first order (K6a)
+__global__ void __launch_bounds__(256)
+upwind_one_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ v,
+                  const double* __restrict__ dx, int N, int nX, double dt) {
+  const long n3 = (long)N * N * N;
+  const int l = blockIdx.y + 1;
+  const double* fl = f + (long)l * n3;
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(p / (N * N));
+    const double cfl = dt * v[i] / dx[l];
+    double r;
+    if (i < N / 2) r = (1.0 + cfl) * fl[p] - cfl * fl[p + n3];
+    else r = (1.0 - cfl) * fl[p] + cfl * fl[p - n3];
+    fc[(long)l * n3 + p] = r;
+  }
+}
+
+void launch_upwind_one(cudaStream_t st, const double* f, double* fc, const double* v, const double* dx, int N, int nX,
+                       double dt) {
+  const long n3 = (long)N * N * N;
+  dim3 grid((unsigned)((n3 + 255) / 256), nX);
+  upwind_one_kernel<<<grid, 256, 0, st>>>(f, fc, v, dx, N, nX, dt);
+}
+
+// ---------------------------------------------------------------- second order (K6b)
+// ghost by linear extrapolation: f[dst] = 2 f[a] - f[b]
+__global__ void extrapolate_kernel(double* __restrict__ f, long n3, int dst, int a, int b) {
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x)
+    f[dst * n3 + p] = 2 * f[a * n3 + p] - f[b * n3 + p];
+}
+void launch_extrapolate(cudaStream_t st, double* f, long n3, int dst, int a, int b) {
+  extrapolate_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(f, n3, dst, a, b);
+}
+
+// wall face values from the limited slope in the wall cell `l` (2 on the left, nX+1 on the right):
+//   left  wall: outgoing half (i <  N/2): face = f_l - dx/2 * s ; no-flux fill (i >= N/2): f_l + dx/2 * s
+//   right wall: outgoing half (i >= N/2): face = f_l + dx/2 * s ; no-flux fill (i <  N/2): f_l - dx/2 * s
+// `fill_noflux` = 1 writes both halves (no wall model); 0 writes only the outgoing half (the diffuse
+// kernel then fills the incoming half).
+__global__ void wall_face_kernel(const double* __restrict__ f, double* __restrict__ face, const double* __restrict__ x,
+                                 const double* __restrict__ dx, int N, int l, int right, int fill_noflux) {
+  const long n3 = (long)N * N * N;
+  const long half = (long)(N / 2) * N * N;
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
+    const bool lower = p < half;                 // i < N/2
+    const bool outgoing = right ? !lower : lower;
+    if (!outgoing && !fill_noflux) continue;
+    const double fm = f[(long)(l - 1) * n3 + p], f0 = f[(long)l * n3 + p], fp = f[(long)(l + 1) * n3 + p];
+    const double s = minmod3((f0 - fm) / (x[l] - x[l - 1]), (fp - f0) / (x[l + 1] - x[l]),
+                             (fp - fm) / (x[l + 1] - x[l - 1]));
+    // both walls: lower half (i < N/2) takes f0 - dx/2 s, upper half takes f0 + dx/2 s
+    const double val = lower ? f0 - 0.5 * dx[l] * s : f0 + 0.5 * dx[l] * s;
+    face[p] = val;
+  }
+}
+void launch_wall_face(cudaStream_t st, const double* f, double* face, const double* x, const double* dx, int N, int l,
+                      int right, int fill_noflux) {
+  const long n3 = (long)N * N * N;
+  wall_face_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(f, face, x, dx, N, l, right, fill_noflux);
+}
+
+// MUSCL / minmod stencil for the owned cells l = 2 .. nX+1. left_wall / right_wall: this rank holds
+// the physical boundary and uses the wall faces fl / fr instead of the neighbour reconstruction.
+__global__ void __launch_bounds__(256)
+upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ fl,
+                  const double* __restrict__ fr, const double* __restrict__ v, const double* __restrict__ x,
+                  const double* __restrict__ dx, int N, int nX, double dt, int left_wall, int right_wall) {
+  const long n3 = (long)N * N * N;
+  const int l = blockIdx.y + 2;
+  const int h = N / 2;
+  const double* c0 = f + (long)l * n3;
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(p / (N * N));
+    const double cfl = 0.5 * dt * v[i] / dx[l];
+    const double f0 = c0[p], fm = c0[p - n3], fp = c0[p + n3];
+    const double s1 = minmod3((f0 - fm) / (x[l] - x[l - 1]), (fp - f0) / (x[l + 1] - x[l]),
+                              (fp - fm) / (x[l + 1] - x[l - 1]));
+    double r;
+    if (i >= h) {
+      if (l == 2 && left_wall) {
+        r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - fl[p]);
+      } else {
+        const double fmm = c0[p - 2 * n3];
+        const double s0 = minmod3((fm - fmm) / (x[l - 1] - x[l - 2]), (f0 - fm) / (x[l] - x[l - 1]),
+                                  (f0 - fmm) / (x[l] - x[l - 2]));
+        r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - (fm + 0.5 * dx[l - 1] * s0));
+      }
+    } else {
+      if (l == nX + 1 && right_wall) {
+        r = f0 - cfl * (fr[p] - (f0 - 0.5 * dx[l] * s1));
+      } else {
+        const double fpp = c0[p + 2 * n3];
+        const double s2 = minmod3((fp - f0) / (x[l + 1] - x[l]), (fpp - fp) / (x[l + 2] - x[l + 1]),
+                                  (fpp - f0) / (x[l + 2] - x[l]));
+        r = f0 - cfl * (fp - 0.5 * dx[l + 1] * s2 - (f0 - 0.5 * dx[l] * s1));
+      }
+    }
+    fc[(long)l * n3 + p] = r;
+  }
+}
+void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const double* fl, const double* fr,
+                       const double* v, const double* x, const double* dx, int N, int nX, double dt, int left_wall,
+                       int right_wall) {
+  const long n3 = (long)N * N * N;
+  dim3 grid((unsigned)((n3 + 255) / 256), nX);
+  upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall);
+}
+
+// fc = 0.5 * (f + fc) on n contiguous doubles (src/transportroutines.c:487-491)
+__global__ void average_kernel(const double* __restrict__ f, double* __restrict__ fc, long n) {
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x)
+    fc[p] = 0.5 * (f[p] + fc[p]);
+}
+void launch_average(cudaStream_t st, const double* f, double* fc, long n) {
+  long blocks = (n + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  average_kernel<<<(unsigned)blocks, 256, 0, st>>>(f, fc, n);
+}
+
+}  // namespace sbte

@@ -1,0 +1,366 @@
+"""GPU parity tests proper: the CUDA path, called through the C ABI (spectralbte_b200 -> ctypes ->
+libsbte_b200.so), against the CPU oracle on the same seeded inputs, against the reference's golden
+files, and through size-independent properties at full size.  Tolerances follow BASELINE.json:
+Q^ relative 1e-12 (normwise), conservation 1e-13, golden moments abs 1e-14 or rel 1e-6 two-sided."""
+import numpy as np
+import pytest
+
+from conftest import check_diff_two_sided, load_moments, relmax, seeded_f
+from oracle import oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL_QHAT = 1e-12
+
+
+def _sbte():
+    import spectralbte_b200 as sb
+    return sb
+
+
+@pytest.fixture(scope="module")
+def sb():
+    return _sbte()
+
+
+# ---------------------------------------------------------------- transforms
+@pytest.mark.parametrize("N,rule", [(6, 0), (8, 0), (8, 1), (12, 0), (16, 1), (22, 1), (24, 0), (32, 0)])
+def test_fft3d_matches_oracle(sb, N, rule):
+    o = orc.Oracle(N, 7.0, rule)
+    c = sb.Collisions(N, 7.0, inhomogeneous=bool(rule))
+    assert np.array_equal(c.v, o.v) and np.array_equal(c.eta, o.eta)
+    rng = np.random.default_rng(N)
+    for inv in (False, True):
+        z = rng.standard_normal((3, o.n3)) + 1j * rng.standard_normal((3, o.n3))
+        got = c.fft3D(z, inv).reshape(3, -1)
+        for b in range(3):
+            assert relmax(got[b], o.fft3d(z[b], inv)) < 1e-13
+
+
+# ---------------------------------------------------------------- the convolution
+def _weights(name, N, W_bkw8, W_heat8):
+    if name == "bkw":
+        return W_bkw8
+    if name == "heat":
+        return W_heat8
+    return orc.synthetic_weights(N)
+
+
+@pytest.mark.parametrize("N,L_v,rule,wname,k2", [
+    (8, 5.0, 0, "bkw", 1), (8, 9.0, 1, "heat", 1), (6, 4.0, 0, "syn", 1), (12, 6.0, 0, "syn", 1),
+    (16, 5.0, 0, "syn", 1), (16, 5.0, 0, "syn", 2), (16, 5.0, 0, "syn", 4), (24, 9.0, 1, "syn", 2)])
+def test_qhat_matches_oracle(sb, W_bkw8, W_heat8, N, L_v, rule, wname, k2):
+    o = orc.Oracle(N, L_v, rule)
+    W = _weights(wname, N, W_bkw8, W_heat8)
+    c = sb.Collisions(N, L_v, inhomogeneous=bool(rule))
+    c.set_weights(W)
+    f, g = seeded_f(o.v, 11), seeded_f(o.v, 12)
+    for ff, gg in ((f, f), (f, g)):
+        _, want = o.compute_q(W, ff, gg, want_qhat=True)
+        got = c.Qhat(ff, None if gg is ff else gg, k2=k2)
+        assert relmax(got, want) < TOL_QHAT
+
+
+def test_qhat_rows_upload_equals_contiguous_upload(sb, W_bkw8):
+    o = orc.Oracle(8, 5.0, 0)
+    f = seeded_f(o.v, 11)
+    a = sb.Collisions(8, 5.0)
+    a.set_weights(W_bkw8)
+    b = sb.Collisions(8, 5.0)
+    b.set_weights_rows(W_bkw8)
+    assert np.array_equal(a.Qhat(f), b.Qhat(f))
+    assert np.array_equal(b.weights_to_host(), W_bkw8)
+
+
+def test_qhat_n32_full_size_properties(sb):
+    """BASELINE config 3 size (N=32, 1.07e9 weights, 8.6 GB): stream kernel vs the independent generic
+    kernel on every row, sampled rows vs a numpy evaluation of the reference formula, linearity."""
+    N, L_v = 32, 5.0
+    o = orc.Oracle(N, L_v, 0)
+    c = sb.Collisions(N, L_v)
+    c.synthetic_weights(20261017)
+    f, g = seeded_f(o.v, 11), seeded_f(o.v, 12)
+    q_stream = c.Qhat(f, g, k2=sb.K2_STREAM)
+    q_deep = c.Qhat(f, g, k2=sb.K2_STREAM_DEEP)
+    q_generic = c.Qhat(f, g, k2=sb.K2_GENERIC)
+    assert relmax(q_stream, q_generic) < TOL_QHAT
+    assert relmax(q_deep, q_generic) < TOL_QHAT
+    # sampled rows against the formula of src/collisions.c:127-165 evaluated with numpy
+    fh = o.fft3d(f.astype(np.complex128)).reshape(N, N, N)
+    gh = o.fft3d(g.astype(np.complex128)).reshape(-1)
+    n3 = N ** 3
+    ar = np.arange(N)
+    rng = np.random.default_rng(0)
+    Wrow = np.empty(n3)
+    scale = np.abs(q_generic).max()
+    for zeta in rng.integers(0, n3, 24):
+        zx, zy, zz = zeta // (N * N), (zeta // N) % N, zeta % N
+        wrap = lambda z: np.where(z < 0, z + N, np.where(z > N - 1, z - N, z))  # noqa: E731
+        X, Y, Z = wrap(zx + N // 2 - ar), wrap(zy + N // 2 - ar), wrap(zz + N // 2 - ar)
+        fsel = fh[np.ix_(X, Y, Z)].reshape(-1)
+        sb._lib.check(c.L.sbte_d2h(c.h, Wrow.ctypes.data, c.L.sbte_weights_device(c.h) + int(zeta) * n3 * 8, n3 * 8))
+        want = np.sum(Wrow * gh * fsel)
+        assert abs(q_stream[zeta] - want) < TOL_QHAT * scale
+    # bilinearity: Q^(a f1 + b f2, g) = a Q^(f1, g) + b Q^(f2, g)
+    f2 = seeded_f(o.v, 13)
+    lhs = c.Qhat(2.0 * f - 0.5 * f2, g, k2=sb.K2_STREAM)
+    rhs = 2.0 * q_stream - 0.5 * c.Qhat(f2, g, k2=sb.K2_STREAM)
+    assert relmax(lhs, rhs) < TOL_QHAT
+
+
+def test_synthetic_weights_device_equals_host_generator(sb):
+    c = sb.Collisions(8, 5.0)
+    c.synthetic_weights(20261017)
+    assert np.array_equal(c.weights_to_host(), orc.synthetic_weights(8, 20261017))
+
+
+# ---------------------------------------------------------------- ComputeQ / maxPreserve / conserve
+@pytest.mark.parametrize("N,L_v,rule,wname", [(8, 5.0, 0, "bkw"), (8, 9.0, 1, "heat"), (12, 6.0, 0, "syn"),
+                                              (16, 5.0, 0, "syn")])
+def test_computeq_and_maxpreserve_match_oracle(sb, ref_vectors, W_bkw8, W_heat8, N, L_v, rule, wname):
+    o = orc.Oracle(N, L_v, rule)
+    W = _weights(wname, N, W_bkw8, W_heat8)
+    c = sb.Collisions(N, L_v, inhomogeneous=bool(rule))
+    c.set_weights(W)
+    f, g = seeded_f(o.v, 11), seeded_f(o.v, 12)
+    assert relmax(c.ComputeQ(f), o.compute_q(W, f, f)) < TOL_QHAT
+    assert relmax(c.ComputeQ(f, g), o.compute_q(W, f, g)) < TOL_QHAT
+    assert relmax(c.ComputeQ_maxPreserve(f), o.compute_q_maxpreserve(W, f, f)) < TOL_QHAT
+    assert relmax(c.ComputeQ_maxPreserve(f, g), o.compute_q_maxpreserve(W, f, g)) < TOL_QHAT
+    # and against the vectors produced by the reference's own code
+    tag = {(8, "bkw"): "n8_l0", (8, "heat"): "n8_l1", (12, "syn"): "n12_syn", (16, "syn"): "n16_syn"}[(N, wname)]
+    assert relmax(c.ComputeQ(f), ref_vectors[f"{tag}_Q_ff"]) < TOL_QHAT
+    assert relmax(c.ComputeQ_maxPreserve(f, g), ref_vectors[f"{tag}_Qmp_fg"]) < TOL_QHAT
+
+
+@pytest.mark.parametrize("N", [8, 12, 16, 32])
+def test_conserve_and_moments(sb, N):
+    o = orc.Oracle(N, 6.0, 0)
+    c = sb.Collisions(N, 6.0)
+    rng = np.random.default_rng(N)
+    Q = np.stack([seeded_f(o.v, s) * rng.standard_normal(o.n3) for s in (1, 2, 3)])
+    got = c.conserveAllMoments(Q).reshape(3, -1)
+    for b in range(3):
+        assert relmax(got[b], o.conserve(Q[b])) < 1e-13
+    res = c.moment_functionals(got)
+    before = np.abs(c.moment_functionals(Q)).max()
+    assert np.abs(res).max() < 1e-13 * max(1.0, before)
+    f = np.stack([seeded_f(o.v, s) for s in (4, 5)])
+    m = c.moments(f)
+    for b in range(2):
+        rho = o.density(f[b]); u = o.bulk_velocity(f[b], rho); T = o.temperature(f[b], u, rho); e = o.energy(f[b])
+        want = np.array([rho, u[0], u[1], u[2], T, e[0], e[1], rho * T])
+        np.testing.assert_allclose(m[b], want, rtol=1e-13, atol=1e-15)
+
+
+# ---------------------------------------------------------------- the reference's own goldens
+def test_bkw8_golden_on_gpu(sb, W_bkw8):
+    """tests/BKW8 of the reference, run through sbte_step_0d with f resident on the device."""
+    o = orc.Oracle(8, 5.0, 0)
+    c = sb.Collisions(8, 5.0)
+    c.set_weights(W_bkw8)
+    f = c.array(o.n3).put(o.init_hom(2))
+    rows = [np.concatenate([[0.0], c.row_0d(f)])]
+    for t in range(100):
+        c.step_0d(f, 0.01, 1.0, 2)
+        rows.append(np.concatenate([[0.01 * (t + 1)], c.row_0d(f)]))
+    got = np.array(rows)
+    want = load_moments("moments_BKW8.test.in")
+    got_r = np.array([[float("%le" % x) for x in r] for r in got])
+    assert check_diff_two_sided(np.delete(got_r, 2, axis=1), np.delete(want, 2, axis=1)) == 0
+    assert np.abs(got[:, 2]).max() < 1e-13
+    # full-precision agreement with the oracle's own trajectory at the end
+    fo = o.init_hom(2)
+    for t in range(100):
+        o.step_0d(W_bkw8, fo, 0.01, 1.0, 2)
+    assert relmax(f.get(), fo) < 1e-11
+
+
+def test_heat_transport_golden_on_gpu(sb, W_heat8):
+    """tests/heat_transport of the reference through the device-resident slab (batched K2)."""
+    N, nX, order, ic, dt, Kn = 8, 250, 1, 3, 1e-4, 3.2
+    o = orc.Oracle(N, 9.0, 1)
+    _, x, dx = orc.make_mesh([250], [1.0], order)
+    c = sb.Collisions(N, 9.0, inhomogeneous=True)
+    c.set_weights(W_heat8)
+    s = sb.Slab(c, nX, order, x, dx, ic, dt)
+    s.upload(o.init_inhom(ic, nX, order))
+
+    def dump(t):
+        m = s.moments()
+        return [[t, x[l + order], m[l, 0], m[l, 1], m[l, 4], m[l, 7]] for l in range(nX)]
+
+    rows = dump(0.0)
+    for t in range(10):
+        s.step(Kn)
+        rows += dump(dt * (t + 1))
+    got = np.array(rows)
+    want = load_moments("moments_heat_transport.test.in")
+    got_r = np.array([[float("%le" % v) for v in r] for r in got])
+    assert check_diff_two_sided(np.delete(got_r, 3, axis=1), np.delete(want, 3, axis=1)) == 0
+    big = np.abs(want[:, 3]) > 1e-9
+    assert check_diff_two_sided(got_r[big, 3], want[big, 3]) == 0
+    assert np.abs(got[~big, 3] - want[~big, 3]).max() < 1e-12
+
+
+# ---------------------------------------------------------------- batched convolution (1D)
+@pytest.mark.parametrize("N,cells,k2", [(8, 5, 3), (8, 37, 3), (16, 33, 3), (8, 5, 1), (12, 3, 1)])
+def test_batched_computeq_matches_oracle(sb, N, cells, k2):
+    o = orc.Oracle(N, 9.0, 1)
+    W = orc.synthetic_weights(N)
+    c = sb.Collisions(N, 9.0, inhomogeneous=True)
+    c.set_weights(W)
+    f = np.stack([seeded_f(o.v, 100 + b, noise=0.2) * (1.0 + 0.1 * b) for b in range(cells)])
+    qh = c.Qhat(f, k2=k2).reshape(cells, -1)
+    Q = c.ComputeQ(f, k2=k2).reshape(cells, -1)
+    for b in range(cells):
+        Qo, qo = o.compute_q(W, f[b], f[b], want_qhat=True)
+        assert relmax(qh[b], qo) < TOL_QHAT
+        assert relmax(Q[b], Qo) < TOL_QHAT
+
+
+# ---------------------------------------------------------------- transport
+@pytest.mark.parametrize("N,L_v,nX,ic,dt", [(8, 9.0, 12, 3, 1e-3), (8, 9.0, 12, 6, 1e-3), (6, 7.0, 10, 0, 2e-3),
+                                             (8, 9.0, 12, 1, 1e-3)])
+def test_transport_matches_oracle(sb, N, L_v, nX, ic, dt):
+    o = orc.Oracle(N, L_v, 1)
+    c = sb.Collisions(N, L_v, inhomogeneous=True)
+    rng = np.random.default_rng(77)
+    for order in (1, 2):
+        _, x, dx = orc.make_mesh([nX // 2, nX - nX // 2], [0.4, 0.6], order)
+        f = o.init_inhom(ic, nX, order)
+        f[order:nX + order] *= 1.0 + 0.2 * rng.standard_normal((nX, o.n3))
+        s = sb.Slab(c, nX, order, x, dx, ic, dt)
+        s.upload(f)
+        s.advect(0)
+        got = s.download_fconv()[order:nX + order]
+        want = (o.upwind_one(nX, x, dx, dt, ic, f.copy()) if order == 1
+                else o.advect_two(nX, x, dx, dt, ic, f.copy()))[order:nX + order]
+        assert relmax(got, want) < 1e-14
+
+
+@pytest.mark.parametrize("order,ic", [(1, 3), (2, 3), (2, 6), (1, 6)])
+def test_1d_step_matches_oracle(sb, W_heat8, order, ic):
+    """exec/boltz.c:264-353 end to end (advect + batched collide + advect), 3 steps, N=8."""
+    N, nX, dt, Kn = 8, 14, 2e-3, 1.52
+    o = orc.Oracle(N, 9.0, 1)
+    _, x, dx = orc.make_mesh([nX], [0.7], order)
+    c = sb.Collisions(N, 9.0, inhomogeneous=True)
+    c.set_weights(W_heat8)
+    s = sb.Slab(c, nX, order, x, dx, ic, dt)
+    f = o.init_inhom(ic, nX, order)
+    s.upload(f)
+    fc, f1, ft = np.zeros_like(f), np.zeros_like(f), np.zeros_like(f)
+    for _ in range(3):
+        s.step(Kn)
+        o.step_1d(W_heat8, nX, x, dx, dt, Kn, order, ic, f, fc, f1, ft)
+    assert relmax(s.download()[order:nX + order], f[order:nX + order]) < 1e-11
+
+
+@pytest.mark.parametrize("order,ic", [(1, 3), (2, 3), (1, 6), (2, 6)])
+def test_two_rank_split_equals_single_rank(sb, W_heat8, order, ic):
+    """Rank-count invariance: two slabs exchanging halos through the regions
+    reported by the library reproduce the single-slab run bit for bit."""
+    N, nX, dt, Kn = 8, 16, 2e-3, 1.52
+    o = orc.Oracle(N, 9.0, 1)
+    _, x, dx = orc.make_mesh([nX], [0.8], order)
+    c = sb.Collisions(N, 9.0, inhomogeneous=True)
+    c.set_weights(W_heat8)
+    f0 = o.init_inhom(ic, nX, order)
+    rng = np.random.default_rng(3)
+    f0[order:nX + order] *= 1.0 + 0.1 * rng.standard_normal((nX, o.n3))
+    one = sb.Slab(c, nX, order, x, dx, ic, dt)
+    one.upload(f0)
+    h = nX // 2
+    parts = []
+    for r in range(2):
+        lo = r * h
+        xs, dxs = x[lo:lo + h + 2 * order].copy(), dx[lo:lo + h + 2 * order].copy()
+        p = sb.Slab(c, h, order, xs, dxs, ic, dt, rank=r, nranks=2)
+        p.upload(f0[lo:lo + h + 2 * order].copy())
+        parts.append(p)
+
+    def exchange(which, stage):
+        # rank 0's right neighbour is rank 1 and vice versa; periodic wrap for IC 6 at order 1
+        s0R, r0R, n = parts[0].halo_regions(which, stage, 1)
+        s1L, r1L, _ = parts[1].halo_regions(which, stage, 0)
+        sb._lib.check(c.L.sbte_d2d(c.h, r1L, s0R, n * 8))
+        sb._lib.check(c.L.sbte_d2d(c.h, r0R, s1L, n * 8))
+        if ic == 6 and order == 1:
+            s0L, r0L, _ = parts[0].halo_regions(which, stage, 0)
+            s1R, r1R, _ = parts[1].halo_regions(which, stage, 1)
+            sb._lib.check(c.L.sbte_d2d(c.h, r1R, s0L, n * 8))
+            sb._lib.check(c.L.sbte_d2d(c.h, r0L, s1R, n * 8))
+
+    def advect(which):
+        for stage in range(order):
+            exchange(which, stage)
+            for p in parts:
+                p.upwind_stage(which, stage)
+        for p in parts:
+            p.advect_finish(which)
+
+    for _ in range(3):
+        one.step(Kn)
+        advect(0)
+        for p in parts:
+            p.collide(Kn)
+        if order == 2:
+            advect(1)
+    whole = one.download()[order:nX + order]
+    split = np.concatenate([p.download()[order:h + order] for p in parts])
+    assert np.array_equal(whole, split)
+
+
+# ---------------------------------------------------------------- drop-in symbols
+def test_dropin_symbols_reproduce_reference_vectors(sb, ref_vectors, W_bkw8):
+    """initialize_coll / ComputeQ / ComputeQ_maxPreserve / conserveAllMoments / fft3D called exactly as
+    exec/boltz.c and src/initializer.c call them (host pointers, N^3 weight row pointers)."""
+    import ctypes as C
+    L = sb._lib.load()
+    dp = C.POINTER(C.c_double)
+    o = orc.Oracle(8, 5.0, 0)
+    v, eta = o.v.copy(), o.eta.copy()
+    L.initialize_coll(8, 5.0, v.ctypes.data_as(dp), eta.ctypes.data_as(dp))
+    L.initialize_conservation_fast(8, v[1] - v[0], v.ctypes.data_as(dp))
+    n3 = 512
+    Wm = W_bkw8.reshape(n3, n3).copy()
+    rows = (dp * n3)(*[C.cast(Wm.ctypes.data + i * n3 * 8, dp) for i in range(n3)])
+    f = seeded_f(o.v, 11)
+    Q = np.empty(n3)
+    L.ComputeQ(f.ctypes.data_as(dp), f.ctypes.data_as(dp), Q.ctypes.data_as(dp), rows)
+    assert relmax(Q, ref_vectors["n8_l0_Q_ff"]) < TOL_QHAT
+    Qp = (dp * 1)(Q.ctypes.data_as(dp))
+    L.conserveAllMoments(Qp)
+    assert relmax(Q, ref_vectors["n8_l0_cons_Q_ff"]) < 1e-12
+    L.ComputeQ_maxPreserve(f.ctypes.data_as(dp), f.ctypes.data_as(dp), Q.ctypes.data_as(dp), rows)
+    assert relmax(Q, ref_vectors["n8_l0_Qmp_ff"]) < TOL_QHAT
+    rng = np.random.default_rng(5)
+    z = rng.standard_normal(n3) + 1j * rng.standard_normal(n3)
+    out = np.empty(n3, dtype=np.complex128)
+    L.fft3D(z.ctypes.data, out.ctypes.data, 0)
+    assert relmax(out, ref_vectors["n8_l0_fft_fwd"]) < 1e-13
+    L.dealloc_conservation()
+    L.dealloc_coll()
+
+
+def test_dropin_advect_reproduces_reference_vectors(sb, ref_vectors):
+    import ctypes as C
+    L = sb._lib.load()
+    dp = C.POINTER(C.c_double)
+    N, L_v, nX, ic, dt = 8, 9.0, 12, 3, 1e-3
+    o = orc.Oracle(N, L_v, 1)
+    v, eta = o.v.copy(), o.eta.copy()
+    L.initialize_coll(N, L_v, v.ctypes.data_as(dp), eta.ctypes.data_as(dp))
+    for order, fn in ((1, L.advectOne), (2, L.advectTwo)):
+        _, x, dx = orc.make_mesh([nX // 2, nX - nX // 2], [0.4, 0.6], order)
+        L.initialize_transport(N, nX, L_v, x.ctypes.data_as(dp), dx.ctypes.data_as(dp), v.ctypes.data_as(dp), ic, dt,
+                               1.0, None)
+        f = np.zeros((nX + 2 * order, o.n3))
+        f[order:nX + order] = ref_vectors[f"tr_ic3_o{order}_in"]
+        fc = np.zeros_like(f)
+        cells = lambda a: (dp * a.shape[0])(*[C.cast(a.ctypes.data + i * a.shape[1] * 8, dp) for i in range(a.shape[0])])  # noqa: E731
+        fn(cells(f), cells(fc), 0)
+        assert relmax(fc[order:nX + order], ref_vectors[f"tr_ic3_o{order}_out"]) < 1e-14
+        L.dealloc_trans()
+    L.dealloc_coll()
