@@ -1,0 +1,312 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the collision hot path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload NAME]
+
+Workloads
+  0d_n32   (default) BASELINE config 3: 0D hard spheres at N=32, 1.07e9 precomputed weights (8.59 GB);
+           one step = one Q(f,f) evaluation = ComputeQ: forward transform, N^6 weighted convolution
+           (one pass over the weight tensor), inverse transform.  At N GPUs: N independent replicas
+           (0D does not shard; "replicas only"), metric = total evals/s.
+  shock1p2 1D-3V Mach-1.2 shock derived from input_examples/Shock1p2: N=16, 640 cells
+           per GPU (weak scaling), Space_order 2; one step = one full time step; metric cells*steps/s.
+
+Every GPU number is timed with CUDA events on the library's stream, max over ranks.  The weights
+(8.59 GB / 134 MB per pass...) are larger than L2 for 0d_n32; for shock1p2 the per-step working set
+(slabs + spectra, > 300 MB) exceeds L2 as well -- no explicit flush is needed (config.l2 says which).
+
+--impl reference times the reference's own CPU implementation (oracle/_ref/libref.so: its C sources
+compiled unmodified; else the oracle port) on the host cores for the same metric/config.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC_0D = "Q(f,f) evals/s at N=32"
+SEED = 20261017
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device):
+        self.device, self.proc, self.lines = device, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU legs (the only place the oracle / oracle/_ref may be executed from bench.py)
+# --------------------------------------------------------------------------------------------
+def cpu_computeq_n32(steps, warmup, distinct_rows=512):
+    """Times full N=32 ComputeQ evaluations (all N^6 = 1.07e9 weight/operand pairs each) with the
+    reference's own code when oracle/_ref/libref.so exists, else with the oracle port.  To bound host
+    memory the N^3 weight-row pointers alias `distinct_rows` distinct rows (134 MB) of the synthetic
+    tensor; the loop, its index arithmetic and its memory stream are unchanged."""
+    import ctypes as C
+    from oracle import oracle as orc
+    from spectralbte_b200 import initial
+    from spectralbte_b200.api import velocity_grids
+    N, L_v = 32, 5.0
+    n3 = N ** 3
+    cores = os.cpu_count() or 1
+    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    v, eta = velocity_grids(N, L_v)
+    f = initial.init_hom(v, L_v, 0)
+    rng = np.random.default_rng(SEED)
+    Wsmall = rng.random((distinct_rows, n3)) - 0.5
+    dp = C.POINTER(C.c_double)
+    Q = np.empty(n3)
+    if orc.have_ref():
+        kind = "reference"
+        R = orc.Reference(N, L_v, 0)
+        rows = (dp * n3)()
+        base = Wsmall.ctypes.data
+        for i in range(n3):
+            rows[i] = C.cast(base + (i % distinct_rows) * n3 * 8, dp)
+        fp, Qp = f.ctypes.data_as(dp), Q.ctypes.data_as(dp)
+        call = lambda: R.R.ComputeQ(fp, fp, Qp, rows)  # noqa: E731
+    else:
+        kind = "port"
+        o = orc.Oracle(N, L_v, 0)
+        fp, Qp, Wp = f.ctypes.data_as(dp), Q.ctypes.data_as(dp), Wsmall.ctypes.data_as(dp)
+        call = lambda: o.L.orc_compute_q_rowmod(o.h, Wp, C.c_long(distinct_rows), fp, fp, Qp)  # noqa: E731
+    for _ in range(warmup):
+        call()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        call()
+    dt = time.perf_counter() - t0
+    return {"value": steps / dt, "unit": "evals/s", "cores": cores, "kind": kind, "seconds": dt,
+            "sample": "%d full N=32 ComputeQ evaluations (1.07e9 pairs each, FFTs included), weight rows "
+                      "aliased to %d distinct synthetic rows, OMP_NUM_THREADS=%s" % (steps, distinct_rows,
+                                                                                   os.environ["OMP_NUM_THREADS"])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    if args.workload != "0d_n32":
+        print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for workload 0d_n32 only"}))
+        return
+    r = cpu_computeq_n32(args.steps, max(1, min(args.warmup, 2)))
+    line = {"metric": METRIC_0D, "value": r["value"], "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * r["seconds"] / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "0d_n32: 0D hard spheres N=32, ComputeQ(f,f), 1.07e9 weights", "N": 32,
+                       "L_v": 5.0, "init_field": 0},
+            "cpu_baseline": {"value": r["value"], "unit": "evals/s", "cores": r["cores"], "kind": r["kind"],
+                             "sample": r["sample"]},
+            "e2e": {"value": r["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def dist_setup(ngpus):
+    import torch
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    else:
+        torch.cuda.set_device(0)
+    return world, rank, local
+
+
+def max_over_ranks(x, world):
+    if world == 1:
+        return x
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([x], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(world):
+    import torch
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+
+
+def run_0d_n32(args):
+    import torch
+    import spectralbte_b200 as sb
+    from spectralbte_b200 import initial
+    world, rank, local = dist_setup(args.gpus)
+    N, L_v = 32, 5.0
+    n3 = N ** 3
+    c = sb.Collisions(N, L_v, device=local)
+    c.synthetic_weights(SEED)
+    f = initial.init_hom(c.v, L_v, 0)
+    df, dQ = c.array(n3).put(f), c.array(n3)
+    stream = torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local))
+    k2 = {"auto": sb.K2_AUTO, "stream": sb.K2_STREAM, "deep": sb.K2_STREAM_DEEP, "generic": sb.K2_GENERIC}[args.k2]
+
+    def step():
+        sb._lib.check(c.L.sbte_compute_q(c.h, df.ptr, df.ptr, dQ.ptr, 1, k2))
+
+    for _ in range(args.warmup):
+        step()
+    c.sync()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier(world)
+    c.k2_profile(True)
+    l0 = c.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    c.sync()
+    barrier(world)
+    ms = e0.elapsed_time(e1)
+    k2_ms, k2_n = c.k2_profile_read()
+    c.k2_profile(False)
+    launches = c.launches - l0
+    clocks = sampler.stop() if rank == 0 else None
+    ms = max_over_ranks(ms, world)
+
+    # end to end: host buffers through the reference-facing ComputeQ entry (H2D f, D2H Q every step)
+    fh = torch.from_numpy(f).pin_memory()
+    Qh = torch.empty(n3, dtype=torch.float64).pin_memory()
+    import ctypes as C
+    dp = C.POINTER(C.c_double)
+    fp, Qp = C.cast(fh.data_ptr(), dp), C.cast(Qh.data_ptr(), dp)
+    for _ in range(max(2, args.warmup // 2)):
+        sb._lib.check(c.L.sbte_compute_q_host(c.h, fp, fp, Qp, k2))
+    barrier(world)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sb._lib.check(c.L.sbte_compute_q_host(c.h, fp, fp, Qp, k2))
+    c.sync()
+    e2e_s = time.perf_counter() - t0
+    e2e_s = max_over_ranks(e2e_s, world)
+    checksum = float(Qh.sum().item())
+
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    wbytes = 8.0 * float(N) ** 6
+    k2_avg_ms = k2_ms / max(1, k2_n)
+    achieved = wbytes / (k2_avg_ms * 1e-3) / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k2_stream_traffic.json")
+    if os.path.exists(tp):
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+    value = world * args.steps / (ms * 1e-3)
+    line = {
+        "metric": METRIC_0D, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "0d_n32: 0D hard spheres N=32, ComputeQ(f,f), 1.07e9 precomputed weights (8.59 GB/GPU)",
+                   "N": N, "L_v": L_v, "init_field": 0, "weights": "synthetic splitmix64(seed=%d)" % SEED,
+                   "k2": args.k2, "replicas": world, "l2": "inputs (8.59 GB weight stream) larger than L2; no flush"},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": traffic, "kernel": "qhat_stream_kernel<32,1>", "kernel_ms": k2_avg_ms,
+                     "kernel_share_of_step": k2_ms / ms, "algorithmic_bytes_per_launch": wbytes, "peak_source": peak_src},
+        "e2e": {"value": world * args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": n3 * 8,
+                "d2h_bytes_per_step": n3 * 8, "api": "sbte_compute_q_host (the body of the drop-in ComputeQ)",
+                "checksum": checksum},
+        "gpu_launches": int(launches), "clocks": clocks,
+    }
+    if world == 1 and not args.no_cpu:
+        cb = cpu_computeq_n32(args.cpu_steps, 1)
+        line["cpu_baseline"] = {k: cb[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="0d_n32", choices=["0d_n32", "shock1p2"])
+    ap.add_argument("--k2", default="auto", choices=["auto", "stream", "deep", "generic"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--cpu-steps", type=int, default=5)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+        return
+    if args.workload == "0d_n32":
+        run_0d_n32(args)
+    else:
+        from spectralbte_b200 import bench1d
+        bench1d.run(args, ROOT)
+
+
+if __name__ == "__main__":
+    main()

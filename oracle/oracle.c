@@ -165,6 +165,8 @@ void orc_fft3d(orc_ctx *c, const double *in, double *out, int invert) {
 /* src/collisions.c:127-165.  Q^[zeta] = sum_xi W[zeta][xi] g^[xi] f^[wrap(zeta + N/2 - xi)], the
  * wrap applied once per dimension (:141-158).  The xi-sum runs in flat xi order, sequentially, as
  * in the reference; the per-dimension wrapped index tables replace its div/mod arithmetic. */
+static long g_row_mod = 0; /* > 0: weight row zeta is read from row (zeta % g_row_mod) (bounded CPU baselines) */
+
 void orc_qhat(orc_ctx *c, const double *W, const double *fhat, const double *ghat, double *qhat) {
   const int N = c->N, n2 = N / 2;
   const long n3 = c->n3;
@@ -174,7 +176,7 @@ void orc_qhat(orc_ctx *c, const double *W, const double *fhat, const double *gha
     const int zx = (int)(zeta / ((long)N * N));
     const int zy = (int)((zeta - (long)zx * N * N) / N);
     const int zz = (int)(zeta - (long)N * (zy + (long)zx * N));
-    const double *w = W + zeta * n3;
+    const double *w = W + (g_row_mod > 0 ? zeta % g_row_mod : zeta) * n3;
     double ar = 0.0, ai = 0.0;
     int ex, ey, ez;
     long xi = 0;
@@ -217,6 +219,14 @@ static void qhat_pipeline(orc_ctx *c, const double *W, const double *f_mat, cons
   orc_fft3d(c, c->out, c->gh, 0);
   orc_qhat(c, W, c->fh, c->gh, c->qh);
   orc_fft3d(c, c->qh, c->out, 1);
+}
+
+/* ComputeQ with the N^3 weight rows aliased onto `distinct` stored rows: same loop, same memory
+ * stream per row, bounded host memory (bench.py cpu_baseline when oracle/_ref is unavailable) */
+void orc_compute_q_rowmod(orc_ctx *c, const double *W, long distinct, const double *f, const double *g, double *Q) {
+  g_row_mod = distinct;
+  orc_compute_q(c, W, f, g, Q, NULL);
+  g_row_mod = 0;
 }
 
 /* src/collisions.c:212-221 */

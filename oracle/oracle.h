@@ -41,6 +41,8 @@ void orc_qhat(orc_ctx *c, const double *W, const double *fhat, const double *gha
 /* src/collisions.c:108-169 + 212-221 ; qhat_out (2*N^3) may be NULL */
 void orc_compute_q(orc_ctx *c, const double *W, const double *f, const double *g, double *Q,
                    double *qhat_out);
+void orc_compute_q_rowmod(orc_ctx *c, const double *W, long distinct_rows, const double *f, const double *g,
+                          double *Q);
 /* src/collisions.c:91-106,178-210 */
 void orc_compute_q_maxpreserve(orc_ctx *c, const double *W, const double *f, const double *g,
                                double *Q);

@@ -230,6 +230,7 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
 }
 
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
+  if (ensure_capacity(c, batch)) return 1;  // before c->d_qhat is read: growth reallocates the scratch
   if (qhat_from_real(c, d_f, d_g, c->d_qhat, batch, k2)) return 1;
   launch_fft3d(c, nullptr, c->d_qhat, 1, batch, nullptr, nullptr, 0, d_Q, false);
   return check_launch("inverse fft");
