@@ -25,4 +25,11 @@ SRC_DRIVER="$REF/exec/boltz.c $REF/src/initializer.c $REF/src/input.c $REF/src/o
 gcc $CFLAGS -o "$OUT/boltz_" $SRC_DRIVER $SRC_COMMON "$HERE/shims/shim.c" "$HERE/qag21.c" -lm
 gcc $CFLAGS -shared -o "$OUT/libref.so" $SRC_COMMON $REF/src/initializer.c $REF/src/restart.c \
   $REF/src/species.c $REF/src/input.c "$HERE/shims/shim.c" "$HERE/qag21.c" -lm
+# The reference driver linked against the B200 library INSTEAD of its own collision / conservation /
+# transport modules (the drop-in claim of include/sbte_b200.h, exercised by tests/test_gpu_dropin_driver.py)
+LIBDIR="$HERE/../spectralbte_b200"
+if [ -f "$LIBDIR/libsbte_b200.so" ]; then
+  gcc $CFLAGS -o "$OUT/boltz_gpu" $SRC_DRIVER $REF/src/momentRoutines.c $REF/src/weights.c \
+    "$HERE/shims/shim.c" "$HERE/qag21.c" -L"$LIBDIR" -lsbte_b200 -Wl,-rpath,'$ORIGIN/../../spectralbte_b200' -lm
+fi
 echo "built $OUT/boltz_ and $OUT/libref.so"

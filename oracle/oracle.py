@@ -30,7 +30,9 @@ def build(force=False):
     ref_root = os.environ.get("SBTE_REFERENCE_ROOT", "/root/reference")
     if os.path.isdir(os.path.join(ref_root, "src")):
         ref_so = os.path.join(HERE, "_ref", "libref.so")
-        if force or not os.path.exists(ref_so):
+        gpu_drv = os.path.join(HERE, "_ref", "boltz_gpu")
+        have_lib = os.path.exists(os.path.join(HERE, "..", "spectralbte_b200", "libsbte_b200.so"))
+        if force or not os.path.exists(ref_so) or (have_lib and not os.path.exists(gpu_drv)):
             subprocess.check_call([os.path.join(HERE, "build_ref.sh")], stdout=subprocess.DEVNULL)
     return so
 

@@ -30,6 +30,11 @@ def copy_reference_goldens():
              ("tests/heat_transport/target/moments_heat_transport.test.in", "moments_heat_transport.test.in")]
     for src, dst in pairs:
         shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, dst))
+    os.makedirs(os.path.join(HERE, "inputs"), exist_ok=True)
+    for src in ("tests/BKW8/input/BKW8.test.in", "tests/BKW8/input/BKW8.test.out",
+                "tests/heat_transport/input/heat_transport.test.in", "tests/heat_transport/input/heat_transport.test.out",
+                "tests/heat_transport/input/heat_transport.test.mesh"):
+        shutil.copyfile(os.path.join(REF, src), os.path.join(HERE, "inputs", os.path.basename(src)))
     for src in ("tests/BKW8/target/N8_isotropic_L_v5_lambda0.wts",
                 "tests/heat_transport/target/N8_isotropic_L_v9_lambda1.wts"):
         raw = open(os.path.join(REF, src), "rb").read()

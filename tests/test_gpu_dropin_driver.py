@@ -1,0 +1,52 @@
+"""The drop-in claim end to end: the reference's OWN driver (exec/boltz.c + initializer/input/output/
+mesh/restart/species/momentRoutines/weights, compiled unmodified by oracle/build_ref.sh) linked against
+libsbte_b200.so instead of src/collisions.c, src/conserve.c, src/transportroutines.c and
+src/boundaryConditions.c, run exactly as tests/run_test.sh runs boltz_ -- and its Data/moments_* files
+compared with the reference's golden files."""
+import lzma
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import GOLDEN, ROOT, check_diff_two_sided, load_moments
+
+pytestmark = pytest.mark.gpu
+DRIVER = os.path.join(ROOT, "oracle", "_ref", "boltz_gpu")
+
+
+def _run(tmp_path, name, wts):
+    for d in ("input", "Data", "Weights", "Restart"):
+        os.makedirs(tmp_path / d, exist_ok=True)
+    for fn in os.listdir(os.path.join(GOLDEN, "inputs")):
+        if fn.startswith(name):
+            shutil.copy(os.path.join(GOLDEN, "inputs", fn), tmp_path / "input" / fn)
+    raw = lzma.decompress(open(os.path.join(GOLDEN, wts + ".xz"), "rb").read())
+    (tmp_path / "Weights" / wts).write_bytes(raw)   # pre-populated: the loader path of src/weights.c:78-88
+    r = subprocess.run([DRIVER, name + ".test.in", name + ".test.out"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=900, env=dict(os.environ, OMP_NUM_THREADS="4"))
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "Loading weights from file" in r.stdout
+    return np.loadtxt(tmp_path / "Data" / ("moments_%s.test.in" % name), comments="#")
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/boltz_gpu not built")
+def test_reference_driver_on_gpu_library_bkw8(tmp_path):
+    got = _run(tmp_path, "BKW8", "N8_isotropic_L_v5_lambda0.wts")
+    want = load_moments("moments_BKW8.test.in")
+    assert got.shape == want.shape
+    assert check_diff_two_sided(np.delete(got, 2, axis=1), np.delete(want, 2, axis=1)) == 0
+    assert np.abs(got[:, 2]).max() < 1e-13
+
+
+@pytest.mark.skipif(not os.path.exists(DRIVER), reason="oracle/_ref/boltz_gpu not built")
+def test_reference_driver_on_gpu_library_heat_transport(tmp_path):
+    got = _run(tmp_path, "heat_transport", "N8_isotropic_L_v9_lambda1.wts")
+    want = load_moments("moments_heat_transport.test.in")
+    assert got.shape == want.shape
+    assert check_diff_two_sided(np.delete(got, 3, axis=1), np.delete(want, 3, axis=1)) == 0
+    big = np.abs(want[:, 3]) > 1e-9
+    assert check_diff_two_sided(got[big, 3], want[big, 3]) == 0
+    assert np.abs(got[~big, 3] - want[~big, 3]).max() < 1e-12
