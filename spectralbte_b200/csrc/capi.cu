@@ -185,6 +185,67 @@ __global__ void synth_weights_kernel(double* __restrict__ W, size_t n, unsigned 
   }
 }
 
+// ---- stream-K schedule of the batched convolution ---------------------------------------------
+// T = groups * row-blocks tiles of N^2 steps; P persistent CTAs take equal contiguous shares of the
+// T*N^2 global steps. tile_first / tile_np tell kernels which CTA writes which partial sum.
+static int ensure_batch_schedule(sbte_ctx* c, int cells) {
+  if (c->sched_cells == cells && c->d_sched_mem) return 0;
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d_sched_mem) { cudaFree(c->d_sched_mem); c->d_sched_mem = nullptr; }
+  if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  const int N = c->N, cols = qhat_batch_cols(N);
+  const int G = (cells + 31) / 32, RB = N * N / cols, T = G * RB;
+  const long long S = (long long)N * N, total = (long long)T * S;
+  int P = c->sm_count;
+  const char* pe = getenv("SBTE_BATCH_CTAS");
+  if (pe && atoi(pe) > 0) P = atoi(pe);
+  const long long min_steps = 4 * (long long)N;  // at least a few xi_x chunks per CTA
+  if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
+  std::vector<long long> begin(P + 1);
+  for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * total) / P);
+  auto owner = [&](long long g) {
+    int lo = 0, hi = P - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (begin[mid] <= g) lo = mid; else hi = mid - 1; }
+    return lo;
+  };
+  std::vector<int> first(T);
+  std::vector<unsigned char> np(T);
+  int kmax = 1;
+  for (int t = 0; t < T; t++) {
+    const int a = owner((long long)t * S), b = owner((long long)(t + 1) * S - 1);
+    first[t] = a;
+    np[t] = (unsigned char)(b - a + 1);
+    kmax = std::max(kmax, b - a + 1);
+  }
+  const size_t o1 = (size_t)(P + 1) * sizeof(long long), o2 = o1 + (size_t)T * sizeof(int);
+  const size_t bytes = o2 + (size_t)T;
+  CK(cudaMalloc(&c->d_sched_mem, bytes));
+  std::vector<unsigned char> blob(bytes);
+  memcpy(blob.data(), begin.data(), o1);
+  memcpy(blob.data() + o1, first.data(), (size_t)T * sizeof(int));
+  memcpy(blob.data() + o2, np.data(), (size_t)T);
+  CK(cudaMemcpy(c->d_sched_mem, blob.data(), bytes, cudaMemcpyHostToDevice));
+  unsigned char* base = (unsigned char*)c->d_sched_mem;
+  c->sched = {(const long long*)base, (const int*)(base + o1), base + o2, G, T, P, cols, kmax};
+  c->sched_cells = cells;
+  // partial-sum workspace: kmax parts of (padded cells) x n3 complex
+  const size_t stride = (size_t)G * 32 * (size_t)c->n3;
+  if (!c->d_parts || c->parts_stride < stride || c->parts_cap < kmax) {
+    if (c->d_parts) cudaFree(c->d_parts);
+    c->d_parts = nullptr;
+    CK(cudaMalloc(&c->d_parts, (size_t)kmax * stride * sizeof(double2)));
+    c->parts_stride = stride;
+    c->parts_cap = kmax;
+  }
+  return 0;
+}
+
+static bool use_batch_v1() {
+  static int v = -1;
+  if (v < 0) { const char* e = getenv("SBTE_BATCH_V1"); v = (e && atoi(e) != 0) ? 1 : 0; }
+  return v == 1;
+}
+
 // ---- convolution dispatch -------------------------------------------------------------------
 // spectra of f (dif side) and g (xi side) -> qhat (natural layout)
 static int resolve_k2(sbte_ctx* c, int batch, int k2) {
@@ -204,7 +265,13 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     if (!same) { set_error("batched convolution requires f == g (single species)"); return 1; }
     if (!qhat_batch_supported(c->N)) { set_error("batched convolution: unsupported N"); return 1; }
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_qhat_batch(c, c->d_lay[0], d_qhat, batch);
+    if (use_batch_v1()) {
+      launch_qhat_batch_v1(c, c->d_lay[0], d_qhat, batch);
+    } else {
+      if (ensure_batch_schedule(c, batch)) return 1;
+      launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+      launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
+    }
   } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
     if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
     launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
@@ -231,6 +298,15 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
 
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
   if (ensure_capacity(c, batch)) return 1;  // before c->d_qhat is read: growth reallocates the scratch
+  if (resolve_k2(c, batch, k2) == SBTE_K2_BATCH && d_f == d_g && qhat_batch_supported(c->N) && !use_batch_v1()) {
+    // fast path: forward transform -> stream-K convolution -> inverse transform summing the partial sums
+    if (!c->d_W) { set_error("no weights bound"); return 1; }
+    if (ensure_batch_schedule(c, batch)) return 1;
+    launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
+    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_fft3d_parts(c, c->d_parts, c->parts_stride, c->sched, 1, batch, nullptr, d_Q);
+    return check_launch("batched compute_q");
+  }
   if (qhat_from_real(c, d_f, d_g, c->d_qhat, batch, k2)) return 1;
   launch_fft3d(c, nullptr, c->d_qhat, 1, batch, nullptr, nullptr, 0, d_Q, false);
   return check_launch("inverse fft");
@@ -342,6 +418,8 @@ int sbte_destroy(sbte_ctx* c) {
   for (int d = 0; d < 2; d++) { cudaFree(c->d_pre[d]); cudaFree(c->d_post[d]); }
   if (c->h_pin) cudaFreeHost(c->h_pin);
   for (cudaEvent_t e : c->k2_ev) cudaEventDestroy(e);
+  if (c->d_sched_mem) cudaFree(c->d_sched_mem);
+  if (c->d_parts) cudaFree(c->d_parts);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;

@@ -40,10 +40,18 @@ __device__ __forceinline__ void dft_tile(const double2* __restrict__ src, double
   }
 }
 
+// optional stream-K input: the complex input is the fixed-order sum of `tile_np[t]` partial sums
+struct PartsIn {
+  const double2* parts;          // null: plain input
+  size_t stride;                 // double2 elements between parts
+  const unsigned char* tile_np;  // partial sums per tile
+  int G, cols;                   // cell groups, zeta columns per tile
+};
+
 __global__ void __launch_bounds__(FFT_THREADS)
 fft_pass_zy(const double* __restrict__ in_real, const double2* __restrict__ in_cplx, double2* __restrict__ tmp,
             const double2* __restrict__ pre, const double* __restrict__ wt, const double2* __restrict__ dft,
-            int N, double prefactor, double sgn) {
+            int N, double prefactor, double sgn, PartsIn pin) {
   extern __shared__ double2 sm[];
   double2* A = sm;
   double2* B = sm + N * N;
@@ -57,6 +65,15 @@ fft_pass_zy(const double* __restrict__ in_real, const double2* __restrict__ in_c
     const long idx = cell * n3 + ((long)i * N + j) * N + k;
     double xr, xi;
     if (in_real) { xr = in_real[idx]; xi = 0.0; }
+    else if (pin.parts) {
+      const int tile = ((i * N + j) / pin.cols) * pin.G + (int)(cell >> 5);
+      const int np = pin.tile_np[tile];
+      xr = 0.0; xi = 0.0;
+      for (int m = 0; m < np; m++) {
+        const double2 z = pin.parts[(size_t)m * pin.stride + idx];
+        xr += z.x; xi += z.y;
+      }
+    }
     else { const double2 z = in_cplx[idx]; xr = z.x; xi = z.y; }
     const double2 cs = pre[i + j + k];
     const double factor = prefactor * wt[i] * wt[j] * wt[k];
@@ -119,11 +136,52 @@ void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, in
   const int d = invert ? 1 : 0;
   const double sgn = invert ? +1.0 : -1.0;  // FFTW_BACKWARD / FFTW_FORWARD exponent sign
   dim3 grid(N, batch);
+  PartsIn none = {nullptr, 0, nullptr, 0, 0};
   fft_pass_zy<<<grid, FFT_THREADS, smem, c->stream>>>(in_real, in_cplx, c->d_tmp, c->d_pre[d], c->d_wt, c->d_dft, N,
-                                                      c->pref[d], sgn);
+                                                      c->pref[d], sgn, none);
   fft_pass_x<<<grid, FFT_THREADS, smem, c->stream>>>(c->d_tmp, c->d_post[d], c->d_dft, N, sgn, out_nat, out_lay,
                                                      layout, out_real, accumulate_real ? 1 : 0);
   c->launches += 2;
+}
+
+void launch_fft3d_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int invert,
+                        int batch, double2* out_nat, double* out_real) {
+  const int N = c->N;
+  const size_t smem = (size_t)(2 * N * N + N) * sizeof(double2);
+  const int d = invert ? 1 : 0;
+  const double sgn = invert ? +1.0 : -1.0;
+  dim3 grid(N, batch);
+  PartsIn pin = {parts, part_stride, sch.tile_np, sch.G, sch.cols};
+  fft_pass_zy<<<grid, FFT_THREADS, smem, c->stream>>>(nullptr, nullptr, c->d_tmp, c->d_pre[d], c->d_wt, c->d_dft, N,
+                                                      c->pref[d], sgn, pin);
+  fft_pass_x<<<grid, FFT_THREADS, smem, c->stream>>>(c->d_tmp, c->d_post[d], c->d_dft, N, sgn, out_nat, nullptr, 0,
+                                                     out_real, 0);
+  c->launches += 2;
+}
+
+// plain sum of the partial sums into a natural-layout Q^ (only used when the caller asks for Q^ itself)
+__global__ void combine_parts_kernel(double2* __restrict__ out, PartsIn pin, int N, long total) {
+  const long n3 = (long)N * N * N;
+  for (long e = blockIdx.x * (long)blockDim.x + threadIdx.x; e < total; e += (long)gridDim.x * blockDim.x) {
+    const long cell = e / n3;
+    const int loc = (int)(e - cell * n3);
+    const int tile = ((loc / N) / pin.cols) * pin.G + (int)(cell >> 5);
+    const int np = pin.tile_np[tile];
+    double xr = 0.0, xi = 0.0;
+    for (int m = 0; m < np; m++) {
+      const double2 z = pin.parts[(size_t)m * pin.stride + e];
+      xr += z.x; xi += z.y;
+    }
+    out[e] = make_double2(xr, xi);
+  }
+}
+
+void launch_combine_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int batch,
+                          double2* out) {
+  PartsIn pin = {parts, part_stride, sch.tile_np, sch.G, sch.cols};
+  const long total = (long)batch * c->n3;
+  combine_parts_kernel<<<148 * 8, 256, 0, c->stream>>>(out, pin, c->N, total);
+  c->launches += 1;
 }
 
 }  // namespace sbte

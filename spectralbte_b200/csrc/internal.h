@@ -15,6 +15,14 @@ struct ConsLU {
   int piv[5];
 };
 
+// stream-K schedule of the batched convolution (device tables, see qhat_batch.cu)
+struct BatchSched {
+  const long long* cta_begin;   // [P+1] first global step of every CTA
+  const int* tile_first;        // [T] first CTA that touches tile t
+  const unsigned char* tile_np; // [T] number of partial sums of tile t
+  int G, T, P, cols, kmax;
+};
+
 struct sbte_ctx {
   int N = 0;
   long n3 = 0;
@@ -53,6 +61,14 @@ struct sbte_ctx {
   double* d_M = nullptr;         // Maxwellian / perturbation scratch (0D)
   double* d_mom = nullptr;       // [cap][8] moments
   double* h_pin = nullptr;       // pinned host staging, 3 * n3 doubles
+  // batched-convolution schedule + partial-sum workspace (valid for sched_cells cells)
+  int sched_cells = 0;
+  BatchSched sched = {nullptr, nullptr, nullptr, 0, 0, 0, 0, 0};
+  void* d_sched_mem = nullptr;
+  double2* d_parts = nullptr;
+  size_t parts_stride = 0;          // double2 elements per part
+  int parts_cap = 0;                // parts allocated
+  int sm_count = 0;
   unsigned long long launches = 0;  // kernels launched through this context
   bool k2_prof = false;             // bracket every K2 launch with CUDA events
   std::vector<cudaEvent_t> k2_ev;   // [2*i], [2*i+1] = start/stop of launch i
@@ -76,6 +92,11 @@ enum SpecLayout {
 // out_nat / out_lay / out_real may each be null. batch = number of cells.
 void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,
                   double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real);
+// same, the complex input being the sum of the stream-K partial sums described by `sch`
+void launch_fft3d_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int invert,
+                        int batch, double2* out_nat, double* out_real);
+void launch_combine_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int batch,
+                          double2* out);
 
 // qhat.cu -- K2
 struct QhatPair {
@@ -89,7 +110,10 @@ bool qhat_stream_supported(int N);
 void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth);
 // batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32
 bool qhat_batch_supported(int N);
-void launch_qhat_batch(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells);
+int qhat_batch_cols(int N);
+void launch_qhat_batch_v1(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells);
+void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
+                        const BatchSched& sch);
 
 // conserve.cu -- K4 / K5 / moments
 void launch_conserve(sbte_ctx* c, double* Q, int batch);

@@ -128,6 +128,7 @@ qhat_batch_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __re
 }
 
 bool qhat_batch_supported(int N) { return N == 8 || N == 16; }
+int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
 
 template <int N>
 static void launch_batch_n(sbte_ctx* c, const double2* spec, double2* qhat, int cells) {
@@ -146,11 +147,221 @@ static void launch_batch_n(sbte_ctx* c, const double2* spec, double2* qhat, int 
   c->launches += 1;
 }
 
-void launch_qhat_batch(sbte_ctx* c, const double2* spec, double2* qhat, int cells) {
+void launch_qhat_batch_v1(sbte_ctx* c, const double2* spec, double2* qhat, int cells) {
   if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
   switch (c->N) {
     case 8: launch_batch_n<8>(c, spec, qhat, cells); break;
     case 16: launch_batch_n<16>(c, spec, qhat, cells); break;
+    default: set_error("qhat_batch: unsupported N"); break;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// v2: persistent CTAs, stream-K split of the (tile, step) iteration space, decoupled warps
+// ------------------------------------------------------------------------------------------
+// The work is T = groups * row-blocks tiles of N^2 steps each.  One CTA per SM takes an equal,
+// contiguous share of the T*N^2 global steps (tile-major, cell group fastest so that concurrently
+// running CTAs read the same weight rows from L2).  A tile cut by a CTA boundary is written as two
+// (or more) partial sums into `parts[k]`; the inverse transform adds the parts in fixed order, so the
+// result is deterministic and independent of the SM count only through that order.
+// Inside a CTA the warps are decoupled: a 4-stage ring of (weight tile, xi-side line) with full
+// (TMA transaction) and empty (one arrival per warp) mbarriers; lane 0 of warp 0 issues the TMA
+// copies two to three steps ahead.  No __syncthreads in the main loop.
+template <int N>
+struct Batch2Cfg {
+  static constexpr int COLS = (N >= 16) ? 8 : 4;
+  static constexpr int CONSUMERS = COLS * 32;      // compute threads: one warp per zeta (x,y) column
+  static constexpr int THREADS = CONSUMERS + 128;  // + one producer warpgroup (one lane issues the TMA copies)
+  // register split (setmaxnreg works on warpgroups): 384 threads compile to <= 168 registers; the
+  // producer warpgroup drops to 24 and the two compute warpgroups grow to 240 (240*256 + 24*128 <= 64512)
+  static constexpr bool REG_SPLIT = THREADS > 256;
+  static constexpr int ROWS = COLS * N;
+  static constexpr int LINE = N * 32;
+  static constexpr int PLANE = N * LINE;
+  static constexpr int STAGES = 4;
+  static constexpr size_t STAGE_BYTES = (size_t)LINE * 16 + (size_t)ROWS * N * 8;
+  static constexpr size_t SMEM = (size_t)PLANE * 16 + STAGES * STAGE_BYTES + 256;
+};
+
+template <int N>
+__global__ void __launch_bounds__(Batch2Cfg<N>::THREADS, 1)
+qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
+                   double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch) {
+  using C = Batch2Cfg<N>;
+  constexpr long n3 = (long)N * N * N;
+  constexpr int NSTEP = N * N;
+  constexpr int S = C::STAGES;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double2* plane = reinterpret_cast<double2*>(smraw);
+  unsigned char* stage0 = smraw + (size_t)C::PLANE * 16;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + S * C::STAGE_BYTES);
+  uint64_t* full = bars;            // [S]  TMA transaction barriers
+  uint64_t* empty = bars + S;       // [S]  one arrival per compute warp
+  uint64_t* fullPlane = bars + 2 * S;
+  uint64_t* emptyPlane = bars + 2 * S + 1;
+  auto stage_line = [&](int s) { return reinterpret_cast<double2*>(stage0 + (size_t)s * C::STAGE_BYTES); };
+  auto stage_w = [&](int s) {
+    return reinterpret_cast<double*>(stage0 + (size_t)s * C::STAGE_BYTES + (size_t)C::LINE * 16);
+  };
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long g0 = sch.cta_begin[blockIdx.x];
+  const int n = (int)(sch.cta_begin[blockIdx.x + 1] - g0);
+  if (n <= 0) return;
+  const int G = sch.G;
+
+  if (tid == 0) {
+    for (int b = 0; b < S; b++) { mbar_init(&full[b], 1); mbar_init(&empty[b], C::COLS); }
+    mbar_init(fullPlane, 1);
+    mbar_init(emptyPlane, C::COLS);
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  // decode of a global step: tile -> (row-block, cell group), step -> (xi_x chunk, xi_y), plane index X
+  auto plane_of = [&](long long g, int& cg, int& X) {
+    const int t = (int)(g / NSTEP), s = (int)(g - (long long)t * NSTEP);
+    const int rb = t / G;
+    cg = t - rb * G;
+    X = (rb * C::COLS) / N + N / 2 - s / N;
+    if (X < 0) X += N; else if (X > N - 1) X -= N;
+  };
+
+  if (warp >= C::COLS) {
+    // ===== producer warpgroup: one lane issues every TMA copy, up to S steps ahead of the consumers =====
+    if (C::REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == C::COLS && lane == 0) {
+      int cur_cg = -1, cur_X = -1, epoch = -1;
+      for (int k = 0; k < n; k++) {
+        const long long g = g0 + k;
+        const int t = (int)(g / NSTEP), s = (int)(g - (long long)t * NSTEP);
+        const int rb = t / G, cg = t - rb * G;
+        int X;
+        { int cgx; plane_of(g, cgx, X); }
+        if (cg != cur_cg || X != cur_X) {
+          if (epoch >= 0) mbar_wait(emptyPlane, epoch & 1);   // every warp released the previous plane
+          epoch++;
+          cur_cg = cg; cur_X = X;
+          mbar_arrive_expect_tx(fullPlane, (uint32_t)(C::PLANE * 16));
+          const double2* src = spec + (size_t)cg * n3 * 32 + (size_t)X * N * C::LINE;
+          for (int y = 0; y < N; y++)
+            tma_bulk_g2s(plane + (size_t)y * C::LINE, src + (size_t)y * C::LINE, C::LINE * 16, fullPlane);
+        }
+        const int st = k % S;
+        if (k >= S) mbar_wait(&empty[st], ((k / S) - 1) & 1);  // consumers finished the previous use of this stage
+        mbar_arrive_expect_tx(&full[st], (uint32_t)C::STAGE_BYTES);
+        tma_bulk_g2s(stage_line(st), spec + (size_t)cg * n3 * 32 + (size_t)s * C::LINE, C::LINE * 16, &full[st]);
+        tma_tensor2d_g2s(stage_w(st), &tmapW, s * N, rb * C::ROWS, &full[st]);
+      }
+    }
+    return;
+  }
+
+  // ===== compute warps =====
+  if (C::REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  double2 acc[N];
+#pragma unroll
+  for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
+
+  int cur_t = -1, cur_cg = -1, cur_X = -1, epoch = -1;
+  int zx = 0, zy = 0;
+
+  auto flush = [&]() {
+    const int rb = cur_t / G, cg = cur_t - rb * G;
+    const long cell = (long)cg * 32 + lane;
+    if (cell < cells) {
+      const int part = (int)blockIdx.x - sch.tile_first[cur_t];
+      double2* out = parts + (size_t)part * part_stride + cell * n3 + ((long)zx * N + zy) * N;
+#pragma unroll
+      for (int r = 0; r < N; r++) out[r] = acc[r];
+    }
+  };
+
+  for (int k = 0; k < n; k++) {
+    const long long g = g0 + k;
+    const int t = (int)(g / NSTEP), s = (int)(g - (long long)t * NSTEP);
+    const int ey = s % N;
+    if (t != cur_t) {
+      if (cur_t >= 0) {
+        flush();
+#pragma unroll
+        for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
+      }
+      cur_t = t;
+      const int q0 = (t / G) * C::COLS;
+      zx = q0 / N;
+      zy = (q0 % N) + warp;
+    }
+    int cg, X;
+    plane_of(g, cg, X);
+    if (cg != cur_cg || X != cur_X) {
+      epoch++;
+      cur_cg = cg; cur_X = X;
+      mbar_wait(fullPlane, epoch & 1);
+    }
+    const int st = k % S;
+    mbar_wait(&full[st], (k / S) & 1);
+
+    int Y = zy + N / 2 - ey;
+    if (Y < 0) Y += N; else if (Y > N - 1) Y -= N;
+    const double2* fl = plane + (size_t)Y * C::LINE + lane;
+    const double2* gl = stage_line(st) + lane;
+    const double* wt = stage_w(st) + warp * N * N;
+
+    double2 fr[N];
+#pragma unroll
+    for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
+#pragma unroll
+    for (int c = 0; c < N; c += 2) {
+      const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
+#pragma unroll
+      for (int r = 0; r < N; r++) {
+        const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
+        const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
+        const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
+        cmac(acc[r], w2.x, p0);
+        cmac(acc[r], w2.y, p1);
+      }
+    }
+
+    // release the stage (and the plane when the next step needs another one)
+    bool plane_done = (k == n - 1);
+    if (!plane_done) {
+      int cg2, X2;
+      plane_of(g + 1, cg2, X2);
+      plane_done = (cg2 != cur_cg) || (X2 != cur_X);
+    }
+    __syncwarp();
+    if (lane == 0) {
+      mbar_arrive(&empty[st]);
+      if (plane_done) mbar_arrive(emptyPlane);
+    }
+  }
+  flush();
+}
+
+template <int N>
+static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
+                            const BatchSched& sch) {
+  using C = Batch2Cfg<N>;
+  auto kern = qhat_batch2_kernel<N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    configured = true;
+  }
+  k2_mark(c);
+  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(c->tmapW, spec, parts, part_stride, cells, sch);
+  k2_mark(c);
+  c->launches += 1;
+}
+
+void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
+                        const BatchSched& sch) {
+  if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
+  switch (c->N) {
+    case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
+    case 16: launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch); break;
     default: set_error("qhat_batch: unsupported N"); break;
   }
 }
