@@ -108,8 +108,12 @@ def cpu_computeq_n32(steps, warmup, distinct_rows=512):
     from spectralbte_b200.api import velocity_grids
     N, L_v = 32, 5.0
     n3 = N ** 3
-    cores = os.cpu_count() or 1
-    os.environ.setdefault("OMP_NUM_THREADS", str(cores))
+    cores = int(os.environ.get("SBTE_CPU_THREADS", os.cpu_count() or 1))
+    os.environ["OMP_NUM_THREADS"] = str(cores)   # torchrun exports OMP_NUM_THREADS=1; the baseline uses every core
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)   # also covers an already-initialised libgomp
+    except OSError:
+        pass
     v, eta = velocity_grids(N, L_v)
     f = initial.init_hom(v, L_v, 0)
     rng = np.random.default_rng(SEED)
@@ -138,8 +142,7 @@ def cpu_computeq_n32(steps, warmup, distinct_rows=512):
     dt = time.perf_counter() - t0
     return {"value": steps / dt, "unit": "evals/s", "cores": cores, "kind": kind, "seconds": dt,
             "sample": "%d full N=32 ComputeQ evaluations (1.07e9 pairs each, FFTs included), weight rows "
-                      "aliased to %d distinct synthetic rows, OMP_NUM_THREADS=%s" % (steps, distinct_rows,
-                                                                                   os.environ["OMP_NUM_THREADS"])}
+                      "aliased to %d distinct synthetic rows, %d OpenMP threads" % (steps, distinct_rows, cores)}
 
 
 def run_reference(args):
@@ -286,6 +289,15 @@ def run_0d_n32(args):
     print(json.dumps(line))
 
 
+def finalize():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            dist.destroy_process_group()
+    except Exception:
+        pass
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -306,6 +318,7 @@ def main():
     else:
         from spectralbte_b200 import bench1d
         bench1d.run(args, ROOT)
+    finalize()
 
 
 if __name__ == "__main__":

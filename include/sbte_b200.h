@@ -108,6 +108,10 @@ SBTE_API int sbte_weights_load_file(sbte_ctx *c, const char *path);
 SBTE_API int sbte_weights_bind_device(sbte_ctx *c, const double *d_W);
 SBTE_API int sbte_weights_fill_synthetic(sbte_ctx *c, unsigned long long seed); /* splitmix64 -> [-0.5,0.5) */
 SBTE_API const double *sbte_weights_device(sbte_ctx *c);
+/* isotropic weights generated on the device (src/weights.c:156-281: adaptive GK21 per (zeta, xi) pair) */
+SBTE_API int sbte_weights_generate_iso(sbte_ctx *c, double lambda);
+/* write the bound weights in the reference's .wts format (src/weights.c:100-103) */
+SBTE_API int sbte_weights_save_file(sbte_ctx *c, const char *path);
 
 /* kernel selection for the convolution */
 enum { SBTE_K2_AUTO = 0, SBTE_K2_GENERIC = 1, SBTE_K2_STREAM = 2, SBTE_K2_BATCH = 3, SBTE_K2_STREAM_DEEP = 4 };

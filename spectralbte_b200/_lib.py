@@ -46,6 +46,8 @@ PROTOTYPES = {
     "sbte_weights_bind_device": (C.c_int, [_vp, _vp]),
     "sbte_weights_fill_synthetic": (C.c_int, [_vp, C.c_ulonglong]),
     "sbte_weights_device": (_vp, [_vp]),
+    "sbte_weights_generate_iso": (C.c_int, [_vp, C.c_double]),
+    "sbte_weights_save_file": (C.c_int, [_vp, C.c_char_p]),
     "sbte_fft3d": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
     "sbte_qhat": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int]),
     "sbte_compute_q": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int]),

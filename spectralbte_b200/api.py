@@ -118,6 +118,13 @@ class Collisions:
     def synthetic_weights(self, seed=20261017):
         check(self.L.sbte_weights_fill_synthetic(self.h, int(seed)))
 
+    def generate_weights(self, lam):
+        """generate_conv_weights_iso on the device (src/weights.c:265-281)."""
+        check(self.L.sbte_weights_generate_iso(self.h, float(lam)))
+
+    def save_weights(self, path):
+        check(self.L.sbte_weights_save_file(self.h, path.encode()))
+
     def weights_to_host(self):
         out = np.empty(self.n3 * self.n3)
         check(self.L.sbte_d2h(self.h, out.ctypes.data, self.L.sbte_weights_device(self.h), out.nbytes))

@@ -20,8 +20,8 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
           "--expt-relaxed-constexpr"]
 # elementwise / reduction kernels keep the reference's operation-by-operation rounding (no FMA
 # contraction); the FP64-bound convolution and the DFTs use FMAs.
-PER_FILE = {"transport.cu": ["-fmad=false"], "conserve.cu": ["-fmad=false"]}
-SOURCES = ["capi.cu", "dropin.cu", "slab.cu", "fft.cu", "qhat.cu", "qhat_batch.cu", "conserve.cu", "transport.cu"]
+PER_FILE = {"transport.cu": ["-fmad=false"], "conserve.cu": ["-fmad=false"], "weightgen.cu": ["-fmad=false"]}
+SOURCES = ["capi.cu", "dropin.cu", "slab.cu", "fft.cu", "qhat.cu", "qhat_batch.cu", "conserve.cu", "transport.cu", "weightgen.cu"]
 
 
 def _nvcc():
@@ -68,7 +68,24 @@ def build(force=False, verbose=False):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed: %s\n%s" % (r.stdout, r.stderr))
+    build_host(force or bool(jobs))
     return LIB
+
+
+HOST_SRC = os.path.join(HERE, "host", "boltz_b200.c")
+HOST_BIN = os.path.join(HERE, "host", "boltz_b200")
+
+
+def build_host(force=False):
+    """The C host driver (reference-style command line, device-resident time loop)."""
+    inc = os.path.join(os.path.dirname(HERE), "include")
+    if force or _stale(HOST_BIN, [HOST_SRC, os.path.join(inc, "sbte_b200.h"), LIB]):
+        cmd = ["gcc", "-std=gnu99", "-O2", "-Wall", "-I", inc, HOST_SRC, "-L", HERE, "-lsbte_b200",
+               "-Wl,-rpath,$ORIGIN/..", "-lm", "-o", HOST_BIN]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("host driver build failed:\n%s\n%s" % (r.stdout, r.stderr))
+    return HOST_BIN
 
 
 if __name__ == "__main__":

@@ -543,6 +543,37 @@ int sbte_weights_fill_synthetic(sbte_ctx* c, unsigned long long seed) {
 
 const double* sbte_weights_device(sbte_ctx* c) { return c->d_W; }
 
+int sbte_weights_generate_iso(sbte_ctx* c, double lambda) {
+  CK(cudaSetDevice(c->device));
+  if (alloc_weights(c)) return 1;
+  int used = 0;
+  if (generate_weights_iso(c, (double*)c->d_W, lambda, &used)) { release_weights(c); return 1; }
+  return make_tensor_map(c);
+}
+
+int sbte_weights_save_file(sbte_ctx* c, const char* path) {
+  if (!c->d_W) { set_error("no weights bound"); return 1; }
+  FILE* fp = fopen(path, "wb");
+  if (!fp) { set_error(std::string("cannot create weight file ") + path); return 1; }
+  const size_t total = (size_t)c->n3 * c->n3;
+  const size_t chunk = (size_t)(64u << 20) / sizeof(double);
+  double* pin = nullptr;
+  CK(cudaMallocHost(&pin, chunk * sizeof(double)));
+  CK(cudaStreamSynchronize(c->stream));
+  for (size_t off = 0; off < total; off += chunk) {
+    const size_t n = std::min(chunk, total - off);
+    CK(cudaMemcpy(pin, c->d_W + off, n * sizeof(double), cudaMemcpyDeviceToHost));
+    if (fwrite(pin, sizeof(double), n, fp) != n) {
+      fclose(fp); cudaFreeHost(pin);
+      set_error("Something is wrong with storing the weights");   // src/weights.c:104-107
+      return 1;
+    }
+  }
+  fclose(fp);
+  cudaFreeHost(pin);
+  return 0;
+}
+
 // ---- device-pointer operations
 int sbte_fft3d(sbte_ctx* c, const double* d_in, double* d_out, int invert, int batch) {
   if (ensure_capacity(c, batch)) return 1;

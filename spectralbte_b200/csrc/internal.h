@@ -124,4 +124,7 @@ void launch_moments(sbte_ctx* c, const double* f, double* mom8, int batch);   //
 void launch_maxwellian_split(sbte_ctx* c, const double* f, const double* Msub, double* M, double* g);
 void launch_moment_functionals(sbte_ctx* c, const double* Q, double* b5, int batch);
 
+// weightgen.cu -- isotropic weights by adaptive GK21 on the device
+int generate_weights_iso(sbte_ctx* c, double* d_W, double lambda, int* max_intervals);
+
 }  // namespace sbte

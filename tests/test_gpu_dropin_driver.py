@@ -50,3 +50,55 @@ def test_reference_driver_on_gpu_library_heat_transport(tmp_path):
     big = np.abs(want[:, 3]) > 1e-9
     assert check_diff_two_sided(got[big, 3], want[big, 3]) == 0
     assert np.abs(got[~big, 3] - want[~big, 3]).max() < 1e-12
+
+
+# ---------------------------------------------------------------- our own C host driver
+HOST = os.path.join(ROOT, "spectralbte_b200", "host", "boltz_b200")
+
+
+def _run_host(tmp_path, name, wts, prepopulate):
+    for d in ("input", "Data", "Weights"):
+        os.makedirs(tmp_path / d, exist_ok=True)
+    for fn in os.listdir(os.path.join(GOLDEN, "inputs")):
+        if fn.startswith(name):
+            shutil.copy(os.path.join(GOLDEN, "inputs", fn), tmp_path / "input" / fn)
+    raw = lzma.decompress(open(os.path.join(GOLDEN, wts + ".xz"), "rb").read())
+    if prepopulate:
+        (tmp_path / "Weights" / wts).write_bytes(raw)
+    r = subprocess.run([HOST, name + ".test.in", name + ".test.out"], cwd=tmp_path, capture_output=True, text=True,
+                       timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    got = np.loadtxt(tmp_path / "Data" / ("moments_%s.test.in" % name), comments="#")
+    header = open(tmp_path / "Data" / ("moments_%s.test.in" % name)).readline()
+    gen = np.frombuffer((tmp_path / "Weights" / wts).read_bytes(), dtype=np.float64)
+    return got, header, gen, np.frombuffer(raw, dtype=np.float64), r.stdout
+
+
+@pytest.mark.parametrize("prepopulate", [True, False])
+def test_c_host_driver_bkw8(tmp_path, prepopulate):
+    """boltz_b200 BKW8.test.in BKW8.test.out: same inputs, same Data/moments_* format, golden values.
+    prepopulate=False exercises the device weight generator + the .wts writer (tests/run_test.sh:41-52
+    diffs the generated file against target/)."""
+    got, header, gen, gold, log = _run_host(tmp_path, "BKW8", "N8_isotropic_L_v5_lambda0.wts", prepopulate)
+    want = load_moments("moments_BKW8.test.in")
+    ref_header = open(os.path.join(GOLDEN, "moments_BKW8.test.in")).readline()
+    assert header == ref_header
+    assert got.shape == want.shape
+    assert check_diff_two_sided(np.delete(got, 2, axis=1), np.delete(want, 2, axis=1)) == 0
+    assert ("Loading weights from file" in log) == prepopulate
+    assert gen.shape == gold.shape
+    if not prepopulate:
+        assert np.abs(gen - gold).max() <= 1e-7 * np.abs(gold).max()
+        assert np.quantile(np.abs(gen - gold), 0.999) <= 1e-13 * np.abs(gold).max()
+
+
+def test_c_host_driver_heat_transport(tmp_path):
+    got, header, gen, gold, log = _run_host(tmp_path, "heat_transport", "N8_isotropic_L_v9_lambda1.wts", False)
+    want = load_moments("moments_heat_transport.test.in")
+    assert header == open(os.path.join(GOLDEN, "moments_heat_transport.test.in")).readline()
+    assert got.shape == want.shape
+    assert check_diff_two_sided(np.delete(got, 3, axis=1), np.delete(want, 3, axis=1)) == 0
+    big = np.abs(want[:, 3]) > 1e-9
+    assert check_diff_two_sided(got[big, 3], want[big, 3]) == 0
+    assert np.abs(gen - gold).max() <= 1e-7 * np.abs(gold).max()
+    assert np.quantile(np.abs(gen - gold), 0.999) <= 1e-13 * np.abs(gold).max()

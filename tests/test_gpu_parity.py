@@ -2,6 +2,8 @@
 libsbte_b200.so), against the CPU oracle on the same seeded inputs, against the reference's golden
 files, and through size-independent properties at full size.  Tolerances follow BASELINE.json:
 Q^ relative 1e-12 (normwise), conservation 1e-13, golden moments abs 1e-14 or rel 1e-6 two-sided."""
+import os
+
 import numpy as np
 import pytest
 
@@ -407,3 +409,43 @@ def test_dropin_advect_reproduces_reference_vectors(sb, ref_vectors):
         assert relmax(fc[order:nX + order], ref_vectors[f"tr_ic3_o{order}_out"]) < 1e-14
         L.dealloc_trans()
     L.dealloc_coll()
+
+
+# ---------------------------------------------------------------- device weight generator (row f1)
+@pytest.mark.parametrize("fix,N,L_v,lam,rule", [("W_bkw8", 8, 5.0, 0.0, 0), ("W_heat8", 8, 9.0, 1.0, 1)])
+def test_device_weight_generator_matches_golden_wts(request, sb, tmp_path, fix, N, L_v, lam, rule):
+    want = request.getfixturevalue(fix)
+    c = sb.Collisions(N, L_v, inhomogeneous=bool(rule))
+    c.generate_weights(lam)
+    got = c.weights_to_host()
+    # device sin/pow are not bit-identical to glibc's, so only round-off-level agreement is asked for
+    # (the CPU restatement of the same algorithm is 99.8 % byte-identical, tests/test_oracle_weights.py)
+    scale = np.abs(want).max()
+    assert np.median(np.abs(got - want)) <= 1e-15 * scale
+    assert np.quantile(np.abs(got - want), 0.999) <= 1e-13 * scale
+    assert np.abs(got - want).max() <= 1e-7 * scale          # adaptive decisions may differ within the 1e-8 tolerance
+    path = str(tmp_path / sb.weights_filename(N, L_v, lam).split("/")[-1])
+    c.save_weights(path)
+    assert np.array_equal(np.fromfile(path), got) and os.path.getsize(path) == 8 * N ** 6
+    d = sb.Collisions(N, L_v, inhomogeneous=bool(rule))
+    d.load_weights(path)
+    o = orc.Oracle(N, L_v, rule)
+    f = seeded_f(o.v, 11)
+    assert np.array_equal(c.Qhat(f), d.Qhat(f))
+    assert relmax(c.ComputeQ(f), o.compute_q(got, f, f)) < TOL_QHAT
+
+
+def test_device_weight_generator_n16_matches_oracle_samples(sb):
+    c = sb.Collisions(16, 9.0, inhomogeneous=True)
+    c.generate_weights(1.0)
+    o = orc.Oracle(16, 9.0, 1)
+    rng = np.random.default_rng(1)
+    n3 = 16 ** 3
+    row = np.empty(n3)
+    worst = 0.0
+    for zeta in rng.integers(0, n3, 6):
+        sb._lib.check(c.L.sbte_d2h(c.h, row.ctypes.data, c.L.sbte_weights_device(c.h) + int(zeta) * n3 * 8, n3 * 8))
+        xs = rng.integers(0, n3, 200)
+        want = np.array([o.weight_one(1.0, int(zeta), int(x)) for x in xs])
+        worst = max(worst, np.abs(row[xs] - want).max() / max(np.abs(want).max(), 1e-300))
+    assert worst < 1e-7
