@@ -34,9 +34,12 @@ def run(args, root):
     if wfile:
         c.load_weights(wfile)
         wdesc = wfile
-    else:
+    elif os.environ.get("SBTE_SYNTHETIC_WEIGHTS"):
         c.synthetic_weights(20261017)
         wdesc = "synthetic splitmix64"
+    else:
+        c.generate_weights(1.0)   # hard spheres, generated on the device (src/weights.c:265-281)
+        wdesc = "isotropic lambda=1, generated on device (adaptive GK21)"
     s = sb.Slab(c, hi - lo, order, x[lo:hi + 2 * order].copy(), dx[lo:hi + 2 * order].copy(), ic, dt, rank, world)
     s.upload(initial.init_inhom(c.v, ic, nX, order, lo, hi))
     halo = H.SlabHalo(s, dev)
@@ -91,7 +94,8 @@ def run(args, root):
     line = {
         "metric": "cells*steps/s (1D)", "value": nX * args.steps / (ms * 1e-3), "unit": "cells*steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (Mach-1.2 shock initial data of the reference, src/initializer.c:341-351,405-420)",
         "config": {"workload": "shock1p2-derived: 1D-3V Mach 1.2 shock, N=16, Space_order 2, %d cells/GPU" % cells_per_gpu,
                    "N": N, "L_v": L_v, "Kn": Kn, "dt": dt, "cells_total": nX, "weights": wdesc,
                    "l2": "per-step working set (slabs+spectra+weights > 400 MB) larger than L2; no flush"},

@@ -202,7 +202,8 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells) {
   const long long min_steps = 4 * (long long)N;  // at least a few xi_x chunks per CTA
   if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
   std::vector<long long> begin(P + 1);
-  for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * total) / P);
+  const long long align = qhat_batch_align(N);   // the line-ring kernel works on whole xi_x chunks
+  for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * (total / align)) / P) * align;
   auto owner = [&](long long g) {
     int lo = 0, hi = P - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (begin[mid] <= g) lo = mid; else hi = mid - 1; }
@@ -265,7 +266,7 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     if (!same) { set_error("batched convolution requires f == g (single species)"); return 1; }
     if (!qhat_batch_supported(c->N)) { set_error("batched convolution: unsupported N"); return 1; }
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    if (use_batch_v1()) {
+    if (use_batch_v1() && c->N != 24) {
       launch_qhat_batch_v1(c, c->d_lay[0], d_qhat, batch);
     } else {
       if (ensure_batch_schedule(c, batch)) return 1;
@@ -298,7 +299,7 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
 
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
   if (ensure_capacity(c, batch)) return 1;  // before c->d_qhat is read: growth reallocates the scratch
-  if (resolve_k2(c, batch, k2) == SBTE_K2_BATCH && d_f == d_g && qhat_batch_supported(c->N) && !use_batch_v1()) {
+  if (resolve_k2(c, batch, k2) == SBTE_K2_BATCH && d_f == d_g && qhat_batch_supported(c->N) && (!use_batch_v1() || c->N == 24)) {
     // fast path: forward transform -> stream-K convolution -> inverse transform summing the partial sums
     if (!c->d_W) { set_error("no weights bound"); return 1; }
     if (ensure_batch_schedule(c, batch)) return 1;

@@ -111,6 +111,7 @@ void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2*
 // batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32
 bool qhat_batch_supported(int N);
 int qhat_batch_cols(int N);
+int qhat_batch_align(int N);
 void launch_qhat_batch_v1(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells);
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);

@@ -127,7 +127,8 @@ qhat_batch_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __re
   }
 }
 
-bool qhat_batch_supported(int N) { return N == 8 || N == 16; }
+bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24; }
+int qhat_batch_align(int N) { return N == 24 ? N : 1; }  // stream-K granularity in steps
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
 
 template <int N>
@@ -356,12 +357,199 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
   c->launches += 1;
 }
 
+// ------------------------------------------------------------------------------------------
+// v3 ("line ring"): same mapping as v2 for N whose (zeta - xi)-side plane does not fit in shared
+// memory (N = 24: 288 KB).  The COLS columns of a CTA need, at step xi_y, the COLS consecutive lines
+// Y = zeta_y0 + w + N/2 - xi_y (w = warp): a window that slides by one line per step.  Per xi_x chunk the
+// producer therefore streams L = N + COLS - 1 lines through an R-slot ring (line j' of the chunk is
+// Y = zeta_y0 + N/2 + COLS-1 - j'; warp w reads line j' = COLS-1 + xi_y - w at step xi_y).  Every slot
+// has a full (TMA) and an empty mbarrier of COLS arrivals; lines at the chunk edges have fewer than COLS
+// readers, so their last reader arrives for the absent ones (mbarrier.arrive with a count).
+// Stream-K ranges are aligned to whole chunks.
+template <int N>
+struct Batch3Cfg {
+  static constexpr int COLS = 8;
+  static constexpr int CONSUMERS = COLS * 32;
+  static constexpr int THREADS = CONSUMERS + 128;
+  static constexpr int ROWS = COLS * N;
+  static constexpr int LINE = N * 32;
+  static constexpr int RING = 10;
+  static constexpr int STAGES = 2;
+  static constexpr int LPC = N + COLS - 1;          // lines streamed per chunk
+  static constexpr size_t LINE_BYTES = (size_t)LINE * 16;
+  static constexpr size_t STAGE_BYTES = LINE_BYTES + (size_t)ROWS * N * 8;
+  static constexpr size_t SMEM = RING * LINE_BYTES + STAGES * STAGE_BYTES + 512;
+  static_assert(N % COLS == 0, "columns must tile zeta_y");
+};
+
+template <int N>
+__global__ void __launch_bounds__(Batch3Cfg<N>::THREADS, 1)
+qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
+                   double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch) {
+  using C = Batch3Cfg<N>;
+  constexpr long n3 = (long)N * N * N;
+  constexpr int NSTEP = N * N;
+  constexpr int S = C::STAGES, R = C::RING, L = C::LPC;
+  extern __shared__ __align__(128) unsigned char smraw[];
+  double2* ring = reinterpret_cast<double2*>(smraw);
+  unsigned char* stage0 = smraw + R * C::LINE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + S * C::STAGE_BYTES);
+  uint64_t* fullS = bars;              // [S]
+  uint64_t* emptyS = bars + S;         // [S]
+  uint64_t* fullL = bars + 2 * S;      // [R]
+  uint64_t* emptyL = bars + 2 * S + R; // [R]
+  auto stage_line = [&](int s) { return reinterpret_cast<double2*>(stage0 + (size_t)s * C::STAGE_BYTES); };
+  auto stage_w = [&](int s) { return reinterpret_cast<double*>(stage0 + (size_t)s * C::STAGE_BYTES + C::LINE_BYTES); };
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const long long g0 = sch.cta_begin[blockIdx.x];
+  const int n = (int)(sch.cta_begin[blockIdx.x + 1] - g0);   // multiple of N (whole chunks)
+  if (n <= 0) return;
+  const int G = sch.G;
+  const int nchunk = n / N;
+
+  if (tid == 0) {
+    for (int b = 0; b < S; b++) { mbar_init(&fullS[b], 1); mbar_init(&emptyS[b], C::COLS); }
+    for (int b = 0; b < R; b++) { mbar_init(&fullL[b], 1); mbar_init(&emptyL[b], C::COLS); }
+    mbar_fence_init();
+  }
+  __syncthreads();
+
+  if (warp >= C::COLS) {
+    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (warp == C::COLS && lane == 0) {
+      int k = 0;          // local step counter (stage ring)
+      long q = 0;         // line sequence number (line ring)
+      for (int ch = 0; ch < nchunk; ch++) {
+        const long long g = g0 + (long long)ch * N;
+        const int t = (int)(g / NSTEP), ex = (int)((g - (long long)t * NSTEP) / N);
+        const int rb = t / G, cg = t - rb * G;
+        const int q0 = rb * C::COLS, zx = q0 / N, zy0 = q0 % N;
+        int X = zx + N / 2 - ex;
+        if (X < 0) X += N; else if (X > N - 1) X -= N;
+        const double2* gs = spec + (size_t)cg * n3 * 32;
+        int issued = 0;   // lines of this chunk issued so far
+        for (int ey = 0; ey < N; ey++, k++) {
+          // lines needed by step ey: j' <= COLS-1 + ey
+          const int need = C::COLS + ey;
+          for (; issued < need && issued < L; issued++, q++) {
+            const int slot = (int)(q % R);
+            if (q >= R) mbar_wait(&emptyL[slot], (uint32_t)(((q / R) - 1) & 1));
+            int Y = (zy0 + N / 2 + C::COLS - 1 - issued) % N;
+            if (Y < 0) Y += N;
+            mbar_arrive_expect_tx(&fullL[slot], (uint32_t)C::LINE_BYTES);
+            tma_bulk_g2s(ring + (size_t)slot * C::LINE, gs + ((size_t)X * N + Y) * C::LINE, (uint32_t)C::LINE_BYTES,
+                         &fullL[slot]);
+          }
+          const int st = k % S;
+          if (k >= S) mbar_wait(&emptyS[st], (uint32_t)(((k / S) - 1) & 1));
+          const int s = ex * N + ey;
+          mbar_arrive_expect_tx(&fullS[st], (uint32_t)C::STAGE_BYTES);
+          tma_bulk_g2s(stage_line(st), gs + (size_t)s * C::LINE, (uint32_t)C::LINE_BYTES, &fullS[st]);
+          tma_tensor2d_g2s(stage_w(st), &tmapW, s * N, rb * C::ROWS, &fullS[st]);
+        }
+      }
+    }
+    return;
+  }
+
+  asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  double2 acc[N];
+#pragma unroll
+  for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
+  int cur_t = -1, zx = 0, zy = 0;
+  int k = 0;
+  long qbase = 0;
+
+  auto flush = [&]() {
+    const int rb = cur_t / G, cg = cur_t - rb * G;
+    const long cell = (long)cg * 32 + lane;
+    if (cell < cells) {
+      const int part = (int)blockIdx.x - sch.tile_first[cur_t];
+      double2* out = parts + (size_t)part * part_stride + cell * n3 + ((long)zx * N + zy) * N;
+#pragma unroll
+      for (int r = 0; r < N; r++) out[r] = acc[r];
+    }
+  };
+
+  for (int ch = 0; ch < nchunk; ch++, qbase += L) {
+    const long long g = g0 + (long long)ch * N;
+    const int t = (int)(g / NSTEP);
+    if (t != cur_t) {
+      if (cur_t >= 0) {
+        flush();
+#pragma unroll
+        for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
+      }
+      cur_t = t;
+      const int q0 = (t / G) * C::COLS;
+      zx = q0 / N;
+      zy = (q0 % N) + warp;
+    }
+    for (int ey = 0; ey < N; ey++, k++) {
+      const int st = k % S;
+      const int jl = C::COLS - 1 + ey - warp;          // this warp's line within the chunk
+      const long q = qbase + jl;
+      const int slot = (int)(q % R);
+      mbar_wait(&fullS[st], (uint32_t)((k / S) & 1));
+      mbar_wait(&fullL[slot], (uint32_t)((q / R) & 1));
+
+      const double2* fl = ring + (size_t)slot * C::LINE + lane;
+      const double2* gl = stage_line(st) + lane;
+      const double* wt = stage_w(st) + warp * N * N;
+      double2 fr[N];
+#pragma unroll
+      for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
+#pragma unroll
+      for (int c = 0; c < N; c += 2) {
+        const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+          const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
+          const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
+          const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
+          cmac(acc[r], w2.x, p0);
+          cmac(acc[r], w2.y, p1);
+        }
+      }
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(&emptyS[st]);
+        // readers of line jl are the warps with 0 <= jl - (COLS-1) + w' < N; the last one in step order
+        // also arrives for the warps that never read it
+        uint32_t cnt = 1;
+        if (jl < C::COLS - 1 && warp == C::COLS - 1) cnt = (uint32_t)(C::COLS - jl);
+        if (jl > N - 1 && warp == N + C::COLS - 2 - jl) cnt = (uint32_t)(jl - N + 2);
+        mbar_arrive_cnt(&emptyL[slot], cnt);
+      }
+    }
+  }
+  flush();
+}
+
+template <int N>
+static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
+                            const BatchSched& sch) {
+  using C = Batch3Cfg<N>;
+  auto kern = qhat_batch3_kernel<N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
+    configured = true;
+  }
+  k2_mark(c);
+  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(c->tmapW, spec, parts, part_stride, cells, sch);
+  k2_mark(c);
+  c->launches += 1;
+}
+
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch) {
   if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
   switch (c->N) {
     case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
     case 16: launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch); break;
+    case 24: launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch); break;
     default: set_error("qhat_batch: unsupported N"); break;
   }
 }

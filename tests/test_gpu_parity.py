@@ -249,7 +249,7 @@ def test_heat_transport_golden_on_gpu(sb, W_heat8):
 
 
 # ---------------------------------------------------------------- batched convolution (1D)
-@pytest.mark.parametrize("N,cells,k2", [(8, 5, 3), (8, 37, 3), (16, 33, 3), (8, 5, 1), (12, 3, 1)])
+@pytest.mark.parametrize("N,cells,k2", [(8, 5, 3), (8, 37, 3), (16, 33, 3), (24, 33, 3), (8, 5, 1), (12, 3, 1)])
 def test_batched_computeq_matches_oracle(sb, N, cells, k2):
     o = orc.Oracle(N, 9.0, 1)
     W = orc.synthetic_weights(N)
@@ -449,3 +449,69 @@ def test_device_weight_generator_n16_matches_oracle_samples(sb):
         want = np.array([o.weight_one(1.0, int(zeta), int(x)) for x in xs])
         worst = max(worst, np.abs(row[xs] - want).max() / max(np.abs(want).max(), 1e-300))
     assert worst < 1e-7
+
+
+# ---------------------------------------------------------------- BASELINE configs with real (generated) weights
+def test_config_bkw16_relaxation_matches_oracle(sb):
+    """BASELINE config 2 (input_examples/BKW16.in): 0D BKW at N=16, L_v=5, lambda=0, dt=0.01, RK2.
+    Weights generated on the device; the SAME tensor is handed to the oracle. 8 steps (48 evaluations)."""
+    N, L_v, lam, dt = 16, 5.0, 0.0, 0.01
+    c = sb.Collisions(N, L_v)
+    c.generate_weights(lam)
+    W = c.weights_to_host()
+    o = orc.Oracle(N, L_v, 0)
+    fo = o.init_hom(2)
+    f = c.array(o.n3).put(fo)
+    rows = []
+    for t in range(8):
+        c.step_0d(f, dt, 1.0, 2)
+        o.step_0d(W, fo, dt, 1.0, 2)
+        rows.append(c.row_0d(f))
+    assert relmax(f.get(), fo) < 1e-11
+    np.testing.assert_allclose(rows[-1], o.row_0d(fo), rtol=1e-10, atol=1e-14)
+    m = c.moments(f.get())[0]
+    # BKW is an exact solution with constant density and temperature: conservation over the run
+    m0 = c.moments(o.init_hom(2))[0]
+    assert abs(m[0] - m0[0]) < 1e-13 and abs(m[4] - m0[4]) < 1e-12 and np.abs(m[1:4]).max() < 1e-13
+
+
+def test_config_n32_hard_spheres_real_weights_vs_oracle(sb):
+    """BASELINE config 3 with REAL weights: N=32, lambda=1 (1.07e9 weights generated on the device),
+    one ComputeQ evaluation on the shifted-isotropic initial data against the CPU oracle reading the
+    same tensor, plus the fused maxPreserve pass against the oracle's three separate passes."""
+    N, L_v = 32, 5.0
+    c = sb.Collisions(N, L_v)
+    c.generate_weights(1.0)
+    W = c.weights_to_host()                     # 8.59 GB on the host
+    o = orc.Oracle(N, L_v, 0)
+    f = o.init_hom(0)
+    Qo, qo = o.compute_q(W, f, f, want_qhat=True)
+    assert relmax(c.Qhat(f, k2=sb.K2_STREAM), qo) < TOL_QHAT
+    Q = c.ComputeQ(f)
+    assert relmax(Q, Qo) < TOL_QHAT
+    Qc = c.conserveAllMoments(Q)
+    assert np.abs(c.moment_functionals(Qc)).max() < 1e-13
+    assert relmax(c.ComputeQ_maxPreserve(f), o.compute_q_maxpreserve(W, f, f)) < TOL_QHAT
+
+
+def test_config_shock1p2_derived_matches_oracle(sb):
+    """BASELINE config 4 (derived): N=16, L_v=9, Kn=1.52, lambda=1, Init_field 6, Space_order 2,
+    dt=1e-3, dx=6/640 -- a 40-cell window around the shock, 3 steps, against the oracle."""
+    N, L_v, Kn, order, ic, dt, nX = 16, 9.0, 1.52, 2, 6, 1e-3, 40
+    c = sb.Collisions(N, L_v, inhomogeneous=True)
+    c.generate_weights(1.0)
+    W = c.weights_to_host()
+    o = orc.Oracle(N, L_v, 1)
+    _, x, dx = orc.make_mesh([nX], [6.0 * nX / 640.0], order)
+    f = o.init_inhom(ic, nX, order)
+    s = sb.Slab(c, nX, order, x, dx, ic, dt)
+    s.upload(f)
+    fc, f1, ft = np.zeros_like(f), np.zeros_like(f), np.zeros_like(f)
+    for _ in range(3):
+        s.step(Kn)
+        o.step_1d(W, nX, x, dx, dt, Kn, order, ic, f, fc, f1, ft)
+    got = s.download()[order:nX + order]
+    assert relmax(got, f[order:nX + order]) < 1e-11
+    mom = s.moments()
+    for l in (0, nX // 2 - 1, nX // 2, nX - 1):
+        np.testing.assert_allclose(mom[l, [0, 1, 4, 7]], o.row_1d(f[l + order]), rtol=1e-10, atol=1e-13)
