@@ -145,12 +145,61 @@ def cpu_computeq_n32(steps, warmup, distinct_rows=512):
                       "aliased to %d distinct synthetic rows, %d OpenMP threads" % (steps, distinct_rows, cores)}
 
 
+def cpu_cell_leg(N, L_v, W_host, f_cell, stages, evals=6):
+    """1D cpu_baseline: seconds per ComputeQ + conserveAllMoments on one cell with the reference's own code
+    (all host threads); the reference processes cells sequentially (exec/boltz.c:285-345)."""
+    import ctypes as C
+    from oracle import oracle as orc
+    cores = int(os.environ.get("SBTE_CPU_THREADS", os.cpu_count() or 1))
+    os.environ["OMP_NUM_THREADS"] = str(cores)
+    try:
+        C.CDLL("libgomp.so.1").omp_set_num_threads(cores)
+    except OSError:
+        pass
+    if orc.have_ref():
+        R = orc.Reference(N, L_v, 1)
+        rows = R.rows(W_host)
+        call = lambda: R.conserve(R.compute_q(rows, f_cell, f_cell))  # noqa: E731
+        kind = "reference"
+    else:
+        o = orc.Oracle(N, L_v, 1)
+        call = lambda: o.conserve(o.compute_q(W_host, f_cell, f_cell))  # noqa: E731
+        kind = "port"
+    call()
+    t0 = time.perf_counter()
+    for _ in range(evals):
+        call()
+    sec = (time.perf_counter() - t0) / evals
+    return {"value": 1.0 / (stages * sec), "unit": "cells*steps/s", "cores": cores, "kind": kind,
+            "sample": "%d x (ComputeQ + conserveAllMoments) on one cell at N=%d with %d OpenMP threads; cells are "
+                      "sequential in the reference, %d evaluation(s) per cell per step, transport excluded"
+                      % (evals, N, cores, stages)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     if args.workload != "0d_n32":
-        print(json.dumps({"impl": "reference", "unavailable": "reference arm implemented for workload 0d_n32 only"}))
+        # 1D: the reference runs ComputeQ + conserveAllMoments cell after cell (exec/boltz.c:285-345); a step of
+        # this arm is one cell advanced by one time step (order evaluations), timed value-independently on
+        # synthetic weights, transport excluded (it is < 3 % of the reference's step)
+        from oracle import oracle as orc
+        from spectralbte_b200 import bench1d, initial
+        from spectralbte_b200.api import velocity_grids
+        cfg = bench1d.WORKLOADS[args.workload]
+        N, L_v, stages = cfg["N"], cfg["L_v"], cfg["order"]
+        v, _ = velocity_grids(N, L_v, True)
+        f_cell = initial.init_inhom(v, cfg["ic"], 4, cfg["order"], 0, 4)[cfg["order"]].copy()
+        W = orc.synthetic_weights(N) * 1e-3
+        cb = cpu_cell_leg(N, L_v, W, f_cell, stages, evals=max(1, args.steps * stages))
+        line = {"metric": "cells*steps/s (1D)", "value": cb["value"], "unit": "cells*steps/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 / cb["value"], "higher_is_better": True,
+                "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+                "config": {"workload": args.workload, "N": N, "L_v": L_v}, "cpu_baseline": cb,
+                "e2e": {"value": cb["value"], "unit": "cells*steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+        print(json.dumps(line))
         return
     r = cpu_computeq_n32(args.steps, max(1, min(args.warmup, 2)))
     line = {"metric": METRIC_0D, "value": r["value"], "unit": "evals/s", "n_gpus": args.gpus, "steps": args.steps,
@@ -208,7 +257,12 @@ def run_0d_n32(args):
     N, L_v = 32, 5.0
     n3 = N ** 3
     c = sb.Collisions(N, L_v, device=local)
-    c.synthetic_weights(SEED)
+    if args.weights == "synthetic":
+        c.synthetic_weights(SEED)
+        wdesc = "synthetic splitmix64(seed=%d)" % SEED
+    else:
+        c.generate_weights(1.0)   # hard spheres; N32_isotropic_L_v5_lambda1.wts content, generated on the device
+        wdesc = "isotropic hard-sphere weights (lambda=1) generated on the device, src/weights.c:265-281"
     f = initial.init_hom(c.v, L_v, 0)
     df, dQ = c.array(n3).put(f), c.array(n3)
     stream = torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local))
@@ -239,6 +293,18 @@ def run_0d_n32(args):
     launches = c.launches - l0
     clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms, world)
+
+    # the 0D driver's call: ComputeQ_maxPreserve = three reference evaluations folded into one weight pass
+    for _ in range(3):
+        sb._lib.check(c.L.sbte_compute_q_maxpreserve(c.h, df.ptr, df.ptr, dQ.ptr, k2))
+    c.sync()
+    m0, m1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    m0.record(stream)
+    for _ in range(args.steps):
+        sb._lib.check(c.L.sbte_compute_q_maxpreserve(c.h, df.ptr, df.ptr, dQ.ptr, k2))
+    m1.record(stream)
+    c.sync()
+    mp_ms = m0.elapsed_time(m1) / args.steps
 
     # end to end: host buffers through the reference-facing ComputeQ entry (H2D f, D2H Q every step)
     fh = torch.from_numpy(f).pin_memory()
@@ -273,7 +339,7 @@ def run_0d_n32(args):
         "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "0d_n32: 0D hard spheres N=32, ComputeQ(f,f), 1.07e9 precomputed weights (8.59 GB/GPU)",
-                   "N": N, "L_v": L_v, "init_field": 0, "weights": "synthetic splitmix64(seed=%d)" % SEED,
+                   "N": N, "L_v": L_v, "init_field": 0, "weights": wdesc,
                    "k2": args.k2, "replicas": world, "l2": "inputs (8.59 GB weight stream) larger than L2; no flush"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": traffic, "kernel": "qhat_stream_kernel<32,1>", "kernel_ms": k2_avg_ms,
@@ -282,6 +348,8 @@ def run_0d_n32(args):
                 "d2h_bytes_per_step": n3 * 8, "api": "sbte_compute_q_host (the body of the drop-in ComputeQ)",
                 "checksum": checksum},
         "gpu_launches": int(launches), "clocks": clocks,
+        "maxpreserve": {"ms_per_call": mp_ms, "calls_per_s": 1e3 / mp_ms, "reference_evals_per_s": 3e3 / mp_ms,
+                        "note": "ComputeQ_maxPreserve (src/collisions.c:178-210): 3 compute_Qhat of the reference in 1 weight pass"},
     }
     if world == 1 and not args.no_cpu:
         cb = cpu_computeq_n32(args.cpu_steps, 1)
@@ -304,8 +372,9 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="0d_n32", choices=["0d_n32", "shock1p2"])
+    ap.add_argument("--workload", default="0d_n32", choices=["0d_n32", "shock1p2", "heattrans"])
     ap.add_argument("--k2", default="auto", choices=["auto", "stream", "deep", "generic"])
+    ap.add_argument("--weights", default="generated", choices=["generated", "synthetic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--cpu-steps", type=int, default=5)
     args = ap.parse_args()
@@ -317,7 +386,7 @@ def main():
         run_0d_n32(args)
     else:
         from spectralbte_b200 import bench1d
-        bench1d.run(args, ROOT)
+        bench1d.run(args, ROOT, cpu_leg=cpu_cell_leg)
     finalize()
 
 

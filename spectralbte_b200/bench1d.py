@@ -1,22 +1,37 @@
-"""1D-3V benchmark workload (bench.py --workload shock1p2): Mach-1.2 shock derived from
-/root/reference/input_examples/Shock1p2.in (the shipped file is unstable and its 601-cell
-mesh is prime).  N=16, L_v=9, Kn=1.52, lambda=1, Init_field 6, Space_order 2, dt=1e-3, dx=6/640;
-640 cells per GPU (weak scaling: the domain grows with the rank count), one process per GPU, ghost
-cells exchanged over NCCL."""
+"""1D-3V benchmark workloads (bench.py --workload shock1p2 | heattrans), one process per GPU, ghost cells
+exchanged over NCCL (spectralbte_b200/halo.py).
+
+shock1p2   derived from /root/reference/input_examples/Shock1p2.in (the shipped file is
+           unstable and its 601-cell mesh is prime): N=16, L_v=9, Kn=1.52, lambda=1, Init_field 6,
+           Space_order 2, dt=1e-3, dx=6/640; 640 cells PER GPU (weak scaling: the domain grows with the ranks).
+heattrans  /root/reference/input_examples/heatTrans.long.in at BASELINE's N=24 (the shipped file says 22):
+           L_v=9, Kn=0.3, lambda=1, Init_field 3 (diffuse walls T=1,2), Space_order 1, dt=1e-4, 250 cells on
+           [0,1] in TOTAL, block-partitioned unevenly over the ranks (strong scaling, 31-32 cells per GPU at 8).
+"""
 import json
 import os
 import time
 
 import numpy as np
 
+WORKLOADS = {
+    "shock1p2": dict(N=16, L_v=9.0, Kn=1.52, lam=1.0, order=2, ic=6, dt=1e-3, cells_per_gpu=640, total_cells=None,
+                     length_per_cell=6.0 / 640.0, scaling="weak",
+                     desc="shock1p2-derived: 1D-3V Mach 1.2 shock, N=16, Space_order 2 (minmod), %d cells/GPU"),
+    "heattrans": dict(N=24, L_v=9.0, Kn=0.3, lam=1.0, order=1, ic=3, dt=1e-4, cells_per_gpu=None, total_cells=250,
+                      length_per_cell=1.0 / 250.0, scaling="strong",
+                      desc="heatTrans.long: 1D-3V heat transfer between diffuse walls, N=24, Space_order 1, %d cells total"),
+}
 
-def run(args, root):
+
+def run(args, root, cpu_leg=None):
     import torch
     import torch.distributed as dist
     import spectralbte_b200 as sb
     from spectralbte_b200 import halo as H
     from spectralbte_b200 import initial
 
+    cfg = WORKLOADS[args.workload]
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
@@ -24,10 +39,15 @@ def run(args, root):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    N, L_v, Kn, order, ic, dt = 16, 9.0, 1.52, 2, 6, 1e-3
-    cells_per_gpu = int(os.environ.get("SBTE_CELLS_PER_GPU", "640"))
-    nX = cells_per_gpu * world
-    _, x, dx = initial.make_mesh([nX], [6.0 * nX / 640.0], order)
+    N, L_v, Kn, order, ic, dt = cfg["N"], cfg["L_v"], cfg["Kn"], cfg["order"], cfg["ic"], cfg["dt"]
+    if cfg["total_cells"] is None:
+        per = int(os.environ.get("SBTE_CELLS_PER_GPU", cfg["cells_per_gpu"]))
+        nX = per * world
+        desc = cfg["desc"] % per
+    else:
+        nX = int(os.environ.get("SBTE_TOTAL_CELLS", cfg["total_cells"]))
+        desc = cfg["desc"] % nX
+    _, x, dx = initial.make_mesh([nX], [cfg["length_per_cell"] * nX], order)
     lo, hi = initial.partition(nX, world)[rank]
     c = sb.Collisions(N, L_v, inhomogeneous=True, device=local)
     wfile = os.environ.get("SBTE_WEIGHTS")
@@ -38,8 +58,8 @@ def run(args, root):
         c.synthetic_weights(20261017)
         wdesc = "synthetic splitmix64"
     else:
-        c.generate_weights(1.0)   # hard spheres, generated on the device (src/weights.c:265-281)
-        wdesc = "isotropic lambda=1, generated on device (adaptive GK21)"
+        c.generate_weights(cfg["lam"])   # generated on the device (src/weights.c:265-281)
+        wdesc = "isotropic lambda=%g, generated on device (adaptive GK21)" % cfg["lam"]
     s = sb.Slab(c, hi - lo, order, x[lo:hi + 2 * order].copy(), dx[lo:hi + 2 * order].copy(), ic, dt, rank, world)
     s.upload(initial.init_inhom(c.v, ic, nX, order, lo, hi))
     halo = H.SlabHalo(s, dev)
@@ -72,39 +92,45 @@ def run(args, root):
         ms = float(t.item())
 
     # end to end: the step's input slab comes from pinned host memory and the moments go back
+    import ctypes as C
     ncell = hi - lo + 2 * order
     host = torch.from_numpy(s.download()).pin_memory()
     mom = np.empty((hi - lo, 8))
-    import ctypes as C
+    reps = max(1, args.steps // 4)
+    sync_all()
     t0 = time.perf_counter()
-    for _ in range(max(1, args.steps // 4)):
+    for _ in range(reps):
         sb._lib.check(c.L.sbte_slab_upload(s.h, C.cast(host.data_ptr(), C.POINTER(C.c_double))))
         H.step(s, halo, Kn, ic)
         mom = s.moments()
     c.sync()
-    e2e_s = (time.perf_counter() - t0) / max(1, args.steps // 4)
+    e2e_s = (time.perf_counter() - t0) / reps
     if world > 1:
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
     if rank != 0:
         return
-    evals = 2.0 * (hi - lo) * args.steps          # cell evaluations on this rank (2 RK stages)
-    flops = 10.0 * float(N) ** 6 * evals
+    stages = order                               # collision evaluations per cell per step (Euler / Heun)
+    flops = 10.0 * float(N) ** 6 * stages * (hi - lo) * args.steps
+    ach = flops / (k2_ms * 1e-3) / 1e12
     line = {
         "metric": "cells*steps/s (1D)", "value": nX * args.steps / (ms * 1e-3), "unit": "cells*steps/s",
         "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
-        "data": "synthetic (Mach-1.2 shock initial data of the reference, src/initializer.c:341-351,405-420)",
-        "config": {"workload": "shock1p2-derived: 1D-3V Mach 1.2 shock, N=16, Space_order 2, %d cells/GPU" % cells_per_gpu,
-                   "N": N, "L_v": L_v, "Kn": Kn, "dt": dt, "cells_total": nX, "weights": wdesc,
-                   "l2": "per-step working set (slabs+spectra+weights > 400 MB) larger than L2; no flush"},
-        "roofline": {"bound": "fp64", "achieved": flops / (k2_ms * 1e-3) / 1e12, "peak": 37.0, "unit": "TFLOP/s",
-                     "frac": flops / (k2_ms * 1e-3) / 1e12 / 37.0, "traffic": None, "kernel": "qhat_batch_kernel<16>",
+        "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64",
+        "data": "synthetic (the reference's own initial data, src/initializer.c:330-351,391-420)",
+        "config": {"workload": desc, "N": N, "L_v": L_v, "Kn": Kn, "dt": dt, "cells_total": nX, "weights": wdesc,
+                   "l2": "per-step working set (slabs + spectra + weights) larger than L2; no flush"},
+        "roofline": {"bound": "fp64", "achieved": ach, "peak": 36.5, "unit": "TFLOP/s", "frac": ach / 36.5,
+                     "traffic": None, "kernel": "qhat_batch%d_kernel<%d>" % (3 if N == 24 else 2, N),
                      "kernel_ms": k2_ms / max(1, k2_n), "kernel_share_of_step": k2_ms / ms,
-                     "peak_source": "datasheet FP64 vector (not in MEASURED_PEAKS.json); 10 counted flops per 6 FP64 instructions"},
+                     "peak_source": "FP64 pipe peak measured with tools/micro/dfma_rf.cu on this pool's B200 (DMUL stream, "
+                                    "36.5 TFLOP/s-equivalent; datasheet 37); the kernel issues 6 FP64 instructions per 10 counted flops"},
         "e2e": {"value": nX / e2e_s, "unit": "cells*steps/s", "h2d_bytes_per_step": ncell * N ** 3 * 8,
                 "d2h_bytes_per_step": int(mom.nbytes), "checksum": float(mom[:, 0].sum())},
         "gpu_launches": int(launches),
     }
+    if world == 1 and cpu_leg is not None and not args.no_cpu:
+        f_cell = s.download()[order + (hi - lo) // 2].copy()
+        line["cpu_baseline"] = cpu_leg(N, L_v, c.weights_to_host(), f_cell, stages)
     print(json.dumps(line))

@@ -515,3 +515,24 @@ def test_config_shock1p2_derived_matches_oracle(sb):
     mom = s.moments()
     for l in (0, nX // 2 - 1, nX // 2, nX - 1):
         np.testing.assert_allclose(mom[l, [0, 1, 4, 7]], o.row_1d(f[l + order]), rtol=1e-10, atol=1e-13)
+
+
+# ---------------------------------------------------------------- error behaviour of the extension surface
+def test_error_paths_report_like_the_reference(sb, tmp_path):
+    from spectralbte_b200._lib import SbteError
+    c = sb.Collisions(8, 5.0)
+    with pytest.raises(SbteError, match="no weights bound"):
+        c.ComputeQ(np.zeros(512))
+    with pytest.raises(SbteError, match="cannot open weight file"):
+        c.load_weights(str(tmp_path / "missing.wts"))
+    bad = tmp_path / "short.wts"
+    bad.write_bytes(b"\0" * 1000)                       # truncated file: src/weights.c:82-86
+    with pytest.raises(SbteError, match="Error reading weight file"):
+        c.load_weights(str(bad))
+    with pytest.raises(SbteError, match="N must be even"):
+        sb.Collisions(7, 5.0)
+    c.synthetic_weights(1)
+    with pytest.raises(SbteError, match="requires f == g"):
+        c.ComputeQ(np.ones((40, 512)), np.ones((40, 512)), k2=sb.K2_BATCH)
+    with pytest.raises(SbteError, match="Poiseuille"):
+        sb.Slab(c, 8, 1, np.zeros(10), np.ones(10), 5, 1e-3)
