@@ -45,18 +45,21 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons (B200_PROFILING.md recipe).  The sampler runs from before the
+    warm-up to after the end-to-end loop (the same kernels throughout); every sample is time-stamped on
+    arrival so the ones inside the timed region can be told apart."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device):
         self.device, self.proc, self.lines = device, None, []
+        self.t0 = self.t1 = None
 
     def start(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.device), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._pump, daemon=True)
             self.thr.start()
@@ -65,33 +68,53 @@ class ClockSampler:
 
     def _pump(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.perf_counter(), line.strip()))
+
+    def mark(self, t0, t1):
+        self.t0, self.t1 = t0, t1
+
+    def wait_first_sample(self, timeout=3.0):
+        t = time.perf_counter()
+        while self.proc and not self.lines and time.perf_counter() - t < timeout:
+            time.sleep(0.01)
 
     def stop(self):
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.05)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for ln in self.lines:
-            parts = [p.strip() for p in ln.split(",")]
-            if len(parts) < 9:
-                continue
-            try:
-                sm.append(float(parts[1]))
-                mx.append(float(parts[2]))
-            except ValueError:
-                continue
-            for nm, val in zip(names, parts[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(nm)
+
+        def digest(rows):
+            sm, mx, pw, reasons = [], [], [], set()
+            for _, ln in rows:
+                parts = [p.strip() for p in ln.split(",")]
+                if len(parts) < 9:
+                    continue
+                try:
+                    sm.append(float(parts[1]))
+                    mx.append(float(parts[2]))
+                    pw.append(float(parts[3]))
+                except ValueError:
+                    continue
+                for nm, val in zip(names, parts[5:9]):
+                    if val.lower().startswith("active"):
+                        reasons.add(nm)
+            return sm, mx, pw, reasons
+
+        inside = [r for r in self.lines if self.t0 is not None and self.t0 - 0.02 <= r[0] <= self.t1 + 0.02]
+        window = "timed region"
+        rows = inside
+        if len(inside) < 2:   # the timed region is shorter than nvidia-smi's sampling period
+            rows, window = self.lines, "warm-up + timed region + end-to-end loop (same kernels)"
+        sm, mx, pw, reasons = digest(rows)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "power_w_max": max(pw) if pw else None, "reasons": sorted(reasons), "samples": len(sm),
+                "samples_in_timed_region": len(inside), "window": window}
 
 
 # --------------------------------------------------------------------------------------------
@@ -271,27 +294,30 @@ def run_0d_n32(args):
     def step():
         sb._lib.check(c.L.sbte_compute_q(c.h, df.ptr, df.ptr, dQ.ptr, 1, k2))
 
-    for _ in range(args.warmup):
-        step()
-    c.sync()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
+        sampler.wait_first_sample()
+    for _ in range(args.warmup):
+        step()
+    c.sync()
     barrier(world)
     c.k2_profile(True)
     l0 = c.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         step()
     e1.record(stream)
     c.sync()
+    tw1 = time.perf_counter()
     barrier(world)
+    sampler.mark(tw0, tw1)
     ms = e0.elapsed_time(e1)
     k2_ms, k2_n = c.k2_profile_read()
     c.k2_profile(False)
     launches = c.launches - l0
-    clocks = sampler.stop() if rank == 0 else None
     ms = max_over_ranks(ms, world)
 
     # the 0D driver's call: ComputeQ_maxPreserve = three reference evaluations folded into one weight pass
@@ -322,6 +348,7 @@ def run_0d_n32(args):
     e2e_s = time.perf_counter() - t0
     e2e_s = max_over_ranks(e2e_s, world)
     checksum = float(Qh.sum().item())
+    clocks = sampler.stop() if rank == 0 else None
 
     if rank != 0:
         return
@@ -386,7 +413,7 @@ def main():
         run_0d_n32(args)
     else:
         from spectralbte_b200 import bench1d
-        bench1d.run(args, ROOT, cpu_leg=cpu_cell_leg)
+        bench1d.run(args, ROOT, cpu_leg=cpu_cell_leg, sampler_cls=ClockSampler)
     finalize()
 
 

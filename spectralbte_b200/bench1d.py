@@ -24,7 +24,7 @@ WORKLOADS = {
 }
 
 
-def run(args, root, cpu_leg=None):
+def run(args, root, cpu_leg=None, sampler_cls=None):
     import torch
     import torch.distributed as dist
     import spectralbte_b200 as sb
@@ -71,17 +71,27 @@ def run(args, root, cpu_leg=None):
             dist.barrier()
         torch.cuda.synchronize()
 
+    sampler = sampler_cls(local) if (sampler_cls is not None and rank == 0) else None
+    if sampler:
+        sampler.start()
+        sampler.wait_first_sample()
     for _ in range(args.warmup):
         H.step(s, halo, Kn, ic)
     sync_all()
     c.k2_profile(True)
     l0 = c.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tw0 = time.perf_counter()
     e0.record(stream)
     for _ in range(args.steps):
         H.step(s, halo, Kn, ic)
     e1.record(stream)
     sync_all()
+    tw1 = time.perf_counter()
+    clocks = None
+    if sampler:
+        sampler.mark(tw0, tw1)
+        clocks = sampler.stop()
     ms = e0.elapsed_time(e1)
     k2_ms, k2_n = c.k2_profile_read()
     c.k2_profile(False)
@@ -128,7 +138,7 @@ def run(args, root, cpu_leg=None):
                                     "36.5 TFLOP/s-equivalent; datasheet 37); the kernel issues 6 FP64 instructions per 10 counted flops"},
         "e2e": {"value": nX / e2e_s, "unit": "cells*steps/s", "h2d_bytes_per_step": ncell * N ** 3 * 8,
                 "d2h_bytes_per_step": int(mom.nbytes), "checksum": float(mom[:, 0].sum())},
-        "gpu_launches": int(launches),
+        "gpu_launches": int(launches), "clocks": clocks,
     }
     if world == 1 and cpu_leg is not None and not args.no_cpu:
         f_cell = s.download()[order + (hi - lo) // 2].copy()

@@ -267,8 +267,10 @@ static void launch_stream_n(sbte_ctx* c, int npairs, const QhatPair* pairs, doub
     if (depth >= 4) launch_stream_inst<N, 1, 4>(c, pairs, qhat);
     else launch_stream_inst<N, 1, 2>(c, pairs, qhat);
   } else {
-    if (depth >= 4) launch_stream_inst<N, 2, 4>(c, pairs, qhat);
-    else launch_stream_inst<N, 2, 2>(c, pairs, qhat);
+    // two operand pairs need 128 KB of plane ring => one CTA per SM: keep four weight tiles per thread in
+    // flight (64 KB per SM) so the HBM stream stays saturated
+    (void)depth;
+    launch_stream_inst<N, 2, 4>(c, pairs, qhat);
   }
 }
 
