@@ -320,6 +320,27 @@ def run_0d_n32(args):
     launches = c.launches - l0
     ms = max_over_ranks(ms, world)
 
+    # the same evaluation with the symmetrised stream switched off: the reference's own 8*N^6-byte formulation
+    plain = None
+    if not os.environ.get("SBTE_NO_SYM"):
+        c.set_symmetrize(False)
+        for _ in range(3):
+            step()
+        c.sync()
+        c.k2_profile(True)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record(stream)
+        for _ in range(args.steps):
+            step()
+        p1.record(stream)
+        c.sync()
+        pk_ms, pk_n = c.k2_profile_read()
+        c.k2_profile(False)
+        c.set_symmetrize(True)
+        plain = {"evals_per_s": args.steps / (p0.elapsed_time(p1) * 1e-3), "kernel_ms": pk_ms / max(1, pk_n),
+                 "bytes_per_launch": 8.0 * float(N) ** 6}
+        plain["achieved_GBs"] = plain["bytes_per_launch"] / (plain["kernel_ms"] * 1e-3) / 1e9
+
     # the 0D driver's call: ComputeQ_maxPreserve = three reference evaluations folded into one weight pass
     for _ in range(3):
         sb._lib.check(c.L.sbte_compute_q_maxpreserve(c.h, df.ptr, df.ptr, dQ.ptr, k2))
@@ -353,13 +374,17 @@ def run_0d_n32(args):
     if rank != 0:
         return
     peak, peak_src = peaks()
-    wbytes = 8.0 * float(N) ** 6
+    sym = not os.environ.get("SBTE_NO_SYM")
+    ref_bytes = 8.0 * float(N) ** 6
+    # symmetrised stream (f == g): rows zeta read nrep(zeta_x) of their N xi_x planes, nrep = N/2+1 | N/2
+    nrep_sum = sum(((zx + N // 2) % N) // 2 + 1 + (((zx + N // 2) % N) + N) // 2 - ((zx + N // 2) % N) for zx in range(N))
+    wbytes = 8.0 * float(N) ** 5 * nrep_sum if sym else ref_bytes
     k2_avg_ms = k2_ms / max(1, k2_n)
     achieved = wbytes / (k2_avg_ms * 1e-3) / 1e9
     traffic = None
     tp = os.path.join(ROOT, "profiles", "k2_stream_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get("dram_bytes_per_launch_sym" if sym else "dram_bytes_per_launch")
     value = world * args.steps / (ms * 1e-3)
     line = {
         "metric": METRIC_0D, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps,
@@ -369,8 +394,15 @@ def run_0d_n32(args):
                    "N": N, "L_v": L_v, "init_field": 0, "weights": wdesc,
                    "k2": args.k2, "replicas": world, "l2": "inputs (8.59 GB weight stream) larger than L2; no flush"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "qhat_stream_kernel<32,1>", "kernel_ms": k2_avg_ms,
-                     "kernel_share_of_step": k2_ms / ms, "algorithmic_bytes_per_launch": wbytes, "peak_source": peak_src},
+                     "traffic": traffic, "kernel": "qhat_stream_kernel<32,1,2,%s>" % ("sym" if sym else "plain"),
+                     "kernel_ms": k2_avg_ms, "kernel_share_of_step": k2_ms / ms, "algorithmic_bytes_per_launch": wbytes,
+                     "reference_formulation_bytes": ref_bytes,
+                     "note": ("f == g: the summand is symmetric under xi <-> zeta-xi, so the kernel streams the symmetrised "
+                              "tensor Ws = W + W o sigma over nrep(zeta_x) of N xi_x planes (4.43 GB at N=32) instead of the "
+                              "reference's 8*N^6 = 8.59 GB; `plain_kernel` times the unsymmetrised stream") if sym else
+                             "unsymmetrised stream (SBTE_NO_SYM): 8*N^6 bytes per evaluation as in the reference",
+                     "plain_kernel": (dict(plain, frac=plain["achieved_GBs"] / peak) if plain else None),
+                     "peak_source": peak_src},
         "e2e": {"value": world * args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": n3 * 8,
                 "d2h_bytes_per_step": n3 * 8, "api": "sbte_compute_q_host (the body of the drop-in ComputeQ)",
                 "checksum": checksum},

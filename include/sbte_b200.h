@@ -113,6 +113,11 @@ SBTE_API int sbte_weights_generate_iso(sbte_ctx *c, double lambda);
 /* write the bound weights in the reference's .wts format (src/weights.c:100-103) */
 SBTE_API int sbte_weights_save_file(sbte_ctx *c, const char *path);
 
+/* For f == g the summand W[zeta][xi] f^[xi] f^[zeta-xi] is symmetric under xi <-> zeta-xi, so the library
+ * streams a symmetrised copy Ws = W + W o sigma over half of the xi_x planes (built lazily on the device;
+ * costs one extra N^6 tensor). On by default; disable to stream the tensor exactly as the reference does. */
+SBTE_API int sbte_set_symmetrize(sbte_ctx *c, int enable);
+
 /* kernel selection for the convolution */
 enum { SBTE_K2_AUTO = 0, SBTE_K2_GENERIC = 1, SBTE_K2_STREAM = 2, SBTE_K2_BATCH = 3, SBTE_K2_STREAM_DEEP = 4 };
 

@@ -33,6 +33,7 @@ PROTOTYPES = {
     "sbte_stream": (_vp, [_vp]),
     "sbte_launch_count": (C.c_ulonglong, [_vp]),
     "sbte_reserve": (C.c_int, [_vp, C.c_int]),
+    "sbte_set_symmetrize": (C.c_int, [_vp, C.c_int]),
     "sbte_k2_profile": (C.c_int, [_vp, C.c_int]),
     "sbte_k2_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
     "sbte_dev_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),

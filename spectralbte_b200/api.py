@@ -145,6 +145,10 @@ class Collisions:
     def array(self, n):
         return DeviceArray(self, n)
 
+    def set_symmetrize(self, enable=True):
+        """Toggle the symmetrised weight stream used when f == g (default on)."""
+        check(self.L.sbte_set_symmetrize(self.h, int(bool(enable))))
+
     def k2_profile(self, enable=True):
         check(self.L.sbte_k2_profile(self.h, int(bool(enable))))
 

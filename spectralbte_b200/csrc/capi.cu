@@ -137,9 +137,7 @@ int ensure_capacity(sbte_ctx* c, int cells) {
   return 0;
 }
 
-static int make_tensor_map(sbte_ctx* c) {
-  c->tmap_ok = false;
-  if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
+static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -153,15 +151,25 @@ static int make_tensor_map(sbte_ctx* c) {
   cuuint64_t gstride[1] = {(cuuint64_t)c->n3 * sizeof(double)};
   cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)(cols_per_cta * N)};
   cuuint32_t estr[2] = {1, 1};
-  CUresult r = ((encode_fn)fn)(&c->tmapW, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)c->d_W, gdim, gstride, box, estr,
+  CUresult r = ((encode_fn)fn)(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, (void*)W, gdim, gstride, box, estr,
                                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
                                CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled failed: " + std::to_string((int)r)); return 1; }
+  return 0;
+}
+
+static int make_tensor_map(sbte_ctx* c) {
+  c->tmap_ok = false;
+  if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copy
+  c->sched_cells = 0;
+  if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
+  if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
   c->tmap_ok = true;
   return 0;
 }
 
 static int release_weights(sbte_ctx* c) {
+  if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }
   if (c->owns_W && c->d_W) cudaFree((void*)c->d_W);
   c->d_W = nullptr; c->owns_W = false; c->host_key = nullptr; c->tmap_ok = false;
   return 0;
@@ -188,14 +196,21 @@ __global__ void synth_weights_kernel(double* __restrict__ W, size_t n, unsigned 
 // ---- stream-K schedule of the batched convolution ---------------------------------------------
 // T = groups * row-blocks tiles of N^2 steps; P persistent CTAs take equal contiguous shares of the
 // T*N^2 global steps. tile_first / tile_np tell kernels which CTA writes which partial sum.
-static int ensure_batch_schedule(sbte_ctx* c, int cells) {
-  if (c->sched_cells == cells && c->d_sched_mem) return 0;
+static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
+  if (c->sched_cells == cells && c->sched_sym == (int)sym && c->d_sched_mem) return 0;
   CK(cudaStreamSynchronize(c->stream));
   if (c->d_sched_mem) { cudaFree(c->d_sched_mem); c->d_sched_mem = nullptr; }
   if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
   const int N = c->N, cols = qhat_batch_cols(N);
   const int G = (cells + 31) / 32, RB = N * N / cols, T = G * RB;
-  const long long S = (long long)N * N, total = (long long)T * S;
+  // tile t = (row-block rb = t / G, cell group cg = t % G); its length is (visited xi_x planes) * N steps
+  std::vector<long long> tbegin(T + 1);
+  tbegin[0] = 0;
+  for (int t = 0; t < T; t++) {
+    const int zx = ((t / G) * cols) / N;
+    tbegin[t + 1] = tbegin[t] + (long long)(sym ? sym_nrep(N, zx) : N) * N;
+  }
+  const long long total = tbegin[T];
   int P = c->sm_count;
   const char* pe = getenv("SBTE_BATCH_CTAS");
   if (pe && atoi(pe) > 0) P = atoi(pe);
@@ -204,31 +219,46 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells) {
   std::vector<long long> begin(P + 1);
   const long long align = qhat_batch_align(N);   // the line-ring kernel works on whole xi_x chunks
   for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * (total / align)) / P) * align;
-  auto owner = [&](long long g) {
+  auto owner = [&](long long g) {   // last CTA whose range starts at or before g
     int lo = 0, hi = P - 1;
     while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (begin[mid] <= g) lo = mid; else hi = mid - 1; }
     return lo;
   };
-  std::vector<int> first(T);
+  auto tile_of = [&](long long g) {
+    int lo = 0, hi = T - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (tbegin[mid] <= g) lo = mid; else hi = mid - 1; }
+    return lo;
+  };
+  std::vector<int> first(T), ctile(P);
   std::vector<unsigned char> np(T);
   int kmax = 1;
   for (int t = 0; t < T; t++) {
-    const int a = owner((long long)t * S), b = owner((long long)(t + 1) * S - 1);
+    // CTAs with an empty range never write: pick owners among non-empty ranges
+    int a = owner(tbegin[t]);
+    const int b = owner(tbegin[t + 1] - 1);
     first[t] = a;
     np[t] = (unsigned char)(b - a + 1);
     kmax = std::max(kmax, b - a + 1);
   }
-  const size_t o1 = (size_t)(P + 1) * sizeof(long long), o2 = o1 + (size_t)T * sizeof(int);
-  const size_t bytes = o2 + (size_t)T;
+  for (int p = 0; p < P; p++) ctile[p] = tile_of(std::min(begin[p], total - 1));
+  const size_t o1 = (size_t)(P + 1) * sizeof(long long);
+  const size_t o2 = o1 + (size_t)(T + 1) * sizeof(long long);
+  const size_t o3 = o2 + (size_t)P * sizeof(int);
+  const size_t o4 = o3 + (size_t)T * sizeof(int);
+  const size_t bytes = o4 + (size_t)T;
   CK(cudaMalloc(&c->d_sched_mem, bytes));
   std::vector<unsigned char> blob(bytes);
   memcpy(blob.data(), begin.data(), o1);
-  memcpy(blob.data() + o1, first.data(), (size_t)T * sizeof(int));
-  memcpy(blob.data() + o2, np.data(), (size_t)T);
+  memcpy(blob.data() + o1, tbegin.data(), o2 - o1);
+  memcpy(blob.data() + o2, ctile.data(), o3 - o2);
+  memcpy(blob.data() + o3, first.data(), o4 - o3);
+  memcpy(blob.data() + o4, np.data(), (size_t)T);
   CK(cudaMemcpy(c->d_sched_mem, blob.data(), bytes, cudaMemcpyHostToDevice));
   unsigned char* base = (unsigned char*)c->d_sched_mem;
-  c->sched = {(const long long*)base, (const int*)(base + o1), base + o2, G, T, P, cols, kmax};
+  c->sched = {(const long long*)base, (const long long*)(base + o1), (const int*)(base + o2), (const int*)(base + o3),
+              base + o4, G, T, P, cols, kmax, sym ? 1 : 0};
   c->sched_cells = cells;
+  c->sched_sym = (int)sym;
   // partial-sum workspace: kmax parts of (padded cells) x n3 complex
   const size_t stride = (size_t)G * 32 * (size_t)c->n3;
   if (!c->d_parts || c->parts_stride < stride || c->parts_cap < kmax) {
@@ -241,10 +271,19 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells) {
   return 0;
 }
 
-static bool use_batch_v1() {
-  static int v = -1;
-  if (v < 0) { const char* e = getenv("SBTE_BATCH_V1"); v = (e && atoi(e) != 0) ? 1 : 0; }
-  return v == 1;
+// Symmetrised weights for f == g (see common.cuh): built lazily, once per bound tensor.
+static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out);
+static int ensure_sym(sbte_ctx* c) {
+  if (c->d_Ws) return 0;
+  CK(cudaMalloc(&c->d_Ws, (size_t)c->n3 * c->n3 * sizeof(double)));
+  launch_symmetrize_weights(c, c->d_W, c->d_Ws);
+  if (qhat_batch_supported(c->N)) return encode_weight_map(c, c->d_Ws, &c->tmapWs);
+  return 0;
+}
+static bool want_sym(sbte_ctx* c, bool same) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("SBTE_NO_SYM"); env = (e && atoi(e) != 0) ? 0 : 1; }
+  return same && c->sym_enabled && env == 1;
 }
 
 // ---- convolution dispatch -------------------------------------------------------------------
@@ -265,14 +304,12 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
   if (k2 == SBTE_K2_BATCH) {
     if (!same) { set_error("batched convolution requires f == g (single species)"); return 1; }
     if (!qhat_batch_supported(c->N)) { set_error("batched convolution: unsupported N"); return 1; }
+    const bool sym = want_sym(c, true);
+    if (sym && ensure_sym(c)) return 1;
+    if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    if (use_batch_v1() && c->N != 24) {
-      launch_qhat_batch_v1(c, c->d_lay[0], d_qhat, batch);
-    } else {
-      if (ensure_batch_schedule(c, batch)) return 1;
-      launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
-      launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
-    }
+    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
   } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
     if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
     launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
@@ -282,7 +319,9 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
       gl = c->d_lay[1];
     }
     QhatPair p = {gl, c->d_lay[0]};
-    launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2);
+    const bool sym = want_sym(c, same);
+    if (sym && ensure_sym(c)) return 1;
+    launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym);
   } else {
     if (!same && batch > 4) { set_error("generic convolution with f != g is limited to 4 cells"); return 1; }
     launch_fft3d(c, d_f, nullptr, 0, batch, c->d_specA, nullptr, 0, nullptr, false);
@@ -299,10 +338,12 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
 
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
   if (ensure_capacity(c, batch)) return 1;  // before c->d_qhat is read: growth reallocates the scratch
-  if (resolve_k2(c, batch, k2) == SBTE_K2_BATCH && d_f == d_g && qhat_batch_supported(c->N) && (!use_batch_v1() || c->N == 24)) {
+  if (resolve_k2(c, batch, k2) == SBTE_K2_BATCH && d_f == d_g && qhat_batch_supported(c->N)) {
     // fast path: forward transform -> stream-K convolution -> inverse transform summing the partial sums
     if (!c->d_W) { set_error("no weights bound"); return 1; }
-    if (ensure_batch_schedule(c, batch)) return 1;
+    const bool sym = want_sym(c, true);
+    if (sym && ensure_sym(c)) return 1;
+    if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
     launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
     launch_fft3d_parts(c, c->d_parts, c->parts_stride, c->sched, 1, batch, nullptr, d_Q);
@@ -338,7 +379,9 @@ int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g,
     gjhat = c->d_specB;
   }
   QhatPair pairs[2] = {{gjhat, c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]}};
-  if (stream) launch_qhat_stream(c, 2, pairs, c->d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2);
+  const bool sym = stream && want_sym(c, same);   // for f == g the three-product summand is symmetric as a whole
+  if (sym && ensure_sym(c)) return 1;
+  if (stream) launch_qhat_stream(c, 2, pairs, c->d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym);
   else launch_qhat_generic(c, 2, pairs, c->d_qhat, 1);
   launch_fft3d(c, nullptr, c->d_qhat, 1, 1, nullptr, nullptr, 0, d_Q, false);
   return check_launch("maxpreserve");
@@ -430,6 +473,11 @@ int sbte_sync(sbte_ctx* c) { CK(cudaStreamSynchronize(c->stream)); return check_
 void* sbte_stream(sbte_ctx* c) { return (void*)c->stream; }
 unsigned long long sbte_launch_count(sbte_ctx* c) { return c->launches; }
 int sbte_reserve(sbte_ctx* c, int cells) { return ensure_capacity(c, cells); }
+
+int sbte_set_symmetrize(sbte_ctx* c, int enable) {
+  c->sym_enabled = enable != 0;
+  return 0;
+}
 
 int sbte_k2_profile(sbte_ctx* c, int enable) {
   c->k2_prof = enable != 0;

@@ -16,6 +16,22 @@ __device__ __forceinline__ void cmac(double2& acc, double w, double2 p) {
   acc.y = fma(w, p.y, acc.y);
 }
 
+// ---------------------------------------------------------------- symmetrised xi_x enumeration
+// For f == g the summand W[zeta][xi] f^[xi] f^[sigma(xi)] pairs up under the involution
+// sigma_zeta(xi) = wrap(zeta + N/2 - xi): with Ws[zeta][xi] = W[zeta][xi] + W[zeta][sigma(xi)] only one xi of
+// each pair has to be visited.  Pairing is decided on the x component: with a = (zeta_x + N/2) mod N the
+// representatives are xi_x in [0, a/2] and [a+1, (a+N)/2] (self-paired planes xi_x = sigma_x(xi_x) keep
+// their original weights and are visited whole).  nrep = N/2 + 1 (a even) or N/2 (a odd).
+__host__ __device__ __forceinline__ int sym_nrep(int N, int zx) {
+  const int a = (zx + N / 2) % N;
+  return a / 2 + 1 + (a + N) / 2 - a;
+}
+__host__ __device__ __forceinline__ int sym_rep(int N, int zx, int c) {   // c-th representative xi_x
+  const int a = (zx + N / 2) % N;
+  const int h = a / 2;
+  return (c <= h) ? c : c + (a - h);
+}
+
 // ---------------------------------------------------------------- shared-memory addressing
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -18,9 +18,11 @@ struct ConsLU {
 // stream-K schedule of the batched convolution (device tables, see qhat_batch.cu)
 struct BatchSched {
   const long long* cta_begin;   // [P+1] first global step of every CTA
+  const long long* tile_begin;  // [T+1] first global step of every tile (tile lengths vary when symmetrised)
+  const int* cta_tile;          // [P] tile that contains cta_begin[p]
   const int* tile_first;        // [T] first CTA that touches tile t
   const unsigned char* tile_np; // [T] number of partial sums of tile t
-  int G, T, P, cols, kmax;
+  int G, T, P, cols, kmax, sym;
 };
 
 struct sbte_ctx {
@@ -46,6 +48,10 @@ struct sbte_ctx {
   const void* host_key = nullptr;  // identity of the host row-pointer array the cached copy came from
   CUtensorMap tmapW;
   bool tmap_ok = false;
+  // symmetrised copy for f == g (Ws[zeta][xi] = W[zeta][xi] + W[zeta][sigma_zeta(xi)], see common.cuh)
+  bool sym_enabled = true;
+  double* d_Ws = nullptr;
+  CUtensorMap tmapWs;
 
   // scratch, sized for `cap` cells
   int cap = 0;
@@ -63,7 +69,8 @@ struct sbte_ctx {
   double* h_pin = nullptr;       // pinned host staging, 3 * n3 doubles
   // batched-convolution schedule + partial-sum workspace (valid for sched_cells cells)
   int sched_cells = 0;
-  BatchSched sched = {nullptr, nullptr, nullptr, 0, 0, 0, 0, 0};
+  int sched_sym = -1;
+  BatchSched sched = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
   void* d_sched_mem = nullptr;
   double2* d_parts = nullptr;
   size_t parts_stride = 0;          // double2 elements per part
@@ -107,12 +114,12 @@ struct QhatPair {
 void launch_qhat_generic(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int batch);
 // stream kernel (N in {16,24,32}, batch 1): parity-layout operands
 bool qhat_stream_supported(int N);
-void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth);
+void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym);
+void launch_symmetrize_weights(sbte_ctx* c, const double* W, double* Ws);
 // batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32
 bool qhat_batch_supported(int N);
 int qhat_batch_cols(int N);
 int qhat_batch_align(int N);
-void launch_qhat_batch_v1(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells);
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);
 

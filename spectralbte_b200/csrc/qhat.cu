@@ -91,7 +91,8 @@ struct StreamCfg {
   static_assert(N % PH == 0, "phases must tile");
 };
 
-template <int N, int NP, int DEPTH>
+// SYM: W is the symmetrised tensor Ws and only the representative xi_x planes are visited (f == g only).
+template <int N, int NP, int DEPTH, bool SYM>
 __global__ void __launch_bounds__(StreamCfg<N>::THREADS, (N == 32 && NP == 1 && DEPTH <= 2) ? 2 : 1)
 qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
                    const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat) {
@@ -108,6 +109,8 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   const int cp = lane % HALF, rgw = lane / HALF;
   const bool active = rgw < C::RGW;
   const int zx = blockIdx.x / N, zy = blockIdx.x % N;
+  const int nchunk = SYM ? sym_nrep(N, zx) : N;             // xi_x planes visited by this CTA
+  auto chunk_ex = [&](int c) { return SYM ? sym_rep(N, zx, c) : c; };
   const int r0 = rb * C::ROWS_W + (active ? rgw : 0) * 4;   // first of this thread's 4 zeta_z rows
   const int c0 = 2 * cp;                                    // first of its 2 xi_z columns
 
@@ -121,16 +124,17 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   }
   const int offg0 = cp, offg1 = HALF + cp;
 
-  auto issue_chunk = [&](int chunk) {  // one thread: stage the operand planes of xi_x = chunk
+  auto issue_chunk = [&](int chunk) {  // one thread: stage the operand planes of the chunk-th visited xi_x
     const int s = chunk & 1;
-    int X = zx + N / 2 - chunk;
+    const int ex = chunk_ex(chunk);
+    int X = zx + N / 2 - ex;
     if (X < 0) X += N; else if (X > N - 1) X -= N;
     double2* dst = planes + (size_t)s * STAGE_ELEMS;
     mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * (uint32_t)sizeof(double2));
-    tma_bulk_g2s(dst, xiA + (size_t)chunk * PLANE, PLANE * sizeof(double2), &full[s]);
+    tma_bulk_g2s(dst, xiA + (size_t)ex * PLANE, PLANE * sizeof(double2), &full[s]);
     tma_bulk_g2s(dst + PLANE, dfA + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
     if (NP > 1) {
-      tma_bulk_g2s(dst + 2 * PLANE, xiB + (size_t)chunk * PLANE, PLANE * sizeof(double2), &full[s]);
+      tma_bulk_g2s(dst + 2 * PLANE, xiB + (size_t)ex * PLANE, PLANE * sizeof(double2), &full[s]);
       tma_bulk_g2s(dst + 3 * PLANE, dfB + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
     }
   };
@@ -143,22 +147,23 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   __syncthreads();
   if (tid == 0) {
     issue_chunk(0);
-    issue_chunk(1);
+    if (nchunk > 1) issue_chunk(1);
   }
 
   // weight stream: rows zeta = (zx, zy, r0 + j), j = 0..3; this thread's 16 bytes sit at column c0
   const double* wrow = W + ((long)blockIdx.x * N + r0) * n3 + c0;
-  constexpr int NIT = N * C::SPC;  // iterations of this warp over (xi_x, xi_y)
+  const int NIT = nchunk * C::SPC;  // iterations of this warp over (visited xi_x, xi_y)
   double2 wb[DEPTH][4];
   auto load_w = [&](int it, double2 (&dst)[4]) {
-    const int ex = it / C::SPC, ey = ph + (it % C::SPC) * C::PH;
+    const int ex = chunk_ex(it / C::SPC), ey = ph + (it % C::SPC) * C::PH;
     const double* p = wrow + ((long)ex * N + ey) * N;
 #pragma unroll
     for (int j = 0; j < 4; j++) dst[j] = ldg_stream_f64x2(p + (long)j * n3);
   };
   if (active) {
 #pragma unroll
-    for (int d = 0; d < DEPTH; d++) load_w(d, wb[d]);
+    for (int d = 0; d < DEPTH; d++)
+      if (d < NIT) load_w(d, wb[d]);
   }
 
   double2 acc[4];
@@ -169,6 +174,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
 #pragma unroll
     for (int d = 0; d < DEPTH; d++) {
       const int it = it0 + d;
+      if (it >= NIT) break;   // block-uniform (NIT need not be a multiple of DEPTH)
       const int chunk = it / C::SPC, step = it % C::SPC;
       const int s = chunk & 1;
       if (step == 0) mbar_wait(&full[s], (chunk >> 1) & 1);
@@ -215,7 +221,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
       if (step == C::SPC - 1) {
         // every warp is done with stage s: refill it with the planes of chunk + 2
         __syncthreads();
-        if (tid == 0 && chunk + 2 < N) issue_chunk(chunk + 2);
+        if (tid == 0 && chunk + 2 < nchunk) issue_chunk(chunk + 2);
       }
     }
   }
@@ -243,44 +249,66 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
 
 bool qhat_stream_supported(int N) { return N == 16 || N == 24 || N == 32; }
 
-template <int N, int NP, int DEPTH>
-static void launch_stream_inst(sbte_ctx* c, const QhatPair* pairs, double2* qhat) {
+template <int N, int NP, int DEPTH, bool SYM>
+static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pairs, double2* qhat) {
   using C = StreamCfg<N>;
   const size_t smem = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2) + 64;
-  auto kern = qhat_stream_kernel<N, NP, DEPTH>;
+  auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     configured = true;
   }
   k2_mark(c);
-  kern<<<N * N, C::THREADS, smem, c->stream>>>(c->d_W, pairs[0].xi_side, pairs[0].dif_side,
+  kern<<<N * N, C::THREADS, smem, c->stream>>>(W, pairs[0].xi_side, pairs[0].dif_side,
                                                NP > 1 ? pairs[1].xi_side : nullptr,
                                                NP > 1 ? pairs[1].dif_side : nullptr, qhat);
   k2_mark(c);
   c->launches += 1;
 }
 
-template <int N>
-static void launch_stream_n(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth) {
+template <int N, bool SYM>
+static void launch_stream_n(sbte_ctx* c, const double* W, int npairs, const QhatPair* pairs, double2* qhat, int depth) {
   if (npairs == 1) {
-    if (depth >= 4) launch_stream_inst<N, 1, 4>(c, pairs, qhat);
-    else launch_stream_inst<N, 1, 2>(c, pairs, qhat);
+    if (depth >= 4) launch_stream_inst<N, 1, 4, SYM>(c, W, pairs, qhat);
+    else launch_stream_inst<N, 1, 2, SYM>(c, W, pairs, qhat);
   } else {
     // two operand pairs need 128 KB of plane ring => one CTA per SM: keep four weight tiles per thread in
     // flight (64 KB per SM) so the HBM stream stays saturated
-    (void)depth;
-    launch_stream_inst<N, 2, 4>(c, pairs, qhat);
+    launch_stream_inst<N, 2, 4, SYM>(c, W, pairs, qhat);
   }
 }
 
-void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth) {
+// sym: stream the symmetrised tensor (caller guarantees xi-side and dif-side operands describe f == g)
+void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym) {
+  const double* W = sym ? c->d_Ws : c->d_W;
   switch (c->N) {
-    case 16: launch_stream_n<16>(c, npairs, pairs, qhat, depth); break;
-    case 24: launch_stream_n<24>(c, npairs, pairs, qhat, depth); break;
-    case 32: launch_stream_n<32>(c, npairs, pairs, qhat, depth); break;
+    case 16: sym ? launch_stream_n<16, true>(c, W, npairs, pairs, qhat, depth) : launch_stream_n<16, false>(c, W, npairs, pairs, qhat, depth); break;
+    case 24: sym ? launch_stream_n<24, true>(c, W, npairs, pairs, qhat, depth) : launch_stream_n<24, false>(c, W, npairs, pairs, qhat, depth); break;
+    case 32: sym ? launch_stream_n<32, true>(c, W, npairs, pairs, qhat, depth) : launch_stream_n<32, false>(c, W, npairs, pairs, qhat, depth); break;
     default: set_error("qhat_stream: unsupported N"); break;
   }
+}
+
+// Ws[zeta][xi] = W[zeta][xi] + W[zeta][sigma(xi)] on representative planes, W on self-paired planes, 0 elsewhere
+__global__ void symmetrize_weights_kernel(const double* __restrict__ W, double* __restrict__ Ws, int N) {
+  const size_t n3 = (size_t)N * N * N, total = n3 * n3;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int zeta = (int)(e / n3), xi = (int)(e - (size_t)zeta * n3);
+    const int zx = zeta / (N * N), zy = (zeta / N) % N, zz = zeta % N;
+    const int ex = xi / (N * N), ey = (xi / N) % N, ez = xi % N;
+    const int X = (zx + N / 2 - ex + N) % N, Y = (zy + N / 2 - ey + N) % N, Z = (zz + N / 2 - ez + N) % N;
+    double v;
+    if (ex < X) v = W[e] + W[(size_t)zeta * n3 + ((size_t)X * N + Y) * N + Z];
+    else if (ex == X) v = W[e];
+    else v = 0.0;
+    Ws[e] = v;
+  }
+}
+
+void launch_symmetrize_weights(sbte_ctx* c, const double* W, double* Ws) {
+  symmetrize_weights_kernel<<<148 * 16, 256, 0, c->stream>>>(W, Ws, c->N);
+  c->launches += 1;
 }
 
 }  // namespace sbte

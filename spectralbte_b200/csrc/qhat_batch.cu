@@ -21,141 +21,9 @@
 
 namespace sbte {
 
-template <int N>
-struct BatchCfg {
-  static constexpr int COLS = (N >= 16) ? 8 : 4;     // zeta_y columns (= warps) per CTA; must be < N
-  static constexpr int THREADS = COLS * 32;
-  static constexpr int ROWS = COLS * N;              // weight rows per CTA
-  static constexpr int LINE = N * 32;                // double2 per operand line (N modes x 32 cells)
-  static constexpr int PLANE = N * LINE;             // double2 per operand plane
-  static constexpr int STAGES = 3;
-  static constexpr size_t STAGE_BYTES = (size_t)LINE * 16 + (size_t)ROWS * N * 8;
-  static constexpr size_t SMEM = (size_t)PLANE * 16 + STAGES * STAGE_BYTES + 128;
-  static_assert(COLS < N && N % COLS == 0, "columns must tile zeta_y");
-};
-
-template <int N>
-__global__ void __launch_bounds__(BatchCfg<N>::THREADS, 1)
-qhat_batch_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
-                  double2* __restrict__ qhat, int cells) {
-  using C = BatchCfg<N>;
-  constexpr long n3 = (long)N * N * N;
-  constexpr int NSTEP = N * N;
-  extern __shared__ __align__(128) unsigned char smraw[];
-  double2* plane = reinterpret_cast<double2*>(smraw);                                  // [N][N][32]
-  unsigned char* stage0 = smraw + (size_t)C::PLANE * 16;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + C::STAGES * C::STAGE_BYTES);  // [0..2] stage, [3] plane
-  auto stage_line = [&](int s) { return reinterpret_cast<double2*>(stage0 + (size_t)s * C::STAGE_BYTES); };
-  auto stage_w = [&](int s) {
-    return reinterpret_cast<double*>(stage0 + (size_t)s * C::STAGE_BYTES + (size_t)C::LINE * 16);
-  };
-
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int cg = blockIdx.x;                       // cell group
-  const int q0 = blockIdx.y * C::COLS;             // first zeta (x,y) column of this CTA
-  const int zx = q0 / N, zy = (q0 % N) + warp;     // this warp's column (COLS divides N: same zeta_x)
-  const double2* gspec = spec + (size_t)cg * n3 * 32;
-
-  auto issue_stage = [&](int step) {
-    const int s = step % C::STAGES;
-    mbar_arrive_expect_tx(&bars[s], (uint32_t)C::STAGE_BYTES);
-    tma_bulk_g2s(stage_line(s), gspec + (size_t)step * C::LINE, C::LINE * 16, &bars[s]);
-    tma_tensor2d_g2s(stage_w(s), &tmapW, step * N, q0 * N, &bars[s]);
-  };
-  auto issue_plane = [&](int chunk) {
-    int X = zx + N / 2 - chunk;
-    if (X < 0) X += N; else if (X > N - 1) X -= N;
-    mbar_arrive_expect_tx(&bars[3], (uint32_t)(C::PLANE * 16));
-    for (int y = 0; y < N; y++)
-      tma_bulk_g2s(plane + (size_t)y * C::LINE, gspec + ((size_t)X * N + y) * C::LINE, C::LINE * 16, &bars[3]);
-  };
-
-  if (tid == 0) {
-    for (int b = 0; b < 4; b++) mbar_init(&bars[b], 1);
-    mbar_fence_init();
-  }
-  __syncthreads();
-  if (tid == 0) {
-    issue_plane(0);
-    for (int s = 0; s < C::STAGES; s++) issue_stage(s);
-  }
-
-  double2 acc[N];
-#pragma unroll
-  for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
-
-  for (int step = 0; step < NSTEP; step++) {
-    const int chunk = step / N, ey = step - chunk * N;
-    const int s = step % C::STAGES;
-    if (ey == 0) mbar_wait(&bars[3], chunk & 1);
-    mbar_wait(&bars[s], (step / C::STAGES) & 1);
-
-    int Y = zy + N / 2 - ey;
-    if (Y < 0) Y += N; else if (Y > N - 1) Y -= N;
-    const double2* fl = plane + (size_t)Y * C::LINE + lane;
-    const double2* gl = stage_line(s) + lane;
-    const double* wt = stage_w(s) + warp * N * N;     // [row r][col c], warp-uniform addresses
-
-    double2 fr[N];
-#pragma unroll
-    for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
-#pragma unroll
-    for (int c = 0; c < N; c += 2) {
-      const double2 g0 = gl[c * 32], g1 = gl[(c + 1) * 32];
-#pragma unroll
-      for (int r = 0; r < N; r++) {
-        const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
-        const double2 p0 = cmul(g0, fr[(r + N / 2 - c + N) % N]);
-        const double2 p1 = cmul(g1, fr[(r + N / 2 - c - 1 + N) % N]);
-        cmac(acc[r], w2.x, p0);
-        cmac(acc[r], w2.y, p1);
-      }
-    }
-
-    __syncthreads();  // all warps done with stage s (and, at ey == N-1, with the plane)
-    if (tid == 0) {
-      if (step + C::STAGES < NSTEP) issue_stage(step + C::STAGES);
-      if (ey == N - 1 && chunk + 1 < N) issue_plane(chunk + 1);
-    }
-  }
-
-  const long cell = (long)cg * 32 + lane;
-  if (cell < cells) {
-    double2* out = qhat + cell * n3 + ((long)zx * N + zy) * N;
-#pragma unroll
-    for (int r = 0; r < N; r++) out[r] = acc[r];
-  }
-}
-
 bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24; }
 int qhat_batch_align(int N) { return N == 24 ? N : 1; }  // stream-K granularity in steps
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
-
-template <int N>
-static void launch_batch_n(sbte_ctx* c, const double2* spec, double2* qhat, int cells) {
-  using C = BatchCfg<N>;
-  auto kern = qhat_batch_kernel<N>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    configured = true;
-  }
-  const int groups = (cells + 31) / 32;
-  dim3 grid(groups, N * N / C::COLS);
-  k2_mark(c);
-  kern<<<grid, C::THREADS, C::SMEM, c->stream>>>(c->tmapW, spec, qhat, cells);
-  k2_mark(c);
-  c->launches += 1;
-}
-
-void launch_qhat_batch_v1(sbte_ctx* c, const double2* spec, double2* qhat, int cells) {
-  if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
-  switch (c->N) {
-    case 8: launch_batch_n<8>(c, spec, qhat, cells); break;
-    case 16: launch_batch_n<16>(c, spec, qhat, cells); break;
-    default: set_error("qhat_batch: unsupported N"); break;
-  }
-}
 
 // ------------------------------------------------------------------------------------------
 // v2: persistent CTAs, stream-K split of the (tile, step) iteration space, decoupled warps
@@ -190,7 +58,6 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
                    double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch) {
   using C = Batch2Cfg<N>;
   constexpr long n3 = (long)N * N * N;
-  constexpr int NSTEP = N * N;
   constexpr int S = C::STAGES;
   extern __shared__ __align__(128) unsigned char smraw[];
   double2* plane = reinterpret_cast<double2*>(smraw);
@@ -210,6 +77,7 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   const int n = (int)(sch.cta_begin[blockIdx.x + 1] - g0);
   if (n <= 0) return;
   const int G = sch.G;
+  const bool sym = sch.sym != 0;
 
   if (tid == 0) {
     for (int b = 0; b < S; b++) { mbar_init(&full[b], 1); mbar_init(&empty[b], C::COLS); }
@@ -219,12 +87,17 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   }
   __syncthreads();
 
-  // decode of a global step: tile -> (row-block, cell group), step -> (xi_x chunk, xi_y), plane index X
-  auto plane_of = [&](long long g, int& cg, int& X) {
-    const int t = (int)(g / NSTEP), s = (int)(g - (long long)t * NSTEP);
-    const int rb = t / G;
+  // A tile (row-block rb, cell group cg) has len = (visited xi_x planes) * N steps; tile_begin[] holds
+  // the global step offsets.  Step s of a tile -> chunk ordinal s / N -> xi_x (all planes, or the
+  // representatives of the symmetrised tensor), xi_y = s % N, dif-side plane X = wrap(zeta_x + N/2 - xi_x).
+  auto decode = [&](int t, int s, int& rb, int& cg, int& ex, int& ey, int& X) {
+    rb = t / G;
     cg = t - rb * G;
-    X = (rb * C::COLS) / N + N / 2 - s / N;
+    const int zxx = (rb * C::COLS) / N;
+    const int c = s / N;
+    ey = s - c * N;
+    ex = sym ? sym_rep(N, zxx, c) : c;
+    X = zxx + N / 2 - ex;
     if (X < 0) X += N; else if (X > N - 1) X -= N;
   };
 
@@ -233,12 +106,14 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     if (C::REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
     if (warp == C::COLS && lane == 0) {
       int cur_cg = -1, cur_X = -1, epoch = -1;
-      for (int k = 0; k < n; k++) {
-        const long long g = g0 + k;
-        const int t = (int)(g / NSTEP), s = (int)(g - (long long)t * NSTEP);
-        const int rb = t / G, cg = t - rb * G;
-        int X;
-        { int cgx; plane_of(g, cgx, X); }
+      int t = sch.cta_tile[blockIdx.x];
+      long long te = sch.tile_begin[t + 1];
+      int sl = (int)(g0 - sch.tile_begin[t]);
+      for (int k = 0; k < n; k++, sl++) {
+        if (g0 + k == te) { t++; te = sch.tile_begin[t + 1]; sl = 0; }
+        int rb, cg, ex, ey, X;
+        decode(t, sl, rb, cg, ex, ey, X);
+        const int s = ex * N + ey;
         if (cg != cur_cg || X != cur_X) {
           if (epoch >= 0) mbar_wait(emptyPlane, epoch & 1);   // every warp released the previous plane
           epoch++;
@@ -278,10 +153,13 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     }
   };
 
-  for (int k = 0; k < n; k++) {
-    const long long g = g0 + k;
-    const int t = (int)(g / NSTEP), s = (int)(g - (long long)t * NSTEP);
-    const int ey = s % N;
+  int t = sch.cta_tile[blockIdx.x];
+  long long te = sch.tile_begin[t + 1];
+  int sl = (int)(g0 - sch.tile_begin[t]);
+  for (int k = 0; k < n; k++, sl++) {
+    if (g0 + k == te) { t++; te = sch.tile_begin[t + 1]; sl = 0; }
+    int rb, cg, ex, ey, X;
+    decode(t, sl, rb, cg, ex, ey, X);
     if (t != cur_t) {
       if (cur_t >= 0) {
         flush();
@@ -289,12 +167,10 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
         for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
       }
       cur_t = t;
-      const int q0 = (t / G) * C::COLS;
+      const int q0 = rb * C::COLS;
       zx = q0 / N;
       zy = (q0 % N) + warp;
     }
-    int cg, X;
-    plane_of(g, cg, X);
     if (cg != cur_cg || X != cur_X) {
       epoch++;
       cur_cg = cg; cur_X = X;
@@ -328,8 +204,9 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     // release the stage (and the plane when the next step needs another one)
     bool plane_done = (k == n - 1);
     if (!plane_done) {
-      int cg2, X2;
-      plane_of(g + 1, cg2, X2);
+      int rb2, cg2, ex2, ey2, X2;
+      if (g0 + k + 1 == te) decode(t + 1, 0, rb2, cg2, ex2, ey2, X2);
+      else decode(t, sl + 1, rb2, cg2, ex2, ey2, X2);
       plane_done = (cg2 != cur_cg) || (X2 != cur_X);
     }
     __syncwarp();
@@ -352,7 +229,7 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
     configured = true;
   }
   k2_mark(c);
-  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(c->tmapW, spec, parts, part_stride, cells, sch);
+  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapWs : c->tmapW, spec, parts, part_stride, cells, sch);
   k2_mark(c);
   c->launches += 1;
 }
@@ -388,7 +265,6 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
                    double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch) {
   using C = Batch3Cfg<N>;
   constexpr long n3 = (long)N * N * N;
-  constexpr int NSTEP = N * N;
   constexpr int S = C::STAGES, R = C::RING, L = C::LPC;
   extern __shared__ __align__(128) unsigned char smraw[];
   double2* ring = reinterpret_cast<double2*>(smraw);
@@ -407,6 +283,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   if (n <= 0) return;
   const int G = sch.G;
   const int nchunk = n / N;
+  const bool sym = sch.sym != 0;
 
   if (tid == 0) {
     for (int b = 0; b < S; b++) { mbar_init(&fullS[b], 1); mbar_init(&emptyS[b], C::COLS); }
@@ -420,11 +297,14 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     if (warp == C::COLS && lane == 0) {
       int k = 0;          // local step counter (stage ring)
       long q = 0;         // line sequence number (line ring)
-      for (int ch = 0; ch < nchunk; ch++) {
-        const long long g = g0 + (long long)ch * N;
-        const int t = (int)(g / NSTEP), ex = (int)((g - (long long)t * NSTEP) / N);
+      int t = sch.cta_tile[blockIdx.x];
+      long long te = sch.tile_begin[t + 1];
+      int cl = (int)((g0 - sch.tile_begin[t]) / N);   // chunk ordinal inside the tile
+      for (int ch = 0; ch < nchunk; ch++, cl++) {
+        if (g0 + (long long)ch * N == te) { t++; te = sch.tile_begin[t + 1]; cl = 0; }
         const int rb = t / G, cg = t - rb * G;
         const int q0 = rb * C::COLS, zx = q0 / N, zy0 = q0 % N;
+        const int ex = sym ? sym_rep(N, zx, cl) : cl;
         int X = zx + N / 2 - ex;
         if (X < 0) X += N; else if (X > N - 1) X -= N;
         const double2* gs = spec + (size_t)cg * n3 * 32;
@@ -472,9 +352,10 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     }
   };
 
+  int t = sch.cta_tile[blockIdx.x];
+  long long te = sch.tile_begin[t + 1];
   for (int ch = 0; ch < nchunk; ch++, qbase += L) {
-    const long long g = g0 + (long long)ch * N;
-    const int t = (int)(g / NSTEP);
+    if (g0 + (long long)ch * N == te) { t++; te = sch.tile_begin[t + 1]; }
     if (t != cur_t) {
       if (cur_t >= 0) {
         flush();
@@ -538,7 +419,7 @@ static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, si
     configured = true;
   }
   k2_mark(c);
-  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(c->tmapW, spec, parts, part_stride, cells, sch);
+  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapWs : c->tmapW, spec, parts, part_stride, cells, sch);
   k2_mark(c);
   c->launches += 1;
 }

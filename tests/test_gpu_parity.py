@@ -536,3 +536,43 @@ def test_error_paths_report_like_the_reference(sb, tmp_path):
         c.ComputeQ(np.ones((40, 512)), np.ones((40, 512)), k2=sb.K2_BATCH)
     with pytest.raises(SbteError, match="Poiseuille"):
         sb.Slab(c, 8, 1, np.zeros(10), np.ones(10), 5, 1e-3)
+
+
+# ---------------------------------------------------------------- symmetrised weight stream (f == g)
+@pytest.mark.parametrize("N,k2,cells", [(16, 2, 1), (24, 2, 1), (16, 4, 1), (8, 3, 37), (16, 3, 40), (24, 3, 33)])
+def test_symmetrised_stream_equals_plain_stream(sb, N, k2, cells):
+    """Ws = W + W o sigma over the representative xi_x planes must reproduce the full sum for f == g."""
+    o = orc.Oracle(N, 7.0, 1)
+    c = sb.Collisions(N, 7.0, inhomogeneous=True)
+    c.synthetic_weights(7)
+    f = np.stack([seeded_f(o.v, 50 + b, noise=0.3) for b in range(cells)])
+    c.set_symmetrize(True)
+    a = c.Qhat(f, k2=k2)
+    qa = c.ComputeQ(f, k2=k2)
+    c.set_symmetrize(False)
+    b = c.Qhat(f, k2=k2)
+    qb = c.ComputeQ(f, k2=k2)
+    assert relmax(a, b) < 1e-13 and relmax(qa, qb) < 1e-13
+    assert relmax(b.reshape(cells, -1)[0], c.Qhat(f[0], k2=sb.K2_GENERIC)) < TOL_QHAT
+    if cells == 1:
+        c.set_symmetrize(True)
+        ma = c.ComputeQ_maxPreserve(f[0], k2=k2)
+        c.set_symmetrize(False)
+        mb = c.ComputeQ_maxPreserve(f[0], k2=k2)
+        assert relmax(ma, mb) < 1e-13
+
+
+def test_symmetrised_representatives_cover_every_pair_once():
+    """Host-side check of the xi_x representative rule used by the kernels (common.cuh sym_nrep/sym_rep)."""
+    for N in (8, 16, 22, 24, 32):
+        for zx in range(N):
+            a = (zx + N // 2) % N
+            h = a // 2
+            nrep = h + 1 + (a + N) // 2 - a
+            reps = [c if c <= h else c + (a - h) for c in range(nrep)]
+            want = [ex for ex in range(N) if ex <= (a - ex) % N]
+            assert reps == want
+            seen = set()
+            for ex in reps:
+                seen.add(ex); seen.add((a - ex) % N)
+            assert seen == set(range(N))
