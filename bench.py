@@ -378,7 +378,7 @@ def run_0d_n32(args):
     ref_bytes = 8.0 * float(N) ** 6
     # symmetrised stream (f == g): rows zeta read nrep(zeta_x) of their N xi_x planes, nrep = N/2+1 | N/2
     nrep_sum = sum(((zx + N // 2) % N) // 2 + 1 + (((zx + N // 2) % N) + N) // 2 - ((zx + N // 2) % N) for zx in range(N))
-    wbytes = 8.0 * float(N) ** 5 * nrep_sum if sym else ref_bytes
+    wbytes = 8.0 * float(N) ** 4 * nrep_sum if sym else ref_bytes
     k2_avg_ms = k2_ms / max(1, k2_n)
     achieved = wbytes / (k2_avg_ms * 1e-3) / 1e9
     traffic = None

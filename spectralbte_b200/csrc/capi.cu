@@ -412,6 +412,7 @@ int sbte_create(sbte_ctx** out, int N, double L_v, const double* v, const double
   c->deta = eta[1] - eta[0];
   c->L_eta = -eta[0];
   CK(cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking));
+  init_fft_constants();
 
   std::vector<double2> tab(N);
   for (int m = 0; m < N; m++) tab[m] = make_double2(cos(2.0 * M_PI * m / N), sin(2.0 * M_PI * m / N));

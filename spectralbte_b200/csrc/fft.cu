@@ -129,8 +129,173 @@ fft_pass_x(const double2* __restrict__ tmp, const double2* __restrict__ post, co
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Whole-cell transform for batches (1D): one CTA per cell, the N^3 complex cell stays in shared memory
+// (z padded to N+1 so that every axis pass reads conflict-free 16-byte words), each thread transforms whole
+// lines held in registers; the DFT matrix entries come from constant memory (c_tw[N][m], compile-time
+// offsets), which keeps every DFMA at two register operands.  One launch instead of two, no round trip
+// through the intermediate buffer.
+// ------------------------------------------------------------------------------------------
+__constant__ double2 c_tw[33][32];   // c_tw[N][m] = (cos, sin)(2 pi m / N), filled once per process
+
+void init_fft_constants() {
+  static bool done = false;
+  if (done) return;
+  static double2 h[33][32];
+  for (int n = 1; n <= 32; n++)
+    for (int m = 0; m < 32; m++) h[n][m] = make_double2(cos(2.0 * M_PI * m / n), sin(2.0 * M_PI * m / n));
+  cudaMemcpyToSymbol(c_tw, h, sizeof(h));
+  done = true;
+}
+
+constexpr int bitrev(int v, int bits) {
+  int r = 0;
+  for (int b = 0; b < bits; b++) r |= ((v >> b) & 1) << (bits - 1 - b);
+  return r;
+}
+constexpr int ilog2(int n) { return n <= 1 ? 0 : 1 + ilog2(n / 2); }
+
+// power-of-two line: radix-2 decimation in frequency, entirely in registers (natural-order loads, bit-reversed
+// stores so that every register index is a compile-time constant), twiddles from constant memory
+template <int N, int M>
+__device__ __forceinline__ void dif_stage(double2 (&x)[N], double sgn) {
+  constexpr int H = M / 2;
+#pragma unroll
+  for (int k = 0; k < N; k += M) {
+#pragma unroll
+    for (int j = 0; j < H; j++) {
+      const double wr = c_tw[N][j * (N / M)].x, wi = sgn * c_tw[N][j * (N / M)].y;
+      const double2 a = x[k + j], b = x[k + j + H];
+      const double dr = a.x - b.x, di = a.y - b.y;
+      x[k + j] = make_double2(a.x + b.x, a.y + b.y);
+      x[k + j + H] = make_double2(dr * wr - di * wi, dr * wi + di * wr);
+    }
+  }
+  if constexpr (M > 2) dif_stage<N, M / 2>(x, sgn);
+}
+
+template <int N>
+__device__ __forceinline__ void fft_line_pow2(double2* __restrict__ base, int stride, double sgn) {
+  constexpr int LG = ilog2(N);
+  double2 x[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) x[k] = base[k * stride];
+  dif_stage<N, N>(x, sgn);
+#pragma unroll
+  for (int k = 0; k < N; k++) base[bitrev(k, LG) * stride] = x[k];
+}
+
+template <int N>
+__device__ __forceinline__ void dft_line(double2* __restrict__ base, int stride, double sgn) {
+  if constexpr ((N & (N - 1)) == 0) {
+    fft_line_pow2<N>(base, stride, sgn);
+    return;
+  }
+  double2 x[N];
+#pragma unroll
+  for (int k = 0; k < N; k++) x[k] = base[k * stride];
+#pragma unroll
+  for (int kp = 0; kp < N; kp++) {
+    double sr = 0.0, si = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; k++) {
+      const double wr = c_tw[N][(k * kp) % N].x, wi = sgn * c_tw[N][(k * kp) % N].y;
+      sr += x[k].x * wr - x[k].y * wi;
+      si += x[k].x * wi + x[k].y * wr;
+    }
+    base[kp * stride] = make_double2(sr, si);
+  }
+}
+
+template <int N>
+__global__ void __launch_bounds__(256, ((N & (N - 1)) == 0) ? 2 : 1)
+fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict__ in_cplx, PartsIn pin,
+                  const double2* __restrict__ pre, const double2* __restrict__ post, const double* __restrict__ wt,
+                  double prefactor, double sgn, double2* __restrict__ out_nat, double2* __restrict__ out_lay, int layout,
+                  double* __restrict__ out_real) {
+  extern __shared__ double2 cellsm[];   // [N][N][N+1]
+  constexpr int P = N + 1;
+  constexpr long n3 = (long)N * N * N;
+  const long cell = blockIdx.x;
+  for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
+    const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
+    const long g = cell * n3 + idx;
+    double xr, xi;
+    if (in_real) { xr = in_real[g]; xi = 0.0; }
+    else if (pin.parts) {
+      const int tile = ((i * N + j) / pin.cols) * pin.G + (int)(cell >> 5);
+      const int np = pin.tile_np[tile];
+      xr = 0.0; xi = 0.0;
+      for (int m = 0; m < np; m++) {
+        const double2 z = pin.parts[(size_t)m * pin.stride + g];
+        xr += z.x; xi += z.y;
+      }
+    } else { const double2 z = in_cplx[g]; xr = z.x; xi = z.y; }
+    const double2 cs = pre[i + j + k];
+    const double factor = prefactor * wt[i] * wt[j] * wt[k];
+    cellsm[(i * N + j) * P + k] = make_double2(factor * (cs.x * xr - cs.y * xi), factor * (cs.x * xi + cs.y * xr));
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < N * N; l += blockDim.x)            // along z: line (i, j)
+    dft_line<N>(cellsm + l * P, 1, sgn);
+  __syncthreads();
+  for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along y: line (i, k)
+    const int i = l / N, k = l % N;
+    dft_line<N>(cellsm + (i * N) * P + k, P, sgn);
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along x: line (j, k)
+    const int j = l / N, k = l % N;
+    dft_line<N>(cellsm + j * P + k, N * P, sgn);
+  }
+  __syncthreads();
+  for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
+    const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
+    const double2 cs = post[idx];
+    const double2 z = cellsm[(i * N + j) * P + k];
+    const double2 o = make_double2(cs.x * z.x - cs.y * z.y, cs.x * z.y + cs.y * z.x);
+    if (out_nat) out_nat[cell * n3 + idx] = o;
+    if (out_real) out_real[cell * n3 + idx] = o.x;
+    if (out_lay) {
+      if (layout == LAY_PARITY) out_lay[cell * n3 + (idx - k) + (k & 1) * (N / 2) + (k >> 1)] = o;
+      else if (layout == LAY_CELLMINOR) out_lay[((cell >> 5) * n3 + idx) * 32 + (cell & 31)] = o;
+      else out_lay[cell * n3 + idx] = o;
+    }
+  }
+}
+
+template <int N>
+static void launch_cell_n(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,
+                          double2* out_nat, double2* out_lay, int layout, double* out_real) {
+  const size_t smem = (size_t)N * N * (N + 1) * sizeof(double2);
+  auto kern = fft3d_cell_kernel<N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  const int d = invert ? 1 : 0;
+  kern<<<batch, 256, smem, c->stream>>>(in_real, in_cplx, pin, c->d_pre[d], c->d_post[d], c->d_wt, c->pref[d],
+                                        invert ? +1.0 : -1.0, out_nat, out_lay, layout, out_real);
+  c->launches += 1;
+}
+
+// returns false when the whole-cell kernel does not apply (small batches keep the plane-parallel pair)
+static bool try_cell_fft(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,
+                         double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real) {
+  if (batch < 8 || accumulate_real) return false;
+  switch (c->N) {
+    case 8: launch_cell_n<8>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real); return true;
+    case 12: launch_cell_n<12>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real); return true;
+    case 16: launch_cell_n<16>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real); return true;
+    default: return false;
+  }
+}
+
 void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,
                   double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real) {
+  PartsIn nopart = {nullptr, 0, nullptr, 0, 0};
+  if (try_cell_fft(c, in_real, in_cplx, nopart, invert, batch, out_nat, out_lay, layout, out_real, accumulate_real)) return;
   const int N = c->N;
   const size_t smem = (size_t)(2 * N * N + N) * sizeof(double2);
   const int d = invert ? 1 : 0;
@@ -146,6 +311,10 @@ void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, in
 
 void launch_fft3d_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int invert,
                         int batch, double2* out_nat, double* out_real) {
+  {
+    PartsIn pin0 = {parts, part_stride, sch.tile_np, sch.G, sch.cols};
+    if (try_cell_fft(c, nullptr, nullptr, pin0, invert, batch, out_nat, nullptr, 0, out_real, false)) return;
+  }
   const int N = c->N;
   const size_t smem = (size_t)(2 * N * N + N) * sizeof(double2);
   const int d = invert ? 1 : 0;

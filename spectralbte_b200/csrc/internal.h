@@ -95,6 +95,7 @@ enum SpecLayout {
   LAY_CELLMINOR = 2  // [cell/32][x][y][z][cell%32]        (batched kernel: lanes = cells)
 };
 
+void init_fft_constants();
 // fft.cu -- K1 / K3. in_real: N^3 doubles per cell; in_cplx: N^3 double2 per cell (exactly one non-null).
 // out_nat / out_lay / out_real may each be null. batch = number of cells.
 void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,

@@ -39,6 +39,21 @@ def test_fft3d_matches_oracle(sb, N, rule):
             assert relmax(got[b], o.fft3d(z[b], inv)) < 1e-13
 
 
+@pytest.mark.parametrize("N", [8, 12, 16])
+def test_fft3d_whole_cell_kernel_matches_oracle(sb, N):
+    """batches >= 8 take the one-launch whole-cell transform (radix-2 in registers for N = 8, 16)."""
+    o = orc.Oracle(N, 7.0, 1)
+    c = sb.Collisions(N, 7.0, inhomogeneous=True)
+    rng = np.random.default_rng(N + 100)
+    for inv in (False, True):
+        z = rng.standard_normal((11, o.n3)) + 1j * rng.standard_normal((11, o.n3))
+        got = c.fft3D(z, inv).reshape(11, -1)
+        small = c.fft3D(z[:3], inv).reshape(3, -1)      # plane-parallel pair of kernels
+        for b in range(11):
+            assert relmax(got[b], o.fft3d(z[b], inv)) < 1e-13
+        assert relmax(got[:3], small) < 1e-13
+
+
 # ---------------------------------------------------------------- the convolution
 def _weights(name, N, W_bkw8, W_heat8):
     if name == "bkw":
