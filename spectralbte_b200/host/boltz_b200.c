@@ -15,6 +15,7 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <time.h>
 
 #include "sbte_b200.h"
 
@@ -91,7 +92,7 @@ static void read_input(const char *name, params *p) {
   fclose(fp);
   if (!strcmp(p->meshFile, "not set") && p->homogFlag == 1) { printf("Error: please specify the mesh\n"); exit(1); }
   if (p->num_species != 1 || p->isoFlag != 0) { printf("boltz_b200: one species, isotropic weights only\n"); exit(1); }
-  if (p->restart) { printf("boltz_b200: Restart is not implemented\n"); exit(1); }
+  if (p->restart && p->homogFlag == 0) { printf("boltz_b200: Restart applies to the inhomogeneous case only\n"); exit(1); }
   printf("done with input file\n");
 }
 
@@ -198,19 +199,24 @@ static void init_inhom(const params *p, const double *v, int nX, double *slab) {
   switch (p->initFlag) {
     case 0: { const double Ma = 1;
               rho_l = 4.0 * Ma * Ma / (Ma * Ma + 3.0); T_l = (5.0 * Ma * Ma - 1.0) * (Ma * Ma + 3.0) / (16.0 * Ma * Ma); break; }
+    case 1: T_r = 1.0; break;                                  /* sudden heating: wall at 2*TWall */
+    case 2: T_r = 2.0; ux_l = -1.0; ux_r = -1.0; break;        /* shifted Maxwellian, uses the "left" state everywhere */
     case 3: T_r = 1.5; break;
     case 6: ux_l = 1.2972; rho_r = 1.297; ux_r = 1.0; T_r = 1.195; break;
     default: printf("boltz_b200: Init_field %d not implemented for the inhomogeneous case\n", p->initFlag); exit(1);
   }
   memset(slab, 0, sizeof(double) * (size_t)(nX + 2 * order) * n3);
   for (l = order; l < nX + order; l++) {
-    const int left = (p->initFlag == 3) ? 0 : (l < nX / 2);
-    const double rho = left ? rho_l : rho_r, ux = (p->initFlag == 6) ? (left ? ux_l : ux_r) : 0.0, T = left ? T_l : T_r;
+    const int left = (p->initFlag == 3 || p->initFlag == 1) ? 0 : (p->initFlag == 2 ? 1 : (l < nX / 2));
+    const double rho = left ? rho_l : rho_r, T = left ? T_l : T_r;
+    const double ux = (p->initFlag == 6 || p->initFlag == 2) ? (left ? ux_l : ux_r) : 0.0;
     for (i = 0; i < N; i++)
       for (j = 0; j < N; j++)
         for (k = 0; k < N; k++)
           slab[l * n3 + k + N * (j + N * i)] =
-              rho * exp(-((v[i] - ux) * (v[i] - ux) + v[j] * v[j] + v[k] * v[k]) / T) / ((T * M_PI) * sqrt(T * M_PI));
+              (p->initFlag == 1)   /* src/initializer.c:381 uses exp(-v^2 / 2T) for this case */
+                  ? pow(0.5 / (M_PI * T), 1.5) * exp(-(0.5 / T) * (v[i] * v[i] + v[j] * v[j] + v[k] * v[k]))
+                  : rho * exp(-((v[i] - ux) * (v[i] - ux) + v[j] * v[j] + v[k] * v[k]) / T) / ((T * M_PI) * sqrt(T * M_PI));
   }
 }
 
@@ -229,6 +235,52 @@ static void setup_weights(sbte_ctx *ctx, const params *p) {
   else printf("Fresh version of weights being computed and stored for this configuration\n");
   CHECK(sbte_weights_generate_iso(ctx, p->lambda));
   CHECK(sbte_weights_save_file(ctx, name));
+}
+
+/* ---- restart files, src/restart.c:24-109: Restart/<input>_rank0_default.plt = the owned cells as raw
+ * doubles, Restart/<input>_time.plt = the step counter (an int). ---- */
+static double now_s(void) {
+  struct timespec ts;
+  clock_gettime(CLOCK_MONOTONIC, &ts);
+  return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
+}
+
+static void store_restart(const char *input, const double *slab_h, int nX, int order, long n3, int t) {
+  char name[300];
+  FILE *fp;
+  snprintf(name, sizeof(name), "Restart/%s_time.plt", input);
+  fp = fopen(name, "w");
+  if (!fp) { printf("Something happened when trying to save the time\n"); exit(1); }
+  printf("Time stored: %d\n", t);
+  fwrite(&t, sizeof(int), 1, fp);
+  fclose(fp);
+  snprintf(name, sizeof(name), "Restart/%s_rank%d_%s.plt", input, 0, "default");
+  printf("%s\n", name);
+  fp = fopen(name, "w");
+  if (!fp || fwrite(slab_h + (size_t)order * n3, sizeof(double), (size_t)nX * n3, fp) != (size_t)nX * n3) {
+    printf("Something happened when trying to save the pdf\n");
+    exit(1);
+  }
+  fclose(fp);
+}
+
+static void load_restart(const char *input, double *slab_h, int nX, int order, long n3, int *t) {
+  char name[300];
+  FILE *fp;
+  snprintf(name, sizeof(name), "Restart/%s_rank%d_%s.plt", input, 0, "default");
+  printf("Loading data %s\n", name);
+  fp = fopen(name, "r");
+  if (!fp) { printf("Error: unable to open restarted file %s\n", name); exit(1); }
+  if (fread(slab_h + (size_t)order * n3, sizeof(double), (size_t)nX * n3, fp) != (size_t)nX * n3) {
+    printf("Error reloading pdf file\n");
+    exit(1);
+  }
+  fclose(fp);
+  snprintf(name, sizeof(name), "Restart/%s_time.plt", input);
+  fp = fopen(name, "r");
+  if (!fp || fread(t, sizeof(int), 1, fp) != 1) { printf("Error: unable to read %s\n", name); exit(1); }
+  fclose(fp);
+  printf("t: %d\n", *t);
 }
 
 int main(int argc, char **argv) {
@@ -252,7 +304,7 @@ int main(int argc, char **argv) {
   setup_weights(ctx, &p);
   snprintf(outname, sizeof(outname), "Data/moments_%s", argv[1]);
   printf("Opening output files \n");
-  out = fopen(outname, "w");
+  out = fopen(outname, p.restart ? "a" : "w");   /* src/output.c:256-262 */
   if (!out) { printf("boltz_b200: cannot open %s\n", outname); return 1; }
   printf("Done with all setup, starting main loop\n");
 
@@ -306,34 +358,62 @@ int main(int argc, char **argv) {
     slab_h = malloc(sizeof(double) * (size_t)(nX + 2 * p.order) * n3);
     mom = malloc(sizeof(double) * (size_t)nX * 8);
     init_inhom(&p, v, nX, slab_h);
+    int t0 = 0;
+    double total_start = now_s(), write_start = now_s();
+    if (p.restart) {
+      printf("Loading from previously generated data\n");
+      load_restart(argv[1], slab_h, nX, p.order, n3, &t0);   /* the loop resumes AT the stored counter, as exec/boltz.c does */
+    }
     CHECK(sbte_slab_create(ctx, &slab, nX, p.order, x, dx, p.initFlag, p.dt, 0, 1));
     CHECK(sbte_slab_upload(slab, slab_h));
-    fprintf(out, "#Time Position ");
-    if (of.dens) fprintf(out, "Density ");
-    if (of.vel) fprintf(out, "Velocity_x ");
-    if (of.temp) fprintf(out, "Temperature ");
-    if (of.pres) fprintf(out, "Pressure ");
-    fprintf(out, "\n");
-    for (t = 0; t <= p.nT; t++) {
-      if (t > 0) {
-        printf("In step %d of %d\n", t, p.nT);
-        CHECK(sbte_slab_step(slab, p.Kn, SBTE_K2_AUTO));
-        outputCount++;
-      }
-      if (t == 0 || outputCount % p.dataFreq == 0) {
-        CHECK(sbte_slab_moments(slab, mom));
-        for (l = 0; l < nX; l++) {
-          const double *m = mom + 8 * l;
-          if (isnan(m[0])) { printf("nan detected in rank 0 cell %d \n", l + p.order); exit(0); }
-          fprintf(out, "%le %le ", p.dt * t, x[l + p.order]);
-          if (of.dens) fprintf(out, "%le ", m[0]);
-          if (of.vel) fprintf(out, "%le ", m[1]);
-          if (of.temp) fprintf(out, "%le ", m[4]);
-          if (of.pres) fprintf(out, "%le ", m[7]);
-          fprintf(out, "\n");
+    if (!p.restart) {
+      fprintf(out, "#Time Position ");
+      if (of.dens) fprintf(out, "Density ");
+      if (of.vel) fprintf(out, "Velocity_x ");
+      if (of.temp) fprintf(out, "Temperature ");
+      if (of.pres) fprintf(out, "Pressure ");
+      fprintf(out, "\n");
+    }
+    /* exec/boltz.c:255-394 */
+#define WRITE_STATE(TIME)                                                                         \
+  do {                                                                                            \
+    CHECK(sbte_slab_moments(slab, mom));                                                          \
+    for (l = 0; l < nX; l++) {                                                                    \
+      const double *m = mom + 8 * l;                                                              \
+      if (isnan(m[0])) { printf("nan detected in rank 0 cell %d \n", l + p.order); exit(0); }     \
+      fprintf(out, "%le %le ", (TIME), x[l + p.order]);                                           \
+      if (of.dens) fprintf(out, "%le ", m[0]);                                                    \
+      if (of.vel) fprintf(out, "%le ", m[1]);                                                     \
+      if (of.temp) fprintf(out, "%le ", m[4]);                                                    \
+      if (of.pres) fprintf(out, "%le ", m[7]);                                                    \
+      fprintf(out, "\n");                                                                         \
+    }                                                                                             \
+  } while (0)
+    if (!p.restart) WRITE_STATE(0.0);
+    t = t0;
+    while (t < p.nT) {
+      printf("In step %d of %d\n", t + 1, p.nT);
+      CHECK(sbte_slab_step(slab, p.Kn, SBTE_K2_AUTO));
+      outputCount++;
+      if (outputCount % p.dataFreq == 0) {
+        if (p.restart_time > 0) {
+          /* wall-clock triggered checkpoint (:361-388): stop when another output interval would not fit */
+          const double write_time = now_s() - write_start, tot_time = now_s() - total_start;
+          write_start = now_s();
+          if (tot_time + write_time > 0.95 * p.restart_time) {
+            printf("RESTART TIME REACHED - STORING CURRENT DISTRIBUTION DATA\n");
+            CHECK(sbte_slab_download(slab, slab_h));
+            store_restart(argv[1], slab_h, nX, p.order, n3, t);
+            fclose(out);
+            sbte_slab_destroy(slab);
+            sbte_destroy(ctx);
+            return 0;
+          }
         }
+        WRITE_STATE(p.dt * (t + 1));
         outputCount = 0;
       }
+      t = t + 1;
     }
     sbte_slab_destroy(slab);
     free(slab_h); free(mom); free(x); free(dx);

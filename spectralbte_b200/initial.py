@@ -37,6 +37,13 @@ def init_inhom(v, init_field, nX_global, order, lo, hi):
     if init_field == 3:
         cell = {None: maxw(1.0, 0.0, 1.5)}
         pick = lambda l: cell[None]  # noqa: E731
+    elif init_field == 1:    # sudden heating: uniform gas at T = 1 (the k_B T = m <v^2>/3 convention of
+        r2 = (vx * vx + vy * vy + vz * vz).reshape(-1)   # src/initializer.c:381), left wall at 2 T
+        cell = {None: (0.5 / np.pi) ** 1.5 * np.exp(-0.5 * r2)}
+        pick = lambda l: cell[None]  # noqa: E731
+    elif init_field == 2:    # uniform shifted Maxwellian (rho 1, u_x -1, T 1)
+        cell = {None: maxw(1.0, -1.0, 1.0)}
+        pick = lambda l: cell[None]  # noqa: E731
     elif init_field == 6:
         left, right = maxw(1.0, 1.2972, 1.0), maxw(1.297, 1.0, 1.195)
         pick = lambda l: left if l < nX_global // 2 else right  # noqa: E731

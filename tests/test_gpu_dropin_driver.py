@@ -102,3 +102,50 @@ def test_c_host_driver_heat_transport(tmp_path):
     assert check_diff_two_sided(got[big, 3], want[big, 3]) == 0
     assert np.abs(gen - gold).max() <= 1e-7 * np.abs(gold).max()
     assert np.quantile(np.abs(gen - gold), 0.999) <= 1e-13 * np.abs(gold).max()
+
+
+def _patch_input(path, **kw):
+    """Rewrite the value token that follows each keyword (src/input.c keyword/next-token format)."""
+    lines = open(path).read().split("\n")
+    for key, val in kw.items():
+        for i, ln in enumerate(lines):
+            if ln.strip() == key:
+                lines[i + 1] = str(val)
+                break
+        else:
+            stop = max(i for i, ln in enumerate(lines) if ln.strip() == "Stop")
+            lines[stop:stop] = [key, str(val)]
+    open(path, "w").write("\n".join(lines))
+
+
+def test_c_host_driver_restart_round_trip(tmp_path):
+    """Restart files (src/restart.c:24-109, exec/boltz.c:361-388): a wall-clock checkpoint after the first
+    output interval, then `Restart 1`. As in the reference the resumed loop restarts AT the stored counter,
+    so the resumed run's row labelled k*dt is the uninterrupted run's row (k+1)*dt."""
+    name, wts = "heat_transport", "N8_isotropic_L_v9_lambda1.wts"
+    for d in ("input", "Data", "Weights", "Restart"):
+        os.makedirs(tmp_path / d, exist_ok=True)
+    for fn in os.listdir(os.path.join(GOLDEN, "inputs")):
+        if fn.startswith(name):
+            shutil.copy(os.path.join(GOLDEN, "inputs", fn), tmp_path / "input" / fn)
+    (tmp_path / "Weights" / wts).write_bytes(lzma.decompress(open(os.path.join(GOLDEN, wts + ".xz"), "rb").read()))
+    inp = str(tmp_path / "input" / (name + ".test.in"))
+    run = lambda: subprocess.run([HOST, name + ".test.in", name + ".test.out"], cwd=tmp_path, capture_output=True,  # noqa: E731
+                                 text=True, timeout=900)
+    data = tmp_path / "Data" / ("moments_%s.test.in" % name)
+    _patch_input(inp, Number_of_time_steps=4, Restart_time=0, Restart=0)
+    r = run(); assert r.returncode == 0, r.stdout[-1500:]
+    full = np.loadtxt(data, comments="#").reshape(5, 250, 6)
+    _patch_input(inp, Restart_time=1e-9)
+    r = run(); assert r.returncode == 0 and "RESTART TIME REACHED" in r.stdout
+    assert os.path.getsize(tmp_path / "Restart" / (name + ".test.in_rank0_default.plt")) == 250 * 512 * 8
+    assert np.fromfile(tmp_path / "Restart" / (name + ".test.in_time.plt"), dtype=np.int32)[0] == 0
+    first = np.loadtxt(data, comments="#").reshape(-1, 250, 6)
+    assert first.shape[0] == 1 and np.array_equal(first[0], full[0])          # only the initial state was written
+    _patch_input(inp, Restart=1, Restart_time=0, Number_of_time_steps=3)
+    r = run(); assert r.returncode == 0 and "Loading from previously generated data" in r.stdout
+    resumed = np.loadtxt(data, comments="#").reshape(-1, 250, 6)               # appended to the same file
+    assert resumed.shape[0] == 4
+    for k in (1, 2, 3):
+        np.testing.assert_allclose(resumed[k][:, 2:], full[k + 1][:, 2:], rtol=1e-12, atol=1e-15)
+        assert np.allclose(resumed[k][:, 0], full[k][:, 0])                    # time labels k*dt
