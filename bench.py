@@ -203,6 +203,9 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    if args.workload == "bkw16":
+        print(json.dumps({"impl": "reference", "unavailable": "bkw16 reference arm not wired; use --workload 0d_n32 or shock1p2"}))
+        return
     if args.workload != "0d_n32":
         # 1D: the reference runs ComputeQ + conserveAllMoments cell after cell (exec/boltz.c:285-345); a step of
         # this arm is one cell advanced by one time step (order evaluations), timed value-independently on
@@ -425,17 +428,80 @@ def finalize():
         pass
 
 
+def run_bkw16(args):
+    """BASELINE config 2 (input_examples/BKW16.in): 0D BKW relaxation, N=16, L_v=5, lambda=0, dt=0.01, RK2.
+    One step = one time step of exec/boltz.c:189-241 = 2 x (ComputeQ_maxPreserve + conserveAllMoments) + updates
+    = 6 compute_Qhat evaluations of the reference; f stays on the device."""
+    import torch
+    import spectralbte_b200 as sb
+    from spectralbte_b200 import initial
+    world, rank, local = dist_setup(args.gpus)
+    N, L_v, lam, dt = 16, 5.0, 0.0, 0.01
+    n3 = N ** 3
+    c = sb.Collisions(N, L_v, device=local)
+    c.generate_weights(lam)
+    f0 = initial.init_hom(c.v, L_v, 2)
+    df = c.array(n3).put(f0)
+    stream = torch.cuda.ExternalStream(c.stream, device=torch.device("cuda", local))
+    for _ in range(args.warmup):
+        c.step_0d(df, dt, 1.0, 2)
+    c.sync()
+    barrier(world)
+    c.k2_profile(True)
+    l0 = c.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        c.step_0d(df, dt, 1.0, 2)
+    e1.record(stream)
+    c.sync()
+    barrier(world)
+    ms = max_over_ranks(e0.elapsed_time(e1), world)
+    k2_ms, k2_n = c.k2_profile_read()
+    c.k2_profile(False)
+    launches = c.launches - l0
+    # end to end: f uploaded from pinned host memory and the output row downloaded every step
+    fh = torch.from_numpy(f0).pin_memory()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        sb._lib.check(c.L.sbte_h2d(c.h, df.ptr, fh.data_ptr(), n3 * 8))
+        c.step_0d(df, dt, 1.0, 2)
+        row = c.row_0d(df)
+    e2e_s = max_over_ranks(time.perf_counter() - t0, world)
+    if rank != 0:
+        return
+    peak, peak_src = peaks()
+    nrep_sum = sum(((zx + N // 2) % N) // 2 + 1 + (((zx + N // 2) % N) + N) // 2 - ((zx + N // 2) % N) for zx in range(N))
+    wbytes = 8.0 * float(N) ** 4 * nrep_sum
+    ach = wbytes / (k2_ms / max(1, k2_n) * 1e-3) / 1e9
+    line = {"metric": "Q(f,f) evals/s at N=16 (0D BKW, 6 compute_Qhat per RK2 step)", "value": 6.0 * world * args.steps / (ms * 1e-3),
+            "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": "bkw16: input_examples/BKW16.in, 0D BKW N=16 lambda=0 RK2, weights generated on device",
+                       "N": N, "L_v": L_v, "dt": dt, "replicas": world,
+                       "l2": "the 134 MB weight tensor (69 MB symmetrised) is L2-resident between the two passes of a step"},
+            "roofline": {"bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None,
+                         "kernel": "qhat_stream_kernel<16,2,4,sym>", "kernel_ms": k2_ms / max(1, k2_n),
+                         "kernel_share_of_step": k2_ms / ms, "algorithmic_bytes_per_launch": wbytes,
+                         "note": "weights are L2-resident at N=16, so this line can exceed the HBM peak; launch latency dominates",
+                         "peak_source": peak_src},
+            "e2e": {"value": 6.0 * world * args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": n3 * 8,
+                    "d2h_bytes_per_step": n3 * 8 + 64, "checksum": float(row[0])},
+            "gpu_launches": int(launches)}
+    print(json.dumps(line))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="0d_n32", choices=["0d_n32", "shock1p2", "heattrans"])
+    ap.add_argument("--workload", default="0d_n32", choices=["0d_n32", "bkw16", "shock1p2", "heattrans", "heattrans22"])
     ap.add_argument("--k2", default="auto", choices=["auto", "stream", "deep", "generic"])
     ap.add_argument("--weights", default="generated", choices=["generated", "synthetic"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
-    ap.add_argument("--cpu-steps", type=int, default=5)
+    ap.add_argument("--cpu-steps", type=int, default=20)
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
@@ -443,6 +509,8 @@ def main():
         return
     if args.workload == "0d_n32":
         run_0d_n32(args)
+    elif args.workload == "bkw16":
+        run_bkw16(args)
     else:
         from spectralbte_b200 import bench1d
         bench1d.run(args, ROOT, cpu_leg=cpu_cell_leg, sampler_cls=ClockSampler)

@@ -288,10 +288,11 @@ static bool want_sym(sbte_ctx* c, bool same) {
 
 // ---- convolution dispatch -------------------------------------------------------------------
 // spectra of f (dif side) and g (xi side) -> qhat (natural layout)
-static int resolve_k2(sbte_ctx* c, int batch, int k2) {
+static int resolve_k2(sbte_ctx* c, int batch, int k2, bool same = true) {
   if (k2 == SBTE_K2_AUTO) {
     if (batch == 1) return qhat_stream_supported(c->N) ? SBTE_K2_STREAM : SBTE_K2_GENERIC;
-    return qhat_batch_supported(c->N) ? SBTE_K2_BATCH : SBTE_K2_GENERIC;
+    if (!same) return SBTE_K2_GENERIC;   // the batched kernels compute Q(f, f)
+    return (batch >= 8 || qhat_batch_supported(c->N)) ? SBTE_K2_BATCH : SBTE_K2_GENERIC;
   }
   return k2;
 }
@@ -299,11 +300,18 @@ static int resolve_k2(sbte_ctx* c, int batch, int k2) {
 int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d_qhat, int batch, int k2) {
   if (!c->d_W) { set_error("no weights bound"); return 1; }
   if (ensure_capacity(c, batch)) return 1;
-  k2 = resolve_k2(c, batch, k2);
   const bool same = (d_f == d_g);
+  k2 = resolve_k2(c, batch, k2, same);
+  if (k2 == SBTE_K2_BATCH && same && !qhat_batch_supported(c->N)) {
+    // any even N: lanes = cells, one warp per zeta row
+    const bool sym = want_sym(c, true);
+    if (sym && ensure_sym(c)) return 1;
+    launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
+    launch_qhat_batch_any(c, c->d_lay[0], d_qhat, batch, sym);
+    return check_launch("qhat");
+  }
   if (k2 == SBTE_K2_BATCH) {
     if (!same) { set_error("batched convolution requires f == g (single species)"); return 1; }
-    if (!qhat_batch_supported(c->N)) { set_error("batched convolution: unsupported N"); return 1; }
     const bool sym = want_sym(c, true);
     if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;

@@ -120,6 +120,7 @@ void launch_symmetrize_weights(sbte_ctx* c, const double* W, double* Ws);
 // batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32
 bool qhat_batch_supported(int N);
 int qhat_batch_cols(int N);
+void launch_qhat_batch_any(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells, bool sym);
 int qhat_batch_align(int N);
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);

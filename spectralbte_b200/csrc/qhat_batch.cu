@@ -21,6 +21,62 @@
 
 namespace sbte {
 
+// ------------------------------------------------------------------------------------------
+// any even N (12, 20, 22, 28, ...): lanes = cells on the cell-minor layout, one warp per zeta row, the
+// xi loop with incrementally wrapped indices.  L1-bound (two 512-byte operand reads per 6 FP64
+// instructions), roughly a third of the tuned kernels' rate but ~20x the row-per-CTA generic kernel on
+// batches; visits only the representative xi_x planes when handed the symmetrised tensor.
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+qhat_batch_any_kernel(const double* __restrict__ W, const double2* __restrict__ spec, double2* __restrict__ qhat,
+                      int N, int cells, int sym) {
+  const long n3 = (long)N * N * N;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int cg = blockIdx.x;
+  const int zeta = blockIdx.y * 8 + warp;
+  if (zeta >= n3) return;
+  const int n2 = N / 2;
+  const int zx = zeta / (N * N), zy = (zeta / N) % N, zz = zeta % N;
+  const double2* S = spec + (size_t)cg * n3 * 32 + lane;
+  const double* w = W + (size_t)zeta * n3;
+  const int nrep = sym ? sym_nrep(N, zx) : N;
+  double ar = 0.0, ai = 0.0;
+  for (int c = 0; c < nrep; c++) {
+    const int ex = sym ? sym_rep(N, zx, c) : c;
+    int x = zx + n2 - ex;
+    if (x < 0) x += N; else if (x > N - 1) x -= N;
+    for (int ey = 0; ey < N; ey++) {
+      int y = zy + n2 - ey;
+      if (y < 0) y += N; else if (y > N - 1) y -= N;
+      const double2* gl = S + (size_t)((ex * N + ey) * N) * 32;
+      const double2* fl = S + (size_t)((x * N + y) * N) * 32;
+      const double* wl = w + (ex * N + ey) * N;
+      int z = zz + n2;            // xi_z = 0
+      if (z > N - 1) z -= N;
+#pragma unroll 2
+      for (int ez = 0; ez < N; ez++) {
+        const double2 g = gl[ez * 32], f = fl[z * 32];
+        const double wv = wl[ez];
+        const double pr = g.x * f.x - g.y * f.y, pi = g.x * f.y + g.y * f.x;
+        ar = fma(wv, pr, ar);
+        ai = fma(wv, pi, ai);
+        z = (z == 0) ? N - 1 : z - 1;
+      }
+    }
+  }
+  const long cell = (long)cg * 32 + lane;
+  if (cell < cells) qhat[cell * n3 + zeta] = make_double2(ar, ai);
+}
+
+void launch_qhat_batch_any(sbte_ctx* c, const double2* spec, double2* qhat, int cells, bool sym) {
+  const int groups = (cells + 31) / 32;
+  dim3 grid(groups, (unsigned)((c->n3 + 7) / 8));
+  k2_mark(c);
+  qhat_batch_any_kernel<<<grid, 256, 0, c->stream>>>(sym ? c->d_Ws : c->d_W, spec, qhat, c->N, cells, sym ? 1 : 0);
+  k2_mark(c);
+  c->launches += 1;
+}
+
 bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24; }
 int qhat_batch_align(int N) { return N == 24 ? N : 1; }  // stream-K granularity in steps
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
