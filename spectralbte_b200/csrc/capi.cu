@@ -99,7 +99,14 @@ static int build_lu(const sbte_ctx* c, ConsLU* out) {
   return 0;
 }
 
+static void invalidate_graphs(sbte_ctx* c) {
+  for (auto& g : c->step_graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
+  c->step_graphs.clear();
+}
+
 static void free_scratch(sbte_ctx* c) {
+  invalidate_graphs(c);
   cudaFree(c->d_tmp); cudaFree(c->d_specA); cudaFree(c->d_specB); cudaFree(c->d_specC);
   for (int i = 0; i < 3; i++) cudaFree(c->d_lay[i]);
   cudaFree(c->d_qhat); cudaFree(c->d_Q); cudaFree(c->d_f); cudaFree(c->d_g); cudaFree(c->d_M); cudaFree(c->d_mom);
@@ -169,6 +176,7 @@ static int make_tensor_map(sbte_ctx* c) {
 }
 
 static int release_weights(sbte_ctx* c) {
+  invalidate_graphs(c);
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }
   if (c->owns_W && c->d_W) cudaFree((void*)c->d_W);
   c->d_W = nullptr; c->owns_W = false; c->host_key = nullptr; c->tmap_ok = false;
@@ -666,9 +674,52 @@ int sbte_moments(sbte_ctx* c, const double* d_f, double* d_mom8, int batch) {
   return check_launch("moments");
 }
 
-// exec/boltz.c:189-241
+static int step_0d_direct(sbte_ctx* c, double* d_f, double dt, double Kn, int order, int k2);
+
+// exec/boltz.c:189-241.  The step is launch-bound at small N (24 launches, ~0.2 ms at N=16), so after one
+// direct execution (allocations, attributes, symmetrised weights) it is captured into a CUDA graph and
+// replayed; profiling, SBTE_NO_GRAPH=1 or a change of arguments fall back to direct launches.
 int sbte_step_0d(sbte_ctx* c, double* d_f, double dt, double Kn, int order, int k2) {
   if (ensure_capacity(c, 1)) return 1;
+  static int no_graph = -1;
+  if (no_graph < 0) { const char* e = getenv("SBTE_NO_GRAPH"); no_graph = (e && atoi(e) != 0) ? 1 : 0; }
+  if (no_graph || c->k2_prof) return step_0d_direct(c, d_f, dt, Kn, order, k2);
+  const int sym = c->sym_enabled ? 1 : 0;
+  sbte_ctx::StepGraph* g = nullptr;
+  for (auto& s : c->step_graphs)
+    if (s.d_f == d_f && s.dt == dt && s.Kn == Kn && s.order == order && s.k2 == k2 && s.sym == sym) g = &s;
+  if (!g) {
+    if (c->step_graphs.size() > 8) invalidate_graphs(c);
+    c->step_graphs.push_back({nullptr, d_f, dt, Kn, order, k2, sym, 0, 0});
+    g = &c->step_graphs.back();
+  }
+  if (g->exec) {
+    CK(cudaGraphLaunch(g->exec, c->stream));
+    c->launches += g->launches;
+    return 0;
+  }
+  if (g->seen++ == 0) return step_0d_direct(c, d_f, dt, Kn, order, k2);   // warm path first
+  const unsigned long long before = c->launches;
+  CK(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = step_0d_direct(c, d_f, dt, Kn, order, k2);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  if (rc != 0 || e != cudaSuccess || !graph) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == 0) set_error(std::string("graph capture of the 0D step failed: ") + cudaGetErrorString(e));
+    return 1;
+  }
+  g->launches = c->launches - before;
+  c->launches = before;
+  e = cudaGraphInstantiate(&g->exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { g->exec = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); return 1; }
+  CK(cudaGraphLaunch(g->exec, c->stream));
+  c->launches += g->launches;
+  return 0;
+}
+
+static int step_0d_direct(sbte_ctx* c, double* d_f, double dt, double Kn, int order, int k2) {
   const long n3 = c->n3;
   double* Q = c->d_Q;
   if (compute_q_maxpreserve_dev(c, d_f, d_f, Q, k2)) return 1;

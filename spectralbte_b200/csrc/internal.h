@@ -76,6 +76,16 @@ struct sbte_ctx {
   size_t parts_stride = 0;          // double2 elements per part
   int parts_cap = 0;                // parts allocated
   int sm_count = 0;
+  // CUDA graphs of the launch-bound 0D time step (24 launches per RK2 step), keyed on its arguments
+  struct StepGraph {
+    cudaGraphExec_t exec;
+    double* d_f;
+    double dt, Kn;
+    int order, k2, sym;
+    unsigned long long launches;
+    int seen;
+  };
+  std::vector<StepGraph> step_graphs;
   unsigned long long launches = 0;  // kernels launched through this context
   bool k2_prof = false;             // bracket every K2 launch with CUDA events
   std::vector<cudaEvent_t> k2_ev;   // [2*i], [2*i+1] = start/stop of launch i
