@@ -162,6 +162,16 @@ SBTE_API int sbte_slab_advect_finish(sbte_slab *s, int which);
  * array the next upwind pass reads. side 0 = left neighbour, 1 = right neighbour */
 SBTE_API int sbte_slab_halo_regions(sbte_slab *s, int which, int stage, int side, double **d_send, double **d_recv,
                            size_t *count);
+/* Peer-memory halo (replaces the MPI_Send/Recv of src/transportroutines.c:107-172,261-344 on one NVLink node,
+ * one process per GPU): every rank exports CUDA IPC handles of its slabs (256 bytes), imports its left (side 0)
+ * and right (side 1) neighbours' (for Init_field 6 at order 1 the ring closes: rank 0's left is the last rank),
+ * then enables the mode. The upwind kernels then read the neighbours' boundary cells directly over NVLink and
+ * ranks are ordered by two device-side counters per rank; no ghost-cell messages, no host synchronisation. */
+SBTE_API int sbte_slab_ipc_export(sbte_slab *s, unsigned char *handles256);
+SBTE_API int sbte_slab_ipc_import(sbte_slab *s, int side, const unsigned char *handles256, int neighbour_cells);
+/* same-process form: `other` is a slab of another context (another stream or GPU with peer access enabled) */
+SBTE_API int sbte_slab_peer_attach(sbte_slab *s, int side, sbte_slab *other);
+SBTE_API int sbte_slab_set_peer_halo(sbte_slab *s, int enable);
 /* collision half: per-cell ComputeQ + conserve + Euler / Heun (exec/boltz.c:285-345) */
 SBTE_API int sbte_slab_collide(sbte_slab *s, double Kn, int k2);
 /* whole single-rank step (exec/boltz.c:264-353) */

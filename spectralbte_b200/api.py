@@ -242,6 +242,7 @@ class Slab:
         self.nX, self.order = int(cells_local), int(order)
         self.ncell = self.nX + 2 * self.order
         self.rank, self.nranks = int(rank), int(nranks)
+        self.cells_local, self.init_field = self.nX, int(init_field)
         x = np.ascontiguousarray(x, dtype=np.float64)
         dx = np.ascontiguousarray(dx, dtype=np.float64)
         assert x.size == self.ncell and dx.size == self.ncell
@@ -290,6 +291,22 @@ class Slab:
         s, r, n = C.c_void_p(), C.c_void_p(), C.c_size_t()
         check(self.L.sbte_slab_halo_regions(self.h, int(which), int(stage), int(side), C.byref(s), C.byref(r), C.byref(n)))
         return s.value, r.value, n.value
+
+    def ipc_export(self):
+        """256 bytes of CUDA IPC handles (f, f_conv, f_tmp, flags) for the neighbouring ranks."""
+        buf = C.create_string_buffer(256)
+        check(self.L.sbte_slab_ipc_export(self.h, buf))
+        return buf.raw
+
+    def ipc_import(self, side, handles, neighbour_cells):
+        check(self.L.sbte_slab_ipc_import(self.h, int(side), handles, int(neighbour_cells)))
+
+    def peer_attach(self, side, other):
+        """Same-process neighbour (another context / GPU): no IPC mapping needed."""
+        check(self.L.sbte_slab_peer_attach(self.h, int(side), other.h))
+
+    def set_peer_halo(self, enable=True):
+        check(self.L.sbte_slab_set_peer_halo(self.h, int(bool(enable))))
 
     def collide(self, Kn, k2=K2_AUTO):
         check(self.L.sbte_slab_collide(self.h, float(Kn), int(k2)))

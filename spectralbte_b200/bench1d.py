@@ -136,6 +136,9 @@ def run(args, root, cpu_leg=None, sampler_cls=None):
         "higher_is_better": True, "scaling": cfg["scaling"], "vs_baseline": None, "dtype": "f64",
         "data": "synthetic (the reference's own initial data, src/initializer.c:330-351,391-420)",
         "config": {"workload": desc, "N": N, "L_v": L_v, "Kn": Kn, "dt": dt, "cells_total": nX, "weights": wdesc,
+                   "halo": ("none (one rank)" if world == 1 else
+                            "peer memory: stencils read neighbour cells over NVLink" if halo.mode == "p2p" else
+                            "NCCL batch_isend_irecv"),
                    "l2": "per-step working set (slabs + spectra + weights) larger than L2; no flush"},
         "roofline": {"bound": "fp64", "achieved": ach, "peak": 36.5, "unit": "TFLOP/s", "frac": ach / 36.5,
                      "traffic": None, "kernel": ("qhat_batch%d_kernel<%d>" % (3 if N == 24 else 2, N)) if N in (8, 16, 24) else "qhat_batch_any_kernel",

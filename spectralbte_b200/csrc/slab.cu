@@ -6,6 +6,7 @@
 // blocking MPI halo replaced by "ghost cells are filled by the caller" (NCCL / peer copies between
 // the regions reported by sbte_slab_halo_regions) so f never leaves the device.
 #include <stdio.h>
+#include <string.h>
 #include <string>
 #include <vector>
 
@@ -26,6 +27,16 @@ struct sbte_slab {
   double *d_fl = nullptr, *d_fr = nullptr;                                   // wall faces
   double* d_Q = nullptr;                                                     // nX cells
   double* d_mom = nullptr;
+  // peer-memory halo (one process per GPU, CUDA IPC): the neighbours' slabs mapped into this process
+  struct Peer {
+    bool on = false, mapped = false;                // mapped: opened through CUDA IPC (closed on destroy)
+    double* arr[3] = {nullptr, nullptr, nullptr};   // their f, f_conv, f_tmp
+    int* flags = nullptr;                           // their {ready, done} counters
+    int cells = 0;
+  } nb[2];
+  int* d_flags = nullptr;   // my {ready, done}
+  int p2p = 0;              // 1: stencils read the neighbours' boundary cells over NVLink
+  int epoch = 0;            // upwind passes issued so far (same sequence on every rank)
 };
 
 using namespace sbte;
@@ -73,6 +84,34 @@ static void fill_ghosts_one(sbte_slab* s, double* f) {
   }
 }
 
+// which of the three exchangeable arrays is `p` (index into Peer::arr), -1 if none
+static int array_id(const sbte_slab* s, const double* p) {
+  if (p == s->d_f) return 0;
+  if (p == s->d_fc) return 1;
+  if (p == s->d_ft) return 2;
+  return -1;
+}
+
+// peer-halo prologue of an upwind pass reading `src`: publish "src complete", wait for the neighbours' src and
+// for their reads of the previous pass, and return the mapped boundary cells (null where there is no peer)
+static void peer_begin(sbte_slab* s, const double* src, const double** peerL, const double** peerR) {
+  *peerL = *peerR = nullptr;
+  if (!s->p2p) return;
+  sbte_ctx* c = s->c;
+  const long n3 = c->n3;
+  const int e = ++s->epoch, id = array_id(s, src);
+  launch_halo_post(c->stream, s->d_flags + 0, e);
+  launch_halo_wait(c->stream, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr, e, e - 1);
+  c->launches += 2;
+  if (s->nb[0].on) *peerL = s->nb[0].arr[id] + (long)s->nb[0].cells * n3;   // their last `order` owned cells
+  if (s->nb[1].on) *peerR = s->nb[1].arr[id] + (long)s->order * n3;         // their first `order` owned cells
+}
+static void peer_end(sbte_slab* s) {
+  if (!s->p2p) return;
+  launch_halo_post(s->c->stream, s->d_flags + 1, s->epoch);
+  s->c->launches += 1;
+}
+
 // one upwindTwo pass src -> dst (src/transportroutines.c:241-470); ghosts from neighbours must be in place
 static void upwind_two_pass(sbte_slab* s, double* src, double* dst) {
   sbte_ctx* c = s->c;
@@ -95,8 +134,12 @@ static void upwind_two_pass(sbte_slab* s, double* src, double* dst) {
     launch_wall_face(st, src, s->d_fr, s->d_x, s->d_dx, N, nX + 1, 1, wall ? 0 : 1); c->launches++;
     if (wall) { launch_diffuse_bc(st, s->d_fr, s->d_fr, c->d_v, c->d_wt, N, c->dv, T1_WALL, 1); c->launches++; }
   }
-  launch_upwind_two(st, src, dst, s->d_fl, s->d_fr, c->d_v, s->d_x, s->d_dx, N, nX, s->dt, first ? 1 : 0, last ? 1 : 0);
+  const double *peerL, *peerR;
+  peer_begin(s, src, &peerL, &peerR);
+  launch_upwind_two(st, src, dst, s->d_fl, s->d_fr, c->d_v, s->d_x, s->d_dx, N, nX, s->dt, first ? 1 : 0, last ? 1 : 0,
+                    peerL, peerR);
   c->launches++;
+  peer_end(s);
 }
 
 static void pick(sbte_slab* s, int which, double*& A, double*& B) {
@@ -149,9 +192,78 @@ int sbte_slab_create(sbte_ctx* c, sbte_slab** out, int cells_local, int order, c
 int sbte_slab_destroy(sbte_slab* s) {
   if (!s) return 0;
   cudaStreamSynchronize(s->c->stream);
+  for (int side = 0; side < 2; side++)
+    if (s->nb[side].on && s->nb[side].mapped) {
+      for (int a = 0; a < 3; a++)
+        if (s->nb[side].arr[a]) cudaIpcCloseMemHandle(s->nb[side].arr[a]);
+      if (s->nb[side].flags) cudaIpcCloseMemHandle(s->nb[side].flags);
+    }
+  cudaFree(s->d_flags);
   cudaFree(s->d_x); cudaFree(s->d_dx); cudaFree(s->d_f); cudaFree(s->d_fc); cudaFree(s->d_f1); cudaFree(s->d_ft);
   cudaFree(s->d_fl); cudaFree(s->d_fr); cudaFree(s->d_Q); cudaFree(s->d_mom);
   delete s;
+  return 0;
+}
+
+// ---- peer-memory halo set-up (one process per GPU): export my slabs, import the neighbours'
+int sbte_slab_ipc_export(sbte_slab* s, unsigned char* handles256) {
+  if (!s->d_flags) {
+    CKS(cudaMalloc(&s->d_flags, 256));
+    CKS(cudaMemset(s->d_flags, 0, 256));
+  }
+  memset(handles256, 0, 256);
+  cudaIpcMemHandle_t h;
+  double* arrs[3] = {s->d_f, s->d_fc, s->d_ft};
+  for (int a = 0; a < 3; a++) {
+    if (!arrs[a]) continue;
+    CKS(cudaIpcGetMemHandle(&h, arrs[a]));
+    memcpy(handles256 + 64 * a, &h, sizeof(h));
+  }
+  CKS(cudaIpcGetMemHandle(&h, s->d_flags));
+  memcpy(handles256 + 192, &h, sizeof(h));
+  return 0;
+}
+
+int sbte_slab_ipc_import(sbte_slab* s, int side, const unsigned char* handles256, int neighbour_cells) {
+  if (side < 0 || side > 1) { set_error("side must be 0 (left) or 1 (right)"); return 1; }
+  sbte_slab::Peer& p = s->nb[side];
+  cudaIpcMemHandle_t h;
+  double* mine[3] = {s->d_f, s->d_fc, s->d_ft};
+  for (int a = 0; a < 3; a++) {
+    if (!mine[a]) continue;
+    memcpy(&h, handles256 + 64 * a, sizeof(h));
+    CKS(cudaIpcOpenMemHandle((void**)&p.arr[a], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  memcpy(&h, handles256 + 192, sizeof(h));
+  CKS(cudaIpcOpenMemHandle((void**)&p.flags, h, cudaIpcMemLazyEnablePeerAccess));
+  p.cells = neighbour_cells;
+  p.on = true;
+  p.mapped = true;
+  return 0;
+}
+
+// same-process form (one process driving several slabs / GPUs with peer access already enabled): no IPC mapping
+int sbte_slab_peer_attach(sbte_slab* s, int side, sbte_slab* other) {
+  if (side < 0 || side > 1) { set_error("side must be 0 (left) or 1 (right)"); return 1; }
+  if (other->order != s->order || other->c->N != s->c->N) { set_error("neighbour slab has a different shape"); return 1; }
+  for (sbte_slab* t : {s, other})
+    if (!t->d_flags) {
+      CKS(cudaSetDevice(t->c->device));
+      CKS(cudaMalloc(&t->d_flags, 256));
+      CKS(cudaMemset(t->d_flags, 0, 256));
+    }
+  sbte_slab::Peer& p = s->nb[side];
+  p.arr[0] = other->d_f; p.arr[1] = other->d_fc; p.arr[2] = other->d_ft;
+  p.flags = other->d_flags;
+  p.cells = other->nX;
+  p.on = true;
+  p.mapped = false;
+  return 0;
+}
+
+int sbte_slab_set_peer_halo(sbte_slab* s, int enable) {
+  if (enable && !s->d_flags) { set_error("export/import the IPC handles before enabling peer halos"); return 1; }
+  s->p2p = enable ? 1 : 0;
   return 0;
 }
 
@@ -189,8 +301,11 @@ int sbte_slab_upwind_stage(sbte_slab* s, int which, int stage) {
   sbte_ctx* c = s->c;
   if (s->order == 1) {
     fill_ghosts_one(s, A);
-    launch_upwind_one(c->stream, A, B, c->d_v, s->d_dx, c->N, s->nX, s->dt);
+    const double *peerL, *peerR;
+    peer_begin(s, A, &peerL, &peerR);
+    launch_upwind_one(c->stream, A, B, c->d_v, s->d_dx, c->N, s->nX, s->dt, peerL, peerR);
     c->launches++;
+    peer_end(s);
   } else {
     if (stage == 0) upwind_two_pass(s, A, s->d_ft);
     else upwind_two_pass(s, s->d_ft, B);
@@ -209,7 +324,7 @@ int sbte_slab_advect_finish(sbte_slab* s, int which) {
 }
 
 int sbte_slab_advect(sbte_slab* s, int which) {
-  if (s->nranks != 1) { set_error("sbte_slab_advect is the single-rank form; use the staged calls with halos"); return 1; }
+  if (s->nranks != 1 && !s->p2p) { set_error("sbte_slab_advect needs ghost cells: exchange halos with the staged calls or enable peer halos"); return 1; }
   if (sbte_slab_upwind_stage(s, which, 0)) return 1;
   if (s->order == 2) {
     if (sbte_slab_upwind_stage(s, which, 1)) return 1;
@@ -226,6 +341,10 @@ int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
   const long n = (long)nX * n3;
   double* fc = cell(s->d_fc, n3, o);
   double* f = cell(s->d_f, n3, o);
+  if (s->p2p) {   // the update below overwrites cells the neighbours may still be reading in their last pass
+    launch_halo_wait(c->stream, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr, 0, s->epoch);
+    c->launches++;
+  }
   if (compute_q_dev(c, fc, fc, s->d_Q, nX, k2)) return 1;
   launch_conserve(c, s->d_Q, nX);
   if (o == 1) {

@@ -52,27 +52,65 @@ void launch_diffuse_bc(cudaStream_t st, const double* in, double* out, const dou
 }
 
 // ---------------------------------------------------------------- first order (K6a)
+// Ghost cells may live on the neighbouring GPU: peerL / peerR (null = use the local ghost cells) point at the
+// neighbour rank's boundary cells mapped over NVLink (CUDA IPC), so the stencil itself performs the halo
+// loads; peerL[g*n3 + p] is my ghost cell g, peerR[g*n3 + p] my ghost cell nX + order + g.
+template <int ORDER>
+__device__ __forceinline__ const double* cell_src(const double* __restrict__ f, const double* __restrict__ peerL,
+                                                  const double* __restrict__ peerR, long n3, int nX, int l) {
+  if (l < ORDER && peerL) return peerL + (long)l * n3;
+  if (l >= nX + ORDER && peerR) return peerR + (long)(l - nX - ORDER) * n3;
+  return f + (long)l * n3;
+}
+
 __global__ void __launch_bounds__(256)
 upwind_one_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ v,
-                  const double* __restrict__ dx, int N, int nX, double dt) {
+                  const double* __restrict__ dx, int N, int nX, double dt, const double* __restrict__ peerL,
+                  const double* __restrict__ peerR) {
   const long n3 = (long)N * N * N;
   const int l = blockIdx.y + 1;
   const double* fl = f + (long)l * n3;
+  const double* fm = cell_src<1>(f, peerL, peerR, n3, nX, l - 1);
+  const double* fp = cell_src<1>(f, peerL, peerR, n3, nX, l + 1);
   for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
     const int i = (int)(p / (N * N));
     const double cfl = dt * v[i] / dx[l];
     double r;
-    if (i < N / 2) r = (1.0 + cfl) * fl[p] - cfl * fl[p + n3];
-    else r = (1.0 - cfl) * fl[p] + cfl * fl[p - n3];
+    if (i < N / 2) r = (1.0 + cfl) * fl[p] - cfl * fp[p];
+    else r = (1.0 - cfl) * fl[p] + cfl * fm[p];
     fc[(long)l * n3 + p] = r;
   }
 }
 
 void launch_upwind_one(cudaStream_t st, const double* f, double* fc, const double* v, const double* dx, int N, int nX,
-                       double dt) {
+                       double dt, const double* peerL, const double* peerR) {
   const long n3 = (long)N * N * N;
   dim3 grid((unsigned)((n3 + 255) / 256), nX);
-  upwind_one_kernel<<<grid, 256, 0, st>>>(f, fc, v, dx, N, nX, dt);
+  upwind_one_kernel<<<grid, 256, 0, st>>>(f, fc, v, dx, N, nX, dt, peerL, peerR);
+}
+
+// ---------------------------------------------------------------- cross-GPU ordering for peer halos
+// Each rank owns two counters in IPC-shared device memory: ready (source array of pass e is complete) and
+// done (my reads of the neighbours' arrays in pass e are complete).  Plain stream order on each GPU plus
+// these two tiny kernels replaces the host-synchronised message exchange.
+__global__ void halo_post_kernel(int* flag, int value) {
+  __threadfence_system();
+  *reinterpret_cast<volatile int*>(flag) = value;
+  __threadfence_system();
+}
+// waits until, for each non-null neighbour flag pair, ready >= vr and done >= vd
+__global__ void halo_wait_kernel(const int* nbL, const int* nbR, int vr, int vd) {
+  const long long t0 = clock64();
+  const volatile int* L = reinterpret_cast<const volatile int*>(nbL);
+  const volatile int* R = reinterpret_cast<const volatile int*>(nbR);
+  while ((L && (L[0] < vr || L[1] < vd)) || (R && (R[0] < vr || R[1] < vd))) {
+    if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s at 2 GHz: a lost neighbour becomes an error, not a hang
+  }
+  __threadfence_system();
+}
+void launch_halo_post(cudaStream_t st, int* flag, int value) { halo_post_kernel<<<1, 1, 0, st>>>(flag, value); }
+void launch_halo_wait(cudaStream_t st, const int* nbL, const int* nbR, int vr, int vd) {
+  halo_wait_kernel<<<1, 1, 0, st>>>(nbL, nbR, vr, vd);
 }
 
 // ---------------------------------------------------------------- second order (K6b)
@@ -117,15 +155,20 @@ void launch_wall_face(cudaStream_t st, const double* f, double* face, const doub
 __global__ void __launch_bounds__(256)
 upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ fl,
                   const double* __restrict__ fr, const double* __restrict__ v, const double* __restrict__ x,
-                  const double* __restrict__ dx, int N, int nX, double dt, int left_wall, int right_wall) {
+                  const double* __restrict__ dx, int N, int nX, double dt, int left_wall, int right_wall,
+                  const double* __restrict__ peerL, const double* __restrict__ peerR) {
   const long n3 = (long)N * N * N;
   const int l = blockIdx.y + 2;
   const int h = N / 2;
   const double* c0 = f + (long)l * n3;
+  const double* cm1 = cell_src<2>(f, peerL, peerR, n3, nX, l - 1);
+  const double* cm2 = cell_src<2>(f, peerL, peerR, n3, nX, l - 2);
+  const double* cp1 = cell_src<2>(f, peerL, peerR, n3, nX, l + 1);
+  const double* cp2 = cell_src<2>(f, peerL, peerR, n3, nX, l + 2);
   for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
     const int i = (int)(p / (N * N));
     const double cfl = 0.5 * dt * v[i] / dx[l];
-    const double f0 = c0[p], fm = c0[p - n3], fp = c0[p + n3];
+    const double f0 = c0[p], fm = cm1[p], fp = cp1[p];
     const double s1 = minmod3((f0 - fm) / (x[l] - x[l - 1]), (fp - f0) / (x[l + 1] - x[l]),
                               (fp - fm) / (x[l + 1] - x[l - 1]));
     double r;
@@ -133,7 +176,7 @@ upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const d
       if (l == 2 && left_wall) {
         r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - fl[p]);
       } else {
-        const double fmm = c0[p - 2 * n3];
+        const double fmm = cm2[p];
         const double s0 = minmod3((fm - fmm) / (x[l - 1] - x[l - 2]), (f0 - fm) / (x[l] - x[l - 1]),
                                   (f0 - fmm) / (x[l] - x[l - 2]));
         r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - (fm + 0.5 * dx[l - 1] * s0));
@@ -142,7 +185,7 @@ upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const d
       if (l == nX + 1 && right_wall) {
         r = f0 - cfl * (fr[p] - (f0 - 0.5 * dx[l] * s1));
       } else {
-        const double fpp = c0[p + 2 * n3];
+        const double fpp = cp2[p];
         const double s2 = minmod3((fp - f0) / (x[l + 1] - x[l]), (fpp - fp) / (x[l + 2] - x[l + 1]),
                                   (fpp - f0) / (x[l + 2] - x[l]));
         r = f0 - cfl * (fp - 0.5 * dx[l + 1] * s2 - (f0 - 0.5 * dx[l] * s1));
@@ -153,10 +196,10 @@ upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const d
 }
 void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const double* fl, const double* fr,
                        const double* v, const double* x, const double* dx, int N, int nX, double dt, int left_wall,
-                       int right_wall) {
+                       int right_wall, const double* peerL, const double* peerR) {
   const long n3 = (long)N * N * N;
   dim3 grid((unsigned)((n3 + 255) / 256), nX);
-  upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall);
+  upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall, peerL, peerR);
 }
 
 // fc = 0.5 * (f + fc) on n contiguous doubles (src/transportroutines.c:487-491)

@@ -5,12 +5,14 @@ namespace sbte {
 void launch_diffuse_bc(cudaStream_t st, const double* in, double* out, const double* v, const double* wt, int N,
                        double hv, double TW, int bdry);
 void launch_upwind_one(cudaStream_t st, const double* f, double* fc, const double* v, const double* dx, int N, int nX,
-                       double dt);
+                       double dt, const double* peerL, const double* peerR);
+void launch_halo_post(cudaStream_t st, int* flag, int value);
+void launch_halo_wait(cudaStream_t st, const int* nbL, const int* nbR, int vr, int vd);
 void launch_extrapolate(cudaStream_t st, double* f, long n3, int dst, int a, int b);
 void launch_wall_face(cudaStream_t st, const double* f, double* face, const double* x, const double* dx, int N, int l,
                       int right, int fill_noflux);
 void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const double* fl, const double* fr,
                        const double* v, const double* x, const double* dx, int N, int nX, double dt, int left_wall,
-                       int right_wall);
+                       int right_wall, const double* peerL, const double* peerR);
 void launch_average(cudaStream_t st, const double* f, double* fc, long n);
 }  // namespace sbte

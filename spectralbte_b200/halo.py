@@ -5,7 +5,14 @@ Replaces the blocking, even/odd-ordered MPI_Send/MPI_Recv sequence of the refere
 non-blocking exchange per upwind pass over torch.distributed (NCCL on GPUs, gloo in the CPU tests):
 each rank sends its first/last `order` owned cells and receives its left/right ghost cells.
 Init_field 6 at order 1 is periodic: rank 0 and rank n-1 also exchange (:156-166).
+
+On one NVLink node there is a second mode with no messages at all (SlabHalo(..., mode="p2p") or SBTE_HALO=p2p):
+the ranks swap CUDA IPC handles once, and from then on the upwind kernels read the neighbours' boundary cells
+directly from peer memory, ordered by device-side counters (csrc/slab.cu peer_begin/peer_end).
 """
+import os
+
+
 import torch
 import torch.distributed as dist
 
@@ -44,6 +51,20 @@ def neighbour_ops(rank, nranks, regions, periodic):
     return ops
 
 
+def peer_neighbours(rank, nranks, periodic):
+    """[(side, neighbour_rank)] of the peer-memory halo; side 0 = left, 1 = right."""
+    out = []
+    if rank > 0:
+        out.append((0, rank - 1))
+    elif periodic and nranks > 1:
+        out.append((0, nranks - 1))
+    if rank < nranks - 1:
+        out.append((1, rank + 1))
+    elif periodic and nranks > 1:
+        out.append((1, 0))
+    return out
+
+
 def exchange(rank, nranks, regions, periodic):
     ops = neighbour_ops(rank, nranks, regions, periodic)
     if not ops:
@@ -56,11 +77,30 @@ class SlabHalo:
     """Halo exchange for a spectralbte_b200.Slab on a GPU: wraps the regions the library reports
     (sbte_slab_halo_regions) as torch tensors on the library's stream."""
 
-    def __init__(self, slab, device):
+    def __init__(self, slab, device, mode=None):
         self.slab, self.device = slab, device
         self.stream = torch.cuda.ExternalStream(slab.coll.stream, device=device)
         self.periodic = False
         self._cache = {}
+        self.mode = mode or os.environ.get("SBTE_HALO", "nccl")
+        if self.mode not in ("nccl", "p2p"):
+            raise ValueError("halo mode must be 'nccl' or 'p2p'")
+        if slab.nranks == 1:
+            self.mode = "nccl"   # nothing to exchange
+        if self.mode == "p2p":
+            self._connect_peers()
+
+    def _connect_peers(self):
+        """Swap IPC handles and map the neighbours' slabs (the ring closes for the periodic order-1 case)."""
+        slab = self.slab
+        mine = (slab.ipc_export(), slab.cells_local)
+        everyone = [None] * slab.nranks
+        dist.all_gather_object(everyone, mine)
+        for side, nb in peer_neighbours(slab.rank, slab.nranks, slab.init_field == 6 and slab.order == 1):
+            handles, cells = everyone[nb]
+            slab.ipc_import(side, handles, cells)
+        slab.set_peer_halo(True)
+        dist.barrier()   # nobody starts polling flags before every mapping exists
 
     def _regions(self, which, stage):
         key = (which, stage)
@@ -81,7 +121,7 @@ class SlabHalo:
 def advect(slab, halo, which, periodic):
     """advectOne / advectTwo across ranks: halo, upwind pass (x2 for order 2), average."""
     for stage in range(slab.order):
-        if slab.nranks > 1:
+        if slab.nranks > 1 and halo.mode == "nccl":
             halo.exchange(which, stage, periodic)
         slab.upwind_stage(which, stage)
     slab.advect_finish(which)

@@ -319,6 +319,58 @@ def test_1d_step_matches_oracle(sb, W_heat8, order, ic):
 
 
 @pytest.mark.parametrize("order,ic", [(1, 3), (2, 3), (1, 6), (2, 6)])
+def test_peer_memory_halo_equals_single_rank(sb, W_heat8, order, ic):
+    """The message-free halo (upwind kernels read the neighbour's boundary cells from peer memory, ordered by
+    device-side counters) on two slabs driven from two streams reproduces the single-slab run bit for bit."""
+    N, nX, dt, Kn = 8, 16, 2e-3, 1.52
+    o = orc.Oracle(N, 9.0, 1)
+    _, x, dx = orc.make_mesh([nX], [0.8], order)
+    f0 = o.init_inhom(ic, nX, order)
+    rng = np.random.default_rng(5)
+    f0[order:nX + order] *= 1.0 + 0.1 * rng.standard_normal((nX, o.n3))
+    ctxs = [sb.Collisions(N, 9.0, inhomogeneous=True) for _ in range(3)]
+    for c in ctxs:
+        c.set_weights(W_heat8)
+    one = sb.Slab(ctxs[2], nX, order, x, dx, ic, dt)
+    one.upload(f0)
+    h = nX // 2
+    parts = []
+    for r in range(2):
+        lo = r * h
+        p = sb.Slab(ctxs[r], h, order, x[lo:lo + h + 2 * order].copy(), dx[lo:lo + h + 2 * order].copy(), ic, dt,
+                    rank=r, nranks=2)
+        p.upload(f0[lo:lo + h + 2 * order].copy())
+        parts.append(p)
+    parts[0].peer_attach(1, parts[1])
+    parts[1].peer_attach(0, parts[0])
+    if ic == 6 and order == 1:   # the ring closes
+        parts[0].peer_attach(0, parts[1])
+        parts[1].peer_attach(1, parts[0])
+    for p in parts:
+        p.set_peer_halo(True)
+    for c in ctxs:
+        c.sync()
+
+    def advect(which):   # enqueue pass by pass on both streams so neither waits for work not yet submitted
+        for stage in range(order):
+            for p in parts:
+                p.upwind_stage(which, stage)
+        for p in parts:
+            p.advect_finish(which)
+
+    for _ in range(4):
+        one.step(Kn)
+        advect(0)
+        for p in parts:
+            p.collide(Kn)
+        if order == 2:
+            advect(1)
+    want = one.download()[order:nX + order]
+    got = np.concatenate([p.download()[order:h + order] for p in parts])
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("order,ic", [(1, 3), (2, 3), (1, 6), (2, 6)])
 def test_two_rank_split_equals_single_rank(sb, W_heat8, order, ic):
     """Rank-count invariance: two slabs exchanging halos through the regions
     reported by the library reproduce the single-slab run bit for bit."""
