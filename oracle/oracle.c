@@ -480,12 +480,17 @@ void orc_upwind_one(const orc_ctx *c, int nX, const double *x, const double *dx,
   int i, l;
   long jk;
   (void)x;
-  if (ic == 5) { fprintf(stderr, "orc_upwind_one: Poiseuille forcing (IC 5) not restated\n"); exit(1); }
+  /* Init_field 5 (Poiseuille): the forcing block of :217-225 sits AFTER the k loop has closed, so with k == N
+   * every write lands on element (i, j+1, 0) -- which the next j (or i) iteration overwrites with its plain
+   * upwind value -- and the very last one falls one double past the cell (into the next cell's allocation in
+   * this process image, never read back).  The observable result at order 1 is therefore the unforced scheme
+   * with the diffuse walls of :117,134; that is what is restated (checked against oracle/_ref in
+   * tests/golden/make_golden.py, vectors tr_ic5_o1_*). */
   /* ghost cells, :107-172 */
-  if (ic == 3) orc_diffuse_bc(c, f + 1 * n3, f + 0 * n3, T0_WALL, 0);
+  if (ic == 3 || ic == 5) orc_diffuse_bc(c, f + 1 * n3, f + 0 * n3, T0_WALL, 0);
   else if (ic == 1) orc_diffuse_bc(c, f + 1 * n3, f + 0 * n3, 2.0 * TWALL_IN, 0);
   else if (ic != 6) memcpy(f, f + n3, sizeof(double) * n3);
-  if (ic == 3) orc_diffuse_bc(c, f + (long)nX * n3, f + (long)(nX + 1) * n3, T1_WALL, 1);
+  if (ic == 3 || ic == 5) orc_diffuse_bc(c, f + (long)nX * n3, f + (long)(nX + 1) * n3, T1_WALL, 1);
   else if (ic != 6) memcpy(f + (long)(nX + 1) * n3, f + (long)nX * n3, sizeof(double) * n3);
   if (ic == 6) {
     memcpy(f, f + (long)nX * n3, sizeof(double) * n3);
@@ -517,7 +522,8 @@ void orc_upwind_two(const orc_ctx *c, int nX, const double *x, const double *dx,
   double *fl = malloc(sizeof(double) * n3), *fr = malloc(sizeof(double) * n3);
   long p;
   int i, l;
-  if (ic == 5) { fprintf(stderr, "orc_upwind_two: Poiseuille forcing (IC 5) not restated\n"); exit(1); }
+  /* Poiseuille forcing, :428-436,457-465: Ma = 1 (:255), h_v = 2 L_v / (N-1) (:37) */
+  const double h_v = 2 * c->L_v / (N - 1), Ma = 1.0;
 #define CELL(m) (f + (long)(m) * n3)
   for (p = 0; p < n3; p++) CELL(1)[p] = 2 * CELL(2)[p] - CELL(3)[p];
   for (p = 0; p < n3; p++) CELL(nX + 2)[p] = 2 * CELL(nX + 1)[p] - CELL(nX)[p];
@@ -527,7 +533,7 @@ void orc_upwind_two(const orc_ctx *c, int nX, const double *x, const double *dx,
                           (CELL(3)[p] - CELL(1)[p]) / (x[3] - x[1]));
     fl[p] = CELL(2)[p] - 0.5 * dx[2] * s1;
   }
-  if (ic == 3) orc_diffuse_bc(c, fl, fl, T0_WALL, 0);
+  if (ic == 3 || ic == 5) orc_diffuse_bc(c, fl, fl, T0_WALL, 0);
   else if (ic == 1) orc_diffuse_bc(c, fl, fl, 2.0 * TWALL_IN, 0);
   else
     for (p = h * nn; p < n3; p++) {
@@ -542,7 +548,7 @@ void orc_upwind_two(const orc_ctx *c, int nX, const double *x, const double *dx,
                           (CELL(nX + 2)[p] - CELL(nX)[p]) / (x[nX + 2] - x[nX]));
     fr[p] = CELL(nX + 1)[p] + 0.5 * dx[nX + 1] * s1;
   }
-  if (ic == 3) orc_diffuse_bc(c, fr, fr, T1_WALL, 1);
+  if (ic == 3 || ic == 5) orc_diffuse_bc(c, fr, fr, T1_WALL, 1);
   else
     for (p = 0; p < h * nn; p++) {
       const double s1 = mm3((CELL(nX + 1)[p] - CELL(nX)[p]) / (x[nX + 1] - x[nX]),
@@ -575,6 +581,12 @@ void orc_upwind_two(const orc_ctx *c, int nX, const double *x, const double *dx,
                                   (CELL(l + 2)[p] - CELL(l)[p]) / (x[l + 2] - x[l]));
             r = CELL(l)[p] - cfl * (CELL(l + 1)[p] - 0.5 * dx[l + 1] * s2 - (CELL(l)[p] - 0.5 * dx[l] * s1));
           }
+        }
+        if (ic == 5) { /* central difference in v_y of the pass input, one-sided (sign as written) at the ends */
+          const int j = (int)((p / N) % N);
+          if (j == 0) r = r - Ma * 0.5 * dt / (2 * h_v) * CELL(l)[p + N];
+          else if (j == N - 1) r = r - Ma * 0.5 * dt / (2 * h_v) * CELL(l)[p - N];
+          else r = r - Ma * 0.5 * dt / (2 * h_v) * (CELL(l)[p + N] - CELL(l)[p - N]);
         }
         fc[(long)l * n3 + p] = r;
       }

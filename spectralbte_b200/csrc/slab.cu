@@ -136,8 +136,10 @@ static void upwind_two_pass(sbte_slab* s, double* src, double* dst) {
   }
   const double *peerL, *peerR;
   peer_begin(s, src, &peerL, &peerR);
+  // Poiseuille forcing coefficient Ma*0.5*dt/(2*h_v), Ma = 1, h_v = 2 L_v/(N-1) (src/transportroutines.c:37,255,431)
+  const double force = (ic == 5) ? 1.0 * 0.5 * s->dt / (2 * (2 * c->L_v / (N - 1))) : 0.0;
   launch_upwind_two(st, src, dst, s->d_fl, s->d_fr, c->d_v, s->d_x, s->d_dx, N, nX, s->dt, first ? 1 : 0, last ? 1 : 0,
-                    peerL, peerR);
+                    peerL, peerR, force);
   c->launches++;
   peer_end(s);
 }
@@ -152,7 +154,8 @@ int sbte_slab_create(sbte_ctx* c, sbte_slab** out, int cells_local, int order, c
                      int init_field, double dt, int rank, int nranks) {
   *out = nullptr;
   if (order != 1 && order != 2) { set_error("Space_order must be 1 or 2"); return 1; }
-  if (init_field == 5) { set_error("Init_field 5 (Poiseuille forcing) is not implemented"); return 1; }
+  // Init_field 5 (Poiseuille): forcing at order 2; at order 1 the reference's forcing block (:217-225) has no
+  // observable effect (it runs after the k loop closed and every write is overwritten), reproduced as such
   if (cells_local < 2 * order) { set_error("too few cells per rank"); return 1; }
   CKS(cudaSetDevice(c->device));
   sbte_slab* s = new sbte_slab();

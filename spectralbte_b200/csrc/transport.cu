@@ -156,7 +156,7 @@ __global__ void __launch_bounds__(256)
 upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ fl,
                   const double* __restrict__ fr, const double* __restrict__ v, const double* __restrict__ x,
                   const double* __restrict__ dx, int N, int nX, double dt, int left_wall, int right_wall,
-                  const double* __restrict__ peerL, const double* __restrict__ peerR) {
+                  const double* __restrict__ peerL, const double* __restrict__ peerR, double force) {
   const long n3 = (long)N * N * N;
   const int l = blockIdx.y + 2;
   const int h = N / 2;
@@ -191,15 +191,22 @@ upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const d
         r = f0 - cfl * (fp - 0.5 * dx[l + 1] * s2 - (f0 - 0.5 * dx[l] * s1));
       }
     }
+    if (force != 0.0) {   // Poiseuille forcing (:428-436,457-465): d/dv_y of the pass input, one-sided at the ends
+      const int j = (int)((p / N) % N);
+      if (j == 0) r = r - force * c0[p + N];
+      else if (j == N - 1) r = r - force * c0[p - N];
+      else r = r - force * (c0[p + N] - c0[p - N]);
+    }
     fc[(long)l * n3 + p] = r;
   }
 }
 void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const double* fl, const double* fr,
                        const double* v, const double* x, const double* dx, int N, int nX, double dt, int left_wall,
-                       int right_wall, const double* peerL, const double* peerR) {
+                       int right_wall, const double* peerL, const double* peerR, double force) {
   const long n3 = (long)N * N * N;
   dim3 grid((unsigned)((n3 + 255) / 256), nX);
-  upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall, peerL, peerR);
+  upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall, peerL, peerR,
+                                          force);
 }
 
 // fc = 0.5 * (f + fc) on n contiguous doubles (src/transportroutines.c:487-491)

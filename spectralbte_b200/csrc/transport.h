@@ -13,6 +13,6 @@ void launch_wall_face(cudaStream_t st, const double* f, double* face, const doub
                       int right, int fill_noflux);
 void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const double* fl, const double* fr,
                        const double* v, const double* x, const double* dx, int N, int nX, double dt, int left_wall,
-                       int right_wall, const double* peerL, const double* peerR);
+                       int right_wall, const double* peerL, const double* peerR, double force);
 void launch_average(cudaStream_t st, const double* f, double* fc, long n);
 }  // namespace sbte

@@ -202,12 +202,13 @@ static void init_inhom(const params *p, const double *v, int nX, double *slab) {
     case 1: T_r = 1.0; break;                                  /* sudden heating: wall at 2*TWall */
     case 2: T_r = 2.0; ux_l = -1.0; ux_r = -1.0; break;        /* shifted Maxwellian, uses the "left" state everywhere */
     case 3: T_r = 1.5; break;
+    case 5: break;                                             /* Poiseuille: rho 1, T 1 at rest (the "left" state) */
     case 6: ux_l = 1.2972; rho_r = 1.297; ux_r = 1.0; T_r = 1.195; break;
     default: printf("boltz_b200: Init_field %d not implemented for the inhomogeneous case\n", p->initFlag); exit(1);
   }
   memset(slab, 0, sizeof(double) * (size_t)(nX + 2 * order) * n3);
   for (l = order; l < nX + order; l++) {
-    const int left = (p->initFlag == 3 || p->initFlag == 1) ? 0 : (p->initFlag == 2 ? 1 : (l < nX / 2));
+    const int left = (p->initFlag == 3 || p->initFlag == 1) ? 0 : ((p->initFlag == 2 || p->initFlag == 5) ? 1 : (l < nX / 2));
     const double rho = left ? rho_l : rho_r, T = left ? T_l : T_r;
     const double ux = (p->initFlag == 6 || p->initFlag == 2) ? (left ? ux_l : ux_r) : 0.0;
     for (i = 0; i < N; i++)

@@ -41,6 +41,9 @@ def init_inhom(v, init_field, nX_global, order, lo, hi):
         r2 = (vx * vx + vy * vy + vz * vz).reshape(-1)   # src/initializer.c:381), left wall at 2 T
         cell = {None: (0.5 / np.pi) ** 1.5 * np.exp(-0.5 * r2)}
         pick = lambda l: cell[None]  # noqa: E731
+    elif init_field == 5:    # Poiseuille: gas at rest, rho 1, T 1, between diffuse walls (src/initializer.c:336-340,398-403)
+        cell = {None: maxw(1.0, 0.0, 1.0)}
+        pick = lambda l: cell[None]  # noqa: E731
     elif init_field == 2:    # uniform shifted Maxwellian (rho 1, u_x -1, T 1)
         cell = {None: maxw(1.0, -1.0, 1.0)}
         pick = lambda l: cell[None]  # noqa: E731

@@ -107,6 +107,8 @@ def main():
     transport_vectors("tr_ic3", 8, 9.0, 12, 3, 1e-3, out)   # diffuse walls
     transport_vectors("tr_ic6", 8, 9.0, 12, 6, 1e-3, out)   # periodic (order 1) / no-flux (order 2)
     transport_vectors("tr_ic0", 6, 7.0, 10, 0, 2e-3, out)   # copy / no-flux, N=6
+    transport_vectors("tr_ic5", 8, 9.0, 12, 5, 1e-3, out)   # Poiseuille: diffuse walls + v_y forcing (order 2)
+    transport_vectors("tr_ic1", 8, 9.0, 12, 1, 1e-3, out)   # sudden heating: left wall at 2 T, right copy
     np.savez_compressed(os.path.join(HERE, "ref_vectors.npz"), **out)
     print("wrote", len(out), "arrays")
 

@@ -282,7 +282,7 @@ def test_batched_computeq_matches_oracle(sb, N, cells, k2):
 
 # ---------------------------------------------------------------- transport
 @pytest.mark.parametrize("N,L_v,nX,ic,dt", [(8, 9.0, 12, 3, 1e-3), (8, 9.0, 12, 6, 1e-3), (6, 7.0, 10, 0, 2e-3),
-                                             (8, 9.0, 12, 1, 1e-3)])
+                                             (8, 9.0, 12, 1, 1e-3), (8, 9.0, 12, 5, 1e-3), (8, 9.0, 12, 2, 1e-3)])
 def test_transport_matches_oracle(sb, N, L_v, nX, ic, dt):
     o = orc.Oracle(N, L_v, 1)
     c = sb.Collisions(N, L_v, inhomogeneous=True)
@@ -300,7 +300,7 @@ def test_transport_matches_oracle(sb, N, L_v, nX, ic, dt):
         assert relmax(got, want) < 1e-14
 
 
-@pytest.mark.parametrize("order,ic", [(1, 3), (2, 3), (2, 6), (1, 6)])
+@pytest.mark.parametrize("order,ic", [(1, 3), (2, 3), (2, 6), (1, 6), (1, 5), (2, 5), (1, 1), (2, 1), (2, 0)])
 def test_1d_step_matches_oracle(sb, W_heat8, order, ic):
     """exec/boltz.c:264-353 end to end (advect + batched collide + advect), 3 steps, N=8."""
     N, nX, dt, Kn = 8, 14, 2e-3, 1.52
@@ -602,8 +602,10 @@ def test_error_paths_report_like_the_reference(sb, tmp_path):
     c.synthetic_weights(1)
     with pytest.raises(SbteError, match="requires f == g"):
         c.ComputeQ(np.ones((40, 512)), np.ones((40, 512)), k2=sb.K2_BATCH)
-    with pytest.raises(SbteError, match="Poiseuille"):
-        sb.Slab(c, 8, 1, np.zeros(10), np.ones(10), 5, 1e-3)
+    with pytest.raises(SbteError, match="Space_order must be 1 or 2"):
+        sb.Slab(c, 8, 3, np.zeros(14), np.ones(14), 3, 1e-3)
+    with pytest.raises(SbteError, match="too few cells"):
+        sb.Slab(c, 3, 2, np.zeros(7), np.ones(7), 3, 1e-3)
 
 
 # ---------------------------------------------------------------- symmetrised weight stream (f == g)

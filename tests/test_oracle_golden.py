@@ -94,7 +94,8 @@ def test_hot_path_vs_reference_vectors(ref_vectors, W_bkw8, W_heat8, tag, N, L_v
 
 
 @pytest.mark.parametrize("tag,N,L_v,nX,ic,dt", [("tr_ic3", 8, 9.0, 12, 3, 1e-3), ("tr_ic6", 8, 9.0, 12, 6, 1e-3),
-                                                 ("tr_ic0", 6, 7.0, 10, 0, 2e-3)])
+                                                 ("tr_ic0", 6, 7.0, 10, 0, 2e-3), ("tr_ic5", 8, 9.0, 12, 5, 1e-3),
+                                                 ("tr_ic1", 8, 9.0, 12, 1, 1e-3)])
 def test_transport_vs_reference_vectors(ref_vectors, tag, N, L_v, nX, ic, dt):
     o = orc.Oracle(N, L_v, 1)
     V = ref_vectors
