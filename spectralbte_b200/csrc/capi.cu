@@ -386,14 +386,12 @@ int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g,
   if (stream && !qhat_stream_supported(c->N)) { set_error("stream convolution: N must be in {16,24,32}"); return 1; }
   const int lay = stream ? LAY_PARITY : LAY_NATURAL;
   // three spectra: f^ (A), g_i^ (B), M_j^ (C); g_j^ == g_i^ for one species (f == g)
-  launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], lay, nullptr, false);
-  launch_fft3d(c, gi, nullptr, 0, 1, nullptr, c->d_lay[1], lay, nullptr, false);
-  launch_fft3d(c, Mj, nullptr, 0, 1, nullptr, c->d_lay[2], lay, nullptr, false);
-  const double2* gjhat = c->d_lay[1];
-  if (!same) {
-    launch_fft3d(c, gj, nullptr, 0, 1, nullptr, c->d_specB, lay, nullptr, false);
-    gjhat = c->d_specB;
+  const double* ins[4] = {d_f, gi, Mj, gj};
+  double2* outs[4] = {c->d_lay[0], c->d_lay[1], c->d_lay[2], c->d_specB};
+  if (!launch_fft3d_multi(c, same ? 3 : 4, ins, outs, lay)) {   // one launch where the cluster kernel exists
+    for (int q = 0; q < (same ? 3 : 4); q++) launch_fft3d(c, ins[q], nullptr, 0, 1, nullptr, outs[q], lay, nullptr, false);
   }
+  const double2* gjhat = same ? c->d_lay[1] : c->d_specB;
   QhatPair pairs[2] = {{gjhat, c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]}};
   const bool sym = stream && want_sym(c, same);   // for f == g the three-product summand is symmetric as a whole
   if (sym && ensure_sym(c)) return 1;

@@ -10,6 +10,9 @@
 // Two launches per transform:
 //   pass ZY : one CTA per (x-plane, cell): twiddle-in, DFT along z, DFT along y   -> tmp
 //   pass X  : one CTA per (y, cell):       DFT along x, twiddle-out, layout write  -> spectra / Re
+#include <cooperative_groups.h>
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -46,6 +49,19 @@ struct PartsIn {
   size_t stride;                 // double2 elements between parts
   const unsigned char* tile_np;  // partial sums per tile
   int G, cols;                   // cell groups, zeta columns per tile
+};
+
+// up to four independent transforms served by one launch of the cluster kernel
+struct FftJob {
+  const double* in_real;
+  const double2* in_cplx;
+  double2* out_nat;
+  double2* out_lay;
+  double* out_real;
+};
+struct FftJobs {
+  FftJob j[4];
+  int cells_per_job, layout, accumulate_real;
 };
 
 __global__ void __launch_bounds__(FFT_THREADS)
@@ -185,6 +201,22 @@ __device__ __forceinline__ void fft_line_pow2(double2* __restrict__ base, int st
   for (int k = 0; k < N; k++) base[bitrev(k, LG) * stride] = x[k];
 }
 
+// one output of a dense N-point DFT of a register-resident line; kp may be a run-time (warp-uniform) value
+template <int N>
+__device__ __forceinline__ double2 dense_output(const double2 (&x)[N], int kp, double sgn) {
+  double sr = 0.0, si = 0.0;
+  int m = 0;
+#pragma unroll
+  for (int k = 0; k < N; k++) {
+    const double wr = c_tw[N][m].x, wi = sgn * c_tw[N][m].y;
+    sr += x[k].x * wr - x[k].y * wi;
+    si += x[k].x * wi + x[k].y * wr;
+    m += kp;
+    if (m >= N) m -= N;
+  }
+  return make_double2(sr, si);
+}
+
 template <int N>
 __device__ __forceinline__ void dft_line(double2* __restrict__ base, int stride, double sgn) {
   if constexpr ((N & (N - 1)) == 0) {
@@ -194,16 +226,23 @@ __device__ __forceinline__ void dft_line(double2* __restrict__ base, int stride,
   double2 x[N];
 #pragma unroll
   for (int k = 0; k < N; k++) x[k] = base[k * stride];
+  if constexpr (N > 16) {
+    // long dense lines: keep the output loop rolled (the twiddle index is warp-uniform, so the constant-memory
+    // reads still broadcast) -- fully unrolled, N = 24 needs more registers than a thread has
+#pragma unroll 1
+    for (int kp = 0; kp < N; kp++) base[kp * stride] = dense_output<N>(x, kp, sgn);
+  } else {
 #pragma unroll
-  for (int kp = 0; kp < N; kp++) {
-    double sr = 0.0, si = 0.0;
+    for (int kp = 0; kp < N; kp++) {
+      double sr = 0.0, si = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; k++) {
-      const double wr = c_tw[N][(k * kp) % N].x, wi = sgn * c_tw[N][(k * kp) % N].y;
-      sr += x[k].x * wr - x[k].y * wi;
-      si += x[k].x * wi + x[k].y * wr;
+      for (int k = 0; k < N; k++) {
+        const double wr = c_tw[N][(k * kp) % N].x, wi = sgn * c_tw[N][(k * kp) % N].y;
+        sr += x[k].x * wr - x[k].y * wi;
+        si += x[k].x * wi + x[k].y * wr;
+      }
+      base[kp * stride] = make_double2(sr, si);
     }
-    base[kp * stride] = make_double2(sr, si);
   }
 }
 
@@ -292,10 +331,204 @@ static bool try_cell_fft(sbte_ctx* c, const double* in_real, const double2* in_c
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Cluster transform (0D and any N the whole-cell kernel cannot hold): one thread-block CLUSTER of 8 CTAs per
+// cell.  CTA r keeps x-planes [r N/8, (r+1) N/8) in shared memory, transforms them along z and y, then -- after
+// a cluster barrier -- owns the x-lines of y in [r N/8, (r+1) N/8) and gathers each line from the eight CTAs'
+// shared memory over DSMEM.  One launch per transform (or per group of up to four independent transforms),
+// nothing round-trips through global memory, and a single N = 32 cell is spread over 8 SMs instead of
+// waiting on two dependent launches of the plane-parallel pair.
+// ------------------------------------------------------------------------------------------
+constexpr int FFT_CL = 8;
+
+template <int N>
+__global__ void __launch_bounds__(256, 1)
+fft3d_cluster_kernel(FftJobs jobs, PartsIn pin, const double2* __restrict__ pre, const double2* __restrict__ post,
+                     const double* __restrict__ wt, double prefactor, double sgn) {
+  namespace cg = cooperative_groups;
+  constexpr int PL = N / FFT_CL;        // x-planes (and later y-rows) per CTA
+  constexpr int P = N + 1;
+  constexpr long n3 = (long)N * N * N;
+  extern __shared__ double2 clsm[];     // [PL][N][P]
+  cg::cluster_group cluster = cg::this_cluster();
+  const int r = (int)cluster.block_rank();
+  const long cell = blockIdx.x / FFT_CL;
+  const int job = (int)(cell / jobs.cells_per_job);
+  const long coff = (cell - (long)job * jobs.cells_per_job) * n3;   // cell offset inside the job's arrays
+  const double* in_real = jobs.j[job].in_real;
+  const double2* in_cplx = jobs.j[job].in_cplx;
+  const int i0 = r * PL;
+  double2* postsm = clsm + PL * N * P;  // [N][PL][N]: post-twiddles of the outputs this CTA emits (rows j in its slice)
+  // Loads are issued in groups of LB independent requests per thread before anything consumes them: this
+  // kernel is latency-bound (8 CTAs, a few KB each), so exposed round trips are what it costs.
+  constexpr int LB = 8;
+  static_assert((PL * N * N) % (256 * LB) == 0 || (PL * N * N) < 256 * LB, "load batches must tile");
+  for (int base = threadIdx.x; base < PL * N * N; base += blockDim.x * LB) {
+    double xr[LB], xi[LB];
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      xr[q] = 0.0; xi[q] = 0.0;
+      if (idx < PL * N * N) {
+        const int il = idx / (N * N), j = (idx / N) % N, k = idx % N, i = i0 + il;
+        const long loc = ((long)i * N + j) * N + k;
+        if (in_real) xr[q] = __ldg(in_real + coff + loc);
+        else if (pin.parts) {
+          const int tile = ((i * N + j) / pin.cols) * pin.G + (int)(cell >> 5);
+          const int np = pin.tile_np[tile];
+          for (int m = 0; m < np; m++) {
+            const double2 z = pin.parts[(size_t)m * pin.stride + cell * n3 + loc];
+            xr[q] += z.x; xi[q] += z.y;
+          }
+        } else { const double2 z = __ldg(in_cplx + coff + loc); xr[q] = z.x; xi[q] = z.y; }
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx < PL * N * N) {
+        const int il = idx / (N * N), j = (idx / N) % N, k = idx % N, i = i0 + il;
+        const double2 cs = __ldg(pre + i + j + k);
+        const double factor = prefactor * __ldg(wt + i) * __ldg(wt + j) * __ldg(wt + k);
+        clsm[(il * N + j) * P + k] =
+            make_double2(factor * (cs.x * xr[q] - cs.y * xi[q]), factor * (cs.x * xi[q] + cs.y * xr[q]));
+      }
+    }
+  }
+  for (int base = threadIdx.x; base < N * PL * N; base += blockDim.x * LB) {   // stage the post-twiddles
+    double2 pv[LB];
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx < N * PL * N) {
+        const int ip = idx / (PL * N), jl = (idx / N) % PL, k = idx % N;
+        pv[q] = __ldg(post + ((long)ip * N + i0 + jl) * N + k);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx < N * PL * N) postsm[idx] = pv[q];
+    }
+  }
+  __syncthreads();
+  for (int l = threadIdx.x; l < PL * N; l += blockDim.x)            // along z: line (il, j)
+    dft_line<N>(clsm + l * P, 1, sgn);
+  __syncthreads();
+  for (int l = threadIdx.x; l < PL * N; l += blockDim.x) {          // along y: line (il, k)
+    const int il = l / N, k = l % N;
+    dft_line<N>(clsm + (il * N) * P + k, P, sgn);
+  }
+  cluster.sync();
+  double2* out_nat = jobs.j[job].out_nat;
+  double2* out_lay = jobs.j[job].out_lay;
+  double* out_real = jobs.j[job].out_real;
+  const int layout = jobs.layout, accumulate = jobs.accumulate_real;
+  for (int l = threadIdx.x; l < PL * N; l += blockDim.x) {          // along x: line (j, k), gathered over DSMEM
+    const int j = i0 + l / N, k = l % N;
+    double2 x[N];
+#pragma unroll
+    for (int i = 0; i < N; i++) {
+      const double2* remote = cluster.map_shared_rank(clsm, i / PL);
+      x[i] = remote[((i % PL) * N + j) * P + k];
+    }
+    auto emit = [&](int ip, double2 z) {   // output frequency ip of this line: post-twiddle and the layout writes
+      const long loc = ((long)ip * N + j) * N + k;
+      const double2 cs = postsm[(ip * PL + (j - i0)) * N + k];
+      const double2 o = make_double2(cs.x * z.x - cs.y * z.y, cs.x * z.y + cs.y * z.x);
+      if (out_nat) out_nat[coff + loc] = o;
+      if (out_real) {
+        if (accumulate) out_real[coff + loc] += o.x;
+        else out_real[coff + loc] = o.x;
+      }
+      if (out_lay) {
+        if (layout == LAY_PARITY) out_lay[coff + (loc - k) + (k & 1) * (N / 2) + (k >> 1)] = o;
+        else if (layout == LAY_CELLMINOR) out_lay[((cell >> 5) * n3 + loc) * 32 + (cell & 31)] = o;
+        else out_lay[coff + loc] = o;
+      }
+    };
+    if constexpr ((N & (N - 1)) == 0) {
+      constexpr int LG = ilog2(N);
+      dif_stage<N, N>(x, sgn);
+#pragma unroll
+      for (int q = 0; q < N; q++) emit(bitrev(q, LG), x[q]);
+    } else {
+#pragma unroll 1
+      for (int ip = 0; ip < N; ip++) emit(ip, dense_output<N>(x, ip, sgn));
+    }
+  }
+  cluster.sync();   // nobody leaves while a neighbour may still read its planes
+}
+
+template <int N>
+static bool launch_cluster_n(sbte_ctx* c, const FftJobs& jobs, PartsIn pin, int invert, int cells) {
+  const size_t smem = (size_t)(N / FFT_CL) * N * (N + 1 + N) * sizeof(double2);   // planes + staged post-twiddles
+  auto kern = fft3d_cluster_kernel<N>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured = true;
+  }
+  const int d = invert ? 1 : 0;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)(cells * FFT_CL));
+  cfg.blockDim = dim3(256);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = FFT_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kern, jobs, pin, (const double2*)c->d_pre[d], (const double2*)c->d_post[d],
+                     (const double*)c->d_wt, c->pref[d], invert ? +1.0 : -1.0);
+  c->launches += 1;
+  return true;
+}
+
+// N = 16, 32: up to four independent groups of `cells_per_job` cells in one launch.  (N = 24 compiles too, but
+// its dense 24-point lines make the cluster kernel slower than the plane-parallel pair: 34.8 vs 18.4 us per
+// transform measured on B200, so it keeps the pair.)
+bool fft_cluster_supported(int N) { return N == 16 || N == 32; }
+static bool launch_cluster(sbte_ctx* c, const FftJobs& jobs, PartsIn pin, int invert, int cells) {
+  switch (c->N) {
+    case 16: return launch_cluster_n<16>(c, jobs, pin, invert, cells);
+    case 24: return launch_cluster_n<24>(c, jobs, pin, invert, cells);
+    case 32: return launch_cluster_n<32>(c, jobs, pin, invert, cells);
+    default: return false;
+  }
+}
+
+// several independent forward transforms (real inputs -> spectra in `layout`) in ONE launch; false if N has no
+// cluster kernel (the caller then issues them one by one)
+bool launch_fft3d_multi(sbte_ctx* c, int njobs, const double* const* in_real, double2* const* out_lay, int layout) {
+  if (!fft_cluster_supported(c->N) || njobs > 4 || getenv("SBTE_NO_CLUSTER_FFT")) return false;
+  FftJobs jobs = {};
+  for (int q = 0; q < njobs; q++) { jobs.j[q].in_real = in_real[q]; jobs.j[q].out_lay = out_lay[q]; }
+  if (layout == LAY_CELLMINOR) return false;   // the cell-minor interleave belongs to one batched job
+  jobs.cells_per_job = 1;
+  jobs.layout = layout;
+  PartsIn nopart = {nullptr, 0, nullptr, 0, 0};
+  return launch_cluster(c, jobs, nopart, 0, njobs);
+}
+
+static bool try_cluster_fft(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,
+                            double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real) {
+  if (!fft_cluster_supported(c->N) || getenv("SBTE_NO_CLUSTER_FFT")) return false;
+  FftJobs jobs = {};
+  jobs.j[0].in_real = in_real; jobs.j[0].in_cplx = in_cplx;
+  jobs.j[0].out_nat = out_nat; jobs.j[0].out_lay = out_lay; jobs.j[0].out_real = out_real;
+  jobs.cells_per_job = batch;
+  jobs.layout = layout;
+  jobs.accumulate_real = accumulate_real ? 1 : 0;
+  return launch_cluster(c, jobs, pin, invert, batch);
+}
+
 void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,
                   double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real) {
   PartsIn nopart = {nullptr, 0, nullptr, 0, 0};
   if (try_cell_fft(c, in_real, in_cplx, nopart, invert, batch, out_nat, out_lay, layout, out_real, accumulate_real)) return;
+  if (try_cluster_fft(c, in_real, in_cplx, nopart, invert, batch, out_nat, out_lay, layout, out_real, accumulate_real)) return;
   const int N = c->N;
   const size_t smem = (size_t)(2 * N * N + N) * sizeof(double2);
   const int d = invert ? 1 : 0;
@@ -314,6 +547,7 @@ void launch_fft3d_parts(sbte_ctx* c, const double2* parts, size_t part_stride, c
   {
     PartsIn pin0 = {parts, part_stride, sch.tile_np, sch.G, sch.cols};
     if (try_cell_fft(c, nullptr, nullptr, pin0, invert, batch, out_nat, nullptr, 0, out_real, false)) return;
+    if (try_cluster_fft(c, nullptr, nullptr, pin0, invert, batch, out_nat, nullptr, 0, out_real, false)) return;
   }
   const int N = c->N;
   const size_t smem = (size_t)(2 * N * N + N) * sizeof(double2);

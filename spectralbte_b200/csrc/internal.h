@@ -111,6 +111,8 @@ void init_fft_constants();
 void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,
                   double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real);
 // same, the complex input being the sum of the stream-K partial sums described by `sch`
+// several single-cell forward transforms in one launch (cluster kernel); false: not available for this N
+bool launch_fft3d_multi(sbte_ctx* c, int njobs, const double* const* in_real, double2* const* out_lay, int layout);
 void launch_fft3d_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int invert,
                         int batch, double2* out_nat, double* out_real);
 void launch_combine_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int batch,
