@@ -14,6 +14,8 @@
 //   qhat_batch   : many cells share each weight (1D).  FP64-bound: lanes = cells, one warp per
 //                  zeta (x,y) column, the whole N x N (zeta_z, xi_z) Toeplitz tile in registers.
 //                  (qhat_batch.cu)
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -75,13 +77,22 @@ void launch_qhat_generic(sbte_ctx* c, int npairs, const QhatPair* pairs, double2
 // ------------------------------------------------------------------------------------------
 // stream kernel
 // ------------------------------------------------------------------------------------------
-template <int N>
+constexpr int largest_divisor_le(int n, int cap) {
+  int best = 1;
+  for (int d = 1; d <= cap; d++)
+    if (n % d == 0) best = d;
+  return best;
+}
+
+// WT: target warps per CTA (8 for one operand pair; 16 for two pairs, whose 128 KB plane ring allows only one
+// CTA per SM so the CTA itself has to bring the latency-hiding warps)
+template <int N, int WT = 8>
 struct StreamCfg {
   static constexpr int HALF = N / 2;            // 2-column groups per N-long weight row segment
   static constexpr int RGW = 32 / HALF;         // 4-row groups handled by one warp
   static constexpr int ROWS_W = RGW * 4;        // rows per warp
   static constexpr int RB = N / ROWS_W;         // warps that tile the N rows of one zeta (x,y) column
-  static constexpr int PH = (8 / RB) < 1 ? 1 : (8 / RB);  // xi_y phases (warps sharing the same rows)
+  static constexpr int PH = largest_divisor_le(N, (WT / RB) < 1 ? 1 : (WT / RB));  // xi_y phases (warps sharing the same rows)
   static constexpr int NWARP = RB * PH;
   static constexpr int THREADS = NWARP * 32;
   static constexpr int SPC = N / PH;            // steps per xi_x chunk per warp
@@ -92,11 +103,11 @@ struct StreamCfg {
 };
 
 // SYM: W is the symmetrised tensor Ws and only the representative xi_x planes are visited (f == g only).
-template <int N, int NP, int DEPTH, bool SYM>
-__global__ void __launch_bounds__(StreamCfg<N>::THREADS, (N == 32 && NP == 1 && DEPTH <= 2) ? 2 : 1)
+template <int N, int NP, int DEPTH, bool SYM, int WT>
+__global__ void __launch_bounds__(StreamCfg<N, WT>::THREADS, (N == 32 && NP == 1 && DEPTH <= 2) ? 2 : 1)
 qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
                    const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat) {
-  using C = StreamCfg<N>;
+  using C = StreamCfg<N, WT>;
   constexpr int HALF = C::HALF, PLANE = C::PLANE;
   constexpr long n3 = (long)N * N * N;
   constexpr uint32_t STAGE_ELEMS = 2 * NP * PLANE;  // per stage: NP x (xi-side plane, dif-side plane)
@@ -205,10 +216,11 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
 #pragma unroll
           for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
 #pragma unroll
-          for (int j = 0; j < 4; j++) {
-            const double2 a = cmul(g0, fw[j + 1]), b = cmul(g1, fw[j]);
-            p[j][0].x += a.x; p[j][0].y += a.y;
-            p[j][1].x += b.x; p[j][1].y += b.y;
+          for (int j = 0; j < 4; j++) {   // p += g * fw as four fused multiply-adds per product
+            p[j][0].x = fma(g0.x, fw[j + 1].x, fma(-g0.y, fw[j + 1].y, p[j][0].x));
+            p[j][0].y = fma(g0.x, fw[j + 1].y, fma(g0.y, fw[j + 1].x, p[j][0].y));
+            p[j][1].x = fma(g1.x, fw[j].x, fma(-g1.y, fw[j].y, p[j][1].x));
+            p[j][1].y = fma(g1.x, fw[j].y, fma(g1.y, fw[j].x, p[j][1].y));
           }
         }
 #pragma unroll
@@ -249,11 +261,11 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
 
 bool qhat_stream_supported(int N) { return N == 16 || N == 24 || N == 32; }
 
-template <int N, int NP, int DEPTH, bool SYM>
+template <int N, int NP, int DEPTH, bool SYM, int WT = 8>
 static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pairs, double2* qhat) {
-  using C = StreamCfg<N>;
+  using C = StreamCfg<N, WT>;
   const size_t smem = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2) + 64;
-  auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM>;
+  auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM, WT>;
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -273,9 +285,11 @@ static void launch_stream_n(sbte_ctx* c, const double* W, int npairs, const Qhat
     if (depth >= 4) launch_stream_inst<N, 1, 4, SYM>(c, W, pairs, qhat);
     else launch_stream_inst<N, 1, 2, SYM>(c, W, pairs, qhat);
   } else {
-    // two operand pairs need 128 KB of plane ring => one CTA per SM: keep four weight tiles per thread in
-    // flight (64 KB per SM) so the HBM stream stays saturated
-    launch_stream_inst<N, 2, 4, SYM>(c, W, pairs, qhat);
+    // two operand pairs need 128 KB of plane ring => one CTA per SM.  Either 8 warps with four weight tiles per
+    // thread in flight, or (default) 16 warps with two: the same 64 KB per SM in flight, twice the warps to
+    // overlap the shared-memory operand reads, the FP64 pipe and the weight stream
+    if (getenv("SBTE_MP_NARROW")) launch_stream_inst<N, 2, 4, SYM>(c, W, pairs, qhat);
+    else launch_stream_inst<N, 2, 2, SYM, 16>(c, W, pairs, qhat);
   }
 }
 
