@@ -256,23 +256,38 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
   constexpr int P = N + 1;
   constexpr long n3 = (long)N * N * N;
   const long cell = blockIdx.x;
-  for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
-    const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
-    const long g = cell * n3 + idx;
-    double xr, xi;
-    if (in_real) { xr = in_real[g]; xi = 0.0; }
-    else if (pin.parts) {
-      const int tile = ((i * N + j) / pin.cols) * pin.G + (int)(cell >> 5);
-      const int np = pin.tile_np[tile];
-      xr = 0.0; xi = 0.0;
-      for (int m = 0; m < np; m++) {
-        const double2 z = pin.parts[(size_t)m * pin.stride + g];
-        xr += z.x; xi += z.y;
+  // loads go out in groups of LB independent requests per thread (the CTA is latency-bound otherwise)
+  constexpr int LB = 8;
+  for (int base = threadIdx.x; base < n3; base += blockDim.x * LB) {
+    double xr[LB], xi[LB];
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      xr[q] = 0.0; xi[q] = 0.0;
+      if (idx < n3) {
+        const long g = cell * n3 + idx;
+        if (in_real) xr[q] = __ldg(in_real + g);
+        else if (pin.parts) {
+          const int tile = ((idx / N) / pin.cols) * pin.G + (int)(cell >> 5);
+          const int np = pin.tile_np[tile];
+          for (int m = 0; m < np; m++) {
+            const double2 z = __ldg(pin.parts + (size_t)m * pin.stride + g);
+            xr[q] += z.x; xi[q] += z.y;
+          }
+        } else { const double2 z = __ldg(in_cplx + g); xr[q] = z.x; xi[q] = z.y; }
       }
-    } else { const double2 z = in_cplx[g]; xr = z.x; xi = z.y; }
-    const double2 cs = pre[i + j + k];
-    const double factor = prefactor * wt[i] * wt[j] * wt[k];
-    cellsm[(i * N + j) * P + k] = make_double2(factor * (cs.x * xr - cs.y * xi), factor * (cs.x * xi + cs.y * xr));
+    }
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx < n3) {
+        const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
+        const double2 cs = __ldg(pre + i + j + k);
+        const double factor = prefactor * __ldg(wt + i) * __ldg(wt + j) * __ldg(wt + k);
+        cellsm[(i * N + j) * P + k] =
+            make_double2(factor * (cs.x * xr[q] - cs.y * xi[q]), factor * (cs.x * xi[q] + cs.y * xr[q]));
+      }
+    }
   }
   __syncthreads();
   for (int l = threadIdx.x; l < N * N; l += blockDim.x)            // along z: line (i, j)
@@ -288,17 +303,27 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
     dft_line<N>(cellsm + j * P + k, N * P, sgn);
   }
   __syncthreads();
-  for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
-    const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
-    const double2 cs = post[idx];
-    const double2 z = cellsm[(i * N + j) * P + k];
-    const double2 o = make_double2(cs.x * z.x - cs.y * z.y, cs.x * z.y + cs.y * z.x);
-    if (out_nat) out_nat[cell * n3 + idx] = o;
-    if (out_real) out_real[cell * n3 + idx] = o.x;
-    if (out_lay) {
-      if (layout == LAY_PARITY) out_lay[cell * n3 + (idx - k) + (k & 1) * (N / 2) + (k >> 1)] = o;
-      else if (layout == LAY_CELLMINOR) out_lay[((cell >> 5) * n3 + idx) * 32 + (cell & 31)] = o;
-      else out_lay[cell * n3 + idx] = o;
+  for (int base = threadIdx.x; base < n3; base += blockDim.x * LB) {
+    double2 cs[LB];
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx < n3) cs[q] = __ldg(post + idx);
+    }
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx >= n3) continue;
+      const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
+      const double2 z = cellsm[(i * N + j) * P + k];
+      const double2 o = make_double2(cs[q].x * z.x - cs[q].y * z.y, cs[q].x * z.y + cs[q].y * z.x);
+      if (out_nat) out_nat[cell * n3 + idx] = o;
+      if (out_real) out_real[cell * n3 + idx] = o.x;
+      if (out_lay) {
+        if (layout == LAY_PARITY) out_lay[cell * n3 + (idx - k) + (k & 1) * (N / 2) + (k >> 1)] = o;
+        else if (layout == LAY_CELLMINOR) out_lay[((cell >> 5) * n3 + idx) * 32 + (cell & 31)] = o;
+        else out_lay[cell * n3 + idx] = o;
+      }
     }
   }
 }

@@ -152,59 +152,81 @@ void launch_wall_face(cudaStream_t st, const double* f, double* face, const doub
 
 // MUSCL / minmod stencil for the owned cells l = 2 .. nX+1. left_wall / right_wall: this rank holds
 // the physical boundary and uses the wall faces fl / fr instead of the neighbour reconstruction.
+//
+// Each thread marches one velocity node through UP_CH consecutive cells: the limited slope of cell l is the
+// "own" slope of cell l and the upwind-neighbour slope of cell l+1 (v_x > 0) or l-1 (v_x < 0), so carrying it
+// along the march computes every slope once (3 FP64 divisions per node and pass instead of 6) with exactly the
+// reference's expressions (src/transportroutines.c:411-416,441-446), i.e. the same bits as the per-cell form.
+constexpr int UP_CH = 8;
+
+__device__ __forceinline__ double slope_at(double fm, double f0, double fp, const double* __restrict__ x, int l) {
+  return minmod3((f0 - fm) / (x[l] - x[l - 1]), (fp - f0) / (x[l + 1] - x[l]), (fp - fm) / (x[l + 1] - x[l - 1]));
+}
+
 __global__ void __launch_bounds__(256)
-upwind_two_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ fl,
+upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __restrict__ fl,
                   const double* __restrict__ fr, const double* __restrict__ v, const double* __restrict__ x,
                   const double* __restrict__ dx, int N, int nX, double dt, int left_wall, int right_wall,
-                  const double* __restrict__ peerL, const double* __restrict__ peerR, double force) {
+                  const double* peerL, const double* peerR, double force) {
   const long n3 = (long)N * N * N;
-  const int l = blockIdx.y + 2;
   const int h = N / 2;
-  const double* c0 = f + (long)l * n3;
-  const double* cm1 = cell_src<2>(f, peerL, peerR, n3, nX, l - 1);
-  const double* cm2 = cell_src<2>(f, peerL, peerR, n3, nX, l - 2);
-  const double* cp1 = cell_src<2>(f, peerL, peerR, n3, nX, l + 1);
-  const double* cp2 = cell_src<2>(f, peerL, peerR, n3, nX, l + 2);
-  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(p / (N * N));
-    const double cfl = 0.5 * dt * v[i] / dx[l];
-    const double f0 = c0[p], fm = cm1[p], fp = cp1[p];
-    const double s1 = minmod3((f0 - fm) / (x[l] - x[l - 1]), (fp - f0) / (x[l + 1] - x[l]),
-                              (fp - fm) / (x[l + 1] - x[l - 1]));
-    double r;
-    if (i >= h) {
-      if (l == 2 && left_wall) {
-        r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - fl[p]);
-      } else {
-        const double fmm = cm2[p];
-        const double s0 = minmod3((fm - fmm) / (x[l - 1] - x[l - 2]), (f0 - fm) / (x[l] - x[l - 1]),
-                                  (f0 - fmm) / (x[l] - x[l - 2]));
-        r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - (fm + 0.5 * dx[l - 1] * s0));
-      }
-    } else {
-      if (l == nX + 1 && right_wall) {
-        r = f0 - cfl * (fr[p] - (f0 - 0.5 * dx[l] * s1));
-      } else {
-        const double fpp = cp2[p];
-        const double s2 = minmod3((fp - f0) / (x[l + 1] - x[l]), (fpp - fp) / (x[l + 2] - x[l + 1]),
-                                  (fpp - f0) / (x[l + 2] - x[l]));
+  const int l0 = 2 + blockIdx.y * UP_CH;
+  const int l1 = min(l0 + UP_CH, nX + 2);
+  const long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
+  if (p >= n3) return;
+  const int i = (int)(p / (N * N));
+  const int j = (int)((p / N) % N);
+  const double hv = 0.5 * dt * v[i];
+  auto F = [&](int l) { return __ldcg(cell_src<2>(f, peerL, peerR, n3, nX, l) + p); };
+  auto forced = [&](double r, int l) {   // Poiseuille forcing (:428-436,457-465): d/dv_y of the pass input
+    if (force == 0.0) return r;
+    const double* c0 = f + (long)l * n3;
+    if (j == 0) return r - force * c0[p + N];
+    if (j == N - 1) return r - force * c0[p - N];
+    return r - force * (c0[p + N] - c0[p - N]);
+  };
+  if (i >= h) {   // information travels to the right: face value of cell l-1 is the upwind one
+    double fm = F(l0 - 1), f0 = F(l0);
+    double sprev = 0.0;
+    if (!(l0 == 2 && left_wall)) sprev = slope_at(F(l0 - 2), fm, f0, x, l0 - 1);
+#pragma unroll
+    for (int q = 0; q < UP_CH; q++) {
+      const int l = l0 + q;
+      if (l >= l1) break;
+      const double fp = F(l + 1);
+      const double s1 = slope_at(fm, f0, fp, x, l);
+      const double cfl = hv / dx[l];
+      double r;
+      if (l == 2 && left_wall) r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - fl[p]);
+      else r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - (fm + 0.5 * dx[l - 1] * sprev));
+      fc[(long)l * n3 + p] = forced(r, l);
+      fm = f0; f0 = fp; sprev = s1;
+    }
+  } else {        // information travels to the left: face value of cell l+1 is the upwind one
+    double fm = F(l0 - 1), f0 = F(l0), fp = F(l0 + 1);
+    double s1 = slope_at(fm, f0, fp, x, l0);
+#pragma unroll
+    for (int q = 0; q < UP_CH; q++) {
+      const int l = l0 + q;
+      if (l >= l1) break;
+      const double cfl = hv / dx[l];
+      double r, fpp = 0.0, s2 = 0.0;
+      if (l == nX + 1 && right_wall) r = f0 - cfl * (fr[p] - (f0 - 0.5 * dx[l] * s1));
+      else {
+        fpp = F(l + 2);
+        s2 = slope_at(f0, fp, fpp, x, l + 1);
         r = f0 - cfl * (fp - 0.5 * dx[l + 1] * s2 - (f0 - 0.5 * dx[l] * s1));
       }
+      fc[(long)l * n3 + p] = forced(r, l);
+      fm = f0; f0 = fp; fp = fpp; s1 = s2;
     }
-    if (force != 0.0) {   // Poiseuille forcing (:428-436,457-465): d/dv_y of the pass input, one-sided at the ends
-      const int j = (int)((p / N) % N);
-      if (j == 0) r = r - force * c0[p + N];
-      else if (j == N - 1) r = r - force * c0[p - N];
-      else r = r - force * (c0[p + N] - c0[p - N]);
-    }
-    fc[(long)l * n3 + p] = r;
   }
 }
 void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const double* fl, const double* fr,
                        const double* v, const double* x, const double* dx, int N, int nX, double dt, int left_wall,
                        int right_wall, const double* peerL, const double* peerR, double force) {
   const long n3 = (long)N * N * N;
-  dim3 grid((unsigned)((n3 + 255) / 256), nX);
+  dim3 grid((unsigned)((n3 + 255) / 256), (unsigned)((nX + UP_CH - 1) / UP_CH));
   upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall, peerL, peerR,
                                           force);
 }
