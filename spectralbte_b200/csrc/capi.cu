@@ -296,6 +296,11 @@ static bool want_sym(sbte_ctx* c, bool same) {
 
 // ---- convolution dispatch -------------------------------------------------------------------
 // spectra of f (dif side) and g (xi side) -> qhat (natural layout)
+bool use_pdl() {
+  static const bool on = getenv("SBTE_NO_PDL") == nullptr;
+  return on;
+}
+
 static int resolve_k2(sbte_ctx* c, int batch, int k2, bool same = true) {
   if (k2 == SBTE_K2_AUTO) {
     if (batch == 1) return qhat_stream_supported(c->N) ? SBTE_K2_STREAM : SBTE_K2_GENERIC;

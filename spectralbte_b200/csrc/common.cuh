@@ -95,6 +95,13 @@ __device__ __forceinline__ void tma_tensor2d_g2s(void* smem_dst, const void* tma
       : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// A kernel launched with cudaLaunchAttributeProgrammaticStreamSerialization may start while its predecessor in
+// the stream is still running: everything before pdl_wait() must not touch the predecessor's output.
+// pdl_launch_dependents() lets the successor's CTAs be scheduled early.  Both are no-ops otherwise.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- streaming global loads
 // 128-bit read-only load that does not allocate in L1 (the weight stream is touched exactly once)
 __device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {

@@ -384,10 +384,28 @@ fft3d_cluster_kernel(FftJobs jobs, PartsIn pin, const double2* __restrict__ pre,
   const double2* in_cplx = jobs.j[job].in_cplx;
   const int i0 = r * PL;
   double2* postsm = clsm + PL * N * P;  // [N][PL][N]: post-twiddles of the outputs this CTA emits (rows j in its slice)
-  // Loads are issued in groups of LB independent requests per thread before anything consumes them: this
-  // kernel is latency-bound (8 CTAs, a few KB each), so exposed round trips are what it costs.
   constexpr int LB = 8;
   static_assert((PL * N * N) % (256 * LB) == 0 || (PL * N * N) < 256 * LB, "load batches must tile");
+  pdl_launch_dependents();   // the convolution kernel may start prefetching weights while this grid runs
+  for (int base = threadIdx.x; base < N * PL * N; base += blockDim.x * LB) {   // stage the post-twiddles
+    double2 pv[LB];
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx < N * PL * N) {
+        const int ip = idx / (PL * N), jl = (idx / N) % PL, k = idx % N;
+        pv[q] = __ldg(post + ((long)ip * N + i0 + jl) * N + k);
+      }
+    }
+#pragma unroll
+    for (int q = 0; q < LB; q++) {
+      const int idx = base + q * blockDim.x;
+      if (idx < N * PL * N) postsm[idx] = pv[q];
+    }
+  }
+  pdl_wait();                // the twiddles above are static; the input below is the previous kernel's output
+  // Loads are issued in groups of LB independent requests per thread before anything consumes them: this
+  // kernel is latency-bound (8 CTAs, a few KB each), so exposed round trips are what it costs.
   for (int base = threadIdx.x; base < PL * N * N; base += blockDim.x * LB) {
     double xr[LB], xi[LB];
 #pragma unroll
@@ -418,22 +436,6 @@ fft3d_cluster_kernel(FftJobs jobs, PartsIn pin, const double2* __restrict__ pre,
         clsm[(il * N + j) * P + k] =
             make_double2(factor * (cs.x * xr[q] - cs.y * xi[q]), factor * (cs.x * xi[q] + cs.y * xr[q]));
       }
-    }
-  }
-  for (int base = threadIdx.x; base < N * PL * N; base += blockDim.x * LB) {   // stage the post-twiddles
-    double2 pv[LB];
-#pragma unroll
-    for (int q = 0; q < LB; q++) {
-      const int idx = base + q * blockDim.x;
-      if (idx < N * PL * N) {
-        const int ip = idx / (PL * N), jl = (idx / N) % PL, k = idx % N;
-        pv[q] = __ldg(post + ((long)ip * N + i0 + jl) * N + k);
-      }
-    }
-#pragma unroll
-    for (int q = 0; q < LB; q++) {
-      const int idx = base + q * blockDim.x;
-      if (idx < N * PL * N) postsm[idx] = pv[q];
     }
   }
   __syncthreads();
@@ -500,11 +502,13 @@ static bool launch_cluster_n(sbte_ctx* c, const FftJobs& jobs, PartsIn pin, int 
   cfg.blockDim = dim3(256);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = FFT_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = use_pdl() ? 2 : 1;
   cudaLaunchKernelEx(&cfg, kern, jobs, pin, (const double2*)c->d_pre[d], (const double2*)c->d_post[d],
                      (const double*)c->d_wt, c->pref[d], invert ? +1.0 : -1.0);
   c->launches += 1;

@@ -106,6 +106,8 @@ enum SpecLayout {
 };
 
 void init_fft_constants();
+// programmatic dependent launch between the 0D transforms and the stream convolution (SBTE_NO_PDL=1 disables)
+bool use_pdl();
 // fft.cu -- K1 / K3. in_real: N^3 doubles per cell; in_cplx: N^3 double2 per cell (exactly one non-null).
 // out_nat / out_lay / out_real may each be null. batch = number of cells.
 void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,

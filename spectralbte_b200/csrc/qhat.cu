@@ -156,10 +156,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
     mbar_fence_init();
   }
   __syncthreads();
-  if (tid == 0) {
-    issue_chunk(0);
-    if (nchunk > 1) issue_chunk(1);
-  }
+  pdl_launch_dependents();   // the inverse transform may stage its twiddles while this grid drains
 
   // weight stream: rows zeta = (zx, zy, r0 + j), j = 0..3; this thread's 16 bytes sit at column c0
   const double* wrow = W + ((long)blockIdx.x * N + r0) * n3 + c0;
@@ -175,6 +172,12 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
 #pragma unroll
     for (int d = 0; d < DEPTH; d++)
       if (d < NIT) load_w(d, wb[d]);
+  }
+  // the weights above do not depend on the forward transform; the operand planes below do
+  pdl_wait();
+  if (tid == 0) {
+    issue_chunk(0);
+    if (nchunk > 1) issue_chunk(1);
   }
 
   double2 acc[4];
@@ -272,9 +275,18 @@ static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pai
     configured = true;
   }
   k2_mark(c);
-  kern<<<N * N, C::THREADS, smem, c->stream>>>(W, pairs[0].xi_side, pairs[0].dif_side,
-                                               NP > 1 ? pairs[1].xi_side : nullptr,
-                                               NP > 1 ? pairs[1].dif_side : nullptr, qhat);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(N * N);
+  cfg.blockDim = dim3(C::THREADS);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;   // overlap the prologue with the transform before it
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = use_pdl() ? 1 : 0;
+  cudaLaunchKernelEx(&cfg, kern, W, pairs[0].xi_side, pairs[0].dif_side, NP > 1 ? pairs[1].xi_side : (const double2*)nullptr,
+                     NP > 1 ? pairs[1].dif_side : (const double2*)nullptr, qhat);
   k2_mark(c);
   c->launches += 1;
 }

@@ -1,0 +1,9 @@
+#!/usr/bin/env bash
+set -u
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+echo "=== tests"; timeout 1500 python -m pytest tests/test_gpu_parity.py -q -x 2>&1 | tail -4 | cut -c1-300
+for env in "SBTE_X=1" "SBTE_NO_PDL=1"; do
+echo "=== bench default $env"; env $env timeout 600 python bench.py --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'], d['e2e']['value'], d['roofline']['frac'], d.get('maxpreserve',{}).get('ms_per_call'))"
+echo "=== bkw16 $env"; env $env timeout 600 python bench.py --workload bkw16 --steps 50 --no-cpu 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['ms_per_step'])"
+done
