@@ -172,6 +172,8 @@ SBTE_API int sbte_slab_ipc_import(sbte_slab *s, int side, const unsigned char *h
 /* same-process form: `other` is a slab of another context (another stream or GPU with peer access enabled) */
 SBTE_API int sbte_slab_peer_attach(sbte_slab *s, int side, sbte_slab *other);
 SBTE_API int sbte_slab_set_peer_halo(sbte_slab *s, int enable);
+/* diagnostic: this rank's {ready, done, epoch} pass counters */
+SBTE_API int sbte_slab_halo_state(sbte_slab *s, int *state3);
 /* collision half: per-cell ComputeQ + conserve + Euler / Heun (exec/boltz.c:285-345) */
 SBTE_API int sbte_slab_collide(sbte_slab *s, double Kn, int k2);
 /* whole single-rank step (exec/boltz.c:264-353) */

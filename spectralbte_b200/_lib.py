@@ -72,6 +72,7 @@ PROTOTYPES = {
     "sbte_slab_ipc_export": (C.c_int, [_vp, C.c_char_p]),
     "sbte_slab_ipc_import": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int]),
     "sbte_slab_peer_attach": (C.c_int, [_vp, C.c_int, _vp]),
+    "sbte_slab_halo_state": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "sbte_slab_set_peer_halo": (C.c_int, [_vp, C.c_int]),
     "sbte_slab_collide": (C.c_int, [_vp, C.c_double, C.c_int]),
     "sbte_slab_step": (C.c_int, [_vp, C.c_double, C.c_int]),

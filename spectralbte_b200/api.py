@@ -305,6 +305,12 @@ class Slab:
         """Same-process neighbour (another context / GPU): no IPC mapping needed."""
         check(self.L.sbte_slab_peer_attach(self.h, int(side), other.h))
 
+    def halo_state(self):
+        """(ready, done, epoch) pass counters of the peer-memory halo."""
+        st = (C.c_int * 3)()
+        check(self.L.sbte_slab_halo_state(self.h, st))
+        return tuple(st)
+
     def set_peer_halo(self, enable=True):
         check(self.L.sbte_slab_set_peer_halo(self.h, int(bool(enable))))
 

@@ -100,6 +100,7 @@ static int build_lu(const sbte_ctx* c, ConsLU* out) {
 }
 
 static void invalidate_graphs(sbte_ctx* c) {
+  c->graph_gen++;
   for (auto& g : c->step_graphs)
     if (g.exec) cudaGraphExecDestroy(g.exec);
   c->step_graphs.clear();
@@ -206,6 +207,7 @@ __global__ void synth_weights_kernel(double* __restrict__ W, size_t n, unsigned 
 // T*N^2 global steps. tile_first / tile_np tell kernels which CTA writes which partial sum.
 static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   if (c->sched_cells == cells && c->sched_sym == (int)sym && c->d_sched_mem) return 0;
+  c->graph_gen++;   // the schedule tables move: captured slab steps must be rebuilt
   CK(cudaStreamSynchronize(c->stream));
   if (c->d_sched_mem) { cudaFree(c->d_sched_mem); c->d_sched_mem = nullptr; }
   if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
@@ -283,6 +285,7 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
 static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out);
 static int ensure_sym(sbte_ctx* c) {
   if (c->d_Ws) return 0;
+  c->graph_gen++;
   CK(cudaMalloc(&c->d_Ws, (size_t)c->n3 * c->n3 * sizeof(double)));
   launch_symmetrize_weights(c, c->d_W, c->d_Ws);
   if (qhat_batch_supported(c->N)) return encode_weight_map(c, c->d_Ws, &c->tmapWs);
@@ -495,6 +498,7 @@ unsigned long long sbte_launch_count(sbte_ctx* c) { return c->launches; }
 int sbte_reserve(sbte_ctx* c, int cells) { return ensure_capacity(c, cells); }
 
 int sbte_set_symmetrize(sbte_ctx* c, int enable) {
+  if (c->sym_enabled != (enable != 0)) c->graph_gen++;
   c->sym_enabled = enable != 0;
   return 0;
 }

@@ -86,6 +86,7 @@ struct sbte_ctx {
     int seen;
   };
   std::vector<StepGraph> step_graphs;
+  unsigned long long graph_gen = 1;   // bumped whenever a buffer a captured graph may reference is replaced
   unsigned long long launches = 0;  // kernels launched through this context
   bool k2_prof = false;             // bracket every K2 launch with CUDA events
   std::vector<cudaEvent_t> k2_ev;   // [2*i], [2*i+1] = start/stop of launch i

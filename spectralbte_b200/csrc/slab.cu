@@ -6,6 +6,7 @@
 // blocking MPI halo replaced by "ghost cells are filled by the caller" (NCCL / peer copies between
 // the regions reported by sbte_slab_halo_regions) so f never leaves the device.
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include <vector>
@@ -34,9 +35,15 @@ struct sbte_slab {
     int* flags = nullptr;                           // their {ready, done} counters
     int cells = 0;
   } nb[2];
-  int* d_flags = nullptr;   // my {ready, done}
+  int* d_flags = nullptr;   // my {ready, done, epoch}; the pass counter lives on the device (graph replay)
   int p2p = 0;              // 1: stencils read the neighbours' boundary cells over NVLink
-  int epoch = 0;            // upwind passes issued so far (same sequence on every rank)
+  // CUDA graph of one whole time step (single rank or peer halos: nothing but launches on one stream)
+  struct StepGraph {
+    cudaGraphExec_t exec = nullptr;
+    double Kn = 0;
+    int k2 = 0, seen = 0;
+    unsigned long long gen = 0, launches = 0;
+  } graph;
 };
 
 using namespace sbte;
@@ -99,16 +106,15 @@ static void peer_begin(sbte_slab* s, const double* src, const double** peerL, co
   if (!s->p2p) return;
   sbte_ctx* c = s->c;
   const long n3 = c->n3;
-  const int e = ++s->epoch, id = array_id(s, src);
-  launch_halo_post(c->stream, s->d_flags + 0, e);
-  launch_halo_wait(c->stream, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr, e, e - 1);
-  c->launches += 2;
+  const int id = array_id(s, src);
+  launch_halo_begin(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr);
+  c->launches += 1;
   if (s->nb[0].on) *peerL = s->nb[0].arr[id] + (long)s->nb[0].cells * n3;   // their last `order` owned cells
   if (s->nb[1].on) *peerR = s->nb[1].arr[id] + (long)s->order * n3;         // their first `order` owned cells
 }
 static void peer_end(sbte_slab* s) {
   if (!s->p2p) return;
-  launch_halo_post(s->c->stream, s->d_flags + 1, s->epoch);
+  launch_halo_end(s->c->stream, s->d_flags);
   s->c->launches += 1;
 }
 
@@ -195,6 +201,7 @@ int sbte_slab_create(sbte_ctx* c, sbte_slab** out, int cells_local, int order, c
 int sbte_slab_destroy(sbte_slab* s) {
   if (!s) return 0;
   cudaStreamSynchronize(s->c->stream);
+  if (s->graph.exec) cudaGraphExecDestroy(s->graph.exec);
   for (int side = 0; side < 2; side++)
     if (s->nb[side].on && s->nb[side].mapped) {
       for (int a = 0; a < 3; a++)
@@ -264,8 +271,17 @@ int sbte_slab_peer_attach(sbte_slab* s, int side, sbte_slab* other) {
   return 0;
 }
 
+// diagnostic: this rank's {ready, done, epoch} counters (synchronous copy on a side stream-less path)
+int sbte_slab_halo_state(sbte_slab* s, int* state3) {
+  state3[0] = state3[1] = state3[2] = 0;
+  if (!s->d_flags) return 0;
+  CKS(cudaMemcpy(state3, s->d_flags, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 int sbte_slab_set_peer_halo(sbte_slab* s, int enable) {
   if (enable && !s->d_flags) { set_error("export/import the IPC handles before enabling peer halos"); return 1; }
+  if (enable && preload_transport_kernels()) { set_error("could not load the transport kernels"); return 1; }
   s->p2p = enable ? 1 : 0;
   return 0;
 }
@@ -345,7 +361,7 @@ int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
   double* fc = cell(s->d_fc, n3, o);
   double* f = cell(s->d_f, n3, o);
   if (s->p2p) {   // the update below overwrites cells the neighbours may still be reading in their last pass
-    launch_halo_wait(c->stream, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr, 0, s->epoch);
+    launch_halo_quiesce(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr);
     c->launches++;
   }
   if (compute_q_dev(c, fc, fc, s->d_Q, nX, k2)) return 1;
@@ -362,10 +378,52 @@ int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
   return launch_ok("collide");
 }
 
-int sbte_slab_step(sbte_slab* s, double Kn, int k2) {
+static int slab_step_direct(sbte_slab* s, double Kn, int k2) {
   if (sbte_slab_advect(s, 0)) return 1;
   if (sbte_slab_collide(s, Kn, k2)) return 1;
   if (s->order == 2 && sbte_slab_advect(s, 1)) return 1;
+  return 0;
+}
+
+// One time step.  After a first direct step (which also sizes every buffer) the launch sequence is captured once
+// and replayed: ~20-40 launches per step become one graph launch, which is what a small slab per GPU needs.
+int sbte_slab_step(sbte_slab* s, double Kn, int k2) {
+  sbte_ctx* c = s->c;
+  static const bool no_graph = getenv("SBTE_NO_GRAPH") != nullptr;
+  if (no_graph || c->k2_prof) return slab_step_direct(s, Kn, k2);
+  sbte_slab::StepGraph& g = s->graph;
+  if (g.exec && (g.Kn != Kn || g.k2 != k2 || g.gen != c->graph_gen)) {   // arguments or the context's buffers changed
+    cudaGraphExecDestroy(g.exec);
+    g = sbte_slab::StepGraph();
+  }
+  if (g.exec) {
+    CKS(cudaGraphLaunch(g.exec, c->stream));
+    c->launches += g.launches;
+    return 0;
+  }
+  if (g.seen == 0 || g.Kn != Kn || g.k2 != k2 || g.gen != c->graph_gen) {
+    if (slab_step_direct(s, Kn, k2)) return 1;
+    g.seen = 1; g.Kn = Kn; g.k2 = k2; g.gen = c->graph_gen;
+    return 0;
+  }
+  const unsigned long long before = c->launches;
+  CKS(cudaStreamBeginCapture(c->stream, cudaStreamCaptureModeThreadLocal));
+  const int rc = slab_step_direct(s, Kn, k2);
+  cudaGraph_t graph = nullptr;
+  cudaError_t e = cudaStreamEndCapture(c->stream, &graph);
+  if (rc != 0 || e != cudaSuccess || !graph || g.gen != c->graph_gen) {
+    if (graph) cudaGraphDestroy(graph);
+    if (rc == 0) set_error(std::string("graph capture of the slab step failed: ") + cudaGetErrorString(e));
+    g.seen = 0;
+    return 1;
+  }
+  g.launches = c->launches - before;
+  c->launches = before;
+  e = cudaGraphInstantiate(&g.exec, graph, 0);
+  cudaGraphDestroy(graph);
+  if (e != cudaSuccess) { g.exec = nullptr; set_error(std::string("cudaGraphInstantiate: ") + cudaGetErrorString(e)); return 1; }
+  CKS(cudaGraphLaunch(g.exec, c->stream));
+  c->launches += g.launches;
   return 0;
 }
 

@@ -93,24 +93,45 @@ void launch_upwind_one(cudaStream_t st, const double* f, double* fc, const doubl
 // Each rank owns two counters in IPC-shared device memory: ready (source array of pass e is complete) and
 // done (my reads of the neighbours' arrays in pass e are complete).  Plain stream order on each GPU plus
 // these two tiny kernels replaces the host-synchronised message exchange.
-__global__ void halo_post_kernel(int* flag, int value) {
-  __threadfence_system();
-  *reinterpret_cast<volatile int*>(flag) = value;
-  __threadfence_system();
-}
-// waits until, for each non-null neighbour flag pair, ready >= vr and done >= vd
-__global__ void halo_wait_kernel(const int* nbL, const int* nbR, int vr, int vd) {
+// Flags of one rank: {ready, done, epoch}.  epoch counts this rank's upwind passes ON THE DEVICE, so the same
+// launches can be replayed from a CUDA graph; every rank issues the same sequence of passes.
+//   begin: epoch++ ; ready = epoch ("my source array is complete") ; wait until each neighbour is ready for
+//          this pass and has finished reading my cells in the previous one (done >= epoch - 1)
+//   end:   done = epoch ("I no longer read my neighbours' source array of this pass")
+//   quiesce: wait until the neighbours' done reaches my epoch (before overwriting cells they may be reading)
+// Bounded spins: a lost neighbour becomes a launch error (~10 s at 2 GHz), not a hung GPU.
+__device__ __forceinline__ void spin_until(const volatile int* L, const volatile int* R, int vr, int vd) {
   const long long t0 = clock64();
-  const volatile int* L = reinterpret_cast<const volatile int*>(nbL);
-  const volatile int* R = reinterpret_cast<const volatile int*>(nbR);
   while ((L && (L[0] < vr || L[1] < vd)) || (R && (R[0] < vr || R[1] < vd))) {
-    if (clock64() - t0 > 20000000000LL) __trap();   // ~10 s at 2 GHz: a lost neighbour becomes an error, not a hang
+    if (clock64() - t0 > 20000000000LL) __trap();
   }
   __threadfence_system();
 }
-void launch_halo_post(cudaStream_t st, int* flag, int value) { halo_post_kernel<<<1, 1, 0, st>>>(flag, value); }
-void launch_halo_wait(cudaStream_t st, const int* nbL, const int* nbR, int vr, int vd) {
-  halo_wait_kernel<<<1, 1, 0, st>>>(nbL, nbR, vr, vd);
+__global__ void halo_begin_kernel(int* my, const int* nbL, const int* nbR) {
+  volatile int* m = reinterpret_cast<volatile int*>(my);
+  const int e = m[2] + 1;
+  m[2] = e;
+  __threadfence_system();
+  m[0] = e;
+  __threadfence_system();
+  spin_until(reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), e, e - 1);
+}
+__global__ void halo_end_kernel(int* my) {
+  __threadfence_system();
+  volatile int* m = reinterpret_cast<volatile int*>(my);
+  m[1] = m[2];
+  __threadfence_system();
+}
+__global__ void halo_quiesce_kernel(const int* my, const int* nbL, const int* nbR) {
+  const int e = reinterpret_cast<const volatile int*>(my)[2];
+  spin_until(reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), 0, e);
+}
+void launch_halo_begin(cudaStream_t st, int* my, const int* nbL, const int* nbR) {
+  halo_begin_kernel<<<1, 1, 0, st>>>(my, nbL, nbR);
+}
+void launch_halo_end(cudaStream_t st, int* my) { halo_end_kernel<<<1, 1, 0, st>>>(my); }
+void launch_halo_quiesce(cudaStream_t st, const int* my, const int* nbL, const int* nbR) {
+  halo_quiesce_kernel<<<1, 1, 0, st>>>(my, nbL, nbR);
 }
 
 // ---------------------------------------------------------------- second order (K6b)
@@ -240,6 +261,20 @@ void launch_average(cudaStream_t st, const double* f, double* fc, long n) {
   long blocks = (n + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
   average_kernel<<<(unsigned)blocks, 256, 0, st>>>(f, fc, n);
+}
+
+// With lazy module loading (the CUDA default) the first launch of a kernel loads it, and the driver cannot do that
+// while another kernel is spinning on the device: a pass that waits for a neighbour driven from the same process
+// (several slabs on one GPU, or one process driving several GPUs) would then wait for a kernel that cannot be
+// loaded.  Loading every transport / halo kernel up front removes that window.
+int preload_transport_kernels() {
+  cudaFuncAttributes a;
+  const void* fns[] = {(const void*)diffuse_bc_kernel, (const void*)upwind_one_kernel, (const void*)upwind_two_kernel,
+                       (const void*)halo_begin_kernel, (const void*)halo_end_kernel, (const void*)halo_quiesce_kernel,
+                       (const void*)extrapolate_kernel, (const void*)wall_face_kernel, (const void*)average_kernel};
+  for (const void* f : fns)
+    if (cudaFuncGetAttributes(&a, f) != cudaSuccess) return 1;
+  return 0;
 }
 
 }  // namespace sbte
