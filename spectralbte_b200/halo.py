@@ -6,7 +6,7 @@ non-blocking exchange per upwind pass over torch.distributed (NCCL on GPUs, gloo
 each rank sends its first/last `order` owned cells and receives its left/right ghost cells.
 Init_field 6 at order 1 is periodic: rank 0 and rank n-1 also exchange (:156-166).
 
-On one NVLink node there is a second mode with no messages at all (SlabHalo(..., mode="p2p") or SBTE_HALO=p2p):
+On one NVLink node the default mode has no messages at all (SlabHalo(..., mode="p2p"); SBTE_HALO=nccl selects messages):
 the ranks swap CUDA IPC handles once, and from then on the upwind kernels read the neighbours' boundary cells
 directly from peer memory, ordered by device-side counters (csrc/slab.cu peer_begin/peer_end).
 """
@@ -82,25 +82,44 @@ class SlabHalo:
         self.stream = torch.cuda.ExternalStream(slab.coll.stream, device=device)
         self.periodic = False
         self._cache = {}
-        self.mode = mode or os.environ.get("SBTE_HALO", "nccl")
+        self.mode = mode or os.environ.get("SBTE_HALO", "p2p")
         if self.mode not in ("nccl", "p2p"):
             raise ValueError("halo mode must be 'nccl' or 'p2p'")
         if slab.nranks == 1:
             self.mode = "nccl"   # nothing to exchange
-        if self.mode == "p2p":
-            self._connect_peers()
+        if self.mode == "p2p" and not self._connect_peers():
+            self.mode = "nccl"   # no peer access between these GPUs: fall back to messages (every rank agrees)
 
     def _connect_peers(self):
-        """Swap IPC handles and map the neighbours' slabs (the ring closes for the periodic order-1 case)."""
+        """Swap IPC handles and map the neighbours' slabs (the ring closes for the periodic order-1 case).
+        Returns False -- on every rank -- if any rank could not map its neighbours."""
         slab = self.slab
-        mine = (slab.ipc_export(), slab.cells_local)
+        ok = 1
+        try:
+            mine = (slab.ipc_export(), slab.cells_local)
+        except Exception:
+            mine, ok = None, 0
         everyone = [None] * slab.nranks
         dist.all_gather_object(everyone, mine)
-        for side, nb in peer_neighbours(slab.rank, slab.nranks, slab.init_field == 6 and slab.order == 1):
-            handles, cells = everyone[nb]
-            slab.ipc_import(side, handles, cells)
-        slab.set_peer_halo(True)
-        dist.barrier()   # nobody starts polling flags before every mapping exists
+        if any(e is None for e in everyone):
+            ok = 0
+        if ok:
+            try:
+                for side, nb in peer_neighbours(slab.rank, slab.nranks, slab.init_field == 6 and slab.order == 1):
+                    handles, cells = everyone[nb]
+                    slab.ipc_import(side, handles, cells)
+                slab.set_peer_halo(True)
+            except Exception:
+                ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)   # also the barrier: nobody polls flags before every mapping exists
+        if int(flag.item()) == 0:
+            try:
+                slab.set_peer_halo(False)
+            except Exception:
+                pass
+            return False
+        return True
 
     def _regions(self, which, stage):
         key = (which, stage)

@@ -78,3 +78,20 @@ def test_partition_allows_uneven_blocks():
                                          (451, 526), (526, 601)]
     assert [b - a for a, b in initial.partition(250, 8)] == [32, 32, 31, 31, 31, 31, 31, 31]
     assert initial.partition(640, 8) == [(80 * r, 80 * (r + 1)) for r in range(8)]
+
+
+def test_peer_neighbours_topology():
+    """Who maps whom in the peer-memory halo: chain for walls / no-flux ends, ring for the periodic order-1 shock."""
+    from spectralbte_b200.halo import peer_neighbours
+    assert peer_neighbours(0, 1, True) == []
+    assert peer_neighbours(0, 4, False) == [(1, 1)]
+    assert peer_neighbours(2, 4, False) == [(0, 1), (1, 3)]
+    assert peer_neighbours(3, 4, False) == [(0, 2)]
+    assert peer_neighbours(0, 4, True) == [(0, 3), (1, 1)]
+    assert peer_neighbours(3, 4, True) == [(0, 2), (1, 0)]
+    assert peer_neighbours(0, 2, True) == [(0, 1), (1, 1)]     # two ranks: both sides are the same neighbour
+    for n in (2, 3, 8):                                          # symmetry: if a maps b on the right, b maps a on the left
+        for periodic in (False, True):
+            for r in range(n):
+                for side, nb in peer_neighbours(r, n, periodic):
+                    assert (1 - side, r) in peer_neighbours(nb, n, periodic)
