@@ -16,31 +16,43 @@
 // Data movement is all TMA: the weight tile (COLS*N rows x N columns of W) is a 2-D tensor-map
 // copy, the xi-side line and the (zeta - xi)-side plane are 1-D bulk copies, each completing on an
 // mbarrier; a 3-stage ring keeps two steps of weights/lines in flight behind the FP64 pipe.
+#include <stdlib.h>
+
 #include "common.cuh"
 #include "internal.h"
 
 namespace sbte {
 
 // ------------------------------------------------------------------------------------------
-// any even N (12, 20, 22, 28, ...): lanes = cells on the cell-minor layout, one warp per zeta row, the
-// xi loop with incrementally wrapped indices.  L1-bound (two 512-byte operand reads per 6 FP64
-// instructions), roughly a third of the tuned kernels' rate but ~20x the row-per-CTA generic kernel on
-// batches; visits only the representative xi_x planes when handed the symmetrised tensor.
+// any even N (12, 20, 22, 28, ...): lanes = cells on the cell-minor layout, operands read straight from L1/L2
+// (no TMA staging), the xi loop with incrementally wrapped indices; visits only the representative xi_x planes
+// when handed the symmetrised tensor.
+// Each warp owns ANY_R consecutive zeta_z rows of one zeta (x,y) column: the xi-side operand is shared by the rows
+// and the (zeta - xi)-side operands form a sliding window (Toeplitz in z), so one step costs two 512-byte operand
+// reads for ANY_R products instead of two per product.
 // ------------------------------------------------------------------------------------------
+template <int ANY_R>
 __global__ void __launch_bounds__(256)
 qhat_batch_any_kernel(const double* __restrict__ W, const double2* __restrict__ spec, double2* __restrict__ qhat,
                       int N, int cells, int sym) {
   const long n3 = (long)N * N * N;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int cg = blockIdx.x;
-  const int zeta = blockIdx.y * 8 + warp;
-  if (zeta >= n3) return;
+  const int groups_z = (N + ANY_R - 1) / ANY_R;
+  const int task = blockIdx.y * 8 + warp;               // (zeta_x, zeta_y, group of ANY_R zeta_z rows)
+  if (task >= N * N * groups_z) return;
+  const int col = task / groups_z, zz0 = (task % groups_z) * ANY_R;
+  const int zx = col / N, zy = col % N;
   const int n2 = N / 2;
-  const int zx = zeta / (N * N), zy = (zeta / N) % N, zz = zeta % N;
   const double2* S = spec + (size_t)cg * n3 * 32 + lane;
-  const double* w = W + (size_t)zeta * n3;
+  const double* w0 = W + ((size_t)col * N + zz0) * n3;   // row zeta = (zx, zy, zz0)
+  bool live[ANY_R];
+#pragma unroll
+  for (int r = 0; r < ANY_R; r++) live[r] = zz0 + r < N;
   const int nrep = sym ? sym_nrep(N, zx) : N;
-  double ar = 0.0, ai = 0.0;
+  double ar[ANY_R], ai[ANY_R];
+#pragma unroll
+  for (int r = 0; r < ANY_R; r++) { ar[r] = 0.0; ai[r] = 0.0; }
   for (int c = 0; c < nrep; c++) {
     const int ex = sym ? sym_rep(N, zx, c) : c;
     int x = zx + n2 - ex;
@@ -50,29 +62,55 @@ qhat_batch_any_kernel(const double* __restrict__ W, const double2* __restrict__ 
       if (y < 0) y += N; else if (y > N - 1) y -= N;
       const double2* gl = S + (size_t)((ex * N + ey) * N) * 32;
       const double2* fl = S + (size_t)((x * N + y) * N) * 32;
-      const double* wl = w + (ex * N + ey) * N;
-      int z = zz + n2;            // xi_z = 0
+      const double* wl = w0 + (ex * N + ey) * N;
+      // window fw[r] = f^[wrap(zz0 + r + N/2 - xi_z)], xi_z = 0
+      double2 fw[ANY_R];
+      int z = zz0 + n2;
       if (z > N - 1) z -= N;
-#pragma unroll 2
+#pragma unroll
+      for (int r = 0; r < ANY_R; r++) {
+        int zr = z + r;
+        if (zr > N - 1) zr -= N;
+        fw[r] = fl[zr * 32];
+      }
       for (int ez = 0; ez < N; ez++) {
-        const double2 g = gl[ez * 32], f = fl[z * 32];
-        const double wv = wl[ez];
-        const double pr = g.x * f.x - g.y * f.y, pi = g.x * f.y + g.y * f.x;
-        ar = fma(wv, pr, ar);
-        ai = fma(wv, pi, ai);
+        const double2 g = gl[ez * 32];
+#pragma unroll
+        for (int r = 0; r < ANY_R; r++) {
+          const double wv = live[r] ? wl[(size_t)r * n3 + ez] : 0.0;
+          const double pr = g.x * fw[r].x - g.y * fw[r].y, pi = g.x * fw[r].y + g.y * fw[r].x;
+          ar[r] = fma(wv, pr, ar[r]);
+          ai[r] = fma(wv, pi, ai[r]);
+        }
+        // xi_z + 1: every row's operand index drops by one
+#pragma unroll
+        for (int r = ANY_R - 1; r > 0; r--) fw[r] = fw[r - 1];
         z = (z == 0) ? N - 1 : z - 1;
+        fw[0] = fl[z * 32];
       }
     }
   }
   const long cell = (long)cg * 32 + lane;
-  if (cell < cells) qhat[cell * n3 + zeta] = make_double2(ar, ai);
+  if (cell < cells) {
+#pragma unroll
+    for (int r = 0; r < ANY_R; r++)
+      if (live[r]) qhat[cell * n3 + (long)col * N + zz0 + r] = make_double2(ar[r], ai[r]);
+  }
 }
 
 void launch_qhat_batch_any(sbte_ctx* c, const double2* spec, double2* qhat, int cells, bool sym) {
   const int groups = (cells + 31) / 32;
-  dim3 grid(groups, (unsigned)((c->n3 + 7) / 8));
+  static const int R0 = getenv("SBTE_ANY_R") ? atoi(getenv("SBTE_ANY_R")) : 4;
+  const int R = (R0 == 8 || R0 == 2) ? R0 : 4;
+  const int tasks = c->N * c->N * ((c->N + R - 1) / R);
+  dim3 grid(groups, (unsigned)((tasks + 7) / 8));
   k2_mark(c);
-  qhat_batch_any_kernel<<<grid, 256, 0, c->stream>>>(sym ? c->d_Ws : c->d_W, spec, qhat, c->N, cells, sym ? 1 : 0);
+  if (R == 8)
+    qhat_batch_any_kernel<8><<<grid, 256, 0, c->stream>>>(sym ? c->d_Ws : c->d_W, spec, qhat, c->N, cells, sym ? 1 : 0);
+  else if (R == 2)
+    qhat_batch_any_kernel<2><<<grid, 256, 0, c->stream>>>(sym ? c->d_Ws : c->d_W, spec, qhat, c->N, cells, sym ? 1 : 0);
+  else
+    qhat_batch_any_kernel<4><<<grid, 256, 0, c->stream>>>(sym ? c->d_Ws : c->d_W, spec, qhat, c->N, cells, sym ? 1 : 0);
   k2_mark(c);
   c->launches += 1;
 }
