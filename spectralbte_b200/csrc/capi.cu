@@ -313,7 +313,11 @@ static int resolve_k2(sbte_ctx* c, int batch, int k2, bool same = true) {
   return k2;
 }
 
-int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d_qhat, int batch, int k2) {
+// nsplit: in = the caller can add this many partial spectra (d_qhat + p * n3), out = how many were written
+int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d_qhat, int batch, int k2,
+                   int* nsplit = nullptr) {
+  const int max_split = nsplit ? *nsplit : 1;
+  if (nsplit) *nsplit = 1;
   if (!c->d_W) { set_error("no weights bound"); return 1; }
   if (ensure_capacity(c, batch)) return 1;
   const bool same = (d_f == d_g);
@@ -345,7 +349,12 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     QhatPair p = {gl, c->d_lay[0]};
     const bool sym = want_sym(c, same);
     if (sym && ensure_sym(c)) return 1;
-    launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym);
+    // one cell keeps 1024 CTAs busy for only 3.5 waves: splitting each column's xi_x planes between two CTAs
+    // shortens the under-filled last wave (the two partial spectra are added by the inverse transform)
+    static const int want = getenv("SBTE_NO_SPLIT") ? 1 : (getenv("SBTE_SPLIT") ? atoi(getenv("SBTE_SPLIT")) : 2);
+    const int ns = (c->N == 32 && want >= 1 && want <= max_split) ? want : 1;
+    launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym, ns);
+    if (nsplit) *nsplit = ns;
   } else {
     if (!same && batch > 4) { set_error("generic convolution with f != g is limited to 4 cells"); return 1; }
     launch_fft3d(c, d_f, nullptr, 0, batch, c->d_specA, nullptr, 0, nullptr, false);
@@ -373,8 +382,10 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
     launch_fft3d_parts(c, c->d_parts, c->parts_stride, c->sched, 1, batch, nullptr, d_Q);
     return check_launch("batched compute_q");
   }
-  if (qhat_from_real(c, d_f, d_g, c->d_qhat, batch, k2)) return 1;
-  launch_fft3d(c, nullptr, c->d_qhat, 1, batch, nullptr, nullptr, 0, d_Q, false);
+  int nsplit = (batch == 1 && fft_cluster_supported(c->N)) ? 8 : 1;   // d_qhat holds 32 cells' worth of spectrum
+  if (qhat_from_real(c, d_f, d_g, c->d_qhat, batch, k2, &nsplit)) return 1;
+  if (nsplit > 1) launch_fft3d_inverse_sum(c, c->d_qhat, nsplit, d_Q);
+  else launch_fft3d(c, nullptr, c->d_qhat, 1, batch, nullptr, nullptr, 0, d_Q, false);
   return check_launch("inverse fft");
 }
 

@@ -55,6 +55,7 @@ struct PartsIn {
 struct FftJob {
   const double* in_real;
   const double2* in_cplx;
+  int in_parts;              // > 1: the input is the sum of in_parts spectra n3 apart (split convolution), added in order
   double2* out_nat;
   double2* out_lay;
   double* out_real;
@@ -382,6 +383,7 @@ fft3d_cluster_kernel(FftJobs jobs, PartsIn pin, const double2* __restrict__ pre,
   const long coff = (cell - (long)job * jobs.cells_per_job) * n3;   // cell offset inside the job's arrays
   const double* in_real = jobs.j[job].in_real;
   const double2* in_cplx = jobs.j[job].in_cplx;
+  const int in_parts = jobs.j[job].in_parts;
   const int i0 = r * PL;
   double2* postsm = clsm + PL * N * P;  // [N][PL][N]: post-twiddles of the outputs this CTA emits (rows j in its slice)
   constexpr int LB = 8;
@@ -423,7 +425,14 @@ fft3d_cluster_kernel(FftJobs jobs, PartsIn pin, const double2* __restrict__ pre,
             const double2 z = pin.parts[(size_t)m * pin.stride + cell * n3 + loc];
             xr[q] += z.x; xi[q] += z.y;
           }
-        } else { const double2 z = __ldg(in_cplx + coff + loc); xr[q] = z.x; xi[q] = z.y; }
+        } else {
+          const double2 z = __ldg(in_cplx + coff + loc);
+          xr[q] = z.x; xi[q] = z.y;
+          for (int m = 1; m < in_parts; m++) {
+            const double2 z2 = __ldg(in_cplx + (long)m * n3 + coff + loc);
+            xr[q] += z2.x; xi[q] += z2.y;
+          }
+        }
       }
     }
 #pragma unroll
@@ -539,6 +548,15 @@ bool launch_fft3d_multi(sbte_ctx* c, int njobs, const double* const* in_real, do
   jobs.layout = layout;
   PartsIn nopart = {nullptr, 0, nullptr, 0, 0};
   return launch_cluster(c, jobs, nopart, 0, njobs);
+}
+
+bool launch_fft3d_inverse_sum(sbte_ctx* c, const double2* parts, int nparts, double* out_real) {
+  if (!fft_cluster_supported(c->N)) return false;
+  FftJobs jobs = {};
+  jobs.j[0].in_cplx = parts; jobs.j[0].in_parts = nparts; jobs.j[0].out_real = out_real;
+  jobs.cells_per_job = 1;
+  PartsIn nopart = {nullptr, 0, nullptr, 0, 0};
+  return launch_cluster(c, jobs, nopart, 1, 1);
 }
 
 static bool try_cluster_fft(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,

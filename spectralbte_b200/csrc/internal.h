@@ -130,7 +130,12 @@ struct QhatPair {
 void launch_qhat_generic(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int batch);
 // stream kernel (N in {16,24,32}, batch 1): parity-layout operands
 bool qhat_stream_supported(int N);
-void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym);
+void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym,
+                        int nsplit = 1);
+// inverse transform of the sum of `nparts` partial spectra (n3 apart, added in order) of one cell into a real field;
+// cluster kernel only
+bool fft_cluster_supported(int N);
+bool launch_fft3d_inverse_sum(sbte_ctx* c, const double2* parts, int nparts, double* out_real);
 void launch_symmetrize_weights(sbte_ctx* c, const double* W, double* Ws);
 // batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32
 bool qhat_batch_supported(int N);

@@ -106,7 +106,8 @@ struct StreamCfg {
 template <int N, int NP, int DEPTH, bool SYM, int WT>
 __global__ void __launch_bounds__(StreamCfg<N, WT>::THREADS, (N == 32 && NP == 1 && DEPTH <= 2) ? 2 : 1)
 qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
-                   const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat) {
+                   const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat,
+                   int nsplit) {
   using C = StreamCfg<N, WT>;
   constexpr int HALF = C::HALF, PLANE = C::PLANE;
   constexpr long n3 = (long)N * N * N;
@@ -119,9 +120,14 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   const int rb = warp % C::RB, ph = warp / C::RB;
   const int cp = lane % HALF, rgw = lane / HALF;
   const bool active = rgw < C::RGW;
-  const int zx = blockIdx.x / N, zy = blockIdx.x % N;
-  const int nchunk = SYM ? sym_nrep(N, zx) : N;             // xi_x planes visited by this CTA
-  auto chunk_ex = [&](int c) { return SYM ? sym_rep(N, zx, c) : c; };
+  // nsplit > 1: the xi_x planes of a column are shared between nsplit CTAs, each writing its own partial
+  // spectrum qhat[part]; the inverse transform adds the parts in order.  More, shorter CTAs = a shorter tail.
+  const int part = blockIdx.x / (N * N), colid = blockIdx.x - part * (N * N);
+  const int zx = colid / N, zy = colid % N;
+  const int nchunk_all = SYM ? sym_nrep(N, zx) : N;
+  const int cbeg = part * nchunk_all / nsplit;
+  const int nchunk = (part + 1) * nchunk_all / nsplit - cbeg;   // xi_x planes visited by this CTA
+  auto chunk_ex = [&](int c) { return SYM ? sym_rep(N, zx, cbeg + c) : cbeg + c; };
   const int r0 = rb * C::ROWS_W + (active ? rgw : 0) * 4;   // first of this thread's 4 zeta_z rows
   const int c0 = 2 * cp;                                    // first of its 2 xi_z columns
 
@@ -159,7 +165,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   pdl_launch_dependents();   // the inverse transform may stage its twiddles while this grid drains
 
   // weight stream: rows zeta = (zx, zy, r0 + j), j = 0..3; this thread's 16 bytes sit at column c0
-  const double* wrow = W + ((long)blockIdx.x * N + r0) * n3 + c0;
+  const double* wrow = W + ((long)colid * N + r0) * n3 + c0;
   const int NIT = nchunk * C::SPC;  // iterations of this warp over (visited xi_x, xi_y)
   double2 wb[DEPTH][4];
   auto load_w = [&](int it, double2 (&dst)[4]) {
@@ -258,14 +264,14 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
         sr += v.x; si += v.y;
       }
     }
-    qhat[(long)blockIdx.x * N + r] = make_double2(sr, si);
+    qhat[(long)part * n3 + (long)colid * N + r] = make_double2(sr, si);
   }
 }
 
 bool qhat_stream_supported(int N) { return N == 16 || N == 24 || N == 32; }
 
 template <int N, int NP, int DEPTH, bool SYM, int WT = 8>
-static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pairs, double2* qhat) {
+static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pairs, double2* qhat, int nsplit = 1) {
   using C = StreamCfg<N, WT>;
   const size_t smem = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2) + 64;
   auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM, WT>;
@@ -276,7 +282,7 @@ static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pai
   }
   k2_mark(c);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(N * N);
+  cfg.gridDim = dim3(N * N * nsplit);
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
@@ -286,16 +292,17 @@ static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pai
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 1 : 0;
   cudaLaunchKernelEx(&cfg, kern, W, pairs[0].xi_side, pairs[0].dif_side, NP > 1 ? pairs[1].xi_side : (const double2*)nullptr,
-                     NP > 1 ? pairs[1].dif_side : (const double2*)nullptr, qhat);
+                     NP > 1 ? pairs[1].dif_side : (const double2*)nullptr, qhat, nsplit);
   k2_mark(c);
   c->launches += 1;
 }
 
 template <int N, bool SYM>
-static void launch_stream_n(sbte_ctx* c, const double* W, int npairs, const QhatPair* pairs, double2* qhat, int depth) {
+static void launch_stream_n(sbte_ctx* c, const double* W, int npairs, const QhatPair* pairs, double2* qhat, int depth,
+                            int nsplit) {
   if (npairs == 1) {
-    if (depth >= 4) launch_stream_inst<N, 1, 4, SYM>(c, W, pairs, qhat);
-    else launch_stream_inst<N, 1, 2, SYM>(c, W, pairs, qhat);
+    if (depth >= 4) launch_stream_inst<N, 1, 4, SYM>(c, W, pairs, qhat, nsplit);
+    else launch_stream_inst<N, 1, 2, SYM>(c, W, pairs, qhat, nsplit);
   } else {
     // two operand pairs need 128 KB of plane ring => one CTA per SM.  Either 8 warps with four weight tiles per
     // thread in flight, or (default) 16 warps with two: the same 64 KB per SM in flight, twice the warps to
@@ -306,12 +313,14 @@ static void launch_stream_n(sbte_ctx* c, const double* W, int npairs, const Qhat
 }
 
 // sym: stream the symmetrised tensor (caller guarantees xi-side and dif-side operands describe f == g)
-void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym) {
+// nsplit (one operand pair only): partial spectra qhat[0..nsplit) of n3 elements each, to be added by the caller
+void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym, int nsplit) {
+  if (npairs != 1) nsplit = 1;
   const double* W = sym ? c->d_Ws : c->d_W;
   switch (c->N) {
-    case 16: sym ? launch_stream_n<16, true>(c, W, npairs, pairs, qhat, depth) : launch_stream_n<16, false>(c, W, npairs, pairs, qhat, depth); break;
-    case 24: sym ? launch_stream_n<24, true>(c, W, npairs, pairs, qhat, depth) : launch_stream_n<24, false>(c, W, npairs, pairs, qhat, depth); break;
-    case 32: sym ? launch_stream_n<32, true>(c, W, npairs, pairs, qhat, depth) : launch_stream_n<32, false>(c, W, npairs, pairs, qhat, depth); break;
+    case 16: sym ? launch_stream_n<16, true>(c, W, npairs, pairs, qhat, depth, nsplit) : launch_stream_n<16, false>(c, W, npairs, pairs, qhat, depth, nsplit); break;
+    case 24: sym ? launch_stream_n<24, true>(c, W, npairs, pairs, qhat, depth, nsplit) : launch_stream_n<24, false>(c, W, npairs, pairs, qhat, depth, nsplit); break;
+    case 32: sym ? launch_stream_n<32, true>(c, W, npairs, pairs, qhat, depth, nsplit) : launch_stream_n<32, false>(c, W, npairs, pairs, qhat, depth, nsplit); break;
     default: set_error("qhat_stream: unsupported N"); break;
   }
 }
