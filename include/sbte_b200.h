@@ -84,6 +84,9 @@ SBTE_API const char *sbte_last_error(void);
 /* One context per (N, L_v) grid and device. v, eta: N host doubles each (src/initializer.c:66-82). */
 SBTE_API int sbte_create(sbte_ctx **out, int N, double L_v, const double *v, const double *eta, int device);
 SBTE_API int sbte_destroy(sbte_ctx *c);
+/* number of visible GPUs; mutual peer access between the GPUs of two contexts (one process driving several GPUs) */
+SBTE_API int sbte_device_count(void);
+SBTE_API int sbte_enable_peer_access(sbte_ctx *a, sbte_ctx *b);
 SBTE_API int sbte_sync(sbte_ctx *c);
 SBTE_API void *sbte_stream(sbte_ctx *c);                      /* the cudaStream_t every kernel is launched on */
 SBTE_API unsigned long long sbte_launch_count(sbte_ctx *c);   /* kernels launched so far through c */

@@ -29,6 +29,8 @@ PROTOTYPES = {
     "sbte_last_error": (C.c_char_p, []),
     "sbte_create": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_double, _dp, _dp, C.c_int]),
     "sbte_destroy": (C.c_int, [_vp]),
+    "sbte_device_count": (C.c_int, []),
+    "sbte_enable_peer_access": (C.c_int, [_vp, _vp]),
     "sbte_sync": (C.c_int, [_vp]),
     "sbte_stream": (_vp, [_vp]),
     "sbte_launch_count": (C.c_ulonglong, [_vp]),

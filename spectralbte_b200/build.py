@@ -81,7 +81,7 @@ def build_host(force=False):
     inc = os.path.join(os.path.dirname(HERE), "include")
     if force or _stale(HOST_BIN, [HOST_SRC, os.path.join(inc, "sbte_b200.h"), LIB]):
         cmd = ["gcc", "-std=gnu99", "-O2", "-Wall", "-I", inc, HOST_SRC, "-L", HERE, "-lsbte_b200",
-               "-Wl,-rpath,$ORIGIN/..", "-lm", "-o", HOST_BIN]
+               "-Wl,-rpath,$ORIGIN/..", "-lm", "-lpthread", "-o", HOST_BIN]
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("host driver build failed:\n%s\n%s" % (r.stdout, r.stderr))

@@ -503,10 +503,39 @@ int sbte_destroy(sbte_ctx* c) {
   return 0;
 }
 
-int sbte_sync(sbte_ctx* c) { CK(cudaStreamSynchronize(c->stream)); return check_launch("sync"); }
+int sbte_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+}
+
+// lets kernels of either context read the other's memory (same-process multi-GPU: sbte_slab_peer_attach)
+int sbte_enable_peer_access(sbte_ctx* a, sbte_ctx* b) {
+  if (a->device == b->device) return 0;
+  for (int dir = 0; dir < 2; dir++) {
+    sbte_ctx* from = dir ? b : a;
+    sbte_ctx* to = dir ? a : b;
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, from->device, to->device));
+    if (!can) { set_error("no peer access between GPU " + std::to_string(from->device) + " and " + std::to_string(to->device)); return 1; }
+    CK(cudaSetDevice(from->device));
+    cudaError_t e = cudaDeviceEnablePeerAccess(to->device, 0);
+    if (e == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();
+    else if (e != cudaSuccess) { set_error(std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e)); return 1; }
+  }
+  return 0;
+}
+
+int sbte_sync(sbte_ctx* c) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
+  CK(cudaStreamSynchronize(c->stream)); return check_launch("sync");
+}
 void* sbte_stream(sbte_ctx* c) { return (void*)c->stream; }
 unsigned long long sbte_launch_count(sbte_ctx* c) { return c->launches; }
-int sbte_reserve(sbte_ctx* c, int cells) { return ensure_capacity(c, cells); }
+int sbte_reserve(sbte_ctx* c, int cells) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
+  return ensure_capacity(c, cells);
+}
 
 int sbte_set_symmetrize(sbte_ctx* c, int enable) {
   if (c->sym_enabled != (enable != 0)) c->graph_gen++;
@@ -521,6 +550,7 @@ int sbte_k2_profile(sbte_ctx* c, int enable) {
 }
 
 int sbte_k2_profile_read(sbte_ctx* c, double* total_ms, int* launches) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   CK(cudaStreamSynchronize(c->stream));
   double sum = 0.0;
   const size_t pairs = c->k2_ev_used / 2;
@@ -538,17 +568,20 @@ int sbte_k2_profile_read(sbte_ctx* c, double* total_ms, int* launches) {
 int sbte_dev_alloc(void** d_ptr, size_t bytes) { CK(cudaMalloc(d_ptr, bytes)); return 0; }
 int sbte_dev_free(void* d_ptr) { CK(cudaFree(d_ptr)); return 0; }
 int sbte_h2d(sbte_ctx* c, void* d_dst, const void* src, size_t bytes) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   CK(cudaMemcpyAsync(d_dst, src, bytes, cudaMemcpyHostToDevice, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 int sbte_d2h(sbte_ctx* c, void* dst, const void* d_src, size_t bytes) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   CK(cudaMemcpyAsync(dst, d_src, bytes, cudaMemcpyDeviceToHost, c->stream));
   CK(cudaStreamSynchronize(c->stream));
   return 0;
 }
 
 int sbte_d2d(sbte_ctx* c, void* d_dst, const void* d_src, size_t bytes) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   CK(cudaMemcpyAsync(d_dst, d_src, bytes, cudaMemcpyDeviceToDevice, c->stream));
   return 0;
 }
@@ -611,6 +644,7 @@ int sbte_weights_load_file(sbte_ctx* c, const char* path) {
 }
 
 int sbte_weights_bind_device(sbte_ctx* c, const double* d_W) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   release_weights(c);
   c->d_W = d_W; c->owns_W = false;
   return make_tensor_map(c);
@@ -636,6 +670,7 @@ int sbte_weights_generate_iso(sbte_ctx* c, double lambda) {
 }
 
 int sbte_weights_save_file(sbte_ctx* c, const char* path) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   if (!c->d_W) { set_error("no weights bound"); return 1; }
   FILE* fp = fopen(path, "wb");
   if (!fp) { set_error(std::string("cannot create weight file ") + path); return 1; }
@@ -660,34 +695,41 @@ int sbte_weights_save_file(sbte_ctx* c, const char* path) {
 
 // ---- device-pointer operations
 int sbte_fft3d(sbte_ctx* c, const double* d_in, double* d_out, int invert, int batch) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   if (ensure_capacity(c, batch)) return 1;
   launch_fft3d(c, nullptr, (const double2*)d_in, invert, batch, (double2*)d_out, nullptr, 0, nullptr, false);
   return check_launch("fft3d");
 }
 
 int sbte_qhat(sbte_ctx* c, const double* d_f, const double* d_g, double* d_qhat, int batch, int k2) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   return qhat_from_real(c, d_f, d_g, (double2*)d_qhat, batch, k2);
 }
 
 int sbte_compute_q(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   return compute_q_dev(c, d_f, d_g, d_Q, batch, k2);
 }
 
 int sbte_compute_q_maxpreserve(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int k2) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   return compute_q_maxpreserve_dev(c, d_f, d_g, d_Q, k2);
 }
 
 int sbte_conserve(sbte_ctx* c, double* d_Q, int batch) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   launch_conserve(c, d_Q, batch);
   return check_launch("conserve");
 }
 
 int sbte_moment_functionals(sbte_ctx* c, const double* d_Q, double* d_b5, int batch) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   launch_moment_functionals(c, d_Q, d_b5, batch);
   return check_launch("moment_functionals");
 }
 
 int sbte_moments(sbte_ctx* c, const double* d_f, double* d_mom8, int batch) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   launch_moments(c, d_f, d_mom8, batch);
   return check_launch("moments");
 }
@@ -698,6 +740,7 @@ static int step_0d_direct(sbte_ctx* c, double* d_f, double dt, double Kn, int or
 // direct execution (allocations, attributes, symmetrised weights) it is captured into a CUDA graph and
 // replayed; profiling, SBTE_NO_GRAPH=1 or a change of arguments fall back to direct launches.
 int sbte_step_0d(sbte_ctx* c, double* d_f, double dt, double Kn, int order, int k2) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   if (ensure_capacity(c, 1)) return 1;
   static int no_graph = -1;
   if (no_graph < 0) { const char* e = getenv("SBTE_NO_GRAPH"); no_graph = (e && atoi(e) != 0) ? 1 : 0; }
@@ -756,6 +799,7 @@ static int step_0d_direct(sbte_ctx* c, double* d_f, double dt, double Kn, int or
 
 // ---- host-pointer forms
 int sbte_compute_q_host(sbte_ctx* c, const double* f, const double* g, double* Q, int k2) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   if (ensure_capacity(c, 1)) return 1;
   const size_t bytes = (size_t)c->n3 * sizeof(double);
   CK(cudaMemcpyAsync(c->d_f, f, bytes, cudaMemcpyHostToDevice, c->stream));
@@ -771,6 +815,7 @@ int sbte_compute_q_host(sbte_ctx* c, const double* f, const double* g, double* Q
 }
 
 int sbte_compute_q_maxpreserve_host(sbte_ctx* c, const double* f, const double* g, double* Q, int k2) {
+  cudaSetDevice(c->device);   // one process may drive several GPUs
   if (ensure_capacity(c, 1)) return 1;
   const size_t bytes = (size_t)c->n3 * sizeof(double);
   CK(cudaMemcpyAsync(c->d_f, f, bytes, cudaMemcpyHostToDevice, c->stream));

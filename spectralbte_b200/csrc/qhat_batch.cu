@@ -317,10 +317,10 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
                             const BatchSched& sch) {
   using C = Batch2Cfg<N>;
   auto kern = qhat_batch2_kernel<N>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned configured = 0;   // per device: function attributes belong to the device context
+  if (!((configured >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    configured = true;
+    configured |= 1u << c->device;
   }
   k2_mark(c);
   kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapWs : c->tmapW, spec, parts, part_stride, cells, sch);
@@ -507,10 +507,10 @@ static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, si
                             const BatchSched& sch) {
   using C = Batch3Cfg<N>;
   auto kern = qhat_batch3_kernel<N>;
-  static bool configured = false;
-  if (!configured) {
+  static unsigned configured = 0;   // per device: function attributes belong to the device context
+  if (!((configured >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    configured = true;
+    configured |= 1u << c->device;
   }
   k2_mark(c);
   kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapWs : c->tmapW, spec, parts, part_stride, cells, sch);

@@ -200,6 +200,7 @@ int sbte_slab_create(sbte_ctx* c, sbte_slab** out, int cells_local, int order, c
 
 int sbte_slab_destroy(sbte_slab* s) {
   if (!s) return 0;
+  cudaSetDevice(s->c->device);
   cudaStreamSynchronize(s->c->stream);
   if (s->graph.exec) cudaGraphExecDestroy(s->graph.exec);
   for (int side = 0; side < 2; side++)
@@ -217,6 +218,7 @@ int sbte_slab_destroy(sbte_slab* s) {
 
 // ---- peer-memory halo set-up (one process per GPU): export my slabs, import the neighbours'
 int sbte_slab_ipc_export(sbte_slab* s, unsigned char* handles256) {
+  cudaSetDevice(s->c->device);
   if (!s->d_flags) {
     CKS(cudaMalloc(&s->d_flags, 256));
     CKS(cudaMemset(s->d_flags, 0, 256));
@@ -235,6 +237,7 @@ int sbte_slab_ipc_export(sbte_slab* s, unsigned char* handles256) {
 }
 
 int sbte_slab_ipc_import(sbte_slab* s, int side, const unsigned char* handles256, int neighbour_cells) {
+  cudaSetDevice(s->c->device);
   if (side < 0 || side > 1) { set_error("side must be 0 (left) or 1 (right)"); return 1; }
   sbte_slab::Peer& p = s->nb[side];
   cudaIpcMemHandle_t h;
@@ -273,6 +276,7 @@ int sbte_slab_peer_attach(sbte_slab* s, int side, sbte_slab* other) {
 
 // diagnostic: this rank's {ready, done, epoch} counters (synchronous copy on a side stream-less path)
 int sbte_slab_halo_state(sbte_slab* s, int* state3) {
+  cudaSetDevice(s->c->device);
   state3[0] = state3[1] = state3[2] = 0;
   if (!s->d_flags) return 0;
   CKS(cudaMemcpy(state3, s->d_flags, 3 * sizeof(int), cudaMemcpyDeviceToHost));
@@ -280,6 +284,7 @@ int sbte_slab_halo_state(sbte_slab* s, int* state3) {
 }
 
 int sbte_slab_set_peer_halo(sbte_slab* s, int enable) {
+  cudaSetDevice(s->c->device);
   if (enable && !s->d_flags) { set_error("export/import the IPC handles before enabling peer halos"); return 1; }
   if (enable && preload_transport_kernels()) { set_error("could not load the transport kernels"); return 1; }
   s->p2p = enable ? 1 : 0;
@@ -290,9 +295,11 @@ double* sbte_slab_f(sbte_slab* s) { return s->d_f; }
 double* sbte_slab_fconv(sbte_slab* s) { return s->d_fc; }
 
 int sbte_slab_upload(sbte_slab* s, const double* f_host) {
+  cudaSetDevice(s->c->device);
   return sbte_h2d(s->c, s->d_f, f_host, (size_t)s->ncell * s->c->n3 * sizeof(double));
 }
 int sbte_slab_download(sbte_slab* s, double* f_host) {
+  cudaSetDevice(s->c->device);
   return sbte_d2h(s->c, f_host, s->d_f, (size_t)s->ncell * s->c->n3 * sizeof(double));
 }
 
@@ -315,6 +322,7 @@ int sbte_slab_halo_regions(sbte_slab* s, int which, int stage, int side, double*
 }
 
 int sbte_slab_upwind_stage(sbte_slab* s, int which, int stage) {
+  cudaSetDevice(s->c->device);
   double *A, *B;
   pick(s, which, A, B);
   sbte_ctx* c = s->c;
@@ -333,6 +341,7 @@ int sbte_slab_upwind_stage(sbte_slab* s, int which, int stage) {
 }
 
 int sbte_slab_advect_finish(sbte_slab* s, int which) {
+  cudaSetDevice(s->c->device);
   if (s->order == 1) return 0;
   double *A, *B;
   pick(s, which, A, B);
@@ -343,6 +352,7 @@ int sbte_slab_advect_finish(sbte_slab* s, int which) {
 }
 
 int sbte_slab_advect(sbte_slab* s, int which) {
+  cudaSetDevice(s->c->device);
   if (s->nranks != 1 && !s->p2p) { set_error("sbte_slab_advect needs ghost cells: exchange halos with the staged calls or enable peer halos"); return 1; }
   if (sbte_slab_upwind_stage(s, which, 0)) return 1;
   if (s->order == 2) {
@@ -354,6 +364,7 @@ int sbte_slab_advect(sbte_slab* s, int which) {
 
 // exec/boltz.c:285-345 for all owned cells at once
 int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
+  cudaSetDevice(s->c->device);
   sbte_ctx* c = s->c;
   const long n3 = c->n3;
   const int o = s->order, nX = s->nX;
@@ -388,6 +399,7 @@ static int slab_step_direct(sbte_slab* s, double Kn, int k2) {
 // One time step.  After a first direct step (which also sizes every buffer) the launch sequence is captured once
 // and replayed: ~20-40 launches per step become one graph launch, which is what a small slab per GPU needs.
 int sbte_slab_step(sbte_slab* s, double Kn, int k2) {
+  cudaSetDevice(s->c->device);
   sbte_ctx* c = s->c;
   static const bool no_graph = getenv("SBTE_NO_GRAPH") != nullptr;
   if (no_graph || c->k2_prof) return slab_step_direct(s, Kn, k2);
@@ -428,6 +440,7 @@ int sbte_slab_step(sbte_slab* s, double Kn, int k2) {
 }
 
 int sbte_slab_moments(sbte_slab* s, double* mom_host) {
+  cudaSetDevice(s->c->device);
   sbte_ctx* c = s->c;
   launch_moments(c, cell(s->d_f, c->n3, s->order), s->d_mom, s->nX);
   if (launch_ok("moments")) return 1;

@@ -12,6 +12,7 @@
  * Scope: one species ("default"), isotropic weights, Init_field 0/2/4/5 (0D) and 0/3/6 (1D).
  */
 #include <math.h>
+#include <pthread.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -222,10 +223,12 @@ static void init_inhom(const params *p, const double *v, int nX, double *slab) {
 }
 
 /* src/weights.c:66-124: load the stored file unless Recompute_weights, else generate (on the device) and store */
-static void setup_weights(sbte_ctx *ctx, const params *p) {
+/* primary = 0: a further GPU of the same run; the file exists by now (loaded or just written by the first GPU) */
+static void setup_weights(sbte_ctx *ctx, const params *p, int primary) {
   char name[200];
   FILE *fp;
   snprintf(name, sizeof(name), "Weights/N%d_isotropic_L_v%g_lambda%g.wts", p->N, p->L_v, p->lambda);
+  if (!primary) { CHECK(sbte_weights_load_file(ctx, name)); return; }
   if (p->weightFlag == 0 && (fp = fopen(name, "r"))) {
     fclose(fp);
     printf("Loading weights from file %s\n", name);
@@ -246,16 +249,18 @@ static double now_s(void) {
   return (double)ts.tv_sec + 1e-9 * (double)ts.tv_nsec;
 }
 
-static void store_restart(const char *input, const double *slab_h, int nX, int order, long n3, int t) {
+static void store_restart(const char *input, const double *slab_h, int nX, int order, long n3, int t, int rank) {
   char name[300];
   FILE *fp;
-  snprintf(name, sizeof(name), "Restart/%s_time.plt", input);
-  fp = fopen(name, "w");
-  if (!fp) { printf("Something happened when trying to save the time\n"); exit(1); }
-  printf("Time stored: %d\n", t);
-  fwrite(&t, sizeof(int), 1, fp);
-  fclose(fp);
-  snprintf(name, sizeof(name), "Restart/%s_rank%d_%s.plt", input, 0, "default");
+  if (rank == 0) {
+    snprintf(name, sizeof(name), "Restart/%s_time.plt", input);
+    fp = fopen(name, "w");
+    if (!fp) { printf("Something happened when trying to save the time\n"); exit(1); }
+    printf("Time stored: %d\n", t);
+    fwrite(&t, sizeof(int), 1, fp);
+    fclose(fp);
+  }
+  snprintf(name, sizeof(name), "Restart/%s_rank%d_%s.plt", input, rank, "default");
   printf("%s\n", name);
   fp = fopen(name, "w");
   if (!fp || fwrite(slab_h + (size_t)order * n3, sizeof(double), (size_t)nX * n3, fp) != (size_t)nX * n3) {
@@ -265,10 +270,10 @@ static void store_restart(const char *input, const double *slab_h, int nX, int o
   fclose(fp);
 }
 
-static void load_restart(const char *input, double *slab_h, int nX, int order, long n3, int *t) {
+static void load_restart(const char *input, double *slab_h, int nX, int order, long n3, int *t, int rank) {
   char name[300];
   FILE *fp;
-  snprintf(name, sizeof(name), "Restart/%s_rank%d_%s.plt", input, 0, "default");
+  snprintf(name, sizeof(name), "Restart/%s_rank%d_%s.plt", input, rank, "default");
   printf("Loading data %s\n", name);
   fp = fopen(name, "r");
   if (!fp) { printf("Error: unable to open restarted file %s\n", name); exit(1); }
@@ -284,6 +289,40 @@ static void load_restart(const char *input, double *slab_h, int nX, int order, l
   printf("t: %d\n", *t);
 }
 
+/* ---- one host thread per GPU for a run of steps: the GPUs wait for each other on the device (peer-memory halo),
+ * so no GPU's step may be held back by a host-side call made on behalf of another one ---- */
+typedef struct {
+  sbte_slab *slab;
+  sbte_ctx *ctx;
+  double Kn;
+  int nsteps, rc;
+  char err[256];
+} step_job;
+
+static void *step_worker(void *arg) {
+  step_job *j = arg;
+  int i;
+  j->rc = 0;
+  for (i = 0; i < j->nsteps && !j->rc; i++) j->rc = sbte_slab_step(j->slab, j->Kn, SBTE_K2_AUTO);
+  if (!j->rc) j->rc = sbte_sync(j->ctx);
+  if (j->rc) snprintf(j->err, sizeof(j->err), "%s", sbte_last_error());
+  return NULL;
+}
+
+static void run_steps(sbte_slab **slabs, sbte_ctx **ctxs, int G, double Kn, int nsteps) {
+  step_job jobs[64];
+  pthread_t th[64];
+  int r;
+  for (r = 0; r < G; r++) { jobs[r].slab = slabs[r]; jobs[r].ctx = ctxs[r]; jobs[r].Kn = Kn; jobs[r].nsteps = nsteps; }
+  if (G == 1) step_worker(&jobs[0]);
+  else {
+    for (r = 0; r < G; r++) pthread_create(&th[r], NULL, step_worker, &jobs[r]);
+    for (r = 0; r < G; r++) pthread_join(th[r], NULL);
+  }
+  for (r = 0; r < G; r++)
+    if (jobs[r].rc) { printf("boltz_b200: time step failed on GPU %d: %s\n", r, jobs[r].err); exit(1); }
+}
+
 int main(int argc, char **argv) {
   params p;
   outflags of;
@@ -294,6 +333,8 @@ int main(int argc, char **argv) {
   long n3;
   int t, l, outputCount = 0;
   if (argc < 3) { printf("usage: boltz_b200 <input file> <output flags file>\n"); return 1; }
+  /* several GPUs in one process wait for each other on the device: no kernel may be loaded lazily behind such a wait */
+  if (getenv("SBTE_GPUS") && atoi(getenv("SBTE_GPUS")) > 1) setenv("CUDA_MODULE_LOADING", "EAGER", 0);
   read_input(argv[1], &p);
   read_flags(argv[2], &of);
   n3 = (long)p.N * p.N * p.N;
@@ -302,7 +343,7 @@ int main(int argc, char **argv) {
   make_grids(&p, v, eta);
   CHECK(sbte_create(&ctx, p.N, p.L_v, v, eta, getenv("SBTE_DEVICE") ? atoi(getenv("SBTE_DEVICE")) : 0));
   printf("Initializing weight info\n");
-  setup_weights(ctx, &p);
+  setup_weights(ctx, &p, 1);
   snprintf(outname, sizeof(outname), "Data/moments_%s", argv[1]);
   printf("Opening output files \n");
   out = fopen(outname, p.restart ? "a" : "w");   /* src/output.c:256-262 */
@@ -350,23 +391,59 @@ int main(int argc, char **argv) {
     }
     sbte_dev_free(d_f); sbte_dev_free(d_mom); free(f);
   } else {
-    /* ---------------- space inhomogeneous: exec/boltz.c:254-395, one rank ---------------- */
-    int nX;
+    /* ---------------- space inhomogeneous: exec/boltz.c:254-395 ----------------
+     * The reference runs one MPI rank per block of cells.  Here one process drives SBTE_GPUS GPUs (default 1):
+     * "rank" r is GPU r with its own context, weight copy and slab; the blocks may be uneven (the reference needs
+     * nX % ranks == 0, src/mesh_setup.c:46-53); ghost cells are never sent -- the stencil kernels read the
+     * neighbouring GPU's cells over NVLink (sbte_slab_peer_attach) -- and every step is one graph replay per GPU. */
+    int nX, G = 1, r;
     double *x, *dx, *slab_h, *mom;
-    sbte_slab *slab;
+    sbte_ctx **ctxs;
+    sbte_slab **slabs;
+    int *lo, *cnt;
     printf("Loading mesh\n");
     make_mesh(p.meshFile, p.order, &nX, &x, &dx);
+    if (getenv("SBTE_GPUS")) G = atoi(getenv("SBTE_GPUS"));
+    if (G > sbte_device_count()) G = sbte_device_count();
+    while (G > 1 && nX / G < 2 * p.order) G--;
+    if (G < 1) G = 1;
+    ctxs = malloc(sizeof(*ctxs) * G); slabs = malloc(sizeof(*slabs) * G);
+    lo = malloc(sizeof(int) * (G + 1)); cnt = malloc(sizeof(int) * G);
+    for (r = 0, lo[0] = 0; r < G; r++) { cnt[r] = nX / G + (r < nX % G ? 1 : 0); lo[r + 1] = lo[r] + cnt[r]; }
+    ctxs[0] = ctx;
+    for (r = 1; r < G; r++) {
+      CHECK(sbte_create(&ctxs[r], p.N, p.L_v, v, eta, r));
+      setup_weights(ctxs[r], &p, 0);
+    }
+    if (G > 1) printf("Running on %d GPUs, %d-%d cells each\n", G, cnt[G - 1], cnt[0]);
     slab_h = malloc(sizeof(double) * (size_t)(nX + 2 * p.order) * n3);
     mom = malloc(sizeof(double) * (size_t)nX * 8);
     init_inhom(&p, v, nX, slab_h);
     int t0 = 0;
     double total_start = now_s(), write_start = now_s();
     if (p.restart) {
-      printf("Loading from previously generated data\n");
-      load_restart(argv[1], slab_h, nX, p.order, n3, &t0);   /* the loop resumes AT the stored counter, as exec/boltz.c does */
+      printf("Loading from previously generated data\n");   /* the loop resumes AT the stored counter, as exec/boltz.c does */
+      for (r = 0; r < G; r++) load_restart(argv[1], slab_h + (size_t)lo[r] * n3, cnt[r], p.order, n3, &t0, r);
     }
-    CHECK(sbte_slab_create(ctx, &slab, nX, p.order, x, dx, p.initFlag, p.dt, 0, 1));
-    CHECK(sbte_slab_upload(slab, slab_h));
+    for (r = 0; r < G; r++) {
+      /* rank r owns cells lo[r] .. lo[r+1]-1: its slab is that window of the global one plus `order` ghosts per side */
+      CHECK(sbte_slab_create(ctxs[r], &slabs[r], cnt[r], p.order, x + lo[r], dx + lo[r], p.initFlag, p.dt, r, G));
+      CHECK(sbte_slab_upload(slabs[r], slab_h + (size_t)lo[r] * n3));
+    }
+    if (G > 1) {
+      const int ring = (p.initFlag == 6 && p.order == 1);   /* periodic: src/transportroutines.c:156-172 */
+      for (r = 0; r + 1 < G; r++) {
+        CHECK(sbte_enable_peer_access(ctxs[r], ctxs[r + 1]));
+        CHECK(sbte_slab_peer_attach(slabs[r], 1, slabs[r + 1]));
+        CHECK(sbte_slab_peer_attach(slabs[r + 1], 0, slabs[r]));
+      }
+      if (ring) {
+        CHECK(sbte_enable_peer_access(ctxs[0], ctxs[G - 1]));
+        CHECK(sbte_slab_peer_attach(slabs[0], 0, slabs[G - 1]));
+        CHECK(sbte_slab_peer_attach(slabs[G - 1], 1, slabs[0]));
+      }
+      for (r = 0; r < G; r++) CHECK(sbte_slab_set_peer_halo(slabs[r], 1));
+    }
     if (!p.restart) {
       fprintf(out, "#Time Position ");
       if (of.dens) fprintf(out, "Density ");
@@ -378,10 +455,10 @@ int main(int argc, char **argv) {
     /* exec/boltz.c:255-394 */
 #define WRITE_STATE(TIME)                                                                         \
   do {                                                                                            \
-    CHECK(sbte_slab_moments(slab, mom));                                                          \
+    for (r = 0; r < G; r++) CHECK(sbte_slab_moments(slabs[r], mom + (size_t)lo[r] * 8));          \
     for (l = 0; l < nX; l++) {                                                                    \
       const double *m = mom + 8 * l;                                                              \
-      if (isnan(m[0])) { printf("nan detected in rank 0 cell %d \n", l + p.order); exit(0); }     \
+      if (isnan(m[0])) { printf("nan detected in cell %d \n", l + p.order); exit(0); }            \
       fprintf(out, "%le %le ", (TIME), x[l + p.order]);                                           \
       if (of.dens) fprintf(out, "%le ", m[0]);                                                    \
       if (of.vel) fprintf(out, "%le ", m[1]);                                                     \
@@ -393,9 +470,13 @@ int main(int argc, char **argv) {
     if (!p.restart) WRITE_STATE(0.0);
     t = t0;
     while (t < p.nT) {
-      printf("In step %d of %d\n", t + 1, p.nT);
-      CHECK(sbte_slab_step(slab, p.Kn, SBTE_K2_AUTO));
-      outputCount++;
+      /* run up to the next output step; every GPU in its own host thread */
+      int chunk = p.dataFreq - outputCount % p.dataFreq, i;
+      if (chunk > p.nT - t) chunk = p.nT - t;
+      for (i = 0; i < chunk; i++) printf("In step %d of %d\n", t + 1 + i, p.nT);
+      run_steps(slabs, ctxs, G, p.Kn, chunk);
+      t += chunk;
+      outputCount += chunk;
       if (outputCount % p.dataFreq == 0) {
         if (p.restart_time > 0) {
           /* wall-clock triggered checkpoint (:361-388): stop when another output interval would not fit */
@@ -403,21 +484,26 @@ int main(int argc, char **argv) {
           write_start = now_s();
           if (tot_time + write_time > 0.95 * p.restart_time) {
             printf("RESTART TIME REACHED - STORING CURRENT DISTRIBUTION DATA\n");
-            CHECK(sbte_slab_download(slab, slab_h));
-            store_restart(argv[1], slab_h, nX, p.order, n3, t);
+            for (r = 0; r < G; r++) {   /* one file per rank, as store_restart writes them under MPI (src/restart.c:24-63) */
+              double *tmp = malloc(sizeof(double) * (size_t)(cnt[r] + 2 * p.order) * n3);
+              CHECK(sbte_slab_download(slabs[r], tmp));
+              store_restart(argv[1], tmp, cnt[r], p.order, n3, t - 1, r);   /* the counter of the last completed step */
+              free(tmp);
+            }
             fclose(out);
-            sbte_slab_destroy(slab);
-            sbte_destroy(ctx);
+            for (r = 0; r < G; r++) sbte_slab_destroy(slabs[r]);
+            for (r = 0; r < G; r++) sbte_destroy(ctxs[r]);
             return 0;
           }
         }
-        WRITE_STATE(p.dt * (t + 1));
+        WRITE_STATE(p.dt * t);
         outputCount = 0;
       }
-      t = t + 1;
     }
-    sbte_slab_destroy(slab);
-    free(slab_h); free(mom); free(x); free(dx);
+    for (r = 0; r < G; r++) sbte_slab_destroy(slabs[r]);
+    for (r = 1; r < G; r++) sbte_destroy(ctxs[r]);
+    free(slab_h); free(mom); free(x); free(dx); free(ctxs); free(slabs); free(lo); free(cnt);
+
   }
   printf("Wrapping up\n");
   fclose(out);

@@ -194,3 +194,38 @@ def test_c_host_driver_matches_reference_exe_on_transport_variants(tmp_path, ic,
     big = np.abs(want[:, 3]) > 1e-9      # bulk velocity: rounding noise where the gas is at rest
     assert check_diff_two_sided(got[big, 3], want[big, 3]) == 0
     assert (~big).sum() == 0 or np.abs(got[~big, 3] - want[~big, 3]).max() < 1e-12
+
+
+def _gpu_count():
+    try:
+        import spectralbte_b200 as sb
+        return int(sb._lib.load().sbte_device_count())
+    except Exception:
+        return 0
+
+
+@pytest.mark.skipif(_gpu_count() < 2, reason="needs two GPUs")
+@pytest.mark.parametrize("ic,order", [(3, 1), (3, 2), (6, 1), (6, 2), (5, 2)])
+def test_c_host_driver_two_gpus_equal_one_gpu(tmp_path, ic, order):
+    """Rank-count invariance of the C host driver: SBTE_GPUS=2 (one process, two contexts,
+    peer-memory halo over NVLink, uneven 125/125 or ring topology) writes the same Data/moments_* file, byte for
+    byte, as one GPU."""
+    name, wts = "heat_transport", "N8_isotropic_L_v9_lambda1.wts"
+    raw = lzma.decompress(open(os.path.join(GOLDEN, wts + ".xz"), "rb").read())
+    texts = {}
+    for g in (1, 2):
+        d = tmp_path / ("g%d" % g)
+        for sub in ("input", "Data", "Weights", "Restart"):
+            os.makedirs(d / sub, exist_ok=True)
+        for fn in os.listdir(os.path.join(GOLDEN, "inputs")):
+            if fn.startswith(name):
+                shutil.copy(os.path.join(GOLDEN, "inputs", fn), d / "input" / fn)
+        (d / "Weights" / wts).write_bytes(raw)
+        _patch_input(str(d / "input" / (name + ".test.in")), Init_field=ic, Space_order=order)
+        r = subprocess.run([HOST, name + ".test.in", name + ".test.out"], cwd=d, capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, SBTE_GPUS=str(g)))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        if g == 2:
+            assert "Running on 2 GPUs" in r.stdout
+        texts[g] = (d / "Data" / ("moments_%s.test.in" % name)).read_text()
+    assert texts[1] == texts[2]
