@@ -389,6 +389,34 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
   return check_launch("inverse fft");
 }
 
+// One collision stage of the 1D step for a slab: out = a x + b y + s conserve(Q(src, src)) / Kn.
+// Fast path (batched kernels with a whole-cell inverse transform): conservation and update run as the
+// epilogue of the inverse transform; otherwise the three separate kernels.
+int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, int k2, double* out, double a,
+                      const double* x, double b, const double* y, double s, double Kn) {
+  static const bool no_fuse = getenv("SBTE_NO_FUSE") != nullptr;
+  if (!no_fuse && resolve_k2(c, batch, k2) == SBTE_K2_BATCH && qhat_batch_supported(c->N) &&
+      batch >= 8 && (c->N == 8 || c->N == 16)) {
+    if (ensure_capacity(c, batch)) return 1;
+    if (!c->d_W) { set_error("no weights bound"); return 1; }
+    const bool sym = want_sym(c, true);
+    if (sym && ensure_sym(c)) return 1;
+    if (ensure_batch_schedule(c, batch, sym)) return 1;
+    launch_fft3d(c, d_src, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
+    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    CellEpi epi = {};
+    epi.mode = 1; epi.v = c->d_v; epi.wt = c->d_wt; epi.dv3 = c->dv * c->dv * c->dv; epi.lu = c->lu;
+    epi.a = a; epi.x = x; epi.b = b; epi.y = y; epi.s = s; epi.Kn = Kn; epi.out = out;
+    if (launch_fft3d_parts_update(c, c->d_parts, c->parts_stride, c->sched, batch, epi)) return check_launch("fused collision stage");
+    set_error("fused collision stage: no whole-cell transform for this N");
+    return 1;
+  }
+  if (compute_q_dev(c, d_src, d_src, d_Q, batch, k2)) return 1;
+  launch_conserve(c, d_Q, batch);
+  launch_update(c, out, a, x, b, y, s, Kn, d_Q, (long)batch * c->n3);
+  return check_launch("collision stage");
+}
+
 // ComputeQ_maxPreserve (src/collisions.c:178-210) with the three products folded into one weight pass:
 //   Q^ = sum W ( g_j^[xi] (M_i + g_i)^[zeta-xi] + M_j^[xi] g_i^[zeta-xi] ),  (M_i + g_i)^ = f^.
 int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int k2) {

@@ -254,7 +254,7 @@ __global__ void __launch_bounds__(256, ((N & (N - 1)) == 0) ? 2 : 1)
 fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict__ in_cplx, PartsIn pin,
                   const double2* __restrict__ pre, const double2* __restrict__ post, const double* __restrict__ wt,
                   double prefactor, double sgn, double2* __restrict__ out_nat, double2* __restrict__ out_lay, int layout,
-                  double* __restrict__ out_real) {
+                  double* __restrict__ out_real, CellEpi epi) {
   extern __shared__ double2 cellsm[];   // [N][N][N+1]
   constexpr int P = N + 1;
   constexpr long n3 = (long)N * N * N;
@@ -306,6 +306,57 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
     dft_line<N>(cellsm + j * P + k, N * P, sgn);
   }
   __syncthreads();
+  if (epi.mode == 1) {
+    // Q = Re(post * z) stays in shared memory; moments -> multipliers -> corrected Q -> update, all here
+    __shared__ double red[5 * 32];
+    __shared__ double lam[5];
+    double bsum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
+      const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
+      const double2 cs = __ldg(post + idx);
+      double2& z = cellsm[(i * N + j) * P + k];
+      const double q = cs.x * z.x - cs.y * z.y;
+      z.x = q;
+      const double vi = __ldg(epi.v + i), vj = __ldg(epi.v + j), vk = __ldg(epi.v + k);
+      const double pre = __ldg(epi.wt + i) * __ldg(epi.wt + j) * __ldg(epi.wt + k) * epi.dv3;
+      bsum[0] += q * pre;
+      bsum[1] += q * (pre * vi);
+      bsum[2] += q * (pre * vj);
+      bsum[3] += q * (pre * vk);
+      bsum[4] += q * (pre * 0.5 * (vi * vi + vj * vj + vk * vk));
+    }
+    block_reduce_sum<5>(bsum, red);
+    if (threadIdx.x == 0) {
+      const int n = 5;
+      for (int k = 0; k < n - 1; k++) {
+        const int p = epi.lu.piv[k];
+        if (p != k) { const double t = bsum[p]; bsum[p] = bsum[k]; bsum[k] = t; }
+        for (int i = k + 1; i < n; i++) bsum[i] -= epi.lu.a[i * n + k] * bsum[k];
+      }
+      bsum[n - 1] = bsum[n - 1] / epi.lu.a[(n - 1) * n + (n - 1)];
+      for (int i = n - 2; i >= 0; i--) {
+        double sum = 0.0;
+        for (int j = i + 1; j < n; j++) sum += epi.lu.a[i * n + j] * bsum[j];
+        bsum[i] = 1.0 / epi.lu.a[i * n + i] * (bsum[i] - sum);
+      }
+      for (int a = 0; a < n; a++) lam[a] = bsum[a];
+    }
+    __syncthreads();
+    const double l0 = lam[0], l1 = lam[1], l2 = lam[2], l3 = lam[3], l4 = lam[4];
+    for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
+      const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
+      const double vi = __ldg(epi.v + i), vj = __ldg(epi.v + j), vk = __ldg(epi.v + k);
+      const double pre = __ldg(epi.wt + i) * __ldg(epi.wt + j) * __ldg(epi.wt + k) * epi.dv3;
+      const double q = cellsm[(i * N + j) * P + k].x -
+                       (pre * l0 + (pre * vi) * l1 + (pre * vj) * l2 + (pre * vk) * l3 +
+                        (pre * 0.5 * (vi * vi + vj * vj + vk * vk)) * l4);
+      const long g = cell * n3 + idx;
+      double basev = (epi.a == 1.0) ? epi.x[g] : epi.a * epi.x[g];
+      if (epi.y) basev = basev + epi.b * epi.y[g];
+      epi.out[g] = basev + epi.s * q / epi.Kn;
+    }
+    return;
+  }
   for (int base = threadIdx.x; base < n3; base += blockDim.x * LB) {
     double2 cs[LB];
 #pragma unroll
@@ -333,7 +384,7 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
 
 template <int N>
 static void launch_cell_n(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,
-                          double2* out_nat, double2* out_lay, int layout, double* out_real) {
+                          double2* out_nat, double2* out_lay, int layout, double* out_real, const CellEpi& epi) {
   const size_t smem = (size_t)N * N * (N + 1) * sizeof(double2);
   auto kern = fft3d_cell_kernel<N>;
   static unsigned configured = 0;   // per device: function attributes belong to the device context
@@ -343,18 +394,21 @@ static void launch_cell_n(sbte_ctx* c, const double* in_real, const double2* in_
   }
   const int d = invert ? 1 : 0;
   kern<<<batch, 256, smem, c->stream>>>(in_real, in_cplx, pin, c->d_pre[d], c->d_post[d], c->d_wt, c->pref[d],
-                                        invert ? +1.0 : -1.0, out_nat, out_lay, layout, out_real);
+                                        invert ? +1.0 : -1.0, out_nat, out_lay, layout, out_real, epi);
   c->launches += 1;
 }
 
 // returns false when the whole-cell kernel does not apply (small batches keep the plane-parallel pair)
 static bool try_cell_fft(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,
-                         double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real) {
+                         double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real,
+                         const CellEpi* epi_in = nullptr) {
   if (batch < 8 || accumulate_real) return false;
+  CellEpi epi = {};
+  if (epi_in) epi = *epi_in;
   switch (c->N) {
-    case 8: launch_cell_n<8>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real); return true;
-    case 12: launch_cell_n<12>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real); return true;
-    case 16: launch_cell_n<16>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real); return true;
+    case 8: launch_cell_n<8>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real, epi); return true;
+    case 12: launch_cell_n<12>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real, epi); return true;
+    case 16: launch_cell_n<16>(c, in_real, in_cplx, pin, invert, batch, out_nat, out_lay, layout, out_real, epi); return true;
     default: return false;
   }
 }
@@ -609,6 +663,12 @@ void launch_fft3d_parts(sbte_ctx* c, const double2* parts, size_t part_stride, c
   fft_pass_x<<<grid, FFT_THREADS, smem, c->stream>>>(c->d_tmp, c->d_post[d], c->d_dft, N, sgn, out_nat, nullptr, 0,
                                                      out_real, 0);
   c->launches += 2;
+}
+
+bool launch_fft3d_parts_update(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int batch,
+                               const CellEpi& epi) {
+  PartsIn pin = {parts, part_stride, sch.tile_np, sch.G, sch.cols};
+  return try_cell_fft(c, nullptr, nullptr, pin, 1, batch, nullptr, nullptr, 0, nullptr, false, &epi);
 }
 
 // plain sum of the partial sums into a natural-layout Q^ (only used when the caller asks for Q^ itself)

@@ -15,6 +15,21 @@ struct ConsLU {
   int piv[5];
 };
 
+// Epilogue of the batched inverse transform: with the cell's Q still in shared memory, project it onto the
+// conserved moments (src/conserve.c:207-264) and apply the Euler / Heun update out = a x + b y + (s Q)/Kn
+// (exec/boltz.c:296-343), instead of three more passes over global memory.
+struct CellEpi {
+  int mode;               // 0: none (Q is written as is); 1: conserve + update
+  const double* v;        // velocity grid
+  const double* wt;       // trapezoid weights
+  double dv3;
+  ConsLU lu;
+  double a; const double* x;
+  double b; const double* y;   // y may be null
+  double s, Kn;
+  double* out;
+};
+
 // stream-K schedule of the batched convolution (device tables, see qhat_batch.cu)
 struct BatchSched {
   const long long* cta_begin;   // [P+1] first global step of every CTA
@@ -118,6 +133,9 @@ void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, in
 bool launch_fft3d_multi(sbte_ctx* c, int njobs, const double* const* in_real, double2* const* out_lay, int layout);
 void launch_fft3d_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int invert,
                         int batch, double2* out_nat, double* out_real);
+// same with the conserve + update epilogue; false when this N has no whole-cell kernel (nothing was launched)
+bool launch_fft3d_parts_update(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int batch,
+                               const CellEpi& epi);
 void launch_combine_parts(sbte_ctx* c, const double2* parts, size_t part_stride, const BatchSched& sch, int batch,
                           double2* out);
 

@@ -17,6 +17,8 @@
 
 namespace sbte {
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2);
+int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, int k2, double* out, double a,
+                      const double* x, double b, const double* y, double s, double Kn);
 }
 
 struct sbte_slab {
@@ -368,23 +370,20 @@ int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
   sbte_ctx* c = s->c;
   const long n3 = c->n3;
   const int o = s->order, nX = s->nX;
-  const long n = (long)nX * n3;
   double* fc = cell(s->d_fc, n3, o);
   double* f = cell(s->d_f, n3, o);
   if (s->p2p) {   // the update below overwrites cells the neighbours may still be reading in their last pass
     launch_halo_quiesce(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr);
     c->launches++;
   }
-  if (compute_q_dev(c, fc, fc, s->d_Q, nX, k2)) return 1;
-  launch_conserve(c, s->d_Q, nX);
   if (o == 1) {
-    launch_update(c, f, 1.0, fc, 0.0, nullptr, s->dt, Kn, s->d_Q, n);          // f = f_conv + dt Q / Kn
+    // f = f_conv + dt Q / Kn
+    if (collide_stage_dev(c, fc, s->d_Q, nX, k2, f, 1.0, fc, 0.0, nullptr, s->dt, Kn)) return 1;
   } else {
     double* f1 = cell(s->d_f1, n3, o);
-    launch_update(c, f1, 1.0, fc, 0.0, nullptr, s->dt, Kn, s->d_Q, n);         // f_1 = f_conv + dt Q / Kn
-    if (compute_q_dev(c, f1, f1, s->d_Q, nX, k2)) return 1;
-    launch_conserve(c, s->d_Q, nX);
-    launch_update(c, fc, 0.5, fc, 0.5, f1, 0.5 * s->dt, Kn, s->d_Q, n);        // Heun average
+    // f_1 = f_conv + dt Q(f_conv) / Kn ;  f_conv = (f_conv + f_1)/2 + dt/2 Q(f_1) / Kn  (Heun)
+    if (collide_stage_dev(c, fc, s->d_Q, nX, k2, f1, 1.0, fc, 0.0, nullptr, s->dt, Kn)) return 1;
+    if (collide_stage_dev(c, f1, s->d_Q, nX, k2, fc, 0.5, fc, 0.5, f1, 0.5 * s->dt, Kn)) return 1;
   }
   return launch_ok("collide");
 }
