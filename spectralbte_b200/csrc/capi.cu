@@ -352,7 +352,8 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     // one cell keeps 1024 CTAs busy for only 3.5 waves: splitting each column's xi_x planes between two CTAs
     // shortens the under-filled last wave (the two partial spectra are added by the inverse transform)
     static const int want = getenv("SBTE_NO_SPLIT") ? 1 : (getenv("SBTE_SPLIT") ? atoi(getenv("SBTE_SPLIT")) : 2);
-    const int ns = (c->N == 32 && want >= 1 && want <= max_split) ? want : 1;
+    static const bool all_n = getenv("SBTE_SPLIT_ALL") != nullptr;   // testing: split the smaller grids too
+    const int ns = ((c->N == 32 || all_n) && want >= 1 && want <= max_split) ? want : 1;
     launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym, ns);
     if (nsplit) *nsplit = ns;
   } else {
