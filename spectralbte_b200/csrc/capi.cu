@@ -443,9 +443,14 @@ int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g,
   QhatPair pairs[2] = {{gjhat, c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]}};
   const bool sym = stream && want_sym(c, same);   // for f == g the three-product summand is symmetric as a whole
   if (sym && ensure_sym(c)) return 1;
-  if (stream) launch_qhat_stream(c, 2, pairs, c->d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym);
+  // splitting the columns between CTAs (as the one-pair kernel does at N = 32) does not pay here: N = 32 already runs
+  // 6.9 waves, and at N = 16 the kernel is 27 us and two parts cost more than they save (measured 27 -> 31 us)
+  static const int mp_split = getenv("SBTE_MP_SPLIT") ? atoi(getenv("SBTE_MP_SPLIT")) : 1;
+  const int ns = (stream && c->N == 16 && fft_cluster_supported(c->N) && mp_split >= 1 && mp_split <= 8) ? mp_split : 1;
+  if (stream) launch_qhat_stream(c, 2, pairs, c->d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym, ns);
   else launch_qhat_generic(c, 2, pairs, c->d_qhat, 1);
-  launch_fft3d(c, nullptr, c->d_qhat, 1, 1, nullptr, nullptr, 0, d_Q, false);
+  if (ns > 1) launch_fft3d_inverse_sum(c, c->d_qhat, ns, d_Q);
+  else launch_fft3d(c, nullptr, c->d_qhat, 1, 1, nullptr, nullptr, 0, d_Q, false);
   return check_launch("maxpreserve");
 }
 

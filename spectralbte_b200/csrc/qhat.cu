@@ -307,15 +307,14 @@ static void launch_stream_n(sbte_ctx* c, const double* W, int npairs, const Qhat
     // two operand pairs need 128 KB of plane ring => one CTA per SM.  Either 8 warps with four weight tiles per
     // thread in flight, or (default) 16 warps with two: the same 64 KB per SM in flight, twice the warps to
     // overlap the shared-memory operand reads, the FP64 pipe and the weight stream
-    if (getenv("SBTE_MP_NARROW")) launch_stream_inst<N, 2, 4, SYM>(c, W, pairs, qhat);
-    else launch_stream_inst<N, 2, 2, SYM, 16>(c, W, pairs, qhat);
+    if (getenv("SBTE_MP_NARROW")) launch_stream_inst<N, 2, 4, SYM>(c, W, pairs, qhat, nsplit);
+    else launch_stream_inst<N, 2, 2, SYM, 16>(c, W, pairs, qhat, nsplit);
   }
 }
 
 // sym: stream the symmetrised tensor (caller guarantees xi-side and dif-side operands describe f == g)
-// nsplit (one operand pair only): partial spectra qhat[0..nsplit) of n3 elements each, to be added by the caller
+// nsplit: partial spectra qhat[0..nsplit) of n3 elements each, to be added by the caller
 void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym, int nsplit) {
-  if (npairs != 1) nsplit = 1;
   const double* W = sym ? c->d_Ws : c->d_W;
   switch (c->N) {
     case 16: sym ? launch_stream_n<16, true>(c, W, npairs, pairs, qhat, depth, nsplit) : launch_stream_n<16, false>(c, W, npairs, pairs, qhat, depth, nsplit); break;
