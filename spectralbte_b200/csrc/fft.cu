@@ -13,6 +13,8 @@
 #include <cooperative_groups.h>
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -156,15 +158,15 @@ fft_pass_x(const double2* __restrict__ tmp, const double2* __restrict__ post, co
 __constant__ double2 c_tw[33][32];   // c_tw[N][m] = (cos, sin)(2 pi m / N), filled once per process
 
 void init_fft_constants() {   // constant memory is per device: call with the context's device current
-  static unsigned done_mask = 0;
+  static std::atomic<unsigned> done_mask{0};
   int dev = 0;
   cudaGetDevice(&dev);
-  if ((done_mask >> dev) & 1u) return;
+  if ((done_mask.load() >> dev) & 1u) return;
   static double2 h[33][32];
   for (int n = 1; n <= 32; n++)
     for (int m = 0; m < 32; m++) h[n][m] = make_double2(cos(2.0 * M_PI * m / n), sin(2.0 * M_PI * m / n));
   cudaMemcpyToSymbol(c_tw, h, sizeof(h));
-  done_mask |= 1u << dev;
+  done_mask.fetch_or(1u << dev);
 }
 
 constexpr int bitrev(int v, int bits) {
@@ -387,10 +389,10 @@ static void launch_cell_n(sbte_ctx* c, const double* in_real, const double2* in_
                           double2* out_nat, double2* out_lay, int layout, double* out_real, const CellEpi& epi) {
   const size_t smem = (size_t)N * N * (N + 1) * sizeof(double2);
   auto kern = fft3d_cell_kernel<N>;
-  static unsigned configured = 0;   // per device: function attributes belong to the device context
-  if (!((configured >> c->device) & 1u)) {
+  static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
+  if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured |= 1u << c->device;
+    configured.fetch_or(1u << c->device);
   }
   const int d = invert ? 1 : 0;
   kern<<<batch, 256, smem, c->stream>>>(in_real, in_cplx, pin, c->d_pre[d], c->d_post[d], c->d_wt, c->pref[d],
@@ -556,10 +558,10 @@ template <int N>
 static bool launch_cluster_n(sbte_ctx* c, const FftJobs& jobs, PartsIn pin, int invert, int cells) {
   const size_t smem = (size_t)(N / FFT_CL) * N * (N + 1 + N) * sizeof(double2);   // planes + staged post-twiddles
   auto kern = fft3d_cluster_kernel<N>;
-  static unsigned configured = 0;   // per device: function attributes belong to the device context
-  if (!((configured >> c->device) & 1u)) {
+  static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
+  if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured |= 1u << c->device;
+    configured.fetch_or(1u << c->device);
   }
   const int d = invert ? 1 : 0;
   cudaLaunchConfig_t cfg = {};

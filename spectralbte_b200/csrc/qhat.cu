@@ -16,6 +16,8 @@
 //                  (qhat_batch.cu)
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -275,10 +277,10 @@ static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pai
   using C = StreamCfg<N, WT>;
   const size_t smem = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2) + 64;
   auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM, WT>;
-  static unsigned configured = 0;   // per device: function attributes belong to the device context
-  if (!((configured >> c->device) & 1u)) {
+  static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
+  if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured |= 1u << c->device;
+    configured.fetch_or(1u << c->device);
   }
   k2_mark(c);
   cudaLaunchConfig_t cfg = {};

@@ -18,6 +18,8 @@
 // mbarrier; a 3-stage ring keeps two steps of weights/lines in flight behind the FP64 pipe.
 #include <stdlib.h>
 
+#include <atomic>
+
 #include "common.cuh"
 #include "internal.h"
 
@@ -317,10 +319,10 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
                             const BatchSched& sch) {
   using C = Batch2Cfg<N>;
   auto kern = qhat_batch2_kernel<N>;
-  static unsigned configured = 0;   // per device: function attributes belong to the device context
-  if (!((configured >> c->device) & 1u)) {
+  static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
+  if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    configured |= 1u << c->device;
+    configured.fetch_or(1u << c->device);
   }
   k2_mark(c);
   kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapWs : c->tmapW, spec, parts, part_stride, cells, sch);
@@ -507,10 +509,10 @@ static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, si
                             const BatchSched& sch) {
   using C = Batch3Cfg<N>;
   auto kern = qhat_batch3_kernel<N>;
-  static unsigned configured = 0;   // per device: function attributes belong to the device context
-  if (!((configured >> c->device) & 1u)) {
+  static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
+  if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
-    configured |= 1u << c->device;
+    configured.fetch_or(1u << c->device);
   }
   k2_mark(c);
   kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapWs : c->tmapW, spec, parts, part_stride, cells, sch);
