@@ -23,8 +23,18 @@ WORKLOADS = {
                       desc="heatTrans.long: 1D-3V heat transfer between diffuse walls, N=24, Space_order 1, %d cells total"),
     "heattrans22": dict(N=22, L_v=9.0, Kn=0.3, lam=1.0, order=1, ic=3, dt=1e-4, cells_per_gpu=None, total_cells=250,
                         length_per_cell=1.0 / 250.0, scaling="strong",
-                        desc="heatTrans.long as shipped: N=22 (any-N batched kernel), Space_order 1, %d cells total"),
+                        desc="heatTrans.long as shipped: N=22, Space_order 1, %d cells total"),
 }
+
+
+
+def _k2_name(N):
+    """The convolution kernel csrc/qhat_batch.cu picks for N (launch_qhat_batch2 / launch_qhat_batch_any)."""
+    if N in (8, 16):
+        return "qhat_batch2_kernel<%d>" % N
+    if N == 24 or (N in (20, 22) and not os.environ.get("SBTE_NO_BATCH3G")):
+        return "qhat_batch3_kernel<%d>" % N
+    return "qhat_batch_any_kernel"
 
 
 def run(args, root, cpu_leg=None, sampler_cls=None):
@@ -151,7 +161,7 @@ def run(args, root, cpu_leg=None, sampler_cls=None):
                             "NCCL batch_isend_irecv"),
                    "l2": "per-step working set (slabs + spectra + weights) larger than L2; no flush"},
         "roofline": {"bound": "fp64", "achieved": ach, "peak": 36.5, "unit": "TFLOP/s", "frac": ach / 36.5,
-                     "traffic": None, "kernel": ("qhat_batch%d_kernel<%d>" % (3 if N == 24 else 2, N)) if N in (8, 16, 24) else "qhat_batch_any_kernel",
+                     "traffic": None, "kernel": _k2_name(N),
                      "kernel_ms": k2_ms / max(1, k2_n), "kernel_share_of_step": k2_ms / ms,
                      "launch_by_launch_ms_per_step": prof_ms / args.steps,
                      "reference_equivalent_tflops": ref_flops / (k2_ms * 1e-3) / 1e12,

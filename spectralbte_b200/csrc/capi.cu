@@ -212,12 +212,15 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   if (c->d_sched_mem) { cudaFree(c->d_sched_mem); c->d_sched_mem = nullptr; }
   if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
   const int N = c->N, cols = qhat_batch_cols(N);
-  const int G = (cells + 31) / 32, RB = N * N / cols, T = G * RB;
+  // row-blocks never straddle a zeta_x plane: bpx blocks of `cols` zeta_y columns per plane, the last one
+  // partly empty when cols does not divide N (N = 20, 22)
+  const int bpx = (N + cols - 1) / cols;
+  const int G = (cells + 31) / 32, RB = N * bpx, T = G * RB;
   // tile t = (row-block rb = t / G, cell group cg = t % G); its length is (visited xi_x planes) * N steps
   std::vector<long long> tbegin(T + 1);
   tbegin[0] = 0;
   for (int t = 0; t < T; t++) {
-    const int zx = ((t / G) * cols) / N;
+    const int zx = (t / G) / bpx;
     tbegin[t + 1] = tbegin[t] + (long long)(sym ? sym_nrep(N, zx) : N) * N;
   }
   const long long total = tbegin[T];
@@ -255,18 +258,27 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   const size_t o2 = o1 + (size_t)(T + 1) * sizeof(long long);
   const size_t o3 = o2 + (size_t)P * sizeof(int);
   const size_t o4 = o3 + (size_t)T * sizeof(int);
-  const size_t bytes = o4 + (size_t)T;
+  // the inverse transform looks the part count up as np[(column / np_cols) * G + cell group]; with partly
+  // empty row-blocks that table is kept per zeta column
+  const bool per_column = (N % cols) != 0;
+  if (per_column) {
+    std::vector<unsigned char> npc((size_t)N * N * G);
+    for (int q = 0; q < N * N; q++)
+      for (int g = 0; g < G; g++) npc[(size_t)q * G + g] = np[(size_t)((q / N) * bpx + (q % N) / cols) * G + g];
+    np.swap(npc);
+  }
+  const size_t bytes = o4 + np.size();
   CK(cudaMalloc(&c->d_sched_mem, bytes));
   std::vector<unsigned char> blob(bytes);
   memcpy(blob.data(), begin.data(), o1);
   memcpy(blob.data() + o1, tbegin.data(), o2 - o1);
   memcpy(blob.data() + o2, ctile.data(), o3 - o2);
   memcpy(blob.data() + o3, first.data(), o4 - o3);
-  memcpy(blob.data() + o4, np.data(), (size_t)T);
+  memcpy(blob.data() + o4, np.data(), np.size());
   CK(cudaMemcpy(c->d_sched_mem, blob.data(), bytes, cudaMemcpyHostToDevice));
   unsigned char* base = (unsigned char*)c->d_sched_mem;
   c->sched = {(const long long*)base, (const long long*)(base + o1), (const int*)(base + o2), (const int*)(base + o3),
-              base + o4, G, T, P, cols, kmax, sym ? 1 : 0};
+              base + o4, G, T, P, per_column ? 1 : cols, kmax, sym ? 1 : 0};
   c->sched_cells = cells;
   c->sched_sym = (int)sym;
   // partial-sum workspace: kmax parts of (padded cells) x n3 complex

@@ -36,8 +36,8 @@ struct BatchSched {
   const long long* tile_begin;  // [T+1] first global step of every tile (tile lengths vary when symmetrised)
   const int* cta_tile;          // [P] tile that contains cta_begin[p]
   const int* tile_first;        // [T] first CTA that touches tile t
-  const unsigned char* tile_np; // [T] number of partial sums of tile t
-  int G, T, P, cols, kmax, sym;
+  const unsigned char* tile_np; // number of partial sums, indexed [(zeta column / cols) * G + cell group]
+  int G, T, P, cols, kmax, sym; // cols: zeta columns per tile_np entry (the tile width, or 1: table kept per column)
 };
 
 struct sbte_ctx {

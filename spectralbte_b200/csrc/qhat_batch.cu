@@ -117,8 +117,13 @@ void launch_qhat_batch_any(sbte_ctx* c, const double2* spec, double2* qhat, int 
   c->launches += 1;
 }
 
-bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24; }
-int qhat_batch_align(int N) { return N == 24 ? N : 1; }  // stream-K granularity in steps
+// N = 20, 22: the line-ring kernel with partly empty row-blocks (SBTE_NO_BATCH3G=1: back to the any-N kernel)
+static bool batch3_general(int N) {
+  static const bool on = getenv("SBTE_NO_BATCH3G") == nullptr;
+  return on && (N == 20 || N == 22);
+}
+bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24 || batch3_general(N); }
+int qhat_batch_align(int N) { return (N == 24 || batch3_general(N)) ? N : 1; }  // stream-K granularity in steps
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
 
 // ------------------------------------------------------------------------------------------
@@ -339,9 +344,14 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
 // has a full (TMA) and an empty mbarrier of COLS arrivals; lines at the chunk edges have fewer than COLS
 // readers, so their last reader arrives for the absent ones (mbarrier.arrive with a count).
 // Stream-K ranges are aligned to whole chunks.
+// When COLS does not divide N (N = 20, 22) the last row-block of every zeta_x plane is partly empty: its surplus
+// warps keep the barrier protocol going (waits and arrivals) but neither multiply nor write, and the weight
+// tile's surplus rows are the next plane's (or, past the end of the tensor, TMA zero fill).
 template <int N>
 struct Batch3Cfg {
   static constexpr int COLS = 8;
+  static constexpr int BPX = (N + COLS - 1) / COLS;  // row-blocks per zeta_x plane
+  static constexpr bool PARTIAL = (N % COLS) != 0;
   static constexpr int CONSUMERS = COLS * 32;
   static constexpr int THREADS = CONSUMERS + 128;
   static constexpr int ROWS = COLS * N;
@@ -352,7 +362,7 @@ struct Batch3Cfg {
   static constexpr size_t LINE_BYTES = (size_t)LINE * 16;
   static constexpr size_t STAGE_BYTES = LINE_BYTES + (size_t)ROWS * N * 8;
   static constexpr size_t SMEM = RING * LINE_BYTES + STAGES * STAGE_BYTES + 512;
-  static_assert(N % COLS == 0, "columns must tile zeta_y");
+  static_assert(SMEM <= 227 * 1024, "line ring + stages must fit in shared memory");
 };
 
 template <int N>
@@ -399,7 +409,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       for (int ch = 0; ch < nchunk; ch++, cl++) {
         if (g0 + (long long)ch * N == te) { t++; te = sch.tile_begin[t + 1]; cl = 0; }
         const int rb = t / G, cg = t - rb * G;
-        const int q0 = rb * C::COLS, zx = q0 / N, zy0 = q0 % N;
+        const int zx = rb / C::BPX, zy0 = (rb % C::BPX) * C::COLS;
         const int ex = sym ? sym_rep(N, zx, cl) : cl;
         int X = zx + N / 2 - ex;
         if (X < 0) X += N; else if (X > N - 1) X -= N;
@@ -422,7 +432,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
           const int s = ex * N + ey;
           mbar_arrive_expect_tx(&fullS[st], (uint32_t)C::STAGE_BYTES);
           tma_bulk_g2s(stage_line(st), gs + (size_t)s * C::LINE, (uint32_t)C::LINE_BYTES, &fullS[st]);
-          tma_tensor2d_g2s(stage_w(st), &tmapW, s * N, rb * C::ROWS, &fullS[st]);
+          tma_tensor2d_g2s(stage_w(st), &tmapW, s * N, (zx * N + zy0) * N, &fullS[st]);
         }
       }
     }
@@ -440,7 +450,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   auto flush = [&]() {
     const int rb = cur_t / G, cg = cur_t - rb * G;
     const long cell = (long)cg * 32 + lane;
-    if (cell < cells) {
+    if (cell < cells && (!C::PARTIAL || zy < N)) {
       const int part = (int)blockIdx.x - sch.tile_first[cur_t];
       double2* out = parts + (size_t)part * part_stride + cell * n3 + ((long)zx * N + zy) * N;
 #pragma unroll
@@ -459,10 +469,11 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
         for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
       }
       cur_t = t;
-      const int q0 = (t / G) * C::COLS;
-      zx = q0 / N;
-      zy = (q0 % N) + warp;
+      const int rb = t / G;
+      zx = rb / C::BPX;
+      zy = (rb % C::BPX) * C::COLS + warp;
     }
+    const bool live = !C::PARTIAL || zy < N;
     for (int ey = 0; ey < N; ey++, k++) {
       const int st = k % S;
       const int jl = C::COLS - 1 + ey - warp;          // this warp's line within the chunk
@@ -471,22 +482,24 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       mbar_wait(&fullS[st], (uint32_t)((k / S) & 1));
       mbar_wait(&fullL[slot], (uint32_t)((q / R) & 1));
 
-      const double2* fl = ring + (size_t)slot * C::LINE + lane;
-      const double2* gl = stage_line(st) + lane;
-      const double* wt = stage_w(st) + warp * N * N;
-      double2 fr[N];
+      if (live) {
+        const double2* fl = ring + (size_t)slot * C::LINE + lane;
+        const double2* gl = stage_line(st) + lane;
+        const double* wt = stage_w(st) + warp * N * N;
+        double2 fr[N];
 #pragma unroll
-      for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
+        for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
 #pragma unroll
-      for (int c = 0; c < N; c += 2) {
-        const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
+        for (int c = 0; c < N; c += 2) {
+          const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
 #pragma unroll
-        for (int r = 0; r < N; r++) {
-          const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
-          const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
-          const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
-          cmac(acc[r], w2.x, p0);
-          cmac(acc[r], w2.y, p1);
+          for (int r = 0; r < N; r++) {
+            const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
+            const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
+            const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
+            cmac(acc[r], w2.x, p0);
+            cmac(acc[r], w2.y, p1);
+          }
         }
       }
       __syncwarp();
@@ -526,6 +539,8 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t
   switch (c->N) {
     case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
     case 16: launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch); break;
+    case 20: launch_batch3_n<20>(c, spec, parts, part_stride, cells, sch); break;
+    case 22: launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch); break;
     case 24: launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch); break;
     default: set_error("qhat_batch: unsupported N"); break;
   }

@@ -280,6 +280,31 @@ def test_batched_computeq_matches_oracle(sb, N, cells, k2):
         assert relmax(Q[b], Qo) < TOL_QHAT
 
 
+@pytest.mark.parametrize("N,cells", [(22, 70), (20, 33), (22, 250)])
+def test_line_ring_with_partial_row_blocks(sb, N, cells):
+    """N = 20, 22: 8 zeta_y columns per CTA do not tile a zeta_x plane, so every third row-block is partly
+    empty. All cells against the generic kernel (one CTA per (zeta, cell), no tiling), three cells against the
+    oracle; several cell groups so that stream-K cuts tiles into partial sums."""
+    o = orc.Oracle(N, 9.0, 1)
+    c = sb.Collisions(N, 9.0, inhomogeneous=True)
+    c.synthetic_weights(11)
+    W = c.weights_to_host()
+    f = np.stack([seeded_f(o.v, 300 + b, noise=0.2) * (1.0 + 0.01 * b) for b in range(cells)])
+    for sym in (True, False):
+        c.set_symmetrize(sym)
+        qh = c.Qhat(f, k2=sb.K2_BATCH).reshape(cells, -1)
+        qg = np.concatenate([c.Qhat(f[b0:b0 + 50], k2=sb.K2_GENERIC).reshape(-1, qh.shape[1])
+                             for b0 in range(0, cells, 50)])
+        for b in range(cells):
+            assert relmax(qh[b], qg[b]) < TOL_QHAT, (sym, b)
+    c.set_symmetrize(True)
+    Q = c.ComputeQ(f, k2=sb.K2_BATCH).reshape(cells, -1)
+    for b in (0, 31, cells - 1):
+        Qo, qo = o.compute_q(W, f[b], f[b], want_qhat=True)
+        assert relmax(qh[b], qo) < TOL_QHAT   # qh: the unsymmetrised pass of the loop above
+        assert relmax(Q[b], Qo) < TOL_QHAT
+
+
 # ---------------------------------------------------------------- transport
 @pytest.mark.parametrize("N,L_v,nX,ic,dt", [(8, 9.0, 12, 3, 1e-3), (8, 9.0, 12, 6, 1e-3), (6, 7.0, 10, 0, 2e-3),
                                              (8, 9.0, 12, 1, 1e-3), (8, 9.0, 12, 5, 1e-3), (8, 9.0, 12, 2, 1e-3)])
