@@ -122,11 +122,6 @@ static bool batch3_general(int N) {
   static const bool on = getenv("SBTE_NO_BATCH3G") == nullptr;
   return on && (N == 20 || N == 22);
 }
-// N = 16: two warps per zeta column (SBTE_ROW_SPLIT=1), see Batch2Cfg
-static bool batch2_row_split() {
-  static const bool on = getenv("SBTE_ROW_SPLIT") != nullptr && atoi(getenv("SBTE_ROW_SPLIT")) != 0;
-  return on;
-}
 bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24 || batch3_general(N); }
 int qhat_batch_align(int N) { return (N == 24 || batch3_general(N)) ? N : 1; }  // stream-K granularity in steps
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
@@ -142,23 +137,14 @@ int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
 // Inside a CTA the warps are decoupled: a 4-stage ring of (weight tile, xi-side line) with full
 // (TMA transaction) and empty (one arrival per warp) mbarriers; lane 0 of warp 0 issues the TMA
 // copies two to three steps ahead.  No __syncthreads in the main loop.
-// SPLIT = 2 ("row split"): two warps share a zeta column, each owning N/2 of its zeta_z rows, so that four compute
-// warps instead of two sit on every SM sub-partition.  A warp then keeps N/2 accumulators and, instead of the
-// whole (zeta - xi)-side line, a sliding window of N/2 + 1 operands read from the shared-memory plane as xi_z
-// advances (Toeplitz in z); results are bit-identical to SPLIT = 1 (same products, same order per row).
-template <int N, int SPLIT = 1>
+template <int N>
 struct Batch2Cfg {
   static constexpr int COLS = (N >= 16) ? 8 : 4;
-  static constexpr int CWARPS = COLS * SPLIT;      // compute warps
-  static constexpr int RH = N / SPLIT;             // zeta_z rows per compute warp
-  static constexpr int CONSUMERS = CWARPS * 32;    // compute threads: SPLIT warps per zeta (x,y) column
+  static constexpr int CONSUMERS = COLS * 32;      // compute threads: one warp per zeta (x,y) column
   static constexpr int THREADS = CONSUMERS + 128;  // + one producer warpgroup (one lane issues the TMA copies)
   // register split (setmaxnreg works on warpgroups): 384 threads compile to <= 168 registers; the
-  // producer warpgroup drops to 24 and the two compute warpgroups grow to 240 (240*256 + 24*128 <= 64512);
-  // with the row split 640 threads start at 96 registers (61440 in the CTA's pool, which is all setmaxnreg can redistribute): four compute warpgroups take 112 each (112*512 + 24*128 = 60416)
+  // producer warpgroup drops to 24 and the two compute warpgroups grow to 240 (240*256 + 24*128 <= 64512)
   static constexpr bool REG_SPLIT = THREADS > 256;
-  static constexpr int CREGS = (SPLIT == 2) ? 112 : 240;
-  static_assert(N % SPLIT == 0 && (SPLIT == 1 || SPLIT == 2), "row split");
   static constexpr int ROWS = COLS * N;
   static constexpr int LINE = N * 32;
   static constexpr int PLANE = N * LINE;
@@ -167,11 +153,11 @@ struct Batch2Cfg {
   static constexpr size_t SMEM = (size_t)PLANE * 16 + STAGES * STAGE_BYTES + 256;
 };
 
-template <int N, int SPLIT>
-__global__ void __launch_bounds__(Batch2Cfg<N, SPLIT>::THREADS, 1)
+template <int N>
+__global__ void __launch_bounds__(Batch2Cfg<N>::THREADS, 1)
 qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
                    double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch) {
-  using C = Batch2Cfg<N, SPLIT>;
+  using C = Batch2Cfg<N>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES;
   extern __shared__ __align__(128) unsigned char smraw[];
@@ -195,9 +181,9 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   const bool sym = sch.sym != 0;
 
   if (tid == 0) {
-    for (int b = 0; b < S; b++) { mbar_init(&full[b], 1); mbar_init(&empty[b], C::CWARPS); }
+    for (int b = 0; b < S; b++) { mbar_init(&full[b], 1); mbar_init(&empty[b], C::COLS); }
     mbar_init(fullPlane, 1);
-    mbar_init(emptyPlane, C::CWARPS);
+    mbar_init(emptyPlane, C::COLS);
     mbar_fence_init();
   }
   __syncthreads();
@@ -216,10 +202,10 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     if (X < 0) X += N; else if (X > N - 1) X -= N;
   };
 
-  if (warp >= C::CWARPS) {
+  if (warp >= C::COLS) {
     // ===== producer warpgroup: one lane issues every TMA copy, up to S steps ahead of the consumers =====
     if (C::REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
-    if (warp == C::CWARPS && lane == 0) {
+    if (warp == C::COLS && lane == 0) {
       int cur_cg = -1, cur_X = -1, epoch = -1;
       int t = sch.cta_tile[blockIdx.x];
       long long te = sch.tile_begin[t + 1];
@@ -249,16 +235,10 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   }
 
   // ===== compute warps =====
-  if (C::REG_SPLIT) {
-    if (SPLIT == 2) asm volatile("setmaxnreg.inc.sync.aligned.u32 112;");
-    else asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
-  }
-  constexpr int RH = C::RH;
-  const int col = (SPLIT == 1) ? warp : (warp % C::COLS);   // zeta (x,y) column within the tile
-  const int r0 = (SPLIT == 1) ? 0 : (warp / C::COLS) * RH;  // first zeta_z row of this warp
-  double2 acc[RH];
+  if (C::REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  double2 acc[N];
 #pragma unroll
-  for (int r = 0; r < RH; r++) acc[r] = make_double2(0.0, 0.0);
+  for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
 
   int cur_t = -1, cur_cg = -1, cur_X = -1, epoch = -1;
   int zx = 0, zy = 0;
@@ -268,9 +248,9 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     const long cell = (long)cg * 32 + lane;
     if (cell < cells) {
       const int part = (int)blockIdx.x - sch.tile_first[cur_t];
-      double2* out = parts + (size_t)part * part_stride + cell * n3 + ((long)zx * N + zy) * N + r0;
+      double2* out = parts + (size_t)part * part_stride + cell * n3 + ((long)zx * N + zy) * N;
 #pragma unroll
-      for (int r = 0; r < RH; r++) out[r] = acc[r];
+      for (int r = 0; r < N; r++) out[r] = acc[r];
     }
   };
 
@@ -285,12 +265,12 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       if (cur_t >= 0) {
         flush();
 #pragma unroll
-        for (int r = 0; r < RH; r++) acc[r] = make_double2(0.0, 0.0);
+        for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
       }
       cur_t = t;
       const int q0 = rb * C::COLS;
       zx = q0 / N;
-      zy = (q0 % N) + col;
+      zy = (q0 % N) + warp;
     }
     if (cg != cur_cg || X != cur_X) {
       epoch++;
@@ -304,59 +284,21 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     if (Y < 0) Y += N; else if (Y > N - 1) Y -= N;
     const double2* fl = plane + (size_t)Y * C::LINE + lane;
     const double2* gl = stage_line(st) + lane;
-    const double* wt = stage_w(st) + col * N * N;
+    const double* wt = stage_w(st) + warp * N * N;
 
-    if constexpr (SPLIT == 1) {
-      double2 fr[N];
+    double2 fr[N];
 #pragma unroll
-      for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
+    for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
 #pragma unroll
-      for (int c = 0; c < N; c += 2) {
-        const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
+    for (int c = 0; c < N; c += 2) {
+      const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
 #pragma unroll
-        for (int r = 0; r < N; r++) {
-          const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
-          const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
-          const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
-          cmac(acc[r], w2.x, p0);
-          cmac(acc[r], w2.y, p1);
-        }
-      }
-    } else {
-      // window fw[j] = f^[wrap(r0 + j + N/2 - c)], j = -1 .. RH-1 (slot j+1): the operands rows r0 .. r0+RH-1 need
-      // at xi_z = c and (slot 0) the one that enters at c + 1; it slides down by two per pair of columns
-      const double* wh = wt + r0 * N;
-      double2 fw[RH + 1];
-      int zi = r0 + N / 2 - 1;               // index of slot 0 at c = 0, in [0, N)
-      if (zi > N - 1) zi -= N;
-#pragma unroll
-      for (int j = 0; j <= RH; j++) {
-        int zj = zi + j;
-        if (zj > N - 1) zj -= N;
-        fw[j] = fl[zj * 32];
-      }
-#pragma unroll
-      for (int c = 0; c < N; c += 2) {
-        const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
-#pragma unroll
-        for (int r = 0; r < RH; r++) {
-          const double2 w2 = *reinterpret_cast<const double2*>(wh + r * N + c);
-          const double2 p0 = cmul(g0v, fw[r + 1]);
-          const double2 p1 = cmul(g1v, fw[r]);
-          cmac(acc[r], w2.x, p0);
-          cmac(acc[r], w2.y, p1);
-        }
-        if (c + 2 < N) {
-          // columns c + 2, c + 3: every operand index drops by two
-#pragma unroll
-          for (int j = RH; j >= 2; j--) fw[j] = fw[j - 2];
-          zi -= 2;
-          if (zi < 0) zi += N;
-          int z1 = zi + 1;
-          if (z1 > N - 1) z1 -= N;
-          fw[0] = fl[zi * 32];
-          fw[1] = fl[z1 * 32];
-        }
+      for (int r = 0; r < N; r++) {
+        const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
+        const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
+        const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
+        cmac(acc[r], w2.x, p0);
+        cmac(acc[r], w2.y, p1);
       }
     }
 
@@ -377,11 +319,11 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   flush();
 }
 
-template <int N, int SPLIT = 1>
+template <int N>
 static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                             const BatchSched& sch) {
-  using C = Batch2Cfg<N, SPLIT>;
-  auto kern = qhat_batch2_kernel<N, SPLIT>;
+  using C = Batch2Cfg<N>;
+  auto kern = qhat_batch2_kernel<N>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
   if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -596,10 +538,7 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t
   if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
   switch (c->N) {
     case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
-    case 16:
-      if (batch2_row_split()) launch_batch2_n<16, 2>(c, spec, parts, part_stride, cells, sch);
-      else launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch);
-      break;
+    case 16: launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch); break;
     case 20: launch_batch3_n<20>(c, spec, parts, part_stride, cells, sch); break;
     case 22: launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch); break;
     case 24: launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch); break;
