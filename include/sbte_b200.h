@@ -121,6 +121,13 @@ SBTE_API int sbte_weights_save_file(sbte_ctx *c, const char *path);
  * costs one extra N^6 tensor). On by default; disable to stream the tensor exactly as the reference does. */
 SBTE_API int sbte_set_symmetrize(sbte_ctx *c, int enable);
 
+/* The stream-K schedule of the batched convolution for `cells` cells on a device with `ctas` SMs (what the
+ * library uploads before a batched ComputeQ; exec/boltz.c:285-345 has no counterpart -- its cells are a plain loop).
+ * Pure host arithmetic, no device needed.  dims = {G, T, P, np_cols, kmax, np_len}; array pointers may be null:
+ * query dims first, then pass arrays of P+1, T+1, P, T and np_len entries.  Fails for N without a scheduled kernel. */
+SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long *cta_begin, long long *tile_begin,
+                                      int *cta_tile, int *tile_first, unsigned char *np, int *dims);
+
 /* kernel selection for the convolution */
 enum { SBTE_K2_AUTO = 0, SBTE_K2_GENERIC = 1, SBTE_K2_STREAM = 2, SBTE_K2_BATCH = 3, SBTE_K2_STREAM_DEEP = 4 };
 

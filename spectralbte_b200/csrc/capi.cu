@@ -205,31 +205,33 @@ __global__ void synth_weights_kernel(double* __restrict__ W, size_t n, unsigned 
 // ---- stream-K schedule of the batched convolution ---------------------------------------------
 // T = groups * row-blocks tiles of N^2 steps; P persistent CTAs take equal contiguous shares of the
 // T*N^2 global steps. tile_first / tile_np tell kernels which CTA writes which partial sum.
-static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
-  if (c->sched_cells == cells && c->sched_sym == (int)sym && c->d_sched_mem) return 0;
-  c->graph_gen++;   // the schedule tables move: captured slab steps must be rebuilt
-  CK(cudaStreamSynchronize(c->stream));
-  if (c->d_sched_mem) { cudaFree(c->d_sched_mem); c->d_sched_mem = nullptr; }
-  if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-  const int N = c->N, cols = qhat_batch_cols(N);
+struct HostSchedule {
+  std::vector<long long> begin, tbegin;   // [P+1], [T+1]
+  std::vector<int> ctile, first;          // [P], [T]
+  std::vector<unsigned char> np;          // [T], or [N*N*G] when kept per zeta column
+  int G = 0, T = 0, P = 0, np_cols = 0, kmax = 1;
+};
+
+// Pure host arithmetic (no CUDA call): also exported as sbte_batch_schedule_host for the CPU tests.
+static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out) {
+  const int cols = qhat_batch_cols(N);
   // row-blocks never straddle a zeta_x plane: bpx blocks of `cols` zeta_y columns per plane, the last one
   // partly empty when cols does not divide N (N = 20, 22)
   const int bpx = (N + cols - 1) / cols;
   const int G = (cells + 31) / 32, RB = N * bpx, T = G * RB;
   // tile t = (row-block rb = t / G, cell group cg = t % G); its length is (visited xi_x planes) * N steps
-  std::vector<long long> tbegin(T + 1);
-  tbegin[0] = 0;
+  std::vector<long long>& tbegin = out->tbegin;
+  tbegin.assign(T + 1, 0);
   for (int t = 0; t < T; t++) {
     const int zx = (t / G) / bpx;
     tbegin[t + 1] = tbegin[t] + (long long)(sym ? sym_nrep(N, zx) : N) * N;
   }
   const long long total = tbegin[T];
-  int P = c->sm_count;
-  const char* pe = getenv("SBTE_BATCH_CTAS");
-  if (pe && atoi(pe) > 0) P = atoi(pe);
+  int P = ctas;
   const long long min_steps = 4 * (long long)N;  // at least a few xi_x chunks per CTA
   if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
-  std::vector<long long> begin(P + 1);
+  std::vector<long long>& begin = out->begin;
+  begin.assign(P + 1, 0);
   const long long align = qhat_batch_align(N);   // the line-ring kernel works on whole xi_x chunks
   for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * (total / align)) / P) * align;
   auto owner = [&](long long g) {   // last CTA whose range starts at or before g
@@ -242,8 +244,10 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
     while (lo < hi) { const int mid = (lo + hi + 1) / 2; if (tbegin[mid] <= g) lo = mid; else hi = mid - 1; }
     return lo;
   };
-  std::vector<int> first(T), ctile(P);
-  std::vector<unsigned char> np(T);
+  std::vector<int>& first = out->first;
+  std::vector<int>& ctile = out->ctile;
+  std::vector<unsigned char>& np = out->np;
+  first.assign(T, 0); ctile.assign(P, 0); np.assign(T, 0);
   int kmax = 1;
   for (int t = 0; t < T; t++) {
     // CTAs with an empty range never write: pick owners among non-empty ranges
@@ -254,10 +258,6 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
     kmax = std::max(kmax, b - a + 1);
   }
   for (int p = 0; p < P; p++) ctile[p] = tile_of(std::min(begin[p], total - 1));
-  const size_t o1 = (size_t)(P + 1) * sizeof(long long);
-  const size_t o2 = o1 + (size_t)(T + 1) * sizeof(long long);
-  const size_t o3 = o2 + (size_t)P * sizeof(int);
-  const size_t o4 = o3 + (size_t)T * sizeof(int);
   // the inverse transform looks the part count up as np[(column / np_cols) * G + cell group]; with partly
   // empty row-blocks that table is kept per zeta column
   const bool per_column = (N % cols) != 0;
@@ -267,18 +267,37 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
       for (int g = 0; g < G; g++) npc[(size_t)q * G + g] = np[(size_t)((q / N) * bpx + (q % N) / cols) * G + g];
     np.swap(npc);
   }
-  const size_t bytes = o4 + np.size();
+  out->G = G; out->T = T; out->P = P; out->np_cols = per_column ? 1 : cols; out->kmax = kmax;
+}
+
+static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
+  if (c->sched_cells == cells && c->sched_sym == (int)sym && c->d_sched_mem) return 0;
+  c->graph_gen++;   // the schedule tables move: captured slab steps must be rebuilt
+  CK(cudaStreamSynchronize(c->stream));
+  if (c->d_sched_mem) { cudaFree(c->d_sched_mem); c->d_sched_mem = nullptr; }
+  if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  int ctas = c->sm_count;
+  const char* pe = getenv("SBTE_BATCH_CTAS");
+  if (pe && atoi(pe) > 0) ctas = atoi(pe);
+  HostSchedule h;
+  build_batch_schedule(c->N, cells, sym, ctas, &h);
+  const int G = h.G, T = h.T, P = h.P, kmax = h.kmax;
+  const size_t o1 = (size_t)(P + 1) * sizeof(long long);
+  const size_t o2 = o1 + (size_t)(T + 1) * sizeof(long long);
+  const size_t o3 = o2 + (size_t)P * sizeof(int);
+  const size_t o4 = o3 + (size_t)T * sizeof(int);
+  const size_t bytes = o4 + h.np.size();
   CK(cudaMalloc(&c->d_sched_mem, bytes));
   std::vector<unsigned char> blob(bytes);
-  memcpy(blob.data(), begin.data(), o1);
-  memcpy(blob.data() + o1, tbegin.data(), o2 - o1);
-  memcpy(blob.data() + o2, ctile.data(), o3 - o2);
-  memcpy(blob.data() + o3, first.data(), o4 - o3);
-  memcpy(blob.data() + o4, np.data(), np.size());
+  memcpy(blob.data(), h.begin.data(), o1);
+  memcpy(blob.data() + o1, h.tbegin.data(), o2 - o1);
+  memcpy(blob.data() + o2, h.ctile.data(), o3 - o2);
+  memcpy(blob.data() + o3, h.first.data(), o4 - o3);
+  memcpy(blob.data() + o4, h.np.data(), h.np.size());
   CK(cudaMemcpy(c->d_sched_mem, blob.data(), bytes, cudaMemcpyHostToDevice));
   unsigned char* base = (unsigned char*)c->d_sched_mem;
   c->sched = {(const long long*)base, (const long long*)(base + o1), (const int*)(base + o2), (const int*)(base + o3),
-              base + o4, G, T, P, per_column ? 1 : cols, kmax, sym ? 1 : 0};
+              base + o4, G, T, P, h.np_cols, kmax, sym ? 1 : 0};
   c->sched_cells = cells;
   c->sched_sym = (int)sym;
   // partial-sum workspace: kmax parts of (padded cells) x n3 complex
@@ -546,6 +565,24 @@ int sbte_destroy(sbte_ctx* c) {
   if (c->d_parts) cudaFree(c->d_parts);
   cudaStreamDestroy(c->stream);
   delete c;
+  return 0;
+}
+
+// The stream-K schedule ensure_batch_schedule() would upload for (N, cells, sym) on a device with `ctas` SMs.
+// Pure host arithmetic: works without a GPU (CPU tests, sizing).  dims = {G, T, P, np_cols, kmax, np_len};
+// any array pointer may be null (query dims first, then call again with arrays of P+1, T+1, P, T, np_len entries).
+int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long* cta_begin, long long* tile_begin,
+                             int* cta_tile, int* tile_first, unsigned char* np, int* dims) {
+  if (N < 2 || N > 32 || (N % 2) != 0 || cells < 1 || ctas < 1) { set_error("batch schedule: bad arguments"); return 1; }
+  if (!qhat_batch_supported(N)) { set_error("batch schedule: this N runs the any-N kernel (no schedule)"); return 1; }
+  HostSchedule h;
+  build_batch_schedule(N, cells, sym != 0, ctas, &h);
+  if (dims) { dims[0] = h.G; dims[1] = h.T; dims[2] = h.P; dims[3] = h.np_cols; dims[4] = h.kmax; dims[5] = (int)h.np.size(); }
+  if (cta_begin) memcpy(cta_begin, h.begin.data(), h.begin.size() * sizeof(long long));
+  if (tile_begin) memcpy(tile_begin, h.tbegin.data(), h.tbegin.size() * sizeof(long long));
+  if (cta_tile) memcpy(cta_tile, h.ctile.data(), h.ctile.size() * sizeof(int));
+  if (tile_first) memcpy(tile_first, h.first.data(), h.first.size() * sizeof(int));
+  if (np) memcpy(np, h.np.data(), h.np.size());
   return 0;
 }
 
