@@ -123,9 +123,10 @@ SBTE_API int sbte_set_symmetrize(sbte_ctx *c, int enable);
 
 /* The stream-K schedule of the batched convolution for `cells` cells on a device with `ctas` SMs (what the
  * library uploads before a batched ComputeQ; exec/boltz.c:285-345 has no counterpart -- its cells are a plain loop).
- * Pure host arithmetic, no device needed.  dims = {G, T, P, np_cols, kmax, np_len}; array pointers may be null:
+ * Pure host arithmetic, no device needed.  mirror != 0: layout of the opt-in mirror-paired kernel (N = 8, 16).
+ * dims = {G, T, P, np_cols, kmax, np_len}; array pointers may be null:
  * query dims first, then pass arrays of P+1, T+1, P, T and np_len entries.  Fails for N without a scheduled kernel. */
-SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long *cta_begin, long long *tile_begin,
+SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int mirror, long long *cta_begin, long long *tile_begin,
                                       int *cta_tile, int *tile_first, unsigned char *np, int *dims);
 
 /* kernel selection for the convolution */

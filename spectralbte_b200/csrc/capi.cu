@@ -11,6 +11,7 @@
 #include "../../include/sbte_b200.h"
 #include "common.cuh"
 #include "internal.h"
+#include "mirror.cuh"
 
 namespace sbte {
 
@@ -145,7 +146,7 @@ int ensure_capacity(sbte_ctx* c, int cells) {
   return 0;
 }
 
-static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out) {
+static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out, int box_columns = 0) {
   typedef CUresult (*encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                 const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
                                 CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -154,7 +155,7 @@ static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out) {
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return 1; }
   const int N = c->N;
-  const int cols_per_cta = (N >= 16) ? 8 : 4;  // BatchCfg<N>::COLS
+  const int cols_per_cta = box_columns > 0 ? box_columns : ((N >= 16) ? 8 : 4);  // BatchCfg<N>::COLS, or 1 (mirror kernel)
   cuuint64_t gdim[2] = {(cuuint64_t)c->n3, (cuuint64_t)c->n3};
   cuuint64_t gstride[1] = {(cuuint64_t)c->n3 * sizeof(double)};
   cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)(cols_per_cta * N)};
@@ -168,17 +169,31 @@ static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out) {
 
 static int make_tensor_map(sbte_ctx* c) {
   c->tmap_ok = false;
-  if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copy
+  c->mirror_ok = false;
+  if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copies
+  if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
   c->sched_cells = 0;
   if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
   if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
   c->tmap_ok = true;
+  if (qhat_mirror_enabled(c->N)) {
+    if (encode_weight_map(c, c->d_W, &c->tmapM, 1)) return 1;
+    if (!c->d_mtiles) {
+      const std::vector<MirrorTile> mt = build_mirror_tiles(c->N, qhat_mirror_pairs(c->N));
+      CK(cudaMalloc(&c->d_mtiles, mt.size() * sizeof(MirrorTile)));
+      CK(cudaMemcpy(c->d_mtiles, mt.data(), mt.size() * sizeof(MirrorTile), cudaMemcpyHostToDevice));
+      c->n_mtiles = (int)mt.size();
+    }
+    c->mirror_ok = true;
+  }
   return 0;
 }
 
 static int release_weights(sbte_ctx* c) {
   invalidate_graphs(c);
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }
+  if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
+  c->mirror_ok = false;
   if (c->owns_W && c->d_W) cudaFree((void*)c->d_W);
   c->d_W = nullptr; c->owns_W = false; c->host_key = nullptr; c->tmap_ok = false;
   return 0;
@@ -213,17 +228,19 @@ struct HostSchedule {
 };
 
 // Pure host arithmetic (no CUDA call): also exported as sbte_batch_schedule_host for the CPU tests.
-static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out) {
+// `mirror` != null: the row-blocks are the column-pair tiles of the mirror kernel (mirror.cuh) instead.
+static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out,
+                                 const std::vector<MirrorTile>* mirror = nullptr) {
   const int cols = qhat_batch_cols(N);
   // row-blocks never straddle a zeta_x plane: bpx blocks of `cols` zeta_y columns per plane, the last one
   // partly empty when cols does not divide N (N = 20, 22)
   const int bpx = (N + cols - 1) / cols;
-  const int G = (cells + 31) / 32, RB = N * bpx, T = G * RB;
+  const int G = (cells + 31) / 32, RB = mirror ? (int)mirror->size() : N * bpx, T = G * RB;
   // tile t = (row-block rb = t / G, cell group cg = t % G); its length is (visited xi_x planes) * N steps
   std::vector<long long>& tbegin = out->tbegin;
   tbegin.assign(T + 1, 0);
   for (int t = 0; t < T; t++) {
-    const int zx = (t / G) / bpx;
+    const int zx = mirror ? (*mirror)[t / G].zx : (t / G) / bpx;
     tbegin[t + 1] = tbegin[t] + (long long)(sym ? sym_nrep(N, zx) : N) * N;
   }
   const long long total = tbegin[T];
@@ -232,7 +249,7 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
   std::vector<long long>& begin = out->begin;
   begin.assign(P + 1, 0);
-  const long long align = qhat_batch_align(N);   // the line-ring kernel works on whole xi_x chunks
+  const long long align = mirror ? 1 : qhat_batch_align(N);   // the line-ring kernel works on whole xi_x chunks
   for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * (total / align)) / P) * align;
   auto owner = [&](long long g) {   // last CTA whose range starts at or before g
     int lo = 0, hi = P - 1;
@@ -260,11 +277,23 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   for (int p = 0; p < P; p++) ctile[p] = tile_of(std::min(begin[p], total - 1));
   // the inverse transform looks the part count up as np[(column / np_cols) * G + cell group]; with partly
   // empty row-blocks that table is kept per zeta column
-  const bool per_column = (N % cols) != 0;
+  const bool per_column = mirror != nullptr || (N % cols) != 0;
   if (per_column) {
+    std::vector<int> col_rb((size_t)N * N, 0);   // row-block that writes zeta column q
+    if (mirror) {
+      for (int rb = 0; rb < RB; rb++) {
+        const MirrorTile& mt = (*mirror)[rb];
+        for (int p = 0; p < 4; p++) {
+          if (mt.zyA[p] >= 0) col_rb[(size_t)mt.zx * N + mt.zyA[p]] = rb;
+          if (mt.zyB[p] >= 0) col_rb[(size_t)mirror_nu(mt.zx, N) * N + mt.zyB[p]] = rb;
+        }
+      }
+    } else {
+      for (int q = 0; q < N * N; q++) col_rb[q] = (q / N) * bpx + (q % N) / cols;
+    }
     std::vector<unsigned char> npc((size_t)N * N * G);
     for (int q = 0; q < N * N; q++)
-      for (int g = 0; g < G; g++) npc[(size_t)q * G + g] = np[(size_t)((q / N) * bpx + (q % N) / cols) * G + g];
+      for (int g = 0; g < G; g++) npc[(size_t)q * G + g] = np[(size_t)col_rb[q] * G + g];
     np.swap(npc);
   }
   out->G = G; out->T = T; out->P = P; out->np_cols = per_column ? 1 : cols; out->kmax = kmax;
@@ -280,7 +309,12 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   const char* pe = getenv("SBTE_BATCH_CTAS");
   if (pe && atoi(pe) > 0) ctas = atoi(pe);
   HostSchedule h;
-  build_batch_schedule(c->N, cells, sym, ctas, &h);
+  if (qhat_mirror_enabled(c->N)) {
+    const std::vector<MirrorTile> mt = build_mirror_tiles(c->N, qhat_mirror_pairs(c->N));
+    build_batch_schedule(c->N, cells, sym, ctas, &h, &mt);
+  } else {
+    build_batch_schedule(c->N, cells, sym, ctas, &h);
+  }
   const int G = h.G, T = h.T, P = h.P, kmax = h.kmax;
   const size_t o1 = (size_t)(P + 1) * sizeof(long long);
   const size_t o2 = o1 + (size_t)(T + 1) * sizeof(long long);
@@ -313,14 +347,28 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
 }
 
 // Symmetrised weights for f == g (see common.cuh): built lazily, once per bound tensor.
-static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out);
+static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out, int box_columns);
+static int ensure_sym_mirror(sbte_ctx* c) {
+  if (c->d_Ws2) return 0;
+  c->graph_gen++;
+  CK(cudaMalloc(&c->d_Ws2, (size_t)c->n3 * c->n3 * sizeof(double)));
+  launch_symmetrize_weights_mirror(c, c->d_W, c->d_Ws2);
+  return encode_weight_map(c, c->d_Ws2, &c->tmapMs, 1);
+}
 static int ensure_sym(sbte_ctx* c) {
   if (c->d_Ws) return 0;
   c->graph_gen++;
   CK(cudaMalloc(&c->d_Ws, (size_t)c->n3 * c->n3 * sizeof(double)));
   launch_symmetrize_weights(c, c->d_W, c->d_Ws);
-  if (qhat_batch_supported(c->N)) return encode_weight_map(c, c->d_Ws, &c->tmapWs);
+  if (qhat_batch_supported(c->N)) return encode_weight_map(c, c->d_Ws, &c->tmapWs, 0);
   return 0;
+}
+// the batched convolution and the symmetrised tensor of whichever batched kernel is active for this N
+static int ensure_sym_batched(sbte_ctx* c) { return qhat_mirror_enabled(c->N) ? ensure_sym_mirror(c) : ensure_sym(c); }
+static void launch_batched_conv(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
+                                const BatchSched& sch) {
+  if (qhat_mirror_enabled(c->N)) launch_qhat_mirror(c, spec, parts, part_stride, cells, sch);
+  else launch_qhat_batch2(c, spec, parts, part_stride, cells, sch);
 }
 static bool want_sym(sbte_ctx* c, bool same) {
   static int env = -1;
@@ -364,10 +412,10 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
   if (k2 == SBTE_K2_BATCH) {
     if (!same) { set_error("batched convolution requires f == g (single species)"); return 1; }
     const bool sym = want_sym(c, true);
-    if (sym && ensure_sym(c)) return 1;
+    if (sym && ensure_sym_batched(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
     launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
   } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
     if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
@@ -407,10 +455,10 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
     // fast path: forward transform -> stream-K convolution -> inverse transform summing the partial sums
     if (!c->d_W) { set_error("no weights bound"); return 1; }
     const bool sym = want_sym(c, true);
-    if (sym && ensure_sym(c)) return 1;
+    if (sym && ensure_sym_batched(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
     launch_fft3d_parts(c, c->d_parts, c->parts_stride, c->sched, 1, batch, nullptr, d_Q);
     return check_launch("batched compute_q");
   }
@@ -432,10 +480,10 @@ int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, 
     if (ensure_capacity(c, batch)) return 1;
     if (!c->d_W) { set_error("no weights bound"); return 1; }
     const bool sym = want_sym(c, true);
-    if (sym && ensure_sym(c)) return 1;
+    if (sym && ensure_sym_batched(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_src, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
     CellEpi epi = {};
     epi.mode = 1; epi.v = c->d_v; epi.wt = c->d_wt; epi.dv3 = c->dv * c->dv * c->dv; epi.lu = c->lu;
     epi.a = a; epi.x = x; epi.b = b; epi.y = y; epi.s = s; epi.Kn = Kn; epi.out = out;
@@ -563,20 +611,28 @@ int sbte_destroy(sbte_ctx* c) {
   for (cudaEvent_t e : c->k2_ev) cudaEventDestroy(e);
   if (c->d_sched_mem) cudaFree(c->d_sched_mem);
   if (c->d_parts) cudaFree(c->d_parts);
+  if (c->d_mtiles) cudaFree(c->d_mtiles);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
 }
 
 // The stream-K schedule ensure_batch_schedule() would upload for (N, cells, sym) on a device with `ctas` SMs.
-// Pure host arithmetic: works without a GPU (CPU tests, sizing).  dims = {G, T, P, np_cols, kmax, np_len};
+// Pure host arithmetic: works without a GPU (CPU tests, sizing).  mirror != 0: the layout of the mirror-paired
+// kernel (column-pair tiles, mirror.cuh).  dims = {G, T, P, np_cols, kmax, np_len};
 // any array pointer may be null (query dims first, then call again with arrays of P+1, T+1, P, T, np_len entries).
-int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long* cta_begin, long long* tile_begin,
+int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int mirror, long long* cta_begin, long long* tile_begin,
                              int* cta_tile, int* tile_first, unsigned char* np, int* dims) {
   if (N < 2 || N > 32 || (N % 2) != 0 || cells < 1 || ctas < 1) { set_error("batch schedule: bad arguments"); return 1; }
   if (!qhat_batch_supported(N)) { set_error("batch schedule: this N runs the any-N kernel (no schedule)"); return 1; }
+  if (mirror && N != 8 && N != 16) { set_error("batch schedule: the mirror-paired kernel exists for N = 8, 16"); return 1; }
   HostSchedule h;
-  build_batch_schedule(N, cells, sym != 0, ctas, &h);
+  if (mirror) {
+    const std::vector<MirrorTile> mt = build_mirror_tiles(N, qhat_mirror_pairs(N));
+    build_batch_schedule(N, cells, sym != 0, ctas, &h, &mt);
+  } else {
+    build_batch_schedule(N, cells, sym != 0, ctas, &h);
+  }
   if (dims) { dims[0] = h.G; dims[1] = h.T; dims[2] = h.P; dims[3] = h.np_cols; dims[4] = h.kmax; dims[5] = (int)h.np.size(); }
   if (cta_begin) memcpy(cta_begin, h.begin.data(), h.begin.size() * sizeof(long long));
   if (tile_begin) memcpy(tile_begin, h.tbegin.data(), h.tbegin.size() * sizeof(long long));

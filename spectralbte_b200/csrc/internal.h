@@ -7,6 +7,7 @@
 #include <vector>
 
 struct sbte_slab;
+namespace sbte { struct MirrorTile; }
 
 // Conservation data handed to kernels by value: the factored Gram matrix of the five moment
 // functionals and its pivots (reference: src/conserve.c:89-168,268-317).
@@ -67,6 +68,13 @@ struct sbte_ctx {
   bool sym_enabled = true;
   double* d_Ws = nullptr;
   CUtensorMap tmapWs;
+  // mirror-paired batched convolution (qhat_mirror.cu, opt-in): one-column tensor maps, its own symmetrised tensor
+  // (mirror.cuh: mirror_sym_weight) and the table of column-pair tiles
+  CUtensorMap tmapM, tmapMs;
+  double* d_Ws2 = nullptr;
+  sbte::MirrorTile* d_mtiles = nullptr;
+  int n_mtiles = 0;
+  bool mirror_ok = false;
 
   // scratch, sized for `cap` cells
   int cap = 0;
@@ -161,6 +169,13 @@ int qhat_batch_cols(int N);
 void launch_qhat_batch_any(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells, bool sym);
 int qhat_batch_align(int N);
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
+                        const BatchSched& sch);
+
+// qhat_mirror.cu -- mirror-paired batched kernel (N in {8,16}, SBTE_MIRROR=1)
+bool qhat_mirror_enabled(int N);
+int qhat_mirror_pairs(int N);
+void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2);
+void launch_qhat_mirror(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);
 
 // conserve.cu -- K4 / K5 / moments

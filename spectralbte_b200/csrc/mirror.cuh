@@ -1,0 +1,160 @@
+// spectralbte_b200/csrc/mirror.cuh -- "mirror-paired" batched convolution for f == g with REAL f.
+//
+// The reference's spectrum of a real distribution function (src/collisions.c:232-283) satisfies, with
+// nu(i) = (N - i) mod N per dimension and z(idx) = number of zero components of idx,
+//     f^[nu(idx)] = theta^z(idx) conj(f^[idx]),      theta = exp(-2i L_eta L_v)
+// (eta_0 = -L_eta has no mirror node on the grid; the transform is quasi-periodic there), and the convolution
+// index sigma_zeta(xi) = wrap(zeta + N/2 - xi) (src/collisions.c:141-160) commutes with nu.  Hence row nu(zeta) of
+//     Q^[zeta] = sum_xi W[zeta][xi] f^[xi] f^[sigma_zeta(xi)]                         (src/collisions.c:127-165)
+// needs, at nu(xi), the complex conjugate of the very product row zeta forms at xi, times theta^(z(xi)+z(sigma)):
+//     Q^[nu(zeta)] = sum_xi W[nu(zeta)][nu(xi)] theta^(z(xi) + z(sigma_zeta(xi))) conj(f^[xi] f^[sigma_zeta(xi)]).
+// Two weights share one complex product: 8 instead of 12 FP64 instructions wherever the phase is 1.  Valid for
+// ARBITRARY real weights (tests/test_hermitian_sharing_cpu.py, tests/test_mirror_emulation_cpu.py).
+//
+// This header holds what the kernel (qhat_mirror.cu) and its CPU emulation (tests/emul/mirror_emul.cu, test
+// infrastructure only) share: the column pairing and the per-step arithmetic of one lane.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <vector>
+
+namespace sbte {
+
+// ---------------------------------------------------------------- column pairing (host)
+// Column (zx, zy) pairs with (nu(zx), nu(zy)).  "A" columns own the products: planes zx in [1, N/2) (paired with
+// plane N - zx), and in the self-mirrored planes zx in {0, N/2} the columns zy in [1, N/2); the four columns with
+// zx, zy in {0, N/2} are their own mirror and run unpaired (zyB = -1).  Tiles hold PAIRS column pairs of one plane.
+struct MirrorTile {
+  int zx;          // plane of the A columns (the B columns lie in plane nu(zx))
+  int zyA[4];      // A columns, -1 = empty slot
+  int zyB[4];      // mirror columns nu(zyA) in plane nu(zx), -1 = none (self-mirrored or empty)
+};
+
+inline int mirror_nu(int i, int N) { return (N - i) % N; }
+
+inline std::vector<MirrorTile> build_mirror_tiles(int N, int pairs) {
+  std::vector<MirrorTile> tiles;
+  auto push = [&](int zx, const std::vector<int>& cols, bool paired) {
+    for (size_t i = 0; i < cols.size(); i += pairs) {
+      MirrorTile t;
+      t.zx = zx;
+      for (int p = 0; p < 4; p++) { t.zyA[p] = -1; t.zyB[p] = -1; }
+      for (int p = 0; p < pairs && i + p < cols.size(); p++) {
+        t.zyA[p] = cols[i + p];
+        t.zyB[p] = paired ? mirror_nu(cols[i + p], N) : -1;
+      }
+      tiles.push_back(t);
+    }
+  };
+  for (int zx = 0; zx <= N / 2; zx++) {
+    std::vector<int> cols;
+    if (zx == 0 || zx == N / 2) {
+      for (int zy = 1; zy < N / 2; zy++) cols.push_back(zy);
+      push(zx, cols, true);
+      push(zx, {0, N / 2}, false);
+    } else {
+      for (int zy = 0; zy < N; zy++) cols.push_back(zy);
+      push(zx, cols, true);
+    }
+  }
+  return tiles;
+}
+
+// role of a zeta row in the symmetrised tensor of the mirror kernel: B rows enumerate the mirrored planes
+__host__ __device__ __forceinline__ bool mirror_is_b_row(int N, int zx, int zy) {
+  if (zx == 0 || zx == N / 2) return zy > N / 2;
+  return zx > N / 2;
+}
+
+// Symmetrised tensor of the mirror kernel (cf. symmetrize_weights_kernel, qhat.cu): A rows (and the unpaired ones)
+// keep the rule of common.cuh -- the sum W + W o sigma on the smaller plane of each pair, W on self-paired planes,
+// 0 elsewhere; B rows apply the same rule to the MIRRORED planes, so that the step (xi_x, xi_y) of an A column and
+// the step (nu xi_x, nu xi_y) of its B column are representatives together.
+__host__ __device__ __forceinline__ double mirror_sym_weight(const double* __restrict__ W, int N, size_t zeta, size_t xi) {
+  const size_t n3 = (size_t)N * N * N;
+  const int zx = (int)(zeta / ((size_t)N * N)), zy = (int)((zeta / N) % N), zz = (int)(zeta % N);
+  const int ex = (int)(xi / ((size_t)N * N)), ey = (int)((xi / N) % N), ez = (int)(xi % N);
+  const int X = (zx + N / 2 - ex + N) % N, Y = (zy + N / 2 - ey + N) % N, Z = (zz + N / 2 - ez + N) % N;
+  const bool b = mirror_is_b_row(N, zx, zy);
+  const int e1 = b ? (N - ex) % N : ex, X1 = b ? (N - X) % N : X;
+  if (e1 < X1) return W[zeta * n3 + xi] + W[zeta * n3 + ((size_t)X * N + Y) * N + Z];
+  if (e1 == X1) return W[zeta * n3 + xi];
+  return 0.0;
+}
+
+// ---------------------------------------------------------------- per-lane arithmetic of one (xi_x, xi_y) step
+__host__ __device__ __forceinline__ double2 mir_cmul(double2 a, double2 b) {
+  return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
+}
+__host__ __device__ __forceinline__ double2 mir_cmul_conj_b(double2 a, double2 b) {   // a * conj(b)
+  return make_double2(a.x * b.x + a.y * b.y, a.y * b.x - a.x * b.y);
+}
+__host__ __device__ __forceinline__ double2 mir_conj(double2 a) { return make_double2(a.x, -a.y); }
+
+// Rows R0 .. R0+RH-1 of column A accumulate into accA; the mirrored rows nu(R) of column B into accB (index r).
+//   fl/fs : the (zeta - xi)-side line f^[X][Y][.] of column A, element z at fl[z * fs]
+//   gl/gs : the xi-side line f^[xi_x][xi_y][.], element c at gl[c * gs]
+//   wA    : N x N weights of column A, row zeta_z, column xi_z          (W[zeta_A][(xi_x, xi_y, .)])
+//   wB    : N x N weights of column B at the MIRRORED step              (W[zeta_B][(nu xi_x, nu xi_y, .)]); zeros if unpaired
+//   theta : exp(-2i L_eta L_v);   phi = theta^([xi_x=0] + [xi_y=0] + [X=0] + [Y=0]) of this step and column
+template <int N, int R0, int RH>
+__host__ __device__ __forceinline__ void mirror_step(double2 (&accA)[RH], double2 (&accB)[RH], const double2* fl, int fs,
+                                                      const double2* gl, int gs, const double* wA, const double* wB,
+                                                      double2 theta, double2 phi) {
+  double2 fr[N];
+#pragma unroll
+  for (int z = 0; z < N; z++) fr[z] = fl[z * fs];
+  const double2 f0B = mir_cmul_conj_b(theta, fr[0]);   // theta conj(f^[.. 0]): entries whose (zeta - xi)_z index is 0
+  double2 sB[RH];
+#pragma unroll
+  for (int r = 0; r < RH; r++) sB[r] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int c = 0; c < N; c += 2) {
+    const double2 g0v = gl[c * gs], g1v = gl[(c + 1) * gs];
+    // xi_z = 0 carries a phase as well: theta conj(g)
+    const double2 g0B = (c == 0) ? mir_cmul_conj_b(theta, g0v) : mir_conj(g0v);
+    const double2 g1B = mir_conj(g1v);
+#pragma unroll
+    for (int r = 0; r < RH; r++) {
+      const int R = R0 + r;
+      const int nuR = (N - R) % N;
+      const int d0 = (R + N / 2 - c + N) % N;          // operand index of column c
+      const int d1 = (R + N / 2 - c - 1 + N) % N;      // ... of column c + 1
+      const int nc0 = (N - c) % N, nc1 = N - c - 1;    // mirrored columns
+      const double2 wa = *reinterpret_cast<const double2*>(wA + R * N + c);
+      const double wb0 = wB[nuR * N + nc0], wb1 = wB[nuR * N + nc1];
+      const double2 p0 = mir_cmul(g0v, fr[d0]);
+      const double2 p1 = mir_cmul(g1v, fr[d1]);
+      accA[r].x = fma(wa.x, p0.x, accA[r].x);
+      accA[r].y = fma(wa.x, p0.y, accA[r].y);
+      accA[r].x = fma(wa.y, p1.x, accA[r].x);
+      accA[r].y = fma(wa.y, p1.y, accA[r].y);
+      if (c != 0 && d0 != 0) {                         // phase-free entry: the mirror row takes conj(p0)
+        sB[r].x = fma(wb0, p0.x, sB[r].x);
+        sB[r].y = fma(-wb0, p0.y, sB[r].y);
+      } else {
+        const double2 q = mir_cmul(g0B, (d0 == 0) ? f0B : mir_conj(fr[d0]));
+        sB[r].x = fma(wb0, q.x, sB[r].x);
+        sB[r].y = fma(wb0, q.y, sB[r].y);
+      }
+      if (d1 != 0) {
+        sB[r].x = fma(wb1, p1.x, sB[r].x);
+        sB[r].y = fma(-wb1, p1.y, sB[r].y);
+      } else {
+        const double2 q = mir_cmul(g1B, f0B);
+        sB[r].x = fma(wb1, q.x, sB[r].x);
+        sB[r].y = fma(wb1, q.y, sB[r].y);
+      }
+    }
+  }
+  // the step-level phase multiplies the whole contribution of this step to the mirror rows
+#pragma unroll
+  for (int r = 0; r < RH; r++) {
+    accB[r].x = fma(phi.x, sB[r].x, accB[r].x);
+    accB[r].x = fma(-phi.y, sB[r].y, accB[r].x);
+    accB[r].y = fma(phi.x, sB[r].y, accB[r].y);
+    accB[r].y = fma(phi.y, sB[r].x, accB[r].y);
+  }
+}
+
+}  // namespace sbte

@@ -1,0 +1,16 @@
+#!/bin/bash
+# First GPU call of the next round: the mirror-paired batched convolution (SBTE_MIRROR=1, csrc/qhat_mirror.cu) has only
+# been checked on the CPU (tests/test_mirror_emulation_cpu.py).  1) the batched / 1D parity tests of the suite with the
+# kernel switched on, 2) time against the default kernel at N=16 (640 and 80 cells), 3) the rolled N=24 line-ring
+# variant (SBTE_ROLL=1) against the default at 250 cells.  Every step under its own timeout (a wrong barrier count
+# would hang, not fail).
+mkdir -p gpurun_out
+SBTE_MIRROR=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+  -k "batched_computeq or symmetrised_stream or 1d_step or heat_transport_golden or shock1p2" > gpurun_out/mirror_tests.log 2>&1
+echo "exit $?" >> gpurun_out/mirror_tests.log
+for m in 0 1; do
+  SBTE_MIRROR=$m timeout 40 python tools/gpu_n22_time.py 16 640 >> gpurun_out/mirror_time.log 2>&1
+  SBTE_MIRROR=$m timeout 40 python tools/gpu_n22_time.py 16 80 >> gpurun_out/mirror_time.log 2>&1
+done
+for r in 0 1; do SBTE_ROLL=$r timeout 40 python tools/gpu_n22_time.py 24 250 >> gpurun_out/roll_time.log 2>&1; done
+tail -n 3 gpurun_out/mirror_tests.log; cat gpurun_out/mirror_time.log gpurun_out/roll_time.log
