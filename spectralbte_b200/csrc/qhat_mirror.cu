@@ -53,7 +53,7 @@ struct MirrorCfg {
   static constexpr int RH = N / 2;
   static constexpr int CONSUMERS = CWARPS * 32;
   static constexpr int THREADS = CONSUMERS + 128;   // + one producer warpgroup
-  static constexpr bool REG_SPLIT = THREADS > 256;  // 384 threads: 24 / 240 registers as in qhat_batch2_kernel
+  static constexpr bool REG_SPLIT = THREADS > 256;  // 384 threads: 40 (producer) / 232 (compute) registers
   static constexpr int LINE = N * 32;
   static constexpr int PLANE = N * LINE;
   static constexpr int STAGES = 4;
@@ -115,7 +115,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
 
   if (warp >= C::CWARPS) {
     // ===== producer warpgroup =====
-    if (C::REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (C::REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 40*128 + 232*256 = 64512 = 384*168
     if (warp == C::CWARPS && lane == 0) {
       int cur_cg = -1, cur_X = -1, epoch = -1;
       int t = sch.cta_tile[blockIdx.x];
@@ -138,11 +138,13 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
         if (k >= S) mbar_wait(&empty[st], ((k / S) - 1) & 1);
         const MirrorTile mt = tiles[rb];
         int boxes = 0;
+#pragma unroll
         for (int p = 0; p < C::PAIRS; p++) boxes += (mt.zyA[p] >= 0) + (mt.zyB[p] >= 0);
         mbar_arrive_expect_tx(&full[st], (uint32_t)(C::LINE * 16 + boxes * C::WTILE * 8));
         const int s = ex * N + ey;
         tma_bulk_g2s(stage_line(st), spec + (size_t)cg * n3 * 32 + (size_t)s * C::LINE, C::LINE * 16, &full[st]);
         const int zxB = (N - zx) % N, sB = ((N - ex) % N) * N + (N - ey) % N;   // mirrored plane and step
+#pragma unroll
         for (int p = 0; p < C::PAIRS; p++) {
           if (mt.zyA[p] >= 0)
             tma_tensor2d_g2s(stage_w(st) + p * C::WTILE, &tmapW, s * N, (zx * N + mt.zyA[p]) * N, &full[st]);
@@ -155,7 +157,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   }
 
   // ===== compute warps =====
-  if (C::REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  if (C::REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
   const int pair = warp % C::PAIRS, half = warp / C::PAIRS;
   double2 accA[RH], accB[RH];
 #pragma unroll
@@ -224,7 +226,8 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       const double2* gl = stage_line(st) + lane;
       const double* wA = stage_w(st) + pair * C::WTILE;
       const double* wB = (zyB >= 0) ? stage_w(st) + (C::PAIRS + pair) * C::WTILE : zero_box;
-      const double2 phi = ph.t[(ex == 0) + (ey == 0) + (X == 0) + (Y == 0)];
+      const int m = (ex == 0) + (ey == 0) + (X == 0) + (Y == 0);
+      const double2 phi = (m == 0) ? ph.t[0] : (m == 1) ? ph.t[1] : (m == 2) ? ph.t[2] : (m == 3) ? ph.t[3] : ph.t[4];
       if (half == 0) mirror_step<N, 0, RH>(accA, accB, fl, 32, gl, 32, wA, wB, ph.t[1], phi);
       else mirror_step<N, RH, RH>(accA, accB, fl, 32, gl, 32, wA, wB, ph.t[1], phi);
     }
