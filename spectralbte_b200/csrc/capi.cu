@@ -249,7 +249,7 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
   std::vector<long long>& begin = out->begin;
   begin.assign(P + 1, 0);
-  const long long align = mirror ? 1 : qhat_batch_align(N);   // the line-ring kernel works on whole xi_x chunks
+  const long long align = mirror ? qhat_mirror_align(N) : qhat_batch_align(N);   // the line-ring kernels work on whole xi_x chunks
   for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * (total / align)) / P) * align;
   auto owner = [&](long long g) {   // last CTA whose range starts at or before g
     int lo = 0, hi = P - 1;
@@ -625,7 +625,10 @@ int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int mirror, lo
                              int* cta_tile, int* tile_first, unsigned char* np, int* dims) {
   if (N < 2 || N > 32 || (N % 2) != 0 || cells < 1 || ctas < 1) { set_error("batch schedule: bad arguments"); return 1; }
   if (!qhat_batch_supported(N)) { set_error("batch schedule: this N runs the any-N kernel (no schedule)"); return 1; }
-  if (mirror && N != 8 && N != 16) { set_error("batch schedule: the mirror-paired kernel exists for N = 8, 16"); return 1; }
+  if (mirror && N != 8 && N != 16 && N != 20 && N != 22 && N != 24) {
+    set_error("batch schedule: the mirror-paired kernels exist for N = 8, 16, 20, 22, 24");
+    return 1;
+  }
   HostSchedule h;
   if (mirror) {
     const std::vector<MirrorTile> mt = build_mirror_tiles(N, qhat_mirror_pairs(N));

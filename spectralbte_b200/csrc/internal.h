@@ -174,6 +174,7 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* par
 // qhat_mirror.cu -- mirror-paired batched kernel (N in {8,16}, SBTE_MIRROR=1)
 bool qhat_mirror_enabled(int N);
 int qhat_mirror_pairs(int N);
+int qhat_mirror_align(int N);
 void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2);
 void launch_qhat_mirror(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);

@@ -51,7 +51,8 @@ inline std::vector<MirrorTile> build_mirror_tiles(int N, int pairs) {
     if (zx == 0 || zx == N / 2) {
       for (int zy = 1; zy < N / 2; zy++) cols.push_back(zy);
       push(zx, cols, true);
-      push(zx, {0, N / 2}, false);
+      push(zx, {0}, false);        // tiles hold CONSECUTIVE A columns (the line-ring variant slides a window over them)
+      push(zx, {N / 2}, false);
     } else {
       for (int zy = 0; zy < N; zy++) cols.push_back(zy);
       push(zx, cols, true);
@@ -96,21 +97,33 @@ __host__ __device__ __forceinline__ double2 mir_conj(double2 a) { return make_do
 //   gl/gs : the xi-side line f^[xi_x][xi_y][.], element c at gl[c * gs]
 //   wA    : N x N weights of column A, row zeta_z, column xi_z          (W[zeta_A][(xi_x, xi_y, .)])
 //   wB    : N x N weights of column B at the MIRRORED step              (W[zeta_B][(nu xi_x, nu xi_y, .)]); zeros if unpaired
-//   theta : exp(-2i L_eta L_v);   phi = theta^([xi_x=0] + [xi_y=0] + [X=0] + [Y=0]) of this step and column
-template <int N, int R0, int RH>
-__host__ __device__ __forceinline__ void mirror_step(double2 (&accA)[RH], double2 (&accB)[RH], const double2* fl, int fs,
+//   theta : exp(-2i L_eta L_v)
+// The step-level phase theta^m, m = [xi_x=0] + [xi_y=0] + [X=0] + [Y=0], is NOT applied here: accB is kept in a frame
+// rotated by the current step's phase (accB = true value * theta^-m), which the caller changes with
+// mirror_frame_update() on the few steps where m changes; that way the mirror rows accumulate directly.
+// LAZY: the (zeta - xi)-side operands are loaded when the sliding window of the rows first needs them (RH + 1 live
+// values instead of N: the N >= 20 kernels do not have the registers for the whole line).
+template <int N, int R0, int RH, bool LAZY = false>
+__host__ __device__ __forceinline__ void mirror_step(double2* accA, double2* accB, const double2* fl, int fs,
                                                       const double2* gl, int gs, const double* wA, const double* wB,
-                                                      double2 theta, double2 phi) {
+                                                      double2 theta) {
   double2 fr[N];
+  if (!LAZY) {
 #pragma unroll
-  for (int z = 0; z < N; z++) fr[z] = fl[z * fs];
-  const double2 f0B = mir_cmul_conj_b(theta, fr[0]);   // theta conj(f^[.. 0]): entries whose (zeta - xi)_z index is 0
-  double2 sB[RH];
+    for (int z = 0; z < N; z++) fr[z] = fl[z * fs];
+  } else {
+    // window of the first column pair: indices R0 + N/2 - 1 .. R0 + N/2 + RH - 1 (mod N)
 #pragma unroll
-  for (int r = 0; r < RH; r++) sB[r] = make_double2(0.0, 0.0);
+    for (int j = 0; j <= RH; j++) fr[(R0 + N / 2 - 1 + j) % N] = fl[((R0 + N / 2 - 1 + j) % N) * fs];
+  }
+  const double2 f0B = mir_cmul_conj_b(theta, fl[0]);   // theta conj(f^[.. 0]): entries whose (zeta - xi)_z index is 0
 #pragma unroll
   for (int c = 0; c < N; c += 2) {
     const double2 g0v = gl[c * gs], g1v = gl[(c + 1) * gs];
+    if (LAZY && c > 0) {   // columns c, c + 1 reach two operands further down
+      fr[(R0 + N / 2 - c + 2 * N) % N] = fl[((R0 + N / 2 - c + 2 * N) % N) * fs];
+      fr[(R0 + N / 2 - c - 1 + 2 * N) % N] = fl[((R0 + N / 2 - c - 1 + 2 * N) % N) * fs];
+    }
     // xi_z = 0 carries a phase as well: theta conj(g)
     const double2 g0B = (c == 0) ? mir_cmul_conj_b(theta, g0v) : mir_conj(g0v);
     const double2 g1B = mir_conj(g1v);
@@ -130,31 +143,41 @@ __host__ __device__ __forceinline__ void mirror_step(double2 (&accA)[RH], double
       accA[r].x = fma(wa.y, p1.x, accA[r].x);
       accA[r].y = fma(wa.y, p1.y, accA[r].y);
       if (c != 0 && d0 != 0) {                         // phase-free entry: the mirror row takes conj(p0)
-        sB[r].x = fma(wb0, p0.x, sB[r].x);
-        sB[r].y = fma(-wb0, p0.y, sB[r].y);
+        accB[r].x = fma(wb0, p0.x, accB[r].x);
+        accB[r].y = fma(-wb0, p0.y, accB[r].y);
       } else {
         const double2 q = mir_cmul(g0B, (d0 == 0) ? f0B : mir_conj(fr[d0]));
-        sB[r].x = fma(wb0, q.x, sB[r].x);
-        sB[r].y = fma(wb0, q.y, sB[r].y);
+        accB[r].x = fma(wb0, q.x, accB[r].x);
+        accB[r].y = fma(wb0, q.y, accB[r].y);
       }
       if (d1 != 0) {
-        sB[r].x = fma(wb1, p1.x, sB[r].x);
-        sB[r].y = fma(-wb1, p1.y, sB[r].y);
+        accB[r].x = fma(wb1, p1.x, accB[r].x);
+        accB[r].y = fma(-wb1, p1.y, accB[r].y);
       } else {
         const double2 q = mir_cmul(g1B, f0B);
-        sB[r].x = fma(wb1, q.x, sB[r].x);
-        sB[r].y = fma(wb1, q.y, sB[r].y);
+        accB[r].x = fma(wb1, q.x, accB[r].x);
+        accB[r].y = fma(wb1, q.y, accB[r].y);
       }
     }
   }
-  // the step-level phase multiplies the whole contribution of this step to the mirror rows
+}
+
+// theta^m for m = 0..4 (the step-level phases), by value in kernel parameters
+struct MirrorPhases {
+  double2 t[5];
+};
+__host__ __device__ __forceinline__ double2 mirror_phase(const MirrorPhases& ph, int m) {
+  return (m == 0) ? ph.t[0] : (m == 1) ? ph.t[1] : (m == 2) ? ph.t[2] : (m == 3) ? ph.t[3] : ph.t[4];
+}
+// accB is held as (true value) * theta^-m_cur.  Moves it to the frame of a step with phase theta^m_new (m_new = 0:
+// back to the true value, before it is written out).
+template <int RH>
+__host__ __device__ __forceinline__ void mirror_frame_update(double2* accB, int& m_cur, int m_new, const MirrorPhases& ph) {
+  if (m_new == m_cur) return;
+  const double2 rot = mir_cmul_conj_b(mirror_phase(ph, m_cur), mirror_phase(ph, m_new));   // theta^(m_cur - m_new)
 #pragma unroll
-  for (int r = 0; r < RH; r++) {
-    accB[r].x = fma(phi.x, sB[r].x, accB[r].x);
-    accB[r].x = fma(-phi.y, sB[r].y, accB[r].x);
-    accB[r].y = fma(phi.x, sB[r].y, accB[r].y);
-    accB[r].y = fma(phi.y, sB[r].x, accB[r].y);
-  }
+  for (int r = 0; r < RH; r++) accB[r] = mir_cmul(accB[r], rot);
+  m_cur = m_new;
 }
 
 }  // namespace sbte

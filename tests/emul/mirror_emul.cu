@@ -14,14 +14,13 @@
 
 using namespace sbte;
 
-template <int N>
+template <int N, bool LAZY>
 static void run(const double* W, int sym, const double2* F, double L_eta, double L_v, double2* qhat) {
-  constexpr int PAIRS = (N >= 16) ? 4 : 2, RH = N / 2;
+  constexpr int PAIRS = (N >= 16) ? 4 : 2, RH = N / 2;   // MirrorCfg / MirrorRingCfg::PAIRS
   const size_t n3 = (size_t)N * N * N;
   const double2 theta = make_double2(cos(-2.0 * L_eta * L_v), sin(-2.0 * L_eta * L_v));
-  double2 th[5];
-  th[0] = make_double2(1.0, 0.0);
-  for (int m = 1; m < 5; m++) th[m] = mir_cmul(th[m - 1], theta);
+  MirrorPhases ph;
+  for (int m = 0; m < 5; m++) ph.t[m] = make_double2(cos(m * -2.0 * L_eta * L_v), sin(m * -2.0 * L_eta * L_v));
   std::vector<double> zero((size_t)N * N, 0.0), wa((size_t)N * N), wb((size_t)N * N);
   for (const MirrorTile& t : build_mirror_tiles(N, PAIRS)) {
     const int zx = t.zx, zxB = mirror_nu(zx, N);
@@ -31,6 +30,7 @@ static void run(const double* W, int sym, const double2* F, double L_eta, double
       for (int half = 0; half < 2; half++) {
         double2 accA[RH], accB[RH];
         for (int r = 0; r < RH; r++) accA[r] = accB[r] = make_double2(0.0, 0.0);
+        int m_cur = 0;   // frame of accB (mirror_frame_update), as the kernels keep it
         const int nrep = sym ? sym_nrep(N, zx) : N;
         for (int cidx = 0; cidx < nrep; cidx++) {
           const int ex = sym ? sym_rep(N, zx, cidx) : cidx;
@@ -52,11 +52,12 @@ static void run(const double* W, int sym, const double2* F, double L_eta, double
                        N * sizeof(double));
               wbp = wb.data();
             }
-            const int m = (ex == 0) + (ey == 0) + (X == 0) + (Y == 0);
-            if (half == 0) mirror_step<N, 0, RH>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, theta, th[m]);
-            else mirror_step<N, RH, RH>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, theta, th[m]);
+            mirror_frame_update<RH>(accB, m_cur, (ex == 0) + (ey == 0) + (X == 0) + (Y == 0), ph);
+            if (half == 0) mirror_step<N, 0, RH, LAZY>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, theta);
+            else mirror_step<N, RH, RH, LAZY>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, theta);
           }
         }
+        mirror_frame_update<RH>(accB, m_cur, 0, ph);
         const int R0 = half * RH;
         for (int r = 0; r < RH; r++) {
           qhat[((size_t)zx * N + zy) * N + R0 + r] = accA[r];
@@ -81,8 +82,13 @@ int mirror_emul_symmetrize(int N, const double* W, double* Ws2) {
 int mirror_emul_qhat(int N, const double* W, int sym, const double* F, double L_eta, double L_v, double* qhat) {
   const size_t n3 = (size_t)N * N * N;
   for (size_t i = 0; i < 2 * n3; i++) qhat[i] = NAN;   // every entry must be written exactly by the pairing
-  if (N == 8) run<8>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
-  else if (N == 16) run<16>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  // the operand-loading variant each N uses in the kernels (qhat_mirror.cu)
+  if (N == 8) run<8, false>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 16) run<16, false>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 12) run<12, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);   // small stand-in for 20..24
+  else if (N == 20) run<20, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 22) run<22, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 24) run<24, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
   else return 1;
   return 0;
 }

@@ -156,14 +156,16 @@ def mirror_tiles(N, pairs):
     nu = lambda i: (N - i) % N  # noqa: E731
     tiles = []
     for zx in range(N // 2 + 1):
-        groups = [(list(range(1, N // 2)), True), ([0, N // 2], False)] if zx in (0, N // 2) else [(list(range(N)), True)]
+        groups = ([(list(range(1, N // 2)), True), ([0], False), ([N // 2], False)] if zx in (0, N // 2)
+                  else [(list(range(N)), True)])
         for cols, paired in groups:
             for i in range(0, len(cols), pairs):
                 tiles.append((zx, [(zy, nu(zy) if paired else -1) for zy in cols[i:i + pairs]]))
     return tiles
 
 
-@pytest.mark.parametrize("N,cells,sym,ctas", [(16, 640, True, 148), (16, 33, False, 148), (8, 37, True, 148), (16, 80, True, 11)])
+@pytest.mark.parametrize("N,cells,sym,ctas", [(16, 640, True, 148), (16, 33, False, 148), (8, 37, True, 148), (16, 80, True, 11),
+                                              (24, 250, True, 148), (22, 70, False, 148), (20, 33, True, 13)])
 def test_mirror_schedule_covers_every_step_once(N, cells, sym, ctas):
     """Layout of the opt-in mirror-paired kernel (csrc/qhat_mirror.cu): a step (xi_x, xi_y) of an A column also serves
     the step (nu xi_x, nu xi_y) of its mirror column."""
@@ -175,6 +177,10 @@ def test_mirror_schedule_covers_every_step_once(N, cells, sym, ctas):
     assert T == G * len(tiles) and s["np_cols"] == 1
     begin, tbegin = s["begin"], s["tbegin"]
     assert begin[0] == 0 and begin[-1] == tbegin[-1]
+    if N >= 20:                                      # line-ring variant: whole xi_x chunks, consecutive A columns per tile
+        assert np.all(begin % N == 0)
+        for zx, slots in tiles:
+            assert [zyA for zyA, _ in slots] == list(range(slots[0][0], slots[0][0] + len(slots)))
     seen, writes = set(), {}
     for p in range(P):
         g0, n = int(begin[p]), int(begin[p + 1] - begin[p])
@@ -213,3 +219,25 @@ def test_mirror_schedule_covers_every_step_once(N, cells, sym, ctas):
                 t = rb * G + cg
                 for q in [zx * N + zyA] + ([nu(zx) * N + zyB] if zyB >= 0 else []):
                     assert writes[t] == set(range(int(s["np"][q * G + cg])))
+
+
+@pytest.mark.parametrize("N", [20, 22, 24])
+def test_mirror_line_ring_arrival_counts(N):
+    """qhat_mirror_ring_kernel: PAIRS = 4 column slots, two warps each; both warps of the slot that reads a line last
+    also arrive for the slots that never read it, so every line's empty barrier sees 2 * PAIRS arrivals."""
+    PAIRS = 4
+    L = N + PAIRS - 1
+    arrivals = [0] * L
+    for ey in range(N):
+        for w in range(PAIRS):
+            jl = PAIRS - 1 + ey - w
+            cnt = 1
+            if jl < PAIRS - 1 and w == PAIRS - 1:
+                cnt = PAIRS - jl
+            if jl > N - 1 and w == N + PAIRS - 2 - jl:
+                cnt = jl - N + 2
+            arrivals[jl] += 2 * cnt                  # both halves
+    assert arrivals == [2 * PAIRS] * L
+    RING = 10
+    for ey in range(N):
+        assert min(L - 1, PAIRS - 1 + ey) - ey + 1 <= RING

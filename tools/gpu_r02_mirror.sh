@@ -13,4 +13,9 @@ for m in 0 1; do
   SBTE_MIRROR=$m timeout 40 python tools/gpu_n22_time.py 16 80 >> gpurun_out/mirror_time.log 2>&1
 done
 for r in 0 1; do SBTE_ROLL=$r timeout 40 python tools/gpu_n22_time.py 24 250 >> gpurun_out/roll_time.log 2>&1; done
-tail -n 3 gpurun_out/mirror_tests.log; cat gpurun_out/mirror_time.log gpurun_out/roll_time.log
+# the line-ring mirror kernels (N = 20, 22, 24) need SBTE_MIRROR=2
+SBTE_MIRROR=2 timeout 150 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+  -k "line_ring or 24-33-3 or 24-3-33 or 22-34-3 or 22-3-33" > gpurun_out/mirror_ring_tests.log 2>&1
+echo "exit $?" >> gpurun_out/mirror_ring_tests.log
+for n in 24 22 20; do SBTE_MIRROR=2 timeout 40 python tools/gpu_n22_time.py $n 250 >> gpurun_out/mirror_time.log 2>&1; done
+tail -n 3 gpurun_out/mirror_tests.log gpurun_out/mirror_ring_tests.log; cat gpurun_out/mirror_time.log gpurun_out/roll_time.log
