@@ -176,7 +176,11 @@ static int make_tensor_map(sbte_ctx* c) {
   if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
   if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
   c->tmap_ok = true;
-  if (qhat_mirror_enabled(c->N)) {
+  // the mirror identity needs the reference's own grids (src/initializer.c:66-82): v_j = -L_v + j dv, eta_{N/2} = 0 and
+  // dv * deta = 2 pi / N, i.e. L_eta * dv = pi; any other grid keeps the ordinary batched kernel
+  const bool grid_ok = fabs(c->v[0] + c->L_v) <= 1e-12 * c->L_v && fabs(c->L_eta * c->dv - M_PI) <= 1e-12 * M_PI &&
+                       fabs(c->dv * c->deta * c->N - 2.0 * M_PI) <= 1e-12 * 2.0 * M_PI;
+  if (qhat_mirror_enabled(c->N) && grid_ok) {
     if (encode_weight_map(c, c->d_W, &c->tmapM, 1)) return 1;
     if (!c->d_mtiles) {
       const std::vector<MirrorTile> mt = build_mirror_tiles(c->N, qhat_mirror_pairs(c->N));
@@ -309,7 +313,7 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   const char* pe = getenv("SBTE_BATCH_CTAS");
   if (pe && atoi(pe) > 0) ctas = atoi(pe);
   HostSchedule h;
-  if (qhat_mirror_enabled(c->N)) {
+  if (c->mirror_ok) {
     const std::vector<MirrorTile> mt = build_mirror_tiles(c->N, qhat_mirror_pairs(c->N));
     build_batch_schedule(c->N, cells, sym, ctas, &h, &mt);
   } else {
@@ -364,10 +368,10 @@ static int ensure_sym(sbte_ctx* c) {
   return 0;
 }
 // the batched convolution and the symmetrised tensor of whichever batched kernel is active for this N
-static int ensure_sym_batched(sbte_ctx* c) { return qhat_mirror_enabled(c->N) ? ensure_sym_mirror(c) : ensure_sym(c); }
+static int ensure_sym_batched(sbte_ctx* c) { return c->mirror_ok ? ensure_sym_mirror(c) : ensure_sym(c); }
 static void launch_batched_conv(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                                 const BatchSched& sch) {
-  if (qhat_mirror_enabled(c->N)) launch_qhat_mirror(c, spec, parts, part_stride, cells, sch);
+  if (c->mirror_ok) launch_qhat_mirror(c, spec, parts, part_stride, cells, sch);
   else launch_qhat_batch2(c, spec, parts, part_stride, cells, sch);
 }
 static bool want_sym(sbte_ctx* c, bool same) {
