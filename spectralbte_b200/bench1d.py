@@ -30,6 +30,9 @@ WORKLOADS = {
 
 def _k2_name(N):
     """The convolution kernel csrc/qhat_batch.cu picks for N (launch_qhat_batch2 / launch_qhat_batch_any)."""
+    mirror = int(os.environ.get("SBTE_MIRROR", "0") or 0)
+    if (mirror >= 1 and N in (8, 16)) or (mirror >= 2 and N in (20, 22, 24)):
+        return ("qhat_mirror_kernel<%d>" if N <= 16 else "qhat_mirror_ring_kernel<%d>") % N
     if N in (8, 16):
         return "qhat_batch2_kernel<%d>" % N
     if N == 24 or (N in (20, 22) and not os.environ.get("SBTE_NO_BATCH3G")):
