@@ -32,6 +32,13 @@ __host__ __device__ __forceinline__ int sym_rep(int N, int zx, int c) {   // c-t
   return (c <= h) ? c : c + (a - h);
 }
 
+// Everything below is inline PTX (or warp intrinsics).  tests/emul/cuda_emul.h -- test infrastructure that runs the
+// batched kernels' control flow on the host -- defines SBTE_HOST_EMUL and supplies same-named host stand-ins.
+#ifndef SBTE_HOST_EMUL
+#define SBTE_DYN_SMEM(name) extern __shared__ __align__(128) unsigned char name[]
+#define SBTE_SETMAXNREG_DEC(n) asm volatile("setmaxnreg.dec.sync.aligned.u32 " #n ";")
+#define SBTE_SETMAXNREG_INC(n) asm volatile("setmaxnreg.inc.sync.aligned.u32 " #n ";")
+
 // ---------------------------------------------------------------- shared-memory addressing
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return static_cast<uint32_t>(__cvta_generic_to_shared(p));
@@ -135,5 +142,7 @@ __device__ __forceinline__ void block_reduce_sum(double (&v)[NV], double* scratc
     v[i] = x;
   }
 }
+
+#endif  // SBTE_HOST_EMUL
 
 }  // namespace sbte

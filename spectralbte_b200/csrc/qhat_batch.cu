@@ -100,6 +100,7 @@ qhat_batch_any_kernel(const double* __restrict__ W, const double2* __restrict__ 
   }
 }
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 void launch_qhat_batch_any(sbte_ctx* c, const double2* spec, double2* qhat, int cells, bool sym) {
   const int groups = (cells + 31) / 32;
   static const int R0 = getenv("SBTE_ANY_R") ? atoi(getenv("SBTE_ANY_R")) : 4;
@@ -116,6 +117,7 @@ void launch_qhat_batch_any(sbte_ctx* c, const double2* spec, double2* qhat, int 
   k2_mark(c);
   c->launches += 1;
 }
+#endif
 
 // N = 20, 22: the line-ring kernel with partly empty row-blocks (SBTE_NO_BATCH3G=1: back to the any-N kernel)
 static bool batch3_general(int N) {
@@ -165,7 +167,7 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   using C = Batch2Cfg<N>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES;
-  extern __shared__ __align__(128) unsigned char smraw[];
+  SBTE_DYN_SMEM(smraw);
   double2* plane = reinterpret_cast<double2*>(smraw);
   unsigned char* stage0 = smraw + (size_t)C::PLANE * 16;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + S * C::STAGE_BYTES);
@@ -209,7 +211,7 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
 
   if (warp >= C::COLS) {
     // ===== producer warpgroup: one lane issues every TMA copy, up to S steps ahead of the consumers =====
-    if (C::REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    if (C::REG_SPLIT) SBTE_SETMAXNREG_DEC(24);
     if (warp == C::COLS && lane == 0) {
       int cur_cg = -1, cur_X = -1, epoch = -1;
       int t = sch.cta_tile[blockIdx.x];
@@ -240,7 +242,7 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   }
 
   // ===== compute warps =====
-  if (C::REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  if (C::REG_SPLIT) SBTE_SETMAXNREG_INC(240);
   double2 acc[N];
 #pragma unroll
   for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
@@ -324,6 +326,7 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   flush();
 }
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 template <int N>
 static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                             const BatchSched& sch) {
@@ -339,6 +342,7 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
   k2_mark(c);
   c->launches += 1;
 }
+#endif
 
 // ------------------------------------------------------------------------------------------
 // v3 ("line ring"): same mapping as v2 for N whose (zeta - xi)-side plane does not fit in shared
@@ -380,7 +384,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   using C = Batch3Cfg<N>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES, R = C::RING, L = C::LPC;
-  extern __shared__ __align__(128) unsigned char smraw[];
+  SBTE_DYN_SMEM(smraw);
   double2* ring = reinterpret_cast<double2*>(smraw);
   unsigned char* stage0 = smraw + R * C::LINE_BYTES;
   uint64_t* bars = reinterpret_cast<uint64_t*>(stage0 + S * C::STAGE_BYTES);
@@ -407,7 +411,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   __syncthreads();
 
   if (warp >= C::COLS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 24;");
+    SBTE_SETMAXNREG_DEC(24);
     if (warp == C::COLS && lane == 0) {
       int k = 0;          // local step counter (stage ring)
       long q = 0;         // line sequence number (line ring)
@@ -447,7 +451,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     return;
   }
 
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 240;");
+  SBTE_SETMAXNREG_INC(240);
   double2 acc[N];
 #pragma unroll
   for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
@@ -556,6 +560,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   flush();
 }
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 template <int N, int ROLL = 1>
 static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                             const BatchSched& sch) {
@@ -571,7 +576,9 @@ static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, si
   k2_mark(c);
   c->launches += 1;
 }
+#endif
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch) {
   if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
@@ -587,5 +594,6 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t
     default: set_error("qhat_batch: unsupported N"); break;
   }
 }
+#endif
 
 }  // namespace sbte

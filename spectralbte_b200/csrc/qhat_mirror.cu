@@ -40,10 +40,12 @@ __global__ void symmetrize_weights_mirror_kernel(const double* __restrict__ W, d
   }
 }
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2) {
   symmetrize_weights_mirror_kernel<<<148 * 16, 256, 0, c->stream>>>(W, Ws2, c->N);
   c->launches += 1;
 }
+#endif
 
 template <int N>
 struct MirrorCfg {
@@ -70,7 +72,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   using C = MirrorCfg<N>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES, RH = C::RH;
-  extern __shared__ __align__(128) unsigned char smraw[];
+  SBTE_DYN_SMEM(smraw);
   double2* plane = reinterpret_cast<double2*>(smraw);
   unsigned char* stage0 = smraw + (size_t)C::PLANE * 16;
   double* zero_box = reinterpret_cast<double*>(stage0 + S * C::STAGE_BYTES);
@@ -114,7 +116,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
 
   if (warp >= C::CWARPS) {
     // ===== producer warpgroup =====
-    if (C::REG_SPLIT) asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");   // 40*128 + 232*256 = 64512 = 384*168
+    if (C::REG_SPLIT) SBTE_SETMAXNREG_DEC(40);   // 40*128 + 232*256 = 64512 = 384*168
     if (warp == C::CWARPS && lane == 0) {
       int cur_cg = -1, cur_X = -1, epoch = -1;
       int t = sch.cta_tile[blockIdx.x];
@@ -156,7 +158,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   }
 
   // ===== compute warps =====
-  if (C::REG_SPLIT) asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  if (C::REG_SPLIT) SBTE_SETMAXNREG_INC(232);
   const int pair = warp % C::PAIRS, half = warp / C::PAIRS;
   double2 accA[RH], accB[RH];
 #pragma unroll
@@ -249,6 +251,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   flush();
 }
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 template <int N>
 static void launch_mirror_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                             const BatchSched& sch) {
@@ -268,6 +271,7 @@ static void launch_mirror_n(sbte_ctx* c, const double2* spec, double2* parts, si
   k2_mark(c);
   c->launches += 1;
 }
+#endif
 
 
 // ------------------------------------------------------------------------------------------
@@ -306,7 +310,7 @@ qhat_mirror_ring_kernel(const __grid_constant__ CUtensorMap tmapW, const double2
   using C = MirrorRingCfg<N>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES, R = C::RING, L = C::LPC, RH = C::RH;
-  extern __shared__ __align__(128) unsigned char smraw[];
+  SBTE_DYN_SMEM(smraw);
   double2* ring = reinterpret_cast<double2*>(smraw);
   unsigned char* stage0 = smraw + R * C::LINE_BYTES;
   double* zero_box = reinterpret_cast<double*>(stage0 + S * C::STAGE_BYTES);
@@ -335,7 +339,7 @@ qhat_mirror_ring_kernel(const __grid_constant__ CUtensorMap tmapW, const double2
   __syncthreads();
 
   if (warp >= C::CWARPS) {
-    asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+    SBTE_SETMAXNREG_DEC(40);
     if (warp == C::CWARPS && lane == 0) {
       int k = 0;          // local step counter (stage ring)
       long q = 0;         // line sequence number (line ring)
@@ -385,7 +389,7 @@ qhat_mirror_ring_kernel(const __grid_constant__ CUtensorMap tmapW, const double2
     return;
   }
 
-  asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+  SBTE_SETMAXNREG_INC(232);
   const int pair = warp % C::PAIRS, half = warp / C::PAIRS;
   double2 accA[RH], accB[RH];
   ring_clear<RH>(accA, accB);
@@ -472,6 +476,7 @@ qhat_mirror_ring_kernel(const __grid_constant__ CUtensorMap tmapW, const double2
   flush();
 }
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 template <int N>
 static void launch_mirror_ring_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                                  const BatchSched& sch) {
@@ -491,7 +496,9 @@ static void launch_mirror_ring_n(sbte_ctx* c, const double2* spec, double2* part
   k2_mark(c);
   c->launches += 1;
 }
+#endif
 
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 void launch_qhat_mirror(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch) {
   if (!c->mirror_ok) { set_error("qhat_mirror: tensor maps / tile table not initialised"); return; }
@@ -504,5 +511,6 @@ void launch_qhat_mirror(sbte_ctx* c, const double2* spec, double2* parts, size_t
     default: set_error("qhat_mirror: unsupported N"); break;
   }
 }
+#endif
 
 }  // namespace sbte

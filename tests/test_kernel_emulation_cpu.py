@@ -1,0 +1,110 @@
+"""Control flow of the batched convolution kernels, checked without a GPU.  tests/emul/kernel_emul.cpp compiles the
+kernel sources of spectralbte_b200/csrc verbatim with g++ through a host shim (tests/emul/cuda_emul.h: one OS thread
+per CUDA thread, emulated mbarriers / TMA copies / shared memory -- test infrastructure, never part of the library)
+and runs them CTA by CTA on the stream-K schedule the library builds (sbte_batch_schedule_host).  The partial sums
+they write, combined the way the inverse transform combines them, must equal the oracle's convolution
+(src/collisions.c:127-165) for every cell.  This covers what arithmetic checks cannot: barrier counts (a wrong one
+hangs; the shim's bounded wait aborts), TMA coordinates, shared-memory offsets, tile switches, flushes -- for the
+GPU-verified kernels (as a check of the emulation itself) and for the opt-in kernels that have not run on a GPU yet."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from conftest import relmax, seeded_f
+from oracle import oracle as orc
+from test_batch_schedule_cpu import schedule
+from test_mirror_emulation_cpu import _emul as _mirror_rule_lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+SRC = os.path.join(HERE, "emul", "kernel_emul.cpp")
+LIB = os.path.join(HERE, "emul", "libkernel_emul.so")
+DEPS = [SRC, os.path.join(HERE, "emul", "cuda_emul.h")] + [
+    os.path.join(ROOT, "spectralbte_b200", "csrc", f) for f in ("qhat_batch.cu", "qhat_mirror.cu", "mirror.cuh", "common.cuh", "internal.h")]
+
+
+def _lib():
+    if not os.path.exists(LIB) or os.path.getmtime(LIB) < max(os.path.getmtime(d) for d in DEPS):
+        cuda_inc = os.path.join(os.environ.get("CUDA_HOME", "/usr/local/cuda"), "include")
+        subprocess.run(["g++", "-std=c++17", "-O1", "-fPIC", "-shared", "-pthread", "-I", cuda_inc, "-I", os.path.join(ROOT, "include"),
+                        "-o", LIB, SRC], check=True, capture_output=True)
+    L = C.CDLL(LIB)
+    dp, llp, ip, ubp = C.POINTER(C.c_double), C.POINTER(C.c_longlong), C.POINTER(C.c_int), C.POINTER(C.c_ubyte)
+    L.emul_batched.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, llp, llp, ip, ip, ubp, C.c_int, C.c_int, C.c_int, C.c_int,
+                               dp, dp, dp, C.c_double, C.c_double]
+    return L
+
+
+def symmetrise_standard(W, N):
+    """symmetrize_weights_kernel (csrc/qhat.cu): W + W o sigma on the smaller plane of each pair, W on self-paired planes, 0 elsewhere."""
+    n3 = N ** 3
+    Wm = W.reshape(n3, n3)
+    idx = np.arange(n3)
+    x, y, z = idx // (N * N), (idx // N) % N, idx % N
+    out = np.zeros_like(Wm)
+    for zeta in range(n3):
+        zx, zy, zz = zeta // (N * N), (zeta // N) % N, zeta % N
+        X, Y, Z = (zx + N // 2 - x) % N, (zy + N // 2 - y) % N, (zz + N // 2 - z) % N
+        sig = (X * N + Y) * N + Z
+        row = Wm[zeta]
+        out[zeta] = np.where(x < X, row + row[sig], np.where(x == X, row, 0.0))
+    return out.reshape(-1)
+
+
+CASES = [  # kind, N, cells, sym, ctas
+    (0, 8, 37, True, 5), (0, 8, 5, False, 3),            # qhat_batch2_kernel<8>      (GPU-verified: checks the emulation)
+    (0, 20, 3, True, 4),                                   # qhat_batch3_kernel<20>     (GPU-verified, partly empty row-blocks)
+    (1, 8, 37, True, 5), (1, 8, 5, False, 3),             # qhat_mirror_kernel<8>
+    (1, 16, 3, True, 3),                                   # qhat_mirror_kernel<16>
+    (1, 20, 3, True, 4), (1, 20, 2, False, 3),            # qhat_mirror_ring_kernel<20>
+]
+
+
+@pytest.mark.parametrize("kind,N,cells,sym,ctas", CASES)
+def test_kernel_control_flow_on_host(kind, N, cells, sym, ctas):
+    L = _lib()
+    o = orc.Oracle(N, 9.0, 1)
+    n3 = N ** 3
+    W = np.random.default_rng(N).standard_normal(n3 * n3) if N <= 8 else orc.synthetic_weights(N)
+    if sym and kind == 1:
+        Wk = np.empty_like(W)
+        R = _mirror_rule_lib()
+        assert R.mirror_emul_symmetrize(N, W.ctypes.data_as(C.POINTER(C.c_double)), Wk.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    elif sym:
+        Wk = symmetrise_standard(W, N)
+    else:
+        Wk = W
+    s = schedule(N, cells, sym, ctas, mirror=(kind == 1))
+    G, T, P, kmax = s["G"], s["T"], s["P"], s["kmax"]
+    # spectra, cell-minor [G][n3][32]; padding cells are zero
+    spec = np.zeros((G, n3, 32), dtype=complex)
+    F = []
+    for b in range(cells):
+        f = seeded_f(o.v, 700 + b, noise=0.3) * (1.0 + 0.05 * b)
+        Fb = o.fft3d(f.astype(complex))
+        F.append(Fb)
+        spec[b // 32, :, b % 32] = Fb
+    stride = G * 32 * n3
+    parts = np.full(kmax * stride, np.nan + 1j * np.nan, dtype=complex)
+    dv = o.v[1] - o.v[0]
+    L_eta = 0.5 * N * (2.0 * np.pi / (N * dv))
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
+    rc = L.emul_batched(kind, N, cells, int(sym), P, p(s["begin"], C.c_longlong), p(s["tbegin"], C.c_longlong), p(s["ctile"], C.c_int),
+                        p(s["first"], C.c_int), p(s["np"], C.c_ubyte), G, T, s["np_cols"], kmax,
+                        p(Wk, C.c_double), p(spec.view(np.float64), C.c_double), p(parts.view(np.float64), C.c_double), L_eta, 9.0)
+    assert rc == 0
+    # combine the partial sums the way the inverse transform does: np[(column / np_cols) * G + cell group] parts per column
+    parts = parts.reshape(kmax, G * 32, n3)
+    for b in range(cells):
+        q = np.zeros(n3, dtype=complex)
+        for col in range(N * N):
+            npc = int(s["np"][(col // s["np_cols"]) * G + b // 32])
+            assert npc >= 1
+            seg = parts[:npc, b, col * N:(col + 1) * N]
+            assert not np.isnan(seg.view(np.float64)).any(), (b, col)       # every part the table promises was written
+            q[col * N:(col + 1) * N] = seg.sum(axis=0)
+        want = o.qhat(W, F[b], F[b])
+        assert relmax(q, want) < 1e-12, b
