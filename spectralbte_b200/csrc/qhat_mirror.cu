@@ -11,7 +11,9 @@
 // memory, decoupled compute warps.  A tile is PAIRS column pairs of one zeta_x plane; two warps share a pair, each
 // owning N/2 zeta_z rows of column A and the mirrored rows of column B.
 // STATUS: arithmetic, pairing and symmetrisation rule are checked on the CPU against the reference restatement
-// (tests/test_mirror_emulation_cpu.py); the kernel itself has not run on a GPU yet, hence off by default.
+// (tests/test_mirror_emulation_cpu.py), and this very source -- barriers, TMA coordinates, shared-memory layout, tile
+// switches, flushes -- runs on the host through tests/emul/cuda_emul.h (tests/test_kernel_emulation_cpu.py, N = 8, 16,
+// 20, 22, 24).  It has not run on a GPU yet (no timing, no sanitizer pass), hence off by default.
 #include <math.h>
 #include <stdlib.h>
 

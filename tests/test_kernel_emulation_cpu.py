@@ -60,6 +60,10 @@ CASES = [  # kind, N, cells, sym, ctas
     (1, 8, 37, True, 5), (1, 8, 5, False, 3),             # qhat_mirror_kernel<8>
     (1, 16, 3, True, 3),                                   # qhat_mirror_kernel<16>
     (1, 20, 3, True, 4), (1, 20, 2, False, 3),            # qhat_mirror_ring_kernel<20>
+    (1, 22, 2, True, 3),                                   # qhat_mirror_ring_kernel<22> (odd N/2, padded box slots, partial tiles)
+    (1, 24, 1, True, 3),                                   # qhat_mirror_ring_kernel<24>
+    (2, 24, 1, True, 3),                                   # qhat_batch3_kernel<24, ROLL=3> (opt-in rolled xi_z loop)
+    (0, 22, 2, True, 3),                                   # qhat_batch3_kernel<22>     (GPU-verified)
 ]
 
 
