@@ -19,3 +19,9 @@ SBTE_MIRROR=2 timeout 150 python -m pytest tests/test_gpu_parity.py -x -q -p no:
 echo "exit $?" >> gpurun_out/mirror_ring_tests.log
 for n in 24 22 20; do SBTE_MIRROR=2 timeout 40 python tools/gpu_n22_time.py $n 250 >> gpurun_out/mirror_time.log 2>&1; done
 tail -n 3 gpurun_out/mirror_tests.log gpurun_out/mirror_ring_tests.log; cat gpurun_out/mirror_time.log gpurun_out/roll_time.log
+# sanitizer pass over the new kernels (small cases): memcheck, then racecheck (shared-memory hazards, barrier misuse)
+SBTE_MIRROR=2 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+  -k "8-5-3 or 8-37-3 or 16-33-3" > gpurun_out/mirror_memcheck.log 2>&1; echo "exit $?" >> gpurun_out/mirror_memcheck.log
+SBTE_MIRROR=2 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+  -k "8-5-3" > gpurun_out/mirror_racecheck.log 2>&1; echo "exit $?" >> gpurun_out/mirror_racecheck.log
+tail -n 4 gpurun_out/mirror_memcheck.log gpurun_out/mirror_racecheck.log
