@@ -16,6 +16,7 @@
 #include <string.h>
 
 #include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
@@ -150,9 +151,11 @@ inline bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 }
 inline void mbar_wait(uint64_t* bar, uint32_t parity) {
   unsigned long long spins = 0;
+  const auto t0 = std::chrono::steady_clock::now();
   while (!mbar_try_wait(bar, parity)) {
     std::this_thread::yield();
-    if (++spins > 400000000ull) __trap();
+    // a deadlocked protocol must fail the test, not hang it: no single wait of these small problems takes 30 s
+    if ((++spins & 1023) == 0 && std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) __trap();
   }
 }
 inline void tma_bulk_g2s(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {

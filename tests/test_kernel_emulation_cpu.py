@@ -7,6 +7,7 @@ they write, combined the way the inverse transform combines them, must equal the
 hangs; the shim's bounded wait aborts), TMA coordinates, shared-memory offsets, tile switches, flushes -- for the
 GPU-verified kernels (as a check of the emulation itself) and for the opt-in kernels that have not run on a GPU yet."""
 import ctypes as C
+import multiprocessing as mp
 import os
 import subprocess
 
@@ -68,7 +69,7 @@ CASES = [  # kind, N, cells, sym, ctas
 
 
 @pytest.mark.parametrize("kind,N,cells,sym,ctas", CASES)
-def test_kernel_control_flow_on_host(kind, N, cells, sym, ctas):
+def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
     L = _lib()
     o = orc.Oracle(N, 9.0, 1)
     n3 = N ** 3
@@ -96,10 +97,21 @@ def test_kernel_control_flow_on_host(kind, N, cells, sym, ctas):
     dv = o.v[1] - o.v[0]
     L_eta = 0.5 * N * (2.0 * np.pi / (N * dv))
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
-    rc = L.emul_batched(kind, N, cells, int(sym), P, p(s["begin"], C.c_longlong), p(s["tbegin"], C.c_longlong), p(s["ctile"], C.c_int),
-                        p(s["first"], C.c_int), p(s["np"], C.c_ubyte), G, T, s["np_cols"], kmax,
-                        p(Wk, C.c_double), p(spec.view(np.float64), C.c_double), p(parts.view(np.float64), C.c_double), L_eta, 9.0)
-    assert rc == 0
+    out = str(tmp_path / "parts.npy")
+
+    def child():   # a deadlocked protocol ends the emulation with _Exit: keep that out of the test runner
+        rc = L.emul_batched(kind, N, cells, int(sym), P, p(s["begin"], C.c_longlong), p(s["tbegin"], C.c_longlong), p(s["ctile"], C.c_int),
+                            p(s["first"], C.c_int), p(s["np"], C.c_ubyte), G, T, s["np_cols"], kmax,
+                            p(Wk, C.c_double), p(spec.view(np.float64), C.c_double), p(parts.view(np.float64), C.c_double), L_eta, 9.0)
+        if rc == 0:
+            np.save(out, parts)
+        os._exit(rc)
+
+    proc = mp.get_context("fork").Process(target=child)
+    proc.start()
+    proc.join(900)
+    assert proc.exitcode == 0, "kernel emulation failed or deadlocked (exit code %s)" % proc.exitcode
+    parts = np.load(out)
     # combine the partial sums the way the inverse transform does: np[(column / np_cols) * G + cell group] parts per column
     parts = parts.reshape(kmax, G * 32, n3)
     for b in range(cells):
