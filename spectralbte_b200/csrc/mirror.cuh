@@ -97,67 +97,93 @@ __host__ __device__ __forceinline__ double2 mir_conj(double2 a) { return make_do
 //   gl/gs : the xi-side line f^[xi_x][xi_y][.], element c at gl[c * gs]
 //   wA    : N x N weights of column A, row zeta_z, column xi_z          (W[zeta_A][(xi_x, xi_y, .)])
 //   wB    : N x N weights of column B at the MIRRORED step              (W[zeta_B][(nu xi_x, nu xi_y, .)]); zeros if unpaired
+//   R0    : first row of this warp, 0 or N - RH (a RUN-TIME value: both halves of a column execute the same code,
+//           which keeps the unrolled body -- and the instruction footprint -- to one copy)
 //   theta : exp(-2i L_eta L_v)
 // The step-level phase theta^m, m = [xi_x=0] + [xi_y=0] + [X=0] + [Y=0], is NOT applied here: accB is kept in a frame
 // rotated by the current step's phase (accB = true value * theta^-m), which the caller changes with
 // mirror_frame_update() on the few steps where m changes; that way the mirror rows accumulate directly.
+// The main loop treats every entry as phase-free (mirror row += w' conj(p)); the entries that do carry a phase --
+// the column xi_z = 0 and the diagonal (zeta - xi)_z = 0, 2 RH of them -- are corrected afterwards by
+// w' (theta^k - 1) conj(p), k = 1 or 2.
 // LAZY: the (zeta - xi)-side operands are loaded when the sliding window of the rows first needs them (RH + 1 live
 // values instead of N: the N >= 20 kernels do not have the registers for the whole line).
-template <int N, int R0, int RH, bool LAZY = false>
+template <int N, int RH, bool LAZY = false>
 __host__ __device__ __forceinline__ void mirror_step(double2* accA, double2* accB, const double2* fl, int fs,
                                                       const double2* gl, int gs, const double* wA, const double* wB,
-                                                      double2 theta) {
+                                                      int R0, double2 theta) {
+  // slot i of fr holds f^[(i + R0) mod N]: row r, column c reads slot (r + N/2 - c) mod N in either half
   double2 fr[N];
+  auto f_at = [&](int slot) {
+    int z = slot + R0;
+    if (z > N - 1) z -= N;
+    return fl[z * fs];
+  };
   if (!LAZY) {
 #pragma unroll
-    for (int z = 0; z < N; z++) fr[z] = fl[z * fs];
+    for (int z = 0; z < N; z++) fr[z] = f_at(z);
   } else {
-    // window of the first column pair: indices R0 + N/2 - 1 .. R0 + N/2 + RH - 1 (mod N)
+    // window of the first column pair: slots N/2 - 1 .. N/2 + RH - 1 (mod N)
 #pragma unroll
-    for (int j = 0; j <= RH; j++) fr[(R0 + N / 2 - 1 + j) % N] = fl[((R0 + N / 2 - 1 + j) % N) * fs];
+    for (int j = 0; j <= RH; j++) fr[(N / 2 - 1 + j) % N] = f_at((N / 2 - 1 + j) % N);
   }
-  const double2 f0B = mir_cmul_conj_b(theta, fl[0]);   // theta conj(f^[.. 0]): entries whose (zeta - xi)_z index is 0
+  const double* wa_rows = wA + R0 * N;
+  // mirrored rows: nu(R0 + r) = (N - R0 - r) mod N, i.e. base - r with base = N (first half; row 0 stays row 0) or N - R0
+  const double* wb_top = wB + ((R0 == 0) ? N : N - R0) * N;
+  const double* wb_row0 = (R0 == 0) ? wB : wb_top;
 #pragma unroll
   for (int c = 0; c < N; c += 2) {
     const double2 g0v = gl[c * gs], g1v = gl[(c + 1) * gs];
     if (LAZY && c > 0) {   // columns c, c + 1 reach two operands further down
-      fr[(R0 + N / 2 - c + 2 * N) % N] = fl[((R0 + N / 2 - c + 2 * N) % N) * fs];
-      fr[(R0 + N / 2 - c - 1 + 2 * N) % N] = fl[((R0 + N / 2 - c - 1 + 2 * N) % N) * fs];
+      fr[(N / 2 - c + 2 * N) % N] = f_at((N / 2 - c + 2 * N) % N);
+      fr[(N / 2 - c - 1 + 2 * N) % N] = f_at((N / 2 - c - 1 + 2 * N) % N);
     }
-    // xi_z = 0 carries a phase as well: theta conj(g)
-    const double2 g0B = (c == 0) ? mir_cmul_conj_b(theta, g0v) : mir_conj(g0v);
-    const double2 g1B = mir_conj(g1v);
 #pragma unroll
     for (int r = 0; r < RH; r++) {
-      const int R = R0 + r;
-      const int nuR = (N - R) % N;
-      const int d0 = (R + N / 2 - c + N) % N;          // operand index of column c
-      const int d1 = (R + N / 2 - c - 1 + N) % N;      // ... of column c + 1
+      const int s0 = (r + N / 2 - c + N) % N;          // operand slot of column c
+      const int s1 = (r + N / 2 - c - 1 + N) % N;      // ... of column c + 1
       const int nc0 = (N - c) % N, nc1 = N - c - 1;    // mirrored columns
-      const double2 wa = *reinterpret_cast<const double2*>(wA + R * N + c);
-      const double wb0 = wB[nuR * N + nc0], wb1 = wB[nuR * N + nc1];
-      const double2 p0 = mir_cmul(g0v, fr[d0]);
-      const double2 p1 = mir_cmul(g1v, fr[d1]);
+      const double2 wa = *reinterpret_cast<const double2*>(wa_rows + r * N + c);
+      const double* wbr = (r == 0) ? wb_row0 : wb_top - r * N;
+      const double wb0 = wbr[nc0], wb1 = wbr[nc1];
+      const double2 p0 = mir_cmul(g0v, fr[s0]);
+      const double2 p1 = mir_cmul(g1v, fr[s1]);
       accA[r].x = fma(wa.x, p0.x, accA[r].x);
       accA[r].y = fma(wa.x, p0.y, accA[r].y);
+      accB[r].x = fma(wb0, p0.x, accB[r].x);
+      accB[r].y = fma(-wb0, p0.y, accB[r].y);
       accA[r].x = fma(wa.y, p1.x, accA[r].x);
       accA[r].y = fma(wa.y, p1.y, accA[r].y);
-      if (c != 0 && d0 != 0) {                         // phase-free entry: the mirror row takes conj(p0)
-        accB[r].x = fma(wb0, p0.x, accB[r].x);
-        accB[r].y = fma(-wb0, p0.y, accB[r].y);
-      } else {
-        const double2 q = mir_cmul(g0B, (d0 == 0) ? f0B : mir_conj(fr[d0]));
-        accB[r].x = fma(wb0, q.x, accB[r].x);
-        accB[r].y = fma(wb0, q.y, accB[r].y);
-      }
-      if (d1 != 0) {
-        accB[r].x = fma(wb1, p1.x, accB[r].x);
-        accB[r].y = fma(-wb1, p1.y, accB[r].y);
-      } else {
-        const double2 q = mir_cmul(g1B, f0B);
-        accB[r].x = fma(wb1, q.x, accB[r].x);
-        accB[r].y = fma(wb1, q.y, accB[r].y);
-      }
+      accB[r].x = fma(wb1, p1.x, accB[r].x);
+      accB[r].y = fma(-wb1, p1.y, accB[r].y);
+    }
+  }
+  // corrections of the mirror rows: the entries with xi_z = 0 and / or (zeta - xi)_z = 0 carry theta^k, k = 1, 2
+  const double2 e1 = make_double2(theta.x - 1.0, theta.y);
+  const double2 th2 = mir_cmul(theta, theta);
+  const double2 e2 = make_double2(th2.x - 1.0, th2.y);
+  const double2 g0 = gl[0], f0 = fl[0];
+  const double2 gE1 = mir_cmul_conj_b(e1, g0), gE2 = mir_cmul_conj_b(e2, g0);   // (theta^k - 1) conj(g^[.. 0])
+  const double2 fE1 = mir_cmul_conj_b(e1, f0);                                  // (theta - 1) conj(f^[.. 0])
+#pragma unroll
+  for (int r = 0; r < RH; r++) {
+    const double* wbr = (r == 0) ? wb_row0 : wb_top - r * N;
+    int d = R0 + r + N / 2;                     // (zeta - xi)_z of the entry in column xi_z = 0; also the column of the
+    if (d > N - 1) d -= N;                      // row's entry with (zeta - xi)_z = 0
+    // column xi_z = 0 (mirrored column 0): w' (theta^k - 1) conj(g_0) conj(f_d), k = 1 + [d = 0]
+    {
+      const double2 ge = (d == 0) ? gE2 : gE1;
+      const double2 q = mir_cmul_conj_b(ge, fl[d * fs]);
+      const double wb = wbr[0];
+      accB[r].x = fma(wb, q.x, accB[r].x);
+      accB[r].y = fma(wb, q.y, accB[r].y);
+    }
+    // diagonal (zeta - xi)_z = 0 at column xi_z = d (d = 0 was handled above): w' (theta - 1) conj(g_d) conj(f_0)
+    if (d != 0) {
+      const double2 q = mir_cmul_conj_b(fE1, gl[d * gs]);
+      const double wb = wbr[N - d];
+      accB[r].x = fma(wb, q.x, accB[r].x);
+      accB[r].y = fma(wb, q.y, accB[r].y);
     }
   }
 }

@@ -232,8 +232,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       const double* wA = stage_w(st) + pair * C::WTILE;
       const double* wB = (zyB >= 0) ? stage_w(st) + (C::PAIRS + pair) * C::WTILE : zero_box;
       mirror_frame_update<RH>(accB, m_cur, (ex == 0) + (ey == 0) + (X == 0) + (Y == 0), ph);
-      if (half == 0) mirror_step<N, 0, RH>(accA, accB, fl, 32, gl, 32, wA, wB, ph.t[1]);
-      else mirror_step<N, RH, RH>(accA, accB, fl, 32, gl, 32, wA, wB, ph.t[1]);
+      mirror_step<N, RH>(accA, accB, fl, 32, gl, 32, wA, wB, half * RH, ph.t[1]);
     }
 
     // release the stage (and the plane when the next step needs another one)
@@ -460,8 +459,7 @@ qhat_mirror_ring_kernel(const __grid_constant__ CUtensorMap tmapW, const double2
         mirror_frame_update<RH>(accB, m_cur, (ex == 0) + (ey == 0) + (X == 0) + (Y == 0), ph);
         // one pass over all RH rows: splitting the rows into several passes lets ptxas hoist the later passes' loads
         // and spills far more (3.3 KB against 0.5 KB at N = 24, none at N = 20)
-        if (half == 0) mirror_step<N, 0, RH, true>(accA, accB, fl, 32, gl, 32, wA, wB, ph.t[1]);
-        else mirror_step<N, RH, RH, true>(accA, accB, fl, 32, gl, 32, wA, wB, ph.t[1]);
+        mirror_step<N, RH, true>(accA, accB, fl, 32, gl, 32, wA, wB, half * RH, ph.t[1]);
       }
       __syncwarp();
       if (lane == 0) {

@@ -53,12 +53,11 @@ static void run(const double* W, int sym, const double2* F, double L_eta, double
               wbp = wb.data();
             }
             mirror_frame_update<RH>(accB, m_cur, (ex == 0) + (ey == 0) + (X == 0) + (Y == 0), ph);
-            if (half == 0) mirror_step<N, 0, RH, LAZY>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, theta);
-            else mirror_step<N, RH, RH, LAZY>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, theta);
+            mirror_step<N, RH, LAZY>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, half * (N - RH), theta);
           }
         }
         mirror_frame_update<RH>(accB, m_cur, 0, ph);
-        const int R0 = half * RH;
+        const int R0 = half * (N - RH);
         for (int r = 0; r < RH; r++) {
           qhat[((size_t)zx * N + zy) * N + R0 + r] = accA[r];
           if (zyB >= 0) qhat[((size_t)zxB * N + zyB) * N + mirror_nu(R0 + r, N)] = accB[r];
