@@ -68,6 +68,7 @@ CASES = [  # kind, N, cells, sym, ctas
 ]
 
 
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")   # the oracle's OpenMP pool; the child only runs the emulation
 @pytest.mark.parametrize("kind,N,cells,sym,ctas", CASES)
 def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
     L = _lib()
