@@ -25,3 +25,13 @@ SBTE_MIRROR=2 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 p
 SBTE_MIRROR=2 timeout 300 compute-sanitizer --tool racecheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
   -k "8-5-3" > gpurun_out/mirror_racecheck.log 2>&1; echo "exit $?" >> gpurun_out/mirror_racecheck.log
 tail -n 4 gpurun_out/mirror_memcheck.log gpurun_out/mirror_racecheck.log
+# one full ncu capture of each new kernel and of the kernels they would replace (FP64 pipe, stall reasons, LSU wavefronts,
+# instruction-fetch stalls): read offline with tools/ncu_summary.py
+for cfg in "1 16 640 mirror_n16" "0 16 640 batch2_n16" "2 24 250 mirror_ring_n24" "0 24 250 batch3_n24"; do
+  set -- $cfg
+  SBTE_MIRROR=$1 timeout 120 ncu --set full --import-source on --clock-control none -k regex:"qhat_(batch2|batch3|mirror)" -s 2 -c 1 \
+    -o gpurun_out/r02_k2_$4 -f python tools/gpu_n22_time.py $2 $3 > gpurun_out/ncu_$4.log 2>&1
+done
+SBTE_ROLL=1 timeout 120 ncu --set full --import-source on --clock-control none -k regex:qhat_batch3 -s 2 -c 1 \
+  -o gpurun_out/r02_k2_batch3_n24_rolled -f python tools/gpu_n22_time.py 24 250 > gpurun_out/ncu_batch3_n24_rolled.log 2>&1
+ls -la gpurun_out/*.ncu-rep
