@@ -172,6 +172,7 @@ static int make_tensor_map(sbte_ctx* c) {
   c->mirror_ok = false;
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copies
   if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
+  if (c->d_Wh) { cudaFree(c->d_Wh); c->d_Wh = nullptr; c->wh_sym = -1; }
   c->sched_cells = 0;
   if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
   if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
@@ -197,6 +198,7 @@ static int release_weights(sbte_ctx* c) {
   invalidate_graphs(c);
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }
   if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
+  if (c->d_Wh) { cudaFree(c->d_Wh); c->d_Wh = nullptr; c->wh_sym = -1; }
   c->mirror_ok = false;
   if (c->owns_W && c->d_W) cudaFree((void*)c->d_W);
   c->d_W = nullptr; c->owns_W = false; c->host_key = nullptr; c->tmap_ok = false;
@@ -359,6 +361,15 @@ static int ensure_sym_mirror(sbte_ctx* c) {
   launch_symmetrize_weights_mirror(c, c->d_W, c->d_Ws2);
   return encode_weight_map(c, c->d_Ws2, &c->tmapMs, 1);
 }
+// folded tensor of the mirror kernels for the current symmetrisation setting (on the way to Q only)
+static int ensure_fold_mirror(sbte_ctx* c, bool sym) {
+  if (c->d_Wh && c->wh_sym == (int)sym) return 0;
+  c->graph_gen++;
+  if (!c->d_Wh) CK(cudaMalloc(&c->d_Wh, (size_t)c->n3 * c->n3 * sizeof(double)));
+  launch_fold_weights_mirror(c, c->d_W, c->d_Wh, sym);
+  c->wh_sym = (int)sym;
+  return encode_weight_map(c, c->d_Wh, &c->tmapMh, 1);
+}
 static int ensure_sym(sbte_ctx* c) {
   if (c->d_Ws) return 0;
   c->graph_gen++;
@@ -369,10 +380,17 @@ static int ensure_sym(sbte_ctx* c) {
 }
 // the batched convolution and the symmetrised tensor of whichever batched kernel is active for this N
 static int ensure_sym_batched(sbte_ctx* c) { return c->mirror_ok ? ensure_sym_mirror(c) : ensure_sym(c); }
-static void launch_batched_conv(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
-                                const BatchSched& sch) {
-  if (c->mirror_ok) launch_qhat_mirror(c, spec, parts, part_stride, cells, sch);
-  else launch_qhat_batch2(c, spec, parts, part_stride, cells, sch);
+// to_q: the spectrum only feeds Re(fft3D^-1(.)) -- the mirror kernels may then stream the folded tensor
+static int launch_batched_conv(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
+                               const BatchSched& sch, bool to_q) {
+  if (c->mirror_ok) {
+    const bool fold = to_q && qhat_mirror_fold_enabled(c->N);
+    if (fold && ensure_fold_mirror(c, sch.sym != 0)) return 1;
+    launch_qhat_mirror(c, spec, parts, part_stride, cells, sch, fold);
+  } else {
+    launch_qhat_batch2(c, spec, parts, part_stride, cells, sch);
+  }
+  return 0;
 }
 static bool want_sym(sbte_ctx* c, bool same) {
   static int env = -1;
@@ -419,7 +437,7 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     if (sym && ensure_sym_batched(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    if (launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched, false)) return 1;
     launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
   } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
     if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
@@ -462,7 +480,7 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
     if (sym && ensure_sym_batched(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    if (launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched, true)) return 1;
     launch_fft3d_parts(c, c->d_parts, c->parts_stride, c->sched, 1, batch, nullptr, d_Q);
     return check_launch("batched compute_q");
   }
@@ -487,7 +505,7 @@ int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, 
     if (sym && ensure_sym_batched(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_src, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    if (launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched, true)) return 1;
     CellEpi epi = {};
     epi.mode = 1; epi.v = c->d_v; epi.wt = c->d_wt; epi.dv3 = c->dv * c->dv * c->dv; epi.lu = c->lu;
     epi.a = a; epi.x = x; epi.b = b; epi.y = y; epi.s = s; epi.Kn = Kn; epi.out = out;

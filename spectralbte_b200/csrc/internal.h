@@ -70,8 +70,10 @@ struct sbte_ctx {
   CUtensorMap tmapWs;
   // mirror-paired batched convolution (qhat_mirror.cu, opt-in): one-column tensor maps, its own symmetrised tensor
   // (mirror.cuh: mirror_sym_weight) and the table of column-pair tiles
-  CUtensorMap tmapM, tmapMs;
+  CUtensorMap tmapM, tmapMs, tmapMh;
   double* d_Ws2 = nullptr;
+  double* d_Wh = nullptr;           // folded tensor (mirror_fold_weight), built for wh_sym
+  int wh_sym = -1;
   sbte::MirrorTile* d_mtiles = nullptr;
   int n_mtiles = 0;
   bool mirror_ok = false;
@@ -175,9 +177,11 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* par
 bool qhat_mirror_enabled(int N);
 int qhat_mirror_pairs(int N);
 int qhat_mirror_align(int N);
+bool qhat_mirror_fold_enabled(int N);
 void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2);
+void launch_fold_weights_mirror(sbte_ctx* c, const double* W, double* Wh, bool sym);
 void launch_qhat_mirror(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
-                        const BatchSched& sch);
+                        const BatchSched& sch, bool fold);
 
 // conserve.cu -- K4 / K5 / moments
 void launch_conserve(sbte_ctx* c, double* Q, int batch);

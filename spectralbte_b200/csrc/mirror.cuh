@@ -83,6 +83,46 @@ __host__ __device__ __forceinline__ double mirror_sym_weight(const double* __res
   return 0.0;
 }
 
+// ---------------------------------------------------------------- folding mirror rows into their partners
+// Q = Re(fft3D^-1(Q^)) (src/collisions.c:212-221) only needs the Hermitian part of Q^: the entry (nu zeta, nu xi) of a
+// mirror ("B") row may be added to the entry (zeta, xi) of its "A" row with the factor rho = omega[nu zeta] / omega[zeta]
+// (omega = trapezoid weights of the inverse transform) wherever the phase exponent
+//     e = z(zeta) - z(xi) - z(zeta - xi)      (z = number of zero index components)
+// is 0 -- the folded weight stays real and Q is unchanged (tests/test_half_spectrum_cpu.py).  Folded here: the entries of
+// the steps whose x/y part of e is 0 ("foldable steps") with regular z components (zeta_z, xi_z, (zeta - xi)_z != 0);
+// every other entry stays in its own row.  What the kernels then form is no longer the reference's Q^ but a spectrum with
+// the same real inverse transform, so folding is only used on the way to Q.
+__host__ __device__ __forceinline__ int mirror_exy(int N, int zx, int zy, int ex, int ey) {
+  const int X = (zx + N / 2 - ex + N) % N, Y = (zy + N / 2 - ey + N) % N;
+  return (zx == 0) + (zy == 0) - (ex == 0) - (X == 0) - (ey == 0) - (Y == 0);
+}
+__host__ __device__ __forceinline__ bool mirror_paired_column(int N, int zx, int zy) {
+  return !((zx == 0 || zx == N / 2) && (zy == 0 || zy == N / 2));
+}
+__host__ __device__ __forceinline__ double mirror_trap(int N, int i) { return (i == 0 || i == N - 1) ? 0.5 : 1.0; }
+
+// Folded tensor of the mirror kernels: sym = 1 starts from the symmetrised weights (mirror_sym_weight), 0 from W.
+__host__ __device__ __forceinline__ double mirror_fold_weight(const double* __restrict__ W, int N, size_t zeta, size_t xi, bool sym) {
+  const size_t n3 = (size_t)N * N * N;
+  const int zx = (int)(zeta / ((size_t)N * N)), zy = (int)((zeta / N) % N), zz = (int)(zeta % N);
+  const int ex = (int)(xi / ((size_t)N * N)), ey = (int)((xi / N) % N), ez = (int)(xi % N);
+  const double own = sym ? mirror_sym_weight(W, N, zeta, xi) : W[zeta * n3 + xi];
+  if (!mirror_paired_column(N, zx, zy)) return own;
+  const bool b = mirror_is_b_row(N, zx, zy);
+  // the "A" member of this pair of entries decides
+  const int azx = b ? (N - zx) % N : zx, azy = b ? (N - zy) % N : zy, azz = b ? (N - zz) % N : zz;
+  const int aex = b ? (N - ex) % N : ex, aey = b ? (N - ey) % N : ey, aez = b ? (N - ez) % N : ez;
+  const int aZ = (azz + N / 2 - aez + N) % N;
+  const bool fold = mirror_exy(N, azx, azy, aex, aey) == 0 && azz != 0 && aez != 0 && aZ != 0;
+  if (!fold) return own;
+  if (b) return 0.0;
+  const size_t zetaB = ((size_t)((N - zx) % N) * N + (N - zy) % N) * N + (N - zz) % N;
+  const size_t xiB = ((size_t)((N - ex) % N) * N + (N - ey) % N) * N + (N - ez) % N;
+  const double rho = mirror_trap(N, (N - zx) % N) * mirror_trap(N, (N - zy) % N) * mirror_trap(N, (N - zz) % N) /
+                     (mirror_trap(N, zx) * mirror_trap(N, zy) * mirror_trap(N, zz));
+  return own + rho * (sym ? mirror_sym_weight(W, N, zetaB, xiB) : W[zetaB * n3 + xiB]);
+}
+
 // ---------------------------------------------------------------- per-lane arithmetic of one (xi_x, xi_y) step
 __host__ __device__ __forceinline__ double2 mir_cmul(double2 a, double2 b) {
   return make_double2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x);
@@ -108,7 +148,11 @@ __host__ __device__ __forceinline__ double2 mir_conj(double2 a) { return make_do
 // w' (theta^k - 1) conj(p), k = 1 or 2.
 // LAZY: the (zeta - xi)-side operands are loaded when the sliding window of the rows first needs them (RH + 1 live
 // values instead of N: the N >= 20 kernels do not have the registers for the whole line).
-template <int N, int RH, bool LAZY = false>
+// COMBINED: the step is foldable and the tensor is the folded one (mirror_fold_weight): the mirror rows' phase-free
+// entries already sit in wA, so the main loop only serves the A rows (6 instead of 8 FP64 instructions per weight pair)
+// -- except for the first row of the warp (zeta_z = 0 is never folded; for the other half its wB entries are zeros) --
+// and the entries with xi_z = 0 or (zeta - xi)_z = 0 are added in full instead of being corrected.
+template <int N, int RH, bool LAZY = false, bool COMBINED = false>
 __host__ __device__ __forceinline__ void mirror_step(double2* accA, double2* accB, const double2* fl, int fs,
                                                       const double2* gl, int gs, const double* wA, const double* wB,
                                                       int R0, double2 theta) {
@@ -145,34 +189,39 @@ __host__ __device__ __forceinline__ void mirror_step(double2* accA, double2* acc
       const int nc0 = (N - c) % N, nc1 = N - c - 1;    // mirrored columns
       const double2 wa = *reinterpret_cast<const double2*>(wa_rows + r * N + c);
       const double* wbr = (r == 0) ? wb_row0 : wb_top - r * N;
-      const double wb0 = wbr[nc0], wb1 = wbr[nc1];
+      const double wb0 = (!COMBINED || r == 0) ? wbr[nc0] : 0.0, wb1 = (!COMBINED || r == 0) ? wbr[nc1] : 0.0;
       const double2 p0 = mir_cmul(g0v, fr[s0]);
       const double2 p1 = mir_cmul(g1v, fr[s1]);
       accA[r].x = fma(wa.x, p0.x, accA[r].x);
       accA[r].y = fma(wa.x, p0.y, accA[r].y);
-      accB[r].x = fma(wb0, p0.x, accB[r].x);
-      accB[r].y = fma(-wb0, p0.y, accB[r].y);
       accA[r].x = fma(wa.y, p1.x, accA[r].x);
       accA[r].y = fma(wa.y, p1.y, accA[r].y);
-      accB[r].x = fma(wb1, p1.x, accB[r].x);
-      accB[r].y = fma(-wb1, p1.y, accB[r].y);
+      if (!COMBINED || r == 0) {
+        accB[r].x = fma(wb0, p0.x, accB[r].x);
+        accB[r].y = fma(-wb0, p0.y, accB[r].y);
+        accB[r].x = fma(wb1, p1.x, accB[r].x);
+        accB[r].y = fma(-wb1, p1.y, accB[r].y);
+      }
     }
   }
-  // corrections of the mirror rows: the entries with xi_z = 0 and / or (zeta - xi)_z = 0 carry theta^k, k = 1, 2
-  const double2 e1 = make_double2(theta.x - 1.0, theta.y);
+  // the entries of the mirror rows with xi_z = 0 and / or (zeta - xi)_z = 0 carry theta^k, k = 1, 2: corrected by
+  // (theta^k - 1) where the main loop has added them phase-free, added in full (theta^k) where it has not
   const double2 th2 = mir_cmul(theta, theta);
-  const double2 e2 = make_double2(th2.x - 1.0, th2.y);
   const double2 g0 = gl[0], f0 = fl[0];
-  const double2 gE1 = mir_cmul_conj_b(e1, g0), gE2 = mir_cmul_conj_b(e2, g0);   // (theta^k - 1) conj(g^[.. 0])
-  const double2 fE1 = mir_cmul_conj_b(e1, f0);                                  // (theta - 1) conj(f^[.. 0])
+  const double2 gE1 = mir_cmul_conj_b(make_double2(theta.x - 1.0, theta.y), g0);   // (theta^k - 1) conj(g^[.. 0])
+  const double2 gE2 = mir_cmul_conj_b(make_double2(th2.x - 1.0, th2.y), g0);
+  const double2 fE1 = mir_cmul_conj_b(make_double2(theta.x - 1.0, theta.y), f0);   // (theta - 1) conj(f^[.. 0])
+  const double2 gF1 = mir_cmul_conj_b(theta, g0), gF2 = mir_cmul_conj_b(th2, g0);  // theta^k conj(g^[.. 0])
+  const double2 fF1 = mir_cmul_conj_b(theta, f0);
 #pragma unroll
   for (int r = 0; r < RH; r++) {
+    const bool full = COMBINED && r != 0;       // the main loop skipped this row's mirror entries
     const double* wbr = (r == 0) ? wb_row0 : wb_top - r * N;
     int d = R0 + r + N / 2;                     // (zeta - xi)_z of the entry in column xi_z = 0; also the column of the
     if (d > N - 1) d -= N;                      // row's entry with (zeta - xi)_z = 0
     // column xi_z = 0 (mirrored column 0): w' (theta^k - 1) conj(g_0) conj(f_d), k = 1 + [d = 0]
     {
-      const double2 ge = (d == 0) ? gE2 : gE1;
+      const double2 ge = full ? ((d == 0) ? gF2 : gF1) : ((d == 0) ? gE2 : gE1);
       const double2 q = mir_cmul_conj_b(ge, fl[d * fs]);
       const double wb = wbr[0];
       accB[r].x = fma(wb, q.x, accB[r].x);
@@ -180,7 +229,7 @@ __host__ __device__ __forceinline__ void mirror_step(double2* accA, double2* acc
     }
     // diagonal (zeta - xi)_z = 0 at column xi_z = d (d = 0 was handled above): w' (theta - 1) conj(g_d) conj(f_0)
     if (d != 0) {
-      const double2 q = mir_cmul_conj_b(fE1, gl[d * gs]);
+      const double2 q = mir_cmul_conj_b(full ? fF1 : fE1, gl[d * gs]);
       const double wb = wbr[N - d];
       accB[r].x = fma(wb, q.x, accB[r].x);
       accB[r].y = fma(wb, q.y, accB[r].y);

@@ -25,12 +25,18 @@
 
 namespace sbte {
 
-// SBTE_MIRROR=1: N = 8, 16 (plane-resident kernel); SBTE_MIRROR=2: also N = 20, 22, 24 (line-ring kernel)
-bool qhat_mirror_enabled(int N) {
+// SBTE_MIRROR=1: N = 8, 16 (plane-resident kernel); SBTE_MIRROR=2: also N = 20, 22, 24 (line-ring kernel);
+// SBTE_MIRROR=3: additionally, on the way to Q (not Q^), N = 8, 16 stream the FOLDED tensor (mirror.cuh:
+// mirror_fold_weight) and run the combined body on the foldable steps
+static int mirror_level() {
   static const int level = getenv("SBTE_MIRROR") ? atoi(getenv("SBTE_MIRROR")) : 0;
-  if (level >= 1 && (N == 8 || N == 16)) return true;
-  return level >= 2 && (N == 20 || N == 22 || N == 24);
+  return level;
 }
+bool qhat_mirror_enabled(int N) {
+  if (mirror_level() >= 1 && (N == 8 || N == 16)) return true;
+  return mirror_level() >= 2 && (N == 20 || N == 22 || N == 24);
+}
+bool qhat_mirror_fold_enabled(int N) { return mirror_level() >= 3 && (N == 8 || N == 16); }
 int qhat_mirror_pairs(int N) { return (N >= 16) ? 4 : 2; }
 int qhat_mirror_align(int N) { return (N >= 20) ? N : 1; }   // the line-ring kernel works on whole xi_x chunks
 
@@ -42,9 +48,21 @@ __global__ void symmetrize_weights_mirror_kernel(const double* __restrict__ W, d
   }
 }
 
+__global__ void fold_weights_mirror_kernel(const double* __restrict__ W, double* __restrict__ Wh, int N, int sym) {
+  const size_t n3 = (size_t)N * N * N, total = n3 * n3;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const size_t zeta = e / n3;
+    Wh[e] = mirror_fold_weight(W, N, zeta, e - zeta * n3, sym != 0);
+  }
+}
+
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2) {
   symmetrize_weights_mirror_kernel<<<148 * 16, 256, 0, c->stream>>>(W, Ws2, c->N);
+  c->launches += 1;
+}
+void launch_fold_weights_mirror(sbte_ctx* c, const double* W, double* Wh, bool sym) {
+  fold_weights_mirror_kernel<<<148 * 16, 256, 0, c->stream>>>(W, Wh, c->N, sym ? 1 : 0);
   c->launches += 1;
 }
 #endif
@@ -70,7 +88,7 @@ template <int N>
 __global__ void __launch_bounds__(MirrorCfg<N>::THREADS, 1)
 qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
                    double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch,
-                   const MirrorTile* __restrict__ tiles, MirrorPhases ph) {
+                   const MirrorTile* __restrict__ tiles, MirrorPhases ph, int fold) {
   using C = MirrorCfg<N>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES, RH = C::RH;
@@ -232,7 +250,11 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       const double* wA = stage_w(st) + pair * C::WTILE;
       const double* wB = (zyB >= 0) ? stage_w(st) + (C::PAIRS + pair) * C::WTILE : zero_box;
       mirror_frame_update<RH>(accB, m_cur, (ex == 0) + (ey == 0) + (X == 0) + (Y == 0), ph);
-      mirror_step<N, RH>(accA, accB, fl, 32, gl, 32, wA, wB, half * RH, ph.t[1]);
+      // folded tensor (fold != 0): the foldable steps of a paired column take the combined body
+      if (fold && zyB >= 0 && mirror_exy(N, zx, zyA, ex, ey) == 0)
+        mirror_step<N, RH, false, true>(accA, accB, fl, 32, gl, 32, wA, wB, half * RH, ph.t[1]);
+      else
+        mirror_step<N, RH, false, false>(accA, accB, fl, 32, gl, 32, wA, wB, half * RH, ph.t[1]);
     }
 
     // release the stage (and the plane when the next step needs another one)
@@ -255,7 +277,7 @@ qhat_mirror_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 template <int N>
 static void launch_mirror_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
-                            const BatchSched& sch) {
+                            const BatchSched& sch, bool fold) {
   using C = MirrorCfg<N>;
   auto kern = qhat_mirror_kernel<N>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
@@ -267,8 +289,8 @@ static void launch_mirror_n(sbte_ctx* c, const double2* spec, double2* parts, si
   const double ang = -2.0 * c->L_eta * c->L_v;
   for (int m = 0; m < 5; m++) ph.t[m] = make_double2(cos(m * ang), sin(m * ang));
   k2_mark(c);
-  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapMs : c->tmapM, spec, parts, part_stride, cells, sch,
-                                                   c->d_mtiles, ph);
+  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(fold ? c->tmapMh : (sch.sym ? c->tmapMs : c->tmapM), spec, parts, part_stride,
+                                                   cells, sch, c->d_mtiles, ph, fold ? 1 : 0);
   k2_mark(c);
   c->launches += 1;
 }
@@ -499,12 +521,14 @@ static void launch_mirror_ring_n(sbte_ctx* c, const double2* spec, double2* part
 #endif
 
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
+// fold: stream the folded tensor (c->tmapMh, built for sch.sym) -- the result is then not Q^ but a spectrum with the same Q
 void launch_qhat_mirror(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
-                        const BatchSched& sch) {
+                        const BatchSched& sch, bool fold) {
   if (!c->mirror_ok) { set_error("qhat_mirror: tensor maps / tile table not initialised"); return; }
+  if (fold && !qhat_mirror_fold_enabled(c->N)) { set_error("qhat_mirror: no folded variant for this N"); return; }
   switch (c->N) {
-    case 8: launch_mirror_n<8>(c, spec, parts, part_stride, cells, sch); break;
-    case 16: launch_mirror_n<16>(c, spec, parts, part_stride, cells, sch); break;
+    case 8: launch_mirror_n<8>(c, spec, parts, part_stride, cells, sch, fold); break;
+    case 16: launch_mirror_n<16>(c, spec, parts, part_stride, cells, sch, fold); break;
     case 20: launch_mirror_ring_n<20>(c, spec, parts, part_stride, cells, sch); break;
     case 22: launch_mirror_ring_n<22>(c, spec, parts, part_stride, cells, sch); break;
     case 24: launch_mirror_ring_n<24>(c, spec, parts, part_stride, cells, sch); break;

@@ -54,14 +54,14 @@ MirrorPhases phases(const Args& a) {
   return ph;
 }
 template <int N>
-void run_mirror(const Args& a) {
+void run_mirror(const Args& a, int fold) {
   using C = MirrorCfg<N>;
   const CUtensorMap tm = fake_map(a.W, (long long)N * N * N, N, N);
   const std::vector<MirrorTile> tiles = build_mirror_tiles(N, C::PAIRS);
   const MirrorPhases ph = phases(a);
   for (int p = 0; p < a.P; p++)
     emul::run_cta(p, a.P, C::THREADS, C::SMEM,
-                  [&](int) { qhat_mirror_kernel<N>(tm, a.spec, a.parts, a.stride, a.cells, a.sch, tiles.data(), ph); });
+                  [&](int) { qhat_mirror_kernel<N>(tm, a.spec, a.parts, a.stride, a.cells, a.sch, tiles.data(), ph, fold); });
 }
 template <int N>
 void run_mirror_ring(const Args& a) {
@@ -78,7 +78,8 @@ void run_mirror_ring(const Args& a) {
 
 extern "C" {
 
-// kind: 0 = default kernels (qhat_batch2 / qhat_batch3), 1 = mirror-paired kernels, 2 = rolled N=24 line ring.
+// kind: 0 = default kernels (qhat_batch2 / qhat_batch3), 1 = mirror-paired kernels, 2 = rolled N=24 line ring,
+// 3 = mirror-paired kernel on the folded tensor (the result then only shares Re(fft3D^-1(.)) with Q^).
 // Schedule tables as returned by sbte_batch_schedule_host (host pointers); W = the tensor the kernel streams
 // (plain, symmetrised or mirror-symmetrised, matching `sym` and `kind`); spec = cell-minor spectra [G][n3][32] complex;
 // parts = kmax * stride complex, pre-filled by the caller.
@@ -99,14 +100,18 @@ int emul_batched(int kind, int N, int cells, int sym, int P, const long long* ct
     else if (N == 24) run_batch3<24, 1>(a);
     else return 1;
   } else if (kind == 1) {
-    if (N == 8) run_mirror<8>(a);
-    else if (N == 16) run_mirror<16>(a);
+    if (N == 8) run_mirror<8>(a, 0);
+    else if (N == 16) run_mirror<16>(a, 0);
     else if (N == 20) run_mirror_ring<20>(a);
     else if (N == 22) run_mirror_ring<22>(a);
     else if (N == 24) run_mirror_ring<24>(a);
     else return 1;
   } else if (kind == 2) {
     if (N == 24) run_batch3<24, 3>(a);
+    else return 1;
+  } else if (kind == 3) {   // folded tensor + combined body on the foldable steps
+    if (N == 8) run_mirror<8>(a, 1);
+    else if (N == 16) run_mirror<16>(a, 1);
     else return 1;
   } else {
     return 1;

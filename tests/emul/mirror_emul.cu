@@ -15,7 +15,7 @@
 using namespace sbte;
 
 template <int N, bool LAZY>
-static void run(const double* W, int sym, const double2* F, double L_eta, double L_v, double2* qhat) {
+static void run(const double* W, int sym, int fold, const double2* F, double L_eta, double L_v, double2* qhat) {
   constexpr int PAIRS = (N >= 16) ? 4 : 2, RH = N / 2;   // MirrorCfg / MirrorRingCfg::PAIRS
   const size_t n3 = (size_t)N * N * N;
   const double2 theta = make_double2(cos(-2.0 * L_eta * L_v), sin(-2.0 * L_eta * L_v));
@@ -53,7 +53,11 @@ static void run(const double* W, int sym, const double2* F, double L_eta, double
               wbp = wb.data();
             }
             mirror_frame_update<RH>(accB, m_cur, (ex == 0) + (ey == 0) + (X == 0) + (Y == 0), ph);
-            mirror_step<N, RH, LAZY>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, half * (N - RH), theta);
+            // with the folded tensor the foldable steps of a paired column take the combined body
+            if (fold && zyB >= 0 && mirror_exy(N, zx, zy, ex, ey) == 0)
+              mirror_step<N, RH, LAZY, true>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, half * (N - RH), theta);
+            else
+              mirror_step<N, RH, LAZY, false>(accA, accB, fl, 1, gl, 1, wa.data(), wbp, half * (N - RH), theta);
           }
         }
         mirror_frame_update<RH>(accB, m_cur, 0, ph);
@@ -77,17 +81,26 @@ int mirror_emul_symmetrize(int N, const double* W, double* Ws2) {
   return 0;
 }
 
-// Q^ of one cell; W = plain tensor (sym = 0) or the mirror-symmetrised one (sym = 1); F, qhat: N^3 complex, natural layout
-int mirror_emul_qhat(int N, const double* W, int sym, const double* F, double L_eta, double L_v, double* qhat) {
+// folded tensor (mirror_fold_weight) from W, both N^3 x N^3 row-major
+int mirror_emul_fold(int N, const double* W, int sym, double* Wh) {
+  const size_t n3 = (size_t)N * N * N;
+  for (size_t zeta = 0; zeta < n3; zeta++)
+    for (size_t xi = 0; xi < n3; xi++) Wh[zeta * n3 + xi] = mirror_fold_weight(W, N, zeta, xi, sym != 0);
+  return 0;
+}
+
+// Q^ of one cell (fold = 0) or, with the folded tensor (fold = 1), a spectrum with the same real inverse transform;
+// W = the tensor the kernel streams (plain / mirror-symmetrised / folded); F, qhat: N^3 complex, natural layout
+int mirror_emul_qhat(int N, const double* W, int sym, int fold, const double* F, double L_eta, double L_v, double* qhat) {
   const size_t n3 = (size_t)N * N * N;
   for (size_t i = 0; i < 2 * n3; i++) qhat[i] = NAN;   // every entry must be written exactly by the pairing
   // the operand-loading variant each N uses in the kernels (qhat_mirror.cu)
-  if (N == 8) run<8, false>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
-  else if (N == 16) run<16, false>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
-  else if (N == 12) run<12, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);   // small stand-in for 20..24
-  else if (N == 20) run<20, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
-  else if (N == 22) run<22, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
-  else if (N == 24) run<24, true>(W, sym, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  if (N == 8) run<8, false>(W, sym, fold, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 16) run<16, false>(W, sym, fold, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 12) run<12, true>(W, sym, fold, (const double2*)F, L_eta, L_v, (double2*)qhat);   // small stand-in for 20..24
+  else if (N == 20) run<20, true>(W, sym, fold, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 22) run<22, true>(W, sym, fold, (const double2*)F, L_eta, L_v, (double2*)qhat);
+  else if (N == 24) run<24, true>(W, sym, fold, (const double2*)F, L_eta, L_v, (double2*)qhat);
   else return 1;
   return 0;
 }

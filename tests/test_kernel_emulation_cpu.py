@@ -65,6 +65,8 @@ CASES = [  # kind, N, cells, sym, ctas
     (1, 24, 1, True, 3),                                   # qhat_mirror_ring_kernel<24>
     (2, 24, 1, True, 3),                                   # qhat_batch3_kernel<24, ROLL=3> (opt-in rolled xi_z loop)
     (0, 22, 2, True, 3),                                   # qhat_batch3_kernel<22>     (GPU-verified)
+    (3, 8, 37, True, 5), (3, 8, 5, False, 3),             # qhat_mirror_kernel<8> on the folded tensor (combined body)
+    (3, 16, 3, True, 3),                                   # qhat_mirror_kernel<16> on the folded tensor
 ]
 
 
@@ -75,7 +77,11 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
     o = orc.Oracle(N, 9.0, 1)
     n3 = N ** 3
     W = np.random.default_rng(N).standard_normal(n3 * n3) if N <= 8 else orc.synthetic_weights(N)
-    if sym and kind == 1:
+    if kind == 3:
+        Wk = np.empty_like(W)
+        R = _mirror_rule_lib()
+        assert R.mirror_emul_fold(N, W.ctypes.data_as(C.POINTER(C.c_double)), int(sym), Wk.ctypes.data_as(C.POINTER(C.c_double))) == 0
+    elif sym and kind == 1:
         Wk = np.empty_like(W)
         R = _mirror_rule_lib()
         assert R.mirror_emul_symmetrize(N, W.ctypes.data_as(C.POINTER(C.c_double)), Wk.ctypes.data_as(C.POINTER(C.c_double))) == 0
@@ -83,15 +89,16 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
         Wk = symmetrise_standard(W, N)
     else:
         Wk = W
-    s = schedule(N, cells, sym, ctas, mirror=(kind == 1))
+    s = schedule(N, cells, sym, ctas, mirror=(kind in (1, 3)))
     G, T, P, kmax = s["G"], s["T"], s["P"], s["kmax"]
     # spectra, cell-minor [G][n3][32]; padding cells are zero
     spec = np.zeros((G, n3, 32), dtype=complex)
-    F = []
+    F, fs = [], []
     for b in range(cells):
         f = seeded_f(o.v, 700 + b, noise=0.3) * (1.0 + 0.05 * b)
         Fb = o.fft3d(f.astype(complex))
         F.append(Fb)
+        fs.append(f)
         spec[b // 32, :, b % 32] = Fb
     stride = G * 32 * n3
     parts = np.full(kmax * stride, np.nan + 1j * np.nan, dtype=complex)
@@ -123,5 +130,7 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
             seg = parts[:npc, b, col * N:(col + 1) * N]
             assert not np.isnan(seg.view(np.float64)).any(), (b, col)       # every part the table promises was written
             q[col * N:(col + 1) * N] = seg.sum(axis=0)
-        want = o.qhat(W, F[b], F[b])
-        assert relmax(q, want) < 1e-12, b
+        if kind == 3:   # the folded tensor does not give Q^ but a spectrum with the same Q = Re(fft3D^-1(.))
+            assert relmax(np.real(o.fft3d(q, invert=True)), o.compute_q(W, fs[b], fs[b])) < 1e-12, b
+        else:
+            assert relmax(q, o.qhat(W, F[b], F[b])) < 1e-12, b

@@ -27,7 +27,8 @@ def _emul():
     L = C.CDLL(LIB)
     dp = C.POINTER(C.c_double)
     L.mirror_emul_symmetrize.argtypes = [C.c_int, dp, dp]
-    L.mirror_emul_qhat.argtypes = [C.c_int, dp, C.c_int, dp, C.c_double, C.c_double, dp]
+    L.mirror_emul_qhat.argtypes = [C.c_int, dp, C.c_int, C.c_int, dp, C.c_double, C.c_double, dp]
+    L.mirror_emul_fold.argtypes = [C.c_int, dp, C.c_int, dp]
     return L
 
 
@@ -50,15 +51,26 @@ def test_mirror_emulation_matches_oracle(N, L_v, rule):
     dv = o.v[1] - o.v[0]
     L_eta = 0.5 * N * (2.0 * np.pi / (N * dv))
     got = np.empty(n3, dtype=complex)
-    assert L.mirror_emul_qhat(N, _p(W), 0, _p(F.view(np.float64)), L_eta, L_v, _p(got.view(np.float64))) == 0
+    assert L.mirror_emul_qhat(N, _p(W), 0, 0, _p(F.view(np.float64)), L_eta, L_v, _p(got.view(np.float64))) == 0
     assert not np.isnan(got.view(np.float64)).any()                # the pairing covers every zeta exactly
     assert relmax(got, want) < 1e-12
     Ws2 = np.empty_like(W)
     assert L.mirror_emul_symmetrize(N, _p(W), _p(Ws2)) == 0
     got2 = np.empty(n3, dtype=complex)
-    assert L.mirror_emul_qhat(N, _p(Ws2), 1, _p(F.view(np.float64)), L_eta, L_v, _p(got2.view(np.float64))) == 0
+    assert L.mirror_emul_qhat(N, _p(Ws2), 1, 0, _p(F.view(np.float64)), L_eta, L_v, _p(got2.view(np.float64))) == 0
     assert not np.isnan(got2.view(np.float64)).any()
     assert relmax(got2, want) < 1e-12
+    # folded tensors (mirror rows folded into their partners where the phase exponent is 0): not Q^ any more, but the
+    # same Q = Re(fft3D^-1(.)), src/collisions.c:212-221
+    Qwant = o.compute_q(W, f, f)
+    for sym in (0, 1):
+        Wh = np.empty_like(W)
+        assert L.mirror_emul_fold(N, _p(W), sym, _p(Wh)) == 0
+        S = np.empty(n3, dtype=complex)
+        assert L.mirror_emul_qhat(N, _p(Wh), sym, 1, _p(F.view(np.float64)), L_eta, L_v, _p(S.view(np.float64))) == 0
+        assert not np.isnan(S.view(np.float64)).any()
+        assert relmax(np.real(o.fft3d(S, invert=True)), Qwant) < 1e-12, sym
+        assert relmax(S, want) > 1e-6          # it really is a different spectrum
 
 
 def test_mirror_tiles_pair_every_column_once():

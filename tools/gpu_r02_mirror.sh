@@ -8,17 +8,20 @@ mkdir -p gpurun_out
 SBTE_MIRROR=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
   -k "batched_computeq or symmetrised_stream or 1d_step or heat_transport_golden or shock1p2" > gpurun_out/mirror_tests.log 2>&1
 echo "exit $?" >> gpurun_out/mirror_tests.log
-for m in 0 1; do
+for m in 0 1 3; do   # 3 = mirror kernel on the folded tensor (combined body on the foldable steps), only on the way to Q
   SBTE_MIRROR=$m timeout 40 python tools/gpu_n22_time.py 16 640 >> gpurun_out/mirror_time.log 2>&1
   SBTE_MIRROR=$m timeout 40 python tools/gpu_n22_time.py 16 80 >> gpurun_out/mirror_time.log 2>&1
 done
+SBTE_MIRROR=3 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+  -k "batched_computeq or symmetrised_stream or 1d_step or heat_transport_golden or shock1p2" > gpurun_out/mirror_fold_tests.log 2>&1
+echo "exit $?" >> gpurun_out/mirror_fold_tests.log
 for r in 0 1; do SBTE_ROLL=$r timeout 40 python tools/gpu_n22_time.py 24 250 >> gpurun_out/roll_time.log 2>&1; done
 # the line-ring mirror kernels (N = 20, 22, 24) need SBTE_MIRROR=2
 SBTE_MIRROR=2 timeout 150 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
   -k "line_ring or 24-33-3 or 24-3-33 or 22-34-3 or 22-3-33" > gpurun_out/mirror_ring_tests.log 2>&1
 echo "exit $?" >> gpurun_out/mirror_ring_tests.log
 for n in 24 22 20; do SBTE_MIRROR=2 timeout 40 python tools/gpu_n22_time.py $n 250 >> gpurun_out/mirror_time.log 2>&1; done
-tail -n 3 gpurun_out/mirror_tests.log gpurun_out/mirror_ring_tests.log; cat gpurun_out/mirror_time.log gpurun_out/roll_time.log
+tail -n 3 gpurun_out/mirror_tests.log gpurun_out/mirror_fold_tests.log gpurun_out/mirror_ring_tests.log; cat gpurun_out/mirror_time.log gpurun_out/roll_time.log
 # sanitizer pass over the new kernels (small cases): memcheck, then racecheck (shared-memory hazards, barrier misuse)
 SBTE_MIRROR=2 timeout 300 compute-sanitizer --tool memcheck --error-exitcode 9 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
   -k "8-5-3 or 8-37-3 or 16-33-3" > gpurun_out/mirror_memcheck.log 2>&1; echo "exit $?" >> gpurun_out/mirror_memcheck.log
