@@ -57,6 +57,7 @@ def symmetrise_standard(W, N):
 
 CASES = [  # kind, N, cells, sym, ctas
     (0, 8, 37, True, 5), (0, 8, 5, False, 3),            # qhat_batch2_kernel<8>      (GPU-verified: checks the emulation)
+    (0, 16, 3, True, 3),                                   # qhat_batch2_kernel<16>     (GPU-verified: the 1D headline kernel)
     (0, 20, 3, True, 4),                                   # qhat_batch3_kernel<20>     (GPU-verified, partly empty row-blocks)
     (1, 8, 37, True, 5), (1, 8, 5, False, 3),             # qhat_mirror_kernel<8>
     (1, 16, 3, True, 3),                                   # qhat_mirror_kernel<16>
