@@ -124,7 +124,8 @@ static bool batch3_general(int N) {
   static const bool on = getenv("SBTE_NO_BATCH3G") == nullptr;
   return on && (N == 20 || N == 22);
 }
-// N = 24: xi_z loop rolled in three blocks of eight columns (SBTE_ROLL=1; unmeasured, off by default)
+// N = 24: xi_z loop rolled in three blocks of eight columns, N = 22: eleven blocks of two (SBTE_ROLL=1; unmeasured,
+// off by default)
 static bool batch3_rolled() {
   static const bool on = getenv("SBTE_ROLL") != nullptr && atoi(getenv("SBTE_ROLL")) != 0;
   return on;
@@ -586,7 +587,10 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t
     case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
     case 16: launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch); break;
     case 20: launch_batch3_n<20>(c, spec, parts, part_stride, cells, sch); break;
-    case 22: launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch); break;
+    case 22:   // rolled: eleven blocks of one column pair (the operand registers rotate by two between blocks)
+      if (batch3_rolled()) launch_batch3_n<22, 11>(c, spec, parts, part_stride, cells, sch);
+      else launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch);
+      break;
     case 24:
       if (batch3_rolled()) launch_batch3_n<24, 3>(c, spec, parts, part_stride, cells, sch);
       else launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch);

@@ -78,7 +78,7 @@ void run_mirror_ring(const Args& a) {
 
 extern "C" {
 
-// kind: 0 = default kernels (qhat_batch2 / qhat_batch3), 1 = mirror-paired kernels, 2 = rolled N=24 line ring,
+// kind: 0 = default kernels (qhat_batch2 / qhat_batch3), 1 = mirror-paired kernels, 2 = rolled line ring (N = 22, 24),
 // 3 = mirror-paired kernel on the folded tensor (the result then only shares Re(fft3D^-1(.)) with Q^).
 // Schedule tables as returned by sbte_batch_schedule_host (host pointers); W = the tensor the kernel streams
 // (plain, symmetrised or mirror-symmetrised, matching `sym` and `kind`); spec = cell-minor spectra [G][n3][32] complex;
@@ -108,6 +108,7 @@ int emul_batched(int kind, int N, int cells, int sym, int P, const long long* ct
     else return 1;
   } else if (kind == 2) {
     if (N == 24) run_batch3<24, 3>(a);
+    else if (N == 22) run_batch3<22, 11>(a);
     else return 1;
   } else if (kind == 3) {   // folded tensor + combined body on the foldable steps
     if (N == 8) run_mirror<8>(a, 1);

@@ -66,6 +66,7 @@ CASES = [  # kind, N, cells, sym, ctas
     (1, 22, 2, True, 3),                                   # qhat_mirror_ring_kernel<22> (odd N/2, padded box slots, partial tiles)
     (1, 24, 1, True, 3),                                   # qhat_mirror_ring_kernel<24>
     (2, 24, 1, True, 3),                                   # qhat_batch3_kernel<24, ROLL=3> (opt-in rolled xi_z loop)
+    (2, 22, 1, False, 3),                                  # qhat_batch3_kernel<22, ROLL=11>
     (3, 8, 37, True, 5), (3, 8, 5, False, 3),             # qhat_mirror_kernel<8> on the folded tensor (combined body)
     (3, 16, 3, True, 3),                                   # qhat_mirror_kernel<16> on the folded tensor
 ]

@@ -15,7 +15,12 @@ done
 SBTE_MIRROR=3 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
   -k "batched_computeq or symmetrised_stream or 1d_step or heat_transport_golden or shock1p2" > gpurun_out/mirror_fold_tests.log 2>&1
 echo "exit $?" >> gpurun_out/mirror_fold_tests.log
-for r in 0 1; do SBTE_ROLL=$r timeout 40 python tools/gpu_n22_time.py 24 250 >> gpurun_out/roll_time.log 2>&1; done
+for r in 0 1; do
+  SBTE_ROLL=$r timeout 40 python tools/gpu_n22_time.py 24 250 >> gpurun_out/roll_time.log 2>&1
+  SBTE_ROLL=$r timeout 40 python tools/gpu_n22_time.py 22 250 >> gpurun_out/roll_time.log 2>&1
+done
+SBTE_ROLL=1 timeout 120 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+  -k "line_ring or 24-33-3 or 24-3-33 or 22-34-3 or 22-3-33" > gpurun_out/roll_tests.log 2>&1; echo "exit $?" >> gpurun_out/roll_tests.log
 # the line-ring mirror kernels (N = 20, 22, 24) need SBTE_MIRROR=2
 SBTE_MIRROR=2 timeout 150 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
   -k "line_ring or 24-33-3 or 24-3-33 or 22-34-3 or 22-3-33" > gpurun_out/mirror_ring_tests.log 2>&1
