@@ -174,14 +174,14 @@ static int make_tensor_map(sbte_ctx* c) {
   if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
   if (c->d_Wh) { cudaFree(c->d_Wh); c->d_Wh = nullptr; c->wh_sym = -1; }
   c->sched_cells = 0;
+  // the mirror identities need the reference's own grids (src/initializer.c:66-82): v_j = -L_v + j dv, eta_{N/2} = 0 and
+  // dv * deta = 2 pi / N, i.e. L_eta * dv = pi; any other grid keeps the ordinary kernels
+  c->grid_mirror_ok = fabs(c->v[0] + c->L_v) <= 1e-12 * c->L_v && fabs(c->L_eta * c->dv - M_PI) <= 1e-12 * M_PI &&
+                      fabs(c->dv * c->deta * c->N - 2.0 * M_PI) <= 1e-12 * 2.0 * M_PI;
   if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
   if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
   c->tmap_ok = true;
-  // the mirror identity needs the reference's own grids (src/initializer.c:66-82): v_j = -L_v + j dv, eta_{N/2} = 0 and
-  // dv * deta = 2 pi / N, i.e. L_eta * dv = pi; any other grid keeps the ordinary batched kernel
-  const bool grid_ok = fabs(c->v[0] + c->L_v) <= 1e-12 * c->L_v && fabs(c->L_eta * c->dv - M_PI) <= 1e-12 * M_PI &&
-                       fabs(c->dv * c->deta * c->N - 2.0 * M_PI) <= 1e-12 * 2.0 * M_PI;
-  if (qhat_mirror_enabled(c->N) && grid_ok) {
+  if (qhat_mirror_enabled(c->N) && c->grid_mirror_ok) {
     if (encode_weight_map(c, c->d_W, &c->tmapM, 1)) return 1;
     if (!c->d_mtiles) {
       const std::vector<MirrorTile> mt = build_mirror_tiles(c->N, qhat_mirror_pairs(c->N));
@@ -473,6 +473,18 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
 
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
   if (ensure_capacity(c, batch)) return 1;  // before c->d_qhat is read: growth reallocates the scratch
+  if (batch == 1 && d_f == d_g && qhat_half0d_enabled(c->N) && c->grid_mirror_ok && want_sym(c, true) &&
+      resolve_k2(c, 1, k2) == SBTE_K2_STREAM && fft_cluster_supported(c->N)) {
+    // opt-in: half of the zeta rows (qhat_half.cu).  The partial spectra do not add up to the reference's Q^, only to a
+    // spectrum with the same real inverse transform -- which is all ComputeQ returns (src/collisions.c:212-221)
+    if (!c->d_W) { set_error("no weights bound"); return 1; }
+    if (ensure_fold_mirror(c, true)) return 1;
+    launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
+    const int ns = (c->N == 32) ? 2 : 1;   // as the full stream kernel: two CTAs per column shorten the tail at N = 32
+    launch_qhat_stream_half(c, c->d_Wh, c->d_lay[0], c->d_qhat, ns);
+    if (!launch_fft3d_inverse_sum(c, c->d_qhat, ns + 1, d_Q)) { set_error("half-spectrum path: no summing inverse transform for this N"); return 1; }
+    return check_launch("half-spectrum compute_q");
+  }
   if (resolve_k2(c, batch, k2) == SBTE_K2_BATCH && d_f == d_g && qhat_batch_supported(c->N)) {
     // fast path: forward transform -> stream-K convolution -> inverse transform summing the partial sums
     if (!c->d_W) { set_error("no weights bound"); return 1; }

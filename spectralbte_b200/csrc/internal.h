@@ -77,6 +77,7 @@ struct sbte_ctx {
   sbte::MirrorTile* d_mtiles = nullptr;
   int n_mtiles = 0;
   bool mirror_ok = false;
+  bool grid_mirror_ok = false;      // v_j = -L_v + j dv, L_eta dv = pi: the grids the mirror / half-spectrum identities need
 
   // scratch, sized for `cap` cells
   int cap = 0;
@@ -182,6 +183,11 @@ void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2)
 void launch_fold_weights_mirror(sbte_ctx* c, const double* W, double* Wh, bool sym);
 void launch_qhat_mirror(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch, bool fold);
+
+// qhat_half.cu -- 0D (one cell, f == g) on half of the zeta rows: folded tensor, mirror columns skip the folded steps
+// (N in {16,32}, SBTE_HALF0D=1).  qhat receives nsplit + 1 partial spectra whose sum has the same Re(fft3D^-1(.)) as Q^.
+bool qhat_half0d_enabled(int N);
+void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double2* spec_parity, double2* qhat, int nsplit);
 
 // conserve.cu -- K4 / K5 / moments
 void launch_conserve(sbte_ctx* c, double* Q, int batch);

@@ -5,8 +5,11 @@
 // coordinates, shared-memory layout, tile switches and partial-sum flushes of the real kernel source.
 #include "cuda_emul.h"
 
+#include <type_traits>
+
 #include "../../spectralbte_b200/csrc/qhat_batch.cu"
 #include "../../spectralbte_b200/csrc/qhat_mirror.cu"
+#include "../../spectralbte_b200/csrc/qhat_half.cu"
 
 using namespace sbte;
 
@@ -117,6 +120,26 @@ int emul_batched(int kind, int N, int cells, int sym, int P, const long long* ct
   } else {
     return 1;
   }
+  return 0;
+}
+
+// 0D half-spectrum path (qhat_half.cu): Wh = folded tensor (mirror rule, symmetrised), spec = parity-split spectrum of one
+// cell, qhat = (nsplit + 1) partial spectra of n3 complex each
+int emul_half0d(int N, int nsplit, const double* Wh, const double* spec, double* qhat) {
+  const size_t n3 = (size_t)N * N * N;
+  auto run = [&](auto tag) {
+    constexpr int M = decltype(tag)::value;
+    using C = HalfCfg<M>;
+    for (int b = 0; b < M * M * nsplit; b++)
+      emul::run_cta(b, M * M * nsplit, C::THREADS, C::SMEM,
+                    [&](int) { qhat_stream_half_kernel<M>(Wh, (const double2*)spec, (double2*)qhat, nsplit); });
+    for (int b = 0; b < M * M; b++)
+      emul::run_cta(b, M * M, 256, 8 * 2 * M * sizeof(double2),
+                    [&](int) { qhat_half_leftover_kernel<M>(Wh, (const double2*)spec, (double2*)qhat + (size_t)nsplit * n3); });
+  };
+  if (N == 16) run(std::integral_constant<int, 16>());
+  else if (N == 32) run(std::integral_constant<int, 32>());
+  else return 1;
   return 0;
 }
 

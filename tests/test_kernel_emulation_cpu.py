@@ -136,3 +136,47 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
             assert relmax(np.real(o.fft3d(q, invert=True)), o.compute_q(W, fs[b], fs[b])) < 1e-12, b
         else:
             assert relmax(q, o.qhat(W, F[b], F[b])) < 1e-12, b
+
+
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
+@pytest.mark.parametrize("N,nsplit", [(16, 1), (16, 2)])
+def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit):
+    """qhat_stream_half_kernel + qhat_half_leftover_kernel (csrc/qhat_half.cu, opt-in SBTE_HALF0D=1): the 0D stream kernel on the
+    folded tensor, mirror columns skipping the folded steps, leftovers added by the second kernel.  The sum of the partial
+    spectra is not the reference's Q^, but Re(fft3D^-1(.)) must be the oracle's Q (src/collisions.c:212-221)."""
+    L = _lib()
+    dp = C.POINTER(C.c_double)
+    L.emul_half0d.argtypes = [C.c_int, C.c_int, dp, dp, dp]
+    o = orc.Oracle(N, 5.0, 0)
+    n3 = N ** 3
+    W = orc.synthetic_weights(N)
+    Wh = np.empty_like(W)
+    R = _mirror_rule_lib()
+    assert R.mirror_emul_fold(N, W.ctypes.data_as(dp), 1, Wh.ctypes.data_as(dp)) == 0
+    f = seeded_f(o.v, 41, noise=0.3)
+    F = o.fft3d(f.astype(complex)).reshape(N, N, N)
+    # parity-split lines [x][y][z & 1][z >> 1] (LAY_PARITY, csrc/internal.h)
+    z = np.arange(N)
+    spec = np.empty((N, N, N), dtype=complex)
+    spec[:, :, (z & 1) * (N // 2) + (z >> 1)] = F
+    spec = np.ascontiguousarray(spec)
+    parts = np.full((nsplit + 1) * n3, np.nan + 1j * np.nan, dtype=complex)
+    out = str(tmp_path / "parts.npy")
+
+    def child():
+        rc = L.emul_half0d(N, nsplit, Wh.ctypes.data_as(dp), spec.view(np.float64).ctypes.data_as(dp),
+                           parts.view(np.float64).ctypes.data_as(dp))
+        if rc == 0:
+            np.save(out, parts)
+        os._exit(rc)
+
+    proc = mp.get_context("fork").Process(target=child)
+    proc.start()
+    proc.join(900)
+    assert proc.exitcode == 0, "kernel emulation failed or deadlocked (exit code %s)" % proc.exitcode
+    parts = np.load(out).reshape(nsplit + 1, n3)
+    assert not np.isnan(parts.view(np.float64)).any()
+    S = parts.sum(axis=0)
+    assert relmax(np.real(o.fft3d(S, invert=True)), o.compute_q(W, f, f)) < 1e-12
+    # the mirror columns really skipped most of their steps: their main-kernel rows are much smaller than the A rows'
+    assert relmax(S, o.qhat(W, F.reshape(-1), F.reshape(-1))) > 1e-6

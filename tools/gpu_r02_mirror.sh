@@ -43,3 +43,9 @@ done
 SBTE_ROLL=1 timeout 120 ncu --set full --import-source on --clock-control none -k regex:qhat_batch3 -s 2 -c 1 \
   -o gpurun_out/r02_k2_batch3_n24_rolled -f python tools/gpu_n22_time.py 24 250 > gpurun_out/ncu_batch3_n24_rolled.log 2>&1
 ls -la gpurun_out/*.ncu-rep
+# 0D on half of the zeta rows (SBTE_HALF0D=1, csrc/qhat_half.cu): parity of ComputeQ at N = 16 / 32 against the oracle, then
+# the headline bench with and without it
+SBTE_HALF0D=1 timeout 300 python -m pytest tests/test_gpu_parity.py -x -q -p no:cacheprovider \
+  -k "computeq_and_maxpreserve or n32 or conservation_to_1e13 or bkw16" > gpurun_out/half0d_tests.log 2>&1; echo "exit $?" >> gpurun_out/half0d_tests.log
+for h in 0 1; do SBTE_HALF0D=$h timeout 300 python bench.py --steps 50 --warmup 5 --no-cpu > gpurun_out/bench_half0d_$h.json 2> gpurun_out/bench_half0d_$h.err; done
+tail -n 3 gpurun_out/half0d_tests.log; cut -c1-400 gpurun_out/bench_half0d_0.json gpurun_out/bench_half0d_1.json
