@@ -139,7 +139,7 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
 
 
 @pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
-@pytest.mark.parametrize("N,nsplit", [(16, 1), (16, 2)])
+@pytest.mark.parametrize("N,nsplit", [(16, 2)])
 def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit):
     """qhat_stream_half_kernel + qhat_half_leftover_kernel (csrc/qhat_half.cu, opt-in SBTE_HALF0D=1): the 0D stream kernel on the
     folded tensor, mirror columns skipping the folded steps, leftovers added by the second kernel.  The sum of the partial
