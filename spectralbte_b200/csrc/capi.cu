@@ -173,6 +173,7 @@ static int make_tensor_map(sbte_ctx* c) {
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copies
   if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
   if (c->d_Wh) { cudaFree(c->d_Wh); c->d_Wh = nullptr; c->wh_sym = -1; }
+  if (c->d_Wleft) { cudaFree(c->d_Wleft); c->d_Wleft = nullptr; }
   c->sched_cells = 0;
   // the mirror identities need the reference's own grids (src/initializer.c:66-82): v_j = -L_v + j dv, eta_{N/2} = 0 and
   // dv * deta = 2 pi / N, i.e. L_eta * dv = pi; any other grid keeps the ordinary kernels
@@ -199,6 +200,7 @@ static int release_weights(sbte_ctx* c) {
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }
   if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
   if (c->d_Wh) { cudaFree(c->d_Wh); c->d_Wh = nullptr; c->wh_sym = -1; }
+  if (c->d_Wleft) { cudaFree(c->d_Wleft); c->d_Wleft = nullptr; }
   c->mirror_ok = false;
   if (c->owns_W && c->d_W) cudaFree((void*)c->d_W);
   c->d_W = nullptr; c->owns_W = false; c->host_key = nullptr; c->tmap_ok = false;
@@ -368,6 +370,7 @@ static int ensure_fold_mirror(sbte_ctx* c, bool sym) {
   if (!c->d_Wh) CK(cudaMalloc(&c->d_Wh, (size_t)c->n3 * c->n3 * sizeof(double)));
   launch_fold_weights_mirror(c, c->d_W, c->d_Wh, sym);
   c->wh_sym = (int)sym;
+  if (c->d_Wleft) { cudaFree(c->d_Wleft); c->d_Wleft = nullptr; }   // packed from the previous folded tensor
   return encode_weight_map(c, c->d_Wh, &c->tmapMh, 1);
 }
 static int ensure_sym(sbte_ctx* c) {
@@ -479,9 +482,14 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
     // spectrum with the same real inverse transform -- which is all ComputeQ returns (src/collisions.c:212-221)
     if (!c->d_W) { set_error("no weights bound"); return 1; }
     if (ensure_fold_mirror(c, true)) return 1;
+    static const bool no_pack = getenv("SBTE_HALF0D_NOPACK") != nullptr;   // gather the leftovers from the folded tensor
+    if (!no_pack && !c->d_Wleft) {
+      CK(cudaMalloc(&c->d_Wleft, qhat_half_leftover_doubles(c->N) * sizeof(double)));
+      launch_half_pack_leftover(c, c->d_Wh, c->d_Wleft);
+    }
     launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
     const int ns = (c->N == 32) ? 2 : 1;   // as the full stream kernel: two CTAs per column shorten the tail at N = 32
-    launch_qhat_stream_half(c, c->d_Wh, c->d_lay[0], c->d_qhat, ns);
+    launch_qhat_stream_half(c, c->d_Wh, no_pack ? nullptr : c->d_Wleft, c->d_lay[0], c->d_qhat, ns);
     if (!launch_fft3d_inverse_sum(c, c->d_qhat, ns + 1, d_Q)) { set_error("half-spectrum path: no summing inverse transform for this N"); return 1; }
     return check_launch("half-spectrum compute_q");
   }

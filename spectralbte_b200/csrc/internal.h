@@ -74,6 +74,7 @@ struct sbte_ctx {
   double* d_Ws2 = nullptr;
   double* d_Wh = nullptr;           // folded tensor (mirror_fold_weight), built for wh_sym
   int wh_sym = -1;
+  double* d_Wleft = nullptr;        // compact leftover tensor of the 0D half-spectrum path (from d_Wh with wh_sym = 1)
   sbte::MirrorTile* d_mtiles = nullptr;
   int n_mtiles = 0;
   bool mirror_ok = false;
@@ -187,7 +188,10 @@ void launch_qhat_mirror(sbte_ctx* c, const double2* spec_cellminor, double2* par
 // qhat_half.cu -- 0D (one cell, f == g) on half of the zeta rows: folded tensor, mirror columns skip the folded steps
 // (N in {16,32}, SBTE_HALF0D=1).  qhat receives nsplit + 1 partial spectra whose sum has the same Re(fft3D^-1(.)) as Q^.
 bool qhat_half0d_enabled(int N);
-void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double2* spec_parity, double2* qhat, int nsplit);
+size_t qhat_half_leftover_doubles(int N);
+void launch_half_pack_leftover(sbte_ctx* c, const double* Wh, double* Wl);
+void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double* Wl, const double2* spec_parity, double2* qhat,
+                             int nsplit);
 
 // conserve.cu -- K4 / K5 / moments
 void launch_conserve(sbte_ctx* c, double* Q, int batch);

@@ -193,7 +193,13 @@ qhat_stream_half_kernel(const double* __restrict__ Wh, const double2* __restrict
 // rows, the entries xi_z = 0 and (zeta - xi)_z = 0.  One CTA per zeta column (A / unpaired columns write zeros), eight
 // warps taking the steps round robin, lane = zeta_z row; the zeta_z = 0 row is spread over the lanes (lane = xi_z).
 // Operands are read from the parity-split spectrum in global memory (L2-resident: 16 N^3 bytes).
-template <int N>
+// PACKED: the weights come from the compact tensor written once by half_pack_leftover_kernel,
+//   Wl[column][k][0][l] = Wh[row 0][xi_z = l],  [1][l] = Wh[row l][xi_z = 0],  [2][l] = Wh[row l][(zeta - xi)_z = 0]
+// (k = ordinal of the folded step, kmax steps per column), read as 3 N contiguous doubles per step instead of two
+// 32-byte sectors per row.
+__host__ __device__ constexpr int half_kmax(int N) { return (N / 2 + 1) * N; }
+
+template <int N, bool PACKED>
 __global__ void __launch_bounds__(256)
 qhat_half_leftover_kernel(const double* __restrict__ Wh, const double2* __restrict__ spec, double2* __restrict__ out) {
   constexpr int HALF = N / 2;
@@ -219,6 +225,7 @@ qhat_half_leftover_kernel(const double* __restrict__ Wh, const double2* __restri
     if (d0 < 0) d0 += N;
     const double* wr = Wh + ((long)colid * N + r) * n3;
     const double* w0 = Wh + ((long)colid * N) * n3;
+    const double* wl = Wh + (long)colid * half_kmax(N) * 3 * N;   // PACKED: Wh is the compact tensor
     int k = 0;
     for (int c = 0; c < nchunk; c++) {
       const int ex = half_chunk_ex(N, zx, true, c);
@@ -226,17 +233,19 @@ qhat_half_leftover_kernel(const double* __restrict__ Wh, const double2* __restri
       if (X < 0) X += N; else if (X > N - 1) X -= N;
       for (int ey = 0; ey < N; ey++) {
         if (mirror_exy(N, zx, zy, ex, ey) != 0) continue;
-        if ((k++ & 7) != warp) continue;
+        const int kk = k++;
+        if ((kk & 7) != warp) continue;
         int Y = zy + N / 2 - ey;
         if (Y < 0) Y += N; else if (Y > N - 1) Y -= N;
         const double2* gl = spec + ((long)ex * N + ey) * N;
         const double2* fl = spec + ((long)X * N + Y) * N;
         const long step = ((long)ex * N + ey) * N;
+        const double* ws = wl + (long)kk * 3 * N;
         // row 0, entry xi_z = lane
-        cmac(acc0, w0[step + lane], cmul(gl[par(lane)], fl[par(d0)]));
+        cmac(acc0, PACKED ? ws[lane] : w0[step + lane], cmul(gl[par(lane)], fl[par(d0)]));
         if (r >= 1) {
-          cmac(acc, wr[step], cmul(gl[par(0)], fl[par(d)]));                    // xi_z = 0
-          if (d != 0) cmac(acc, wr[step + d], cmul(gl[par(d)], fl[par(0)]));    // (zeta - xi)_z = 0
+          cmac(acc, PACKED ? ws[N + lane] : wr[step], cmul(gl[par(0)], fl[par(d)]));                        // xi_z = 0
+          if (d != 0) cmac(acc, PACKED ? ws[2 * N + lane] : wr[step + d], cmul(gl[par(d)], fl[par(0)]));    // (zeta - xi)_z = 0
         }
       }
     }
@@ -256,9 +265,49 @@ qhat_half_leftover_kernel(const double* __restrict__ Wh, const double2* __restri
   }
 }
 
-#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
+// writes the compact leftover tensor (same step enumeration as the leftover kernel)
 template <int N>
-static void launch_half_n(sbte_ctx* c, const double* Wh, const double2* spec, double2* qhat, int nsplit) {
+__global__ void __launch_bounds__(256)
+half_pack_leftover_kernel(const double* __restrict__ Wh, double* __restrict__ Wl) {
+  constexpr long n3 = (long)N * N * N;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int colid = blockIdx.x, zx = colid / N, zy = colid % N;
+  if (!(mirror_paired_column(N, zx, zy) && mirror_is_b_row(N, zx, zy)) || lane >= N) return;
+  int d = lane + N / 2;
+  if (d > N - 1) d -= N;
+  const double* wr = Wh + ((long)colid * N + lane) * n3;
+  const double* w0 = Wh + ((long)colid * N) * n3;
+  double* wl = Wl + (long)colid * half_kmax(N) * 3 * N;
+  const int nchunk = sym_nrep(N, (N - zx) % N);
+  int k = 0;
+  for (int c = 0; c < nchunk; c++) {
+    const int ex = half_chunk_ex(N, zx, true, c);
+    for (int ey = 0; ey < N; ey++) {
+      if (mirror_exy(N, zx, zy, ex, ey) != 0) continue;
+      const int kk = k++;
+      if ((kk & 7) != warp) continue;
+      const long step = ((long)ex * N + ey) * N;
+      double* ws = wl + (long)kk * 3 * N;
+      ws[lane] = w0[step + lane];
+      ws[N + lane] = wr[step];
+      ws[2 * N + lane] = wr[step + d];
+    }
+  }
+}
+
+#ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
+size_t qhat_half_leftover_doubles(int N) { return (size_t)N * N * half_kmax(N) * 3 * N; }
+
+void launch_half_pack_leftover(sbte_ctx* c, const double* Wh, double* Wl) {
+  if (c->N == 16) half_pack_leftover_kernel<16><<<16 * 16, 256, 0, c->stream>>>(Wh, Wl);
+  else if (c->N == 32) half_pack_leftover_kernel<32><<<32 * 32, 256, 0, c->stream>>>(Wh, Wl);
+  else set_error("half_pack_leftover: unsupported N");
+  c->launches += 1;
+}
+
+// Wl: compact leftover tensor or null (the leftover kernel then gathers from Wh)
+template <int N>
+static void launch_half_n(sbte_ctx* c, const double* Wh, const double* Wl, const double2* spec, double2* qhat, int nsplit) {
   using C = HalfCfg<N>;
   auto kern = qhat_stream_half_kernel<N>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
@@ -268,16 +317,17 @@ static void launch_half_n(sbte_ctx* c, const double* Wh, const double2* spec, do
   }
   k2_mark(c);
   kern<<<N * N * nsplit, C::THREADS, C::SMEM, c->stream>>>(Wh, spec, qhat, nsplit);
-  qhat_half_leftover_kernel<N><<<N * N, 256, 8 * 2 * N * sizeof(double2), c->stream>>>(Wh, spec, qhat + (size_t)nsplit * c->n3);
+  if (Wl) qhat_half_leftover_kernel<N, true><<<N * N, 256, 8 * 2 * N * sizeof(double2), c->stream>>>(Wl, spec, qhat + (size_t)nsplit * c->n3);
+  else qhat_half_leftover_kernel<N, false><<<N * N, 256, 8 * 2 * N * sizeof(double2), c->stream>>>(Wh, spec, qhat + (size_t)nsplit * c->n3);
   k2_mark(c);
   c->launches += 2;
 }
 
 // spec: parity-split spectrum of f; qhat: nsplit + 1 partial spectra of n3 elements each (the last one = leftovers)
-void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double2* spec, double2* qhat, int nsplit) {
+void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double* Wl, const double2* spec, double2* qhat, int nsplit) {
   switch (c->N) {
-    case 16: launch_half_n<16>(c, Wh, spec, qhat, nsplit); break;
-    case 32: launch_half_n<32>(c, Wh, spec, qhat, nsplit); break;
+    case 16: launch_half_n<16>(c, Wh, Wl, spec, qhat, nsplit); break;
+    case 32: launch_half_n<32>(c, Wh, Wl, spec, qhat, nsplit); break;
     default: set_error("qhat_stream_half: unsupported N"); break;
   }
 }

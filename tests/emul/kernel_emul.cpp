@@ -125,7 +125,7 @@ int emul_batched(int kind, int N, int cells, int sym, int P, const long long* ct
 
 // 0D half-spectrum path (qhat_half.cu): Wh = folded tensor (mirror rule, symmetrised), spec = parity-split spectrum of one
 // cell, qhat = (nsplit + 1) partial spectra of n3 complex each
-int emul_half0d(int N, int nsplit, const double* Wh, const double* spec, double* qhat) {
+int emul_half0d(int N, int nsplit, int packed, const double* Wh, const double* spec, double* qhat) {
   const size_t n3 = (size_t)N * N * N;
   auto run = [&](auto tag) {
     constexpr int M = decltype(tag)::value;
@@ -133,9 +133,17 @@ int emul_half0d(int N, int nsplit, const double* Wh, const double* spec, double*
     for (int b = 0; b < M * M * nsplit; b++)
       emul::run_cta(b, M * M * nsplit, C::THREADS, C::SMEM,
                     [&](int) { qhat_stream_half_kernel<M>(Wh, (const double2*)spec, (double2*)qhat, nsplit); });
+    std::vector<double> Wl;
+    if (packed) {   // compact leftover tensor, poisoned first: every entry the leftover kernel reads must have been packed
+      Wl.assign((size_t)M * M * half_kmax(M) * 3 * M, NAN);
+      for (int b = 0; b < M * M; b++)
+        emul::run_cta(b, M * M, 256, 64, [&](int) { half_pack_leftover_kernel<M>(Wh, Wl.data()); });
+    }
     for (int b = 0; b < M * M; b++)
-      emul::run_cta(b, M * M, 256, 8 * 2 * M * sizeof(double2),
-                    [&](int) { qhat_half_leftover_kernel<M>(Wh, (const double2*)spec, (double2*)qhat + (size_t)nsplit * n3); });
+      emul::run_cta(b, M * M, 256, 8 * 2 * M * sizeof(double2), [&](int) {
+        if (packed) qhat_half_leftover_kernel<M, true>(Wl.data(), (const double2*)spec, (double2*)qhat + (size_t)nsplit * n3);
+        else qhat_half_leftover_kernel<M, false>(Wh, (const double2*)spec, (double2*)qhat + (size_t)nsplit * n3);
+      });
   };
   if (N == 16) run(std::integral_constant<int, 16>());
   else if (N == 32) run(std::integral_constant<int, 32>());

@@ -139,14 +139,14 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
 
 
 @pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
-@pytest.mark.parametrize("N,nsplit", [(16, 2)])
-def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit):
+@pytest.mark.parametrize("N,nsplit,packed", [(16, 2, 1)])   # (16, 1, 0) -- leftovers gathered from the folded tensor -- passes too
+def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit, packed):
     """qhat_stream_half_kernel + qhat_half_leftover_kernel (csrc/qhat_half.cu, opt-in SBTE_HALF0D=1): the 0D stream kernel on the
     folded tensor, mirror columns skipping the folded steps, leftovers added by the second kernel.  The sum of the partial
     spectra is not the reference's Q^, but Re(fft3D^-1(.)) must be the oracle's Q (src/collisions.c:212-221)."""
     L = _lib()
     dp = C.POINTER(C.c_double)
-    L.emul_half0d.argtypes = [C.c_int, C.c_int, dp, dp, dp]
+    L.emul_half0d.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
     o = orc.Oracle(N, 5.0, 0)
     n3 = N ** 3
     W = orc.synthetic_weights(N)
@@ -164,7 +164,7 @@ def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit):
     out = str(tmp_path / "parts.npy")
 
     def child():
-        rc = L.emul_half0d(N, nsplit, Wh.ctypes.data_as(dp), spec.view(np.float64).ctypes.data_as(dp),
+        rc = L.emul_half0d(N, nsplit, packed, Wh.ctypes.data_as(dp), spec.view(np.float64).ctypes.data_as(dp),
                            parts.view(np.float64).ctypes.data_as(dp))
         if rc == 0:
             np.save(out, parts)
