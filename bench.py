@@ -36,6 +36,38 @@ METRIC_0D = "Q(f,f) evals/s at N=32"
 SEED = 20261017
 
 
+def half0d_bytes(N):
+    """Weight bytes one evaluation of the opt-in half-spectrum path must stream (csrc/qhat_half.cu): every representative
+    xi_x plane of the A / unpaired zeta columns, the steps of the mirror columns whose x/y phase exponent is not 0, and
+    3 N doubles per folded step of a mirror column from the compact leftover tensor."""
+    def nrep(zx):
+        a = (zx + N // 2) % N
+        return a // 2 + 1 + (a + N) // 2 - a
+
+    def rep(zx, c):
+        a = (zx + N // 2) % N
+        h = a // 2
+        return c if c <= h else c + (a - h)
+
+    nu = lambda i: (N - i) % N  # noqa: E731
+    total = 0.0
+    for zx in range(N):
+        for zy in range(N):
+            paired = not (zx in (0, N // 2) and zy in (0, N // 2))
+            b = paired and ((zy > N // 2) if zx in (0, N // 2) else (zx > N // 2))
+            if not b:
+                total += nrep(zx) * N * N * N * 8.0
+                continue
+            for c in range(nrep(nu(zx))):
+                ex = nu(rep(nu(zx), c))
+                X = (zx + N // 2 - ex) % N
+                for ey in range(N):
+                    Y = (zy + N // 2 - ey) % N
+                    exy = (zx == 0) + (zy == 0) - (ex == 0) - (X == 0) - (ey == 0) - (Y == 0)
+                    total += (N * N * 8.0) if exy != 0 else (3 * N * 8.0)
+    return total
+
+
 def peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -382,6 +414,9 @@ def run_0d_n32(args):
     # symmetrised stream (f == g): rows zeta read nrep(zeta_x) of their N xi_x planes, nrep = N/2+1 | N/2
     nrep_sum = sum(((zx + N // 2) % N) // 2 + 1 + (((zx + N // 2) % N) + N) // 2 - ((zx + N // 2) % N) for zx in range(N))
     wbytes = 8.0 * float(N) ** 4 * nrep_sum if sym else ref_bytes
+    half0d = sym and bool(int(os.environ.get("SBTE_HALF0D", "0") or 0)) and N in (16, 32)
+    if half0d:
+        wbytes = half0d_bytes(N)
     k2_avg_ms = k2_ms / max(1, k2_n)
     achieved = wbytes / (k2_avg_ms * 1e-3) / 1e9
     traffic = None
@@ -397,10 +432,15 @@ def run_0d_n32(args):
                    "N": N, "L_v": L_v, "init_field": 0, "weights": wdesc,
                    "k2": args.k2, "replicas": world, "l2": "inputs (8.59 GB weight stream) larger than L2; no flush"},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": traffic, "kernel": "qhat_stream_kernel<32,1,2,%s>" % ("sym" if sym else "plain"),
+                     "traffic": None if half0d else traffic,
+                     "kernel": ("qhat_stream_half_kernel<32> + qhat_half_leftover_kernel<32>" if half0d else
+                                "qhat_stream_kernel<32,1,2,%s>" % ("sym" if sym else "plain")),
                      "kernel_ms": k2_avg_ms, "kernel_share_of_step": k2_ms / ms, "algorithmic_bytes_per_launch": wbytes,
                      "reference_formulation_bytes": ref_bytes,
-                     "note": ("f == g: the summand is symmetric under xi <-> zeta-xi, so the kernel streams the symmetrised "
+                     "note": ("SBTE_HALF0D (opt-in, csrc/qhat_half.cu): Q = Re(ifft(Q^)) only needs half of the zeta rows; "
+                              "bytes = folded tensor rows of the A / unpaired columns, the unfolded steps of the mirror columns "
+                              "and the compact leftover tensor") if half0d else
+                             ("f == g: the summand is symmetric under xi <-> zeta-xi, so the kernel streams the symmetrised "
                               "tensor Ws = W + W o sigma over nrep(zeta_x) of N xi_x planes (4.43 GB at N=32) instead of the "
                               "reference's 8*N^6 = 8.59 GB; `plain_kernel` times the unsymmetrised stream") if sym else
                              "unsymmetrised stream (SBTE_NO_SYM): 8*N^6 bytes per evaluation as in the reference",
