@@ -70,8 +70,14 @@ qhat_stream_half_kernel(const double* __restrict__ Wh, const double2* __restrict
   const int zx = colid / N, zy = colid % N;
   const bool bcol = mirror_paired_column(N, zx, zy) && mirror_is_b_row(N, zx, zy);
   const int nchunk_all = sym_nrep(N, bcol ? (N - zx) % N : zx);
-  const int cbeg = part * nchunk_all / nsplit;
-  const int nchunk = (part + 1) * nchunk_all / nsplit - cbeg;   // xi_x planes visited by this CTA
+  // the xi_x planes of an A column are shared between nsplit CTAs (shorter tail); a B column keeps so few steps that one
+  // CTA takes them all and the others only write their zero partial spectrum
+  if (bcol && part > 0) {
+    if (tid < N) qhat[(long)part * n3 + (long)colid * N + tid] = make_double2(0.0, 0.0);
+    return;
+  }
+  const int cbeg = bcol ? 0 : part * nchunk_all / nsplit;
+  const int nchunk = bcol ? nchunk_all : (part + 1) * nchunk_all / nsplit - cbeg;   // xi_x planes visited by this CTA
   auto chunk_ex = [&](int c) { return half_chunk_ex(N, zx, bcol, cbeg + c); };
   // B columns keep only the steps whose x/y phase exponent is not 0 (the rest is qhat_half_leftover_kernel's)
   auto skipped = [&](int ex, int ey) { return bcol && mirror_exy(N, zx, zy, ex, ey) == 0; };
