@@ -373,6 +373,17 @@ static int ensure_fold_mirror(sbte_ctx* c, bool sym) {
   if (c->d_Wleft) { cudaFree(c->d_Wleft); c->d_Wleft = nullptr; }   // packed from the previous folded tensor
   return encode_weight_map(c, c->d_Wh, &c->tmapMh, 1);
 }
+// tensors of the 0D half-spectrum path (qhat_half.cu): the folded symmetrised tensor and, unless SBTE_HALF0D_NOPACK is
+// set (the leftover kernel then gathers from the folded tensor), the compact leftover tensor packed from it
+static int ensure_half0d_tensors(sbte_ctx* c) {
+  if (ensure_fold_mirror(c, true)) return 1;
+  static const bool no_pack = getenv("SBTE_HALF0D_NOPACK") != nullptr;
+  if (!no_pack && !c->d_Wleft) {
+    CK(cudaMalloc(&c->d_Wleft, qhat_half_leftover_doubles(c->N) * sizeof(double)));
+    launch_half_pack_leftover(c, c->d_Wh, c->d_Wleft);
+  }
+  return 0;
+}
 static int ensure_sym(sbte_ctx* c) {
   if (c->d_Ws) return 0;
   c->graph_gen++;
@@ -481,15 +492,11 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
     // opt-in: half of the zeta rows (qhat_half.cu).  The partial spectra do not add up to the reference's Q^, only to a
     // spectrum with the same real inverse transform -- which is all ComputeQ returns (src/collisions.c:212-221)
     if (!c->d_W) { set_error("no weights bound"); return 1; }
-    if (ensure_fold_mirror(c, true)) return 1;
-    static const bool no_pack = getenv("SBTE_HALF0D_NOPACK") != nullptr;   // gather the leftovers from the folded tensor
-    if (!no_pack && !c->d_Wleft) {
-      CK(cudaMalloc(&c->d_Wleft, qhat_half_leftover_doubles(c->N) * sizeof(double)));
-      launch_half_pack_leftover(c, c->d_Wh, c->d_Wleft);
-    }
+    if (ensure_half0d_tensors(c)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
     const int ns = (c->N == 32) ? 2 : 1;   // as the full stream kernel: two CTAs per column shorten the tail at N = 32
-    launch_qhat_stream_half(c, c->d_Wh, no_pack ? nullptr : c->d_Wleft, c->d_lay[0], c->d_qhat, ns);
+    const QhatPair pr = {c->d_lay[0], c->d_lay[0]};
+    launch_qhat_stream_half(c, c->d_Wh, c->d_Wleft, 1, &pr, c->d_qhat, ns);
     if (!launch_fft3d_inverse_sum(c, c->d_qhat, ns + 1, d_Q)) { set_error("half-spectrum path: no summing inverse transform for this N"); return 1; }
     return check_launch("half-spectrum compute_q");
   }
@@ -562,6 +569,13 @@ int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g,
   }
   const double2* gjhat = same ? c->d_lay[1] : c->d_specB;
   QhatPair pairs[2] = {{gjhat, c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]}};
+  if (stream && same && qhat_half0d_enabled(c->N) && c->grid_mirror_ok && want_sym(c, true) && fft_cluster_supported(c->N)) {
+    // opt-in: half of the zeta rows (qhat_half.cu); the summed product of the two pairs obeys the same mirror relation
+    if (ensure_half0d_tensors(c)) return 1;
+    launch_qhat_stream_half(c, c->d_Wh, c->d_Wleft, 2, pairs, c->d_qhat, 1);
+    if (!launch_fft3d_inverse_sum(c, c->d_qhat, 2, d_Q)) { set_error("half-spectrum path: no summing inverse transform for this N"); return 1; }
+    return check_launch("half-spectrum maxpreserve");
+  }
   const bool sym = stream && want_sym(c, same);   // for f == g the three-product summand is symmetric as a whole
   if (sym && ensure_sym(c)) return 1;
   // splitting the columns between CTAs (as the one-pair kernel does at N = 32) does not pay here: N = 32 already runs

@@ -156,6 +156,14 @@ struct QhatPair {
   const double2* xi_side;    // g^[xi]
   const double2* dif_side;   // f^[zeta - xi]
 };
+// qhat_half.cu -- 0D (one cell, f == g) on half of the zeta rows: folded tensor, mirror columns skip the folded steps
+// (N in {16,32}, SBTE_HALF0D=1).  qhat receives nsplit + 1 partial spectra whose sum has the same Re(fft3D^-1(.)) as Q^.
+bool qhat_half0d_enabled(int N);
+size_t qhat_half_leftover_doubles(int N);
+void launch_half_pack_leftover(sbte_ctx* c, const double* Wh, double* Wl);
+void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double* Wl, int npairs, const QhatPair* pairs_parity,
+                             double2* qhat, int nsplit);
+
 // generic: natural-layout operands, any N, any batch (one CTA per (zeta, cell))
 void launch_qhat_generic(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int batch);
 // stream kernel (N in {16,24,32}, batch 1): parity-layout operands
@@ -184,14 +192,6 @@ void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2)
 void launch_fold_weights_mirror(sbte_ctx* c, const double* W, double* Wh, bool sym);
 void launch_qhat_mirror(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch, bool fold);
-
-// qhat_half.cu -- 0D (one cell, f == g) on half of the zeta rows: folded tensor, mirror columns skip the folded steps
-// (N in {16,32}, SBTE_HALF0D=1).  qhat receives nsplit + 1 partial spectra whose sum has the same Re(fft3D^-1(.)) as Q^.
-bool qhat_half0d_enabled(int N);
-size_t qhat_half_leftover_doubles(int N);
-void launch_half_pack_leftover(sbte_ctx* c, const double* Wh, double* Wl);
-void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double* Wl, const double2* spec_parity, double2* qhat,
-                             int nsplit);
 
 // conserve.cu -- K4 / K5 / moments
 void launch_conserve(sbte_ctx* c, double* Q, int batch);

@@ -29,20 +29,23 @@ bool qhat_half0d_enabled(int N) {
   return on && (N == 16 || N == 32);
 }
 
-template <int N>
+// WT: warps per CTA (8 for one operand pair; 16 for the two pairs of ComputeQ_maxPreserve, whose 128 KB plane ring allows
+// only one CTA per SM), as in StreamCfg (qhat.cu)
+template <int N, int WT = 8>
 struct HalfCfg {
   static constexpr int HALF = N / 2;            // 2-column groups per N-long weight row segment
   static constexpr int RGW = 32 / HALF;         // 4-row groups handled by one warp
   static constexpr int ROWS_W = RGW * 4;        // rows per warp
   static constexpr int RB = N / ROWS_W;         // warps that tile the N rows of one zeta (x,y) column
-  static constexpr int PH = 8 / RB;             // xi_y phases (warps sharing the same rows)
+  static constexpr int PH = WT / RB;            // xi_y phases (warps sharing the same rows)
   static constexpr int NWARP = RB * PH;
   static constexpr int THREADS = NWARP * 32;
   static constexpr int SPC = N / PH;            // steps per xi_x chunk per warp
   static constexpr int PLANE = N * N;           // complex elements per operand plane
   static constexpr int DEPTH = 2;               // weight tiles in flight per thread
-  static constexpr size_t SMEM = (size_t)2 * 2 * PLANE * sizeof(double2) + 64;
-  static_assert(32 % HALF == 0 && N % ROWS_W == 0 && 8 % RB == 0 && N % PH == 0, "unsupported N");
+  static constexpr int NP = WT / 8;             // operand pairs sharing the weight pass
+  static constexpr size_t SMEM = (size_t)2 * 2 * NP * PLANE * sizeof(double2) + 64;
+  static_assert(32 % HALF == 0 && N % ROWS_W == 0 && WT % RB == 0 && N % PH == 0 && (WT == 8 || WT == 16), "unsupported N");
 };
 
 // the c-th xi_x plane a column visits: the representatives of its own plane (A, unpaired) or the mirror images of its
@@ -51,15 +54,19 @@ __device__ __forceinline__ int half_chunk_ex(int N, int zx, bool b, int c) {
   return b ? (N - sym_rep(N, (N - zx) % N, c)) % N : sym_rep(N, zx, c);
 }
 
-template <int N>
-__global__ void __launch_bounds__(HalfCfg<N>::THREADS, (N == 32) ? 2 : 1)
-qhat_stream_half_kernel(const double* __restrict__ Wh, const double2* __restrict__ spec, double2* __restrict__ qhat, int nsplit) {
-  using C = HalfCfg<N>;
+// NP = 2 (ComputeQ_maxPreserve, src/collisions.c:178-210): the summand is g_j^[xi] f^[zeta-xi] + M_j^[xi] g_i^[zeta-xi]
+// (xiA/dfA and xiB/dfB); it obeys the same mirror relation, so the same folded tensor serves it.
+template <int N, int NP>
+__global__ void __launch_bounds__(HalfCfg<N, 8 * NP>::THREADS, (N == 32 && NP == 1) ? 2 : 1)
+qhat_stream_half_kernel(const double* __restrict__ Wh, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
+                        const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat,
+                        int nsplit) {
+  using C = HalfCfg<N, 8 * NP>;
   constexpr int HALF = C::HALF, PLANE = C::PLANE, DEPTH = C::DEPTH;
   constexpr long n3 = (long)N * N * N;
-  constexpr uint32_t STAGE_ELEMS = 2 * PLANE;   // per stage: xi-side plane, dif-side plane
+  constexpr uint32_t STAGE_ELEMS = 2 * NP * PLANE;   // per stage: NP x (xi-side plane, dif-side plane)
   SBTE_DYN_SMEM(smraw);
-  double2* planes = reinterpret_cast<double2*>(smraw);                       // [2][2][PLANE]
+  double2* planes = reinterpret_cast<double2*>(smraw);                       // [2][NP][2][PLANE]
   uint64_t* full = reinterpret_cast<uint64_t*>(smraw + 2 * STAGE_ELEMS * sizeof(double2));
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -101,8 +108,12 @@ qhat_stream_half_kernel(const double* __restrict__ Wh, const double2* __restrict
     if (X < 0) X += N; else if (X > N - 1) X -= N;
     double2* dst = planes + (size_t)s * STAGE_ELEMS;
     mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * (uint32_t)sizeof(double2));
-    tma_bulk_g2s(dst, spec + (size_t)ex * PLANE, PLANE * sizeof(double2), &full[s]);
-    tma_bulk_g2s(dst + PLANE, spec + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
+    tma_bulk_g2s(dst, xiA + (size_t)ex * PLANE, PLANE * sizeof(double2), &full[s]);
+    tma_bulk_g2s(dst + PLANE, dfA + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
+    if (NP > 1) {
+      tma_bulk_g2s(dst + 2 * PLANE, xiB + (size_t)ex * PLANE, PLANE * sizeof(double2), &full[s]);
+      tma_bulk_g2s(dst + 3 * PLANE, dfB + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
+    }
   };
 
   if (tid == 0) {
@@ -153,16 +164,39 @@ qhat_stream_half_kernel(const double* __restrict__ Wh, const double2* __restrict
       const double2* st = planes + (size_t)s * STAGE_ELEMS;
       if (active) {
         if (!skipped(ex, ey)) {
-          const double2* gl = st + ey * N;
-          const double2* fl = st + PLANE + Y * N;
-          const double2 g0 = gl[offg0], g1 = gl[offg1];
-          double2 fw[5];
+          double2 p[4][2];
+          {
+            const double2* gl = st + ey * N;
+            const double2* fl = st + PLANE + Y * N;
+            const double2 g0 = gl[offg0], g1 = gl[offg1];
+            double2 fw[5];
 #pragma unroll
-          for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
+            for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+              p[j][0] = cmul(g0, fw[j + 1]);
+              p[j][1] = cmul(g1, fw[j]);
+            }
+          }
+          if (NP > 1) {
+            const double2* gl = st + 2 * PLANE + ey * N;
+            const double2* fl = st + 3 * PLANE + Y * N;
+            const double2 g0 = gl[offg0], g1 = gl[offg1];
+            double2 fw[5];
+#pragma unroll
+            for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
+#pragma unroll
+            for (int j = 0; j < 4; j++) {   // p += g * fw as four fused multiply-adds per product
+              p[j][0].x = fma(g0.x, fw[j + 1].x, fma(-g0.y, fw[j + 1].y, p[j][0].x));
+              p[j][0].y = fma(g0.x, fw[j + 1].y, fma(g0.y, fw[j + 1].x, p[j][0].y));
+              p[j][1].x = fma(g1.x, fw[j].x, fma(-g1.y, fw[j].y, p[j][1].x));
+              p[j][1].y = fma(g1.x, fw[j].y, fma(g1.y, fw[j].x, p[j][1].y));
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            cmac(acc[j], wb[d][j].x, cmul(g0, fw[j + 1]));
-            cmac(acc[j], wb[d][j].y, cmul(g1, fw[j]));
+            cmac(acc[j], wb[d][j].x, p[j][0]);
+            cmac(acc[j], wb[d][j].y, p[j][1]);
           }
         }
         if (it + DEPTH < NIT) load_w(it + DEPTH, wb[d]);
@@ -205,9 +239,10 @@ qhat_stream_half_kernel(const double* __restrict__ Wh, const double2* __restrict
 // 32-byte sectors per row.
 __host__ __device__ constexpr int half_kmax(int N) { return (N / 2 + 1) * N; }
 
-template <int N, bool PACKED>
+template <int N, bool PACKED, int NP>
 __global__ void __launch_bounds__(256)
-qhat_half_leftover_kernel(const double* __restrict__ Wh, const double2* __restrict__ spec, double2* __restrict__ out) {
+qhat_half_leftover_kernel(const double* __restrict__ Wh, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
+                          const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ out) {
   constexpr int HALF = N / 2;
   constexpr long n3 = (long)N * N * N;
   SBTE_DYN_SMEM(smraw);   // 8 warps x {rows >= 1, row 0} x N partial sums
@@ -243,15 +278,23 @@ qhat_half_leftover_kernel(const double* __restrict__ Wh, const double2* __restri
         if ((kk & 7) != warp) continue;
         int Y = zy + N / 2 - ey;
         if (Y < 0) Y += N; else if (Y > N - 1) Y -= N;
-        const double2* gl = spec + ((long)ex * N + ey) * N;
-        const double2* fl = spec + ((long)X * N + Y) * N;
+        const long lg = ((long)ex * N + ey) * N, lf = ((long)X * N + Y) * N;
+        // product of the entry (xi_z = a, (zeta - xi)_z = b), summed over the operand pairs
+        auto prod = [&](int a, int b) {
+          double2 p = cmul(xiA[lg + par(a)], dfA[lf + par(b)]);
+          if (NP > 1) {
+            const double2 q = cmul(xiB[lg + par(a)], dfB[lf + par(b)]);
+            p.x += q.x; p.y += q.y;
+          }
+          return p;
+        };
         const long step = ((long)ex * N + ey) * N;
         const double* ws = wl + (long)kk * 3 * N;
         // row 0, entry xi_z = lane
-        cmac(acc0, PACKED ? ws[lane] : w0[step + lane], cmul(gl[par(lane)], fl[par(d0)]));
+        cmac(acc0, PACKED ? ws[lane] : w0[step + lane], prod(lane, d0));
         if (r >= 1) {
-          cmac(acc, PACKED ? ws[N + lane] : wr[step], cmul(gl[par(0)], fl[par(d)]));                        // xi_z = 0
-          if (d != 0) cmac(acc, PACKED ? ws[2 * N + lane] : wr[step + d], cmul(gl[par(d)], fl[par(0)]));    // (zeta - xi)_z = 0
+          cmac(acc, PACKED ? ws[N + lane] : wr[step], prod(0, d));                        // xi_z = 0
+          if (d != 0) cmac(acc, PACKED ? ws[2 * N + lane] : wr[step + d], prod(d, 0));    // (zeta - xi)_z = 0
         }
       }
     }
@@ -312,29 +355,37 @@ void launch_half_pack_leftover(sbte_ctx* c, const double* Wh, double* Wl) {
 }
 
 // Wl: compact leftover tensor or null (the leftover kernel then gathers from Wh)
-template <int N>
-static void launch_half_n(sbte_ctx* c, const double* Wh, const double* Wl, const double2* spec, double2* qhat, int nsplit) {
-  using C = HalfCfg<N>;
-  auto kern = qhat_stream_half_kernel<N>;
+template <int N, int NP>
+static void launch_half_n(sbte_ctx* c, const double* Wh, const double* Wl, const QhatPair* pr, double2* qhat, int nsplit) {
+  using C = HalfCfg<N, 8 * NP>;
+  auto kern = qhat_stream_half_kernel<N, NP>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
   if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     configured.fetch_or(1u << c->device);
   }
   k2_mark(c);
-  kern<<<N * N * nsplit, C::THREADS, C::SMEM, c->stream>>>(Wh, spec, qhat, nsplit);
-  if (Wl) qhat_half_leftover_kernel<N, true><<<N * N, 256, 8 * 2 * N * sizeof(double2), c->stream>>>(Wl, spec, qhat + (size_t)nsplit * c->n3);
-  else qhat_half_leftover_kernel<N, false><<<N * N, 256, 8 * 2 * N * sizeof(double2), c->stream>>>(Wh, spec, qhat + (size_t)nsplit * c->n3);
+  const double2* xB = NP > 1 ? pr[1].xi_side : nullptr;
+  const double2* dB = NP > 1 ? pr[1].dif_side : nullptr;
+  double2* left = qhat + (size_t)nsplit * c->n3;
+  kern<<<N * N * nsplit, C::THREADS, C::SMEM, c->stream>>>(Wh, pr[0].xi_side, pr[0].dif_side, xB, dB, qhat, nsplit);
+  if (Wl) qhat_half_leftover_kernel<N, true, NP><<<N * N, 256, 8 * 2 * N * sizeof(double2), c->stream>>>(Wl, pr[0].xi_side, pr[0].dif_side, xB, dB, left);
+  else qhat_half_leftover_kernel<N, false, NP><<<N * N, 256, 8 * 2 * N * sizeof(double2), c->stream>>>(Wh, pr[0].xi_side, pr[0].dif_side, xB, dB, left);
   k2_mark(c);
   c->launches += 2;
 }
 
-// spec: parity-split spectrum of f; qhat: nsplit + 1 partial spectra of n3 elements each (the last one = leftovers)
-void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double* Wl, const double2* spec, double2* qhat, int nsplit) {
-  switch (c->N) {
-    case 16: launch_half_n<16>(c, Wh, Wl, spec, qhat, nsplit); break;
-    case 32: launch_half_n<32>(c, Wh, Wl, spec, qhat, nsplit); break;
-    default: set_error("qhat_stream_half: unsupported N"); break;
+// pairs: parity-split operand spectra (one pair: ComputeQ(f, f); two: ComputeQ_maxPreserve); qhat: nsplit + 1 partial
+// spectra of n3 elements each (the last one = leftovers)
+void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double* Wl, int npairs, const QhatPair* pairs, double2* qhat,
+                             int nsplit) {
+  const int key = c->N * 10 + npairs;
+  switch (key) {
+    case 161: launch_half_n<16, 1>(c, Wh, Wl, pairs, qhat, nsplit); break;
+    case 162: launch_half_n<16, 2>(c, Wh, Wl, pairs, qhat, nsplit); break;
+    case 321: launch_half_n<32, 1>(c, Wh, Wl, pairs, qhat, nsplit); break;
+    case 322: launch_half_n<32, 2>(c, Wh, Wl, pairs, qhat, nsplit); break;
+    default: set_error("qhat_stream_half: unsupported N / number of operand pairs"); break;
   }
 }
 #endif

@@ -123,31 +123,37 @@ int emul_batched(int kind, int N, int cells, int sym, int P, const long long* ct
   return 0;
 }
 
-// 0D half-spectrum path (qhat_half.cu): Wh = folded tensor (mirror rule, symmetrised), spec = parity-split spectrum of one
-// cell, qhat = (nsplit + 1) partial spectra of n3 complex each
-int emul_half0d(int N, int nsplit, int packed, const double* Wh, const double* spec, double* qhat) {
+// 0D half-spectrum path (qhat_half.cu): Wh = folded tensor (mirror rule, symmetrised); xiA/dfA (and xiB/dfB when npairs = 2:
+// ComputeQ_maxPreserve) = parity-split operand spectra of one cell; qhat = (nsplit + 1) partial spectra of n3 complex each
+int emul_half0d(int N, int nsplit, int packed, int npairs, const double* Wh, const double* xiA, const double* dfA, const double* xiB,
+                const double* dfB, double* qhat) {
   const size_t n3 = (size_t)N * N * N;
-  auto run = [&](auto tag) {
-    constexpr int M = decltype(tag)::value;
-    using C = HalfCfg<M>;
+  const double2 *xa = (const double2*)xiA, *da = (const double2*)dfA, *xb = (const double2*)xiB, *db = (const double2*)dfB;
+  auto run = [&](auto ntag, auto ptag) {
+    constexpr int M = decltype(ntag)::value, NP = decltype(ptag)::value;
+    using C = HalfCfg<M, 8 * NP>;
     for (int b = 0; b < M * M * nsplit; b++)
       emul::run_cta(b, M * M * nsplit, C::THREADS, C::SMEM,
-                    [&](int) { qhat_stream_half_kernel<M>(Wh, (const double2*)spec, (double2*)qhat, nsplit); });
+                    [&](int) { qhat_stream_half_kernel<M, NP>(Wh, xa, da, xb, db, (double2*)qhat, nsplit); });
     std::vector<double> Wl;
     if (packed) {   // compact leftover tensor, poisoned first: every entry the leftover kernel reads must have been packed
       Wl.assign((size_t)M * M * half_kmax(M) * 3 * M, NAN);
       for (int b = 0; b < M * M; b++)
         emul::run_cta(b, M * M, 256, 64, [&](int) { half_pack_leftover_kernel<M>(Wh, Wl.data()); });
     }
+    double2* left = (double2*)qhat + (size_t)nsplit * n3;
     for (int b = 0; b < M * M; b++)
       emul::run_cta(b, M * M, 256, 8 * 2 * M * sizeof(double2), [&](int) {
-        if (packed) qhat_half_leftover_kernel<M, true>(Wl.data(), (const double2*)spec, (double2*)qhat + (size_t)nsplit * n3);
-        else qhat_half_leftover_kernel<M, false>(Wh, (const double2*)spec, (double2*)qhat + (size_t)nsplit * n3);
+        if (packed) qhat_half_leftover_kernel<M, true, NP>(Wl.data(), xa, da, xb, db, left);
+        else qhat_half_leftover_kernel<M, false, NP>(Wh, xa, da, xb, db, left);
       });
   };
-  if (N == 16) run(std::integral_constant<int, 16>());
-  else if (N == 32) run(std::integral_constant<int, 32>());
-  else return 1;
+  using I16 = std::integral_constant<int, 16>;
+  using I1 = std::integral_constant<int, 1>;
+  using I2 = std::integral_constant<int, 2>;
+  if (N == 16 && npairs == 1) run(I16(), I1());
+  else if (N == 16 && npairs == 2) run(I16(), I2());
+  else return 1;   // N = 32 is the same template; its tensors do not fit a CPU test
   return 0;
 }
 

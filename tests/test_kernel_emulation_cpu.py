@@ -139,14 +139,15 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
 
 
 @pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
-@pytest.mark.parametrize("N,nsplit,packed", [(16, 2, 1)])   # (16, 1, 0) -- leftovers gathered from the folded tensor -- passes too
-def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit, packed):
+@pytest.mark.parametrize("N,nsplit,packed,npairs", [(16, 2, 1, 1), (16, 1, 1, 2)])   # (16, 1, 0, 1) -- leftovers gathered -- passes too
+def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit, packed, npairs):
     """qhat_stream_half_kernel + qhat_half_leftover_kernel (csrc/qhat_half.cu, opt-in SBTE_HALF0D=1): the 0D stream kernel on the
-    folded tensor, mirror columns skipping the folded steps, leftovers added by the second kernel.  The sum of the partial
-    spectra is not the reference's Q^, but Re(fft3D^-1(.)) must be the oracle's Q (src/collisions.c:212-221)."""
+    folded tensor, mirror columns skipping the folded steps, leftovers added by the second kernel -- for ComputeQ(f, f) (one
+    operand pair) and ComputeQ_maxPreserve (two pairs sharing the weight pass, src/collisions.c:178-210).  The sum of the
+    partial spectra is not the reference's Q^, but Re(fft3D^-1(.)) must be the oracle's Q (src/collisions.c:212-221)."""
     L = _lib()
     dp = C.POINTER(C.c_double)
-    L.emul_half0d.argtypes = [C.c_int, C.c_int, C.c_int, dp, dp, dp]
+    L.emul_half0d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
     o = orc.Oracle(N, 5.0, 0)
     n3 = N ** 3
     W = orc.synthetic_weights(N)
@@ -154,18 +155,30 @@ def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit, packed):
     R = _mirror_rule_lib()
     assert R.mirror_emul_fold(N, W.ctypes.data_as(dp), 1, Wh.ctypes.data_as(dp)) == 0
     f = seeded_f(o.v, 41, noise=0.3)
-    F = o.fft3d(f.astype(complex)).reshape(N, N, N)
-    # parity-split lines [x][y][z & 1][z >> 1] (LAY_PARITY, csrc/internal.h)
     z = np.arange(N)
-    spec = np.empty((N, N, N), dtype=complex)
-    spec[:, :, (z & 1) * (N // 2) + (z >> 1)] = F
-    spec = np.ascontiguousarray(spec)
+
+    def parity(x):   # spectrum of a real field in parity-split lines [x][y][z & 1][z >> 1] (LAY_PARITY, csrc/internal.h)
+        F = o.fft3d(np.asarray(x).astype(complex)).reshape(N, N, N)
+        out = np.empty((N, N, N), dtype=complex)
+        out[:, :, (z & 1) * (N // 2) + (z >> 1)] = F
+        return np.ascontiguousarray(out)
+
+    if npairs == 1:
+        xiA = dfA = parity(f)
+        xiB = dfB = xiA
+        want = o.compute_q(W, f, f)
+    else:                       # one species: M_i = M_j = M, g_i = g_j = f - M  (csrc/capi.cu: compute_q_maxpreserve_dev)
+        M, _ = o.find_maxwellian(f)
+        g = f - M
+        xiA, dfA = parity(g), parity(f)      # g_j^[xi] f^[zeta - xi]
+        xiB, dfB = parity(M), parity(g)      # M_j^[xi] g_i^[zeta - xi]
+        want = o.compute_q_maxpreserve(W, f, f)
     parts = np.full((nsplit + 1) * n3, np.nan + 1j * np.nan, dtype=complex)
     out = str(tmp_path / "parts.npy")
+    pd = lambda a: a.view(np.float64).ctypes.data_as(dp)  # noqa: E731
 
     def child():
-        rc = L.emul_half0d(N, nsplit, packed, Wh.ctypes.data_as(dp), spec.view(np.float64).ctypes.data_as(dp),
-                           parts.view(np.float64).ctypes.data_as(dp))
+        rc = L.emul_half0d(N, nsplit, packed, npairs, Wh.ctypes.data_as(dp), pd(xiA), pd(dfA), pd(xiB), pd(dfB), pd(parts))
         if rc == 0:
             np.save(out, parts)
         os._exit(rc)
@@ -177,6 +190,4 @@ def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit, packed):
     parts = np.load(out).reshape(nsplit + 1, n3)
     assert not np.isnan(parts.view(np.float64)).any()
     S = parts.sum(axis=0)
-    assert relmax(np.real(o.fft3d(S, invert=True)), o.compute_q(W, f, f)) < 1e-12
-    # the mirror columns really skipped most of their steps: their main-kernel rows are much smaller than the A rows'
-    assert relmax(S, o.qhat(W, F.reshape(-1), F.reshape(-1))) > 1e-6
+    assert relmax(np.real(o.fft3d(S, invert=True)), want) < 1e-12
