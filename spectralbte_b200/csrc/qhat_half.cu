@@ -12,7 +12,7 @@
 // the few entries it needs.  Weight bytes per evaluation: about 0.5 + 0.5 * 0.12 of the symmetrised stream, plus the sectors
 // the leftover entries touch.
 // Numerical margin: the reference's spectrum is Hermitian only to round-off (3e-13 of max|f^| at N = 32: its twiddle
-// arguments carry the rounding of pi), so this path agrees with the reference's Q to ~1e-13 (N = 16) ... 6e-13 (N = 32)
+// arguments carry the rounding of pi), so this path agrees with the reference's Q to ~3e-14 (N = 16) ... 6e-13 (N = 32, random weights)
 // instead of the 1e-14 of qhat_stream_kernel; the tolerance is 1e-12.
 // STATUS: runs on the host through tests/emul (tests/test_kernel_emulation_cpu.py: Q to 1e-12); not yet run on a GPU, off by
 // default.  The result is NOT the reference's Q^ -- only its real inverse transform is the same -- so this path serves
