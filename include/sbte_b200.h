@@ -123,10 +123,10 @@ SBTE_API int sbte_set_symmetrize(sbte_ctx *c, int enable);
 
 /* The stream-K schedule of the batched convolution for `cells` cells on a device with `ctas` SMs (what the
  * library uploads before a batched ComputeQ; exec/boltz.c:285-345 has no counterpart -- its cells are a plain loop).
- * Pure host arithmetic, no device needed.  mirror != 0: layout of the opt-in mirror-paired kernel (N = 8, 16).
+ * Pure host arithmetic, no device needed.
  * dims = {G, T, P, np_cols, kmax, np_len}; array pointers may be null:
  * query dims first, then pass arrays of P+1, T+1, P, T and np_len entries.  Fails for N without a scheduled kernel. */
-SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int mirror, long long *cta_begin, long long *tile_begin,
+SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long *cta_begin, long long *tile_begin,
                                       int *cta_tile, int *tile_first, unsigned char *np, int *dims);
 
 /* kernel selection for the convolution */
@@ -159,6 +159,9 @@ SBTE_API int sbte_compute_q_maxpreserve_host(sbte_ctx *c, const double *f, const
 SBTE_API int sbte_slab_create(sbte_ctx *c, sbte_slab **out, int cells_local, int order, const double *x, const double *dx,
                      int init_field, double dt, int rank, int nranks);
 SBTE_API int sbte_slab_destroy(sbte_slab *s);
+/* TWall_in of initialize_transport (src/transportroutines.c:57; default 1 = src/initializer.c:275): Init_field 1's
+ * left wall is a diffuse wall at 2 * TWall_in */
+SBTE_API int sbte_slab_set_twall_in(sbte_slab *s, double TWall_in);
 SBTE_API double *sbte_slab_f(sbte_slab *s);        /* device pointer of the f slab   (exec/boltz.c f_inhom) */
 SBTE_API double *sbte_slab_fconv(sbte_slab *s);    /* device pointer of f_conv */
 SBTE_API int sbte_slab_upload(sbte_slab *s, const double *f_host);      /* (cells_local + 2*order) x N^3 */
@@ -183,8 +186,12 @@ SBTE_API int sbte_slab_ipc_import(sbte_slab *s, int side, const unsigned char *h
 /* same-process form: `other` is a slab of another context (another stream or GPU with peer access enabled) */
 SBTE_API int sbte_slab_peer_attach(sbte_slab *s, int side, sbte_slab *other);
 SBTE_API int sbte_slab_set_peer_halo(sbte_slab *s, int enable);
-/* diagnostic: this rank's {ready, done, epoch} pass counters */
-SBTE_API int sbte_slab_halo_state(sbte_slab *s, int *state3);
+/* this rank's {ready, done, epoch, error} words.  error != 0: a device-side wait for a neighbour ran out of time
+ * (the waiting kernels do not trap: they raise this word, stop waiting, and sbte_slab_moments / sbte_slab_download
+ * then fail with a message). */
+SBTE_API int sbte_slab_halo_state(sbte_slab *s, int *state4);
+/* bound of those waits in seconds (default 120, or SBTE_HALO_TIMEOUT_S); <= 0: wait for ever */
+SBTE_API int sbte_slab_set_halo_timeout(sbte_slab *s, double seconds);
 /* collision half: per-cell ComputeQ + conserve + Euler / Heun (exec/boltz.c:285-345) */
 SBTE_API int sbte_slab_collide(sbte_slab *s, double Kn, int k2);
 /* whole single-rank step (exec/boltz.c:264-353) */

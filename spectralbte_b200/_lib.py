@@ -36,7 +36,7 @@ PROTOTYPES = {
     "sbte_launch_count": (C.c_ulonglong, [_vp]),
     "sbte_reserve": (C.c_int, [_vp, C.c_int]),
     "sbte_set_symmetrize": (C.c_int, [_vp, C.c_int]),
-    "sbte_batch_schedule_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+    "sbte_batch_schedule_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_ubyte), C.POINTER(C.c_int)]),
     "sbte_k2_profile": (C.c_int, [_vp, C.c_int]),
     "sbte_k2_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),
@@ -65,6 +65,7 @@ PROTOTYPES = {
     "sbte_compute_q_maxpreserve_host": (C.c_int, [_vp, _dp, _dp, _dp, C.c_int]),
     "sbte_slab_create": (C.c_int, [_vp, C.POINTER(_vp), C.c_int, C.c_int, _dp, _dp, C.c_int, C.c_double, C.c_int, C.c_int]),
     "sbte_slab_destroy": (C.c_int, [_vp]),
+    "sbte_slab_set_twall_in": (C.c_int, [_vp, C.c_double]),
     "sbte_slab_f": (_vp, [_vp]),
     "sbte_slab_fconv": (_vp, [_vp]),
     "sbte_slab_upload": (C.c_int, [_vp, _dp]),
@@ -77,6 +78,7 @@ PROTOTYPES = {
     "sbte_slab_ipc_import": (C.c_int, [_vp, C.c_int, C.c_char_p, C.c_int]),
     "sbte_slab_peer_attach": (C.c_int, [_vp, C.c_int, _vp]),
     "sbte_slab_halo_state": (C.c_int, [_vp, C.POINTER(C.c_int)]),
+    "sbte_slab_set_halo_timeout": (C.c_int, [_vp, C.c_double]),
     "sbte_slab_set_peer_halo": (C.c_int, [_vp, C.c_int]),
     "sbte_slab_collide": (C.c_int, [_vp, C.c_double, C.c_int]),
     "sbte_slab_step": (C.c_int, [_vp, C.c_double, C.c_int]),

@@ -306,10 +306,14 @@ class Slab:
         check(self.L.sbte_slab_peer_attach(self.h, int(side), other.h))
 
     def halo_state(self):
-        """(ready, done, epoch) pass counters of the peer-memory halo."""
-        st = (C.c_int * 3)()
+        """(ready, done, epoch, error) words of the peer-memory halo; error != 0: a wait for a neighbour timed out."""
+        st = (C.c_int * 4)()
         check(self.L.sbte_slab_halo_state(self.h, st))
         return tuple(st)
+
+    def set_halo_timeout(self, seconds):
+        """Bound of the device-side waits for a neighbouring rank (<= 0: wait for ever)."""
+        check(self.L.sbte_slab_set_halo_timeout(self.h, float(seconds)))
 
     def set_peer_halo(self, enable=True):
         check(self.L.sbte_slab_set_peer_halo(self.h, int(bool(enable))))

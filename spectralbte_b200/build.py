@@ -21,7 +21,7 @@ COMMON = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "-Xcompiler",
 # elementwise / reduction kernels keep the reference's operation-by-operation rounding (no FMA
 # contraction); the FP64-bound convolution and the DFTs use FMAs.
 PER_FILE = {"transport.cu": ["-fmad=false"], "conserve.cu": ["-fmad=false"], "weightgen.cu": ["-fmad=false"]}
-SOURCES = ["capi.cu", "dropin.cu", "slab.cu", "fft.cu", "qhat.cu", "qhat_batch.cu", "qhat_mirror.cu", "qhat_half.cu", "conserve.cu", "transport.cu", "weightgen.cu"]
+SOURCES = ["capi.cu", "dropin.cu", "slab.cu", "fft.cu", "qhat.cu", "qhat_batch.cu", "conserve.cu", "transport.cu", "weightgen.cu"]
 
 
 def _nvcc():

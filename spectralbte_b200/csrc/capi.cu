@@ -11,7 +11,6 @@
 #include "../../include/sbte_b200.h"
 #include "common.cuh"
 #include "internal.h"
-#include "mirror.cuh"
 
 namespace sbte {
 
@@ -155,7 +154,7 @@ static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out, int
   CK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres));
   if (!fn || qres != cudaDriverEntryPointSuccess) { set_error("cuTensorMapEncodeTiled not available"); return 1; }
   const int N = c->N;
-  const int cols_per_cta = box_columns > 0 ? box_columns : ((N >= 16) ? 8 : 4);  // BatchCfg<N>::COLS, or 1 (mirror kernel)
+  const int cols_per_cta = box_columns > 0 ? box_columns : ((N >= 16) ? 8 : 4);  // Batch2Cfg<N>::COLS unless given
   cuuint64_t gdim[2] = {(cuuint64_t)c->n3, (cuuint64_t)c->n3};
   cuuint64_t gstride[1] = {(cuuint64_t)c->n3 * sizeof(double)};
   cuuint32_t box[2] = {(cuuint32_t)N, (cuuint32_t)(cols_per_cta * N)};
@@ -169,39 +168,17 @@ static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out, int
 
 static int make_tensor_map(sbte_ctx* c) {
   c->tmap_ok = false;
-  c->mirror_ok = false;
-  if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copies
-  if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
-  if (c->d_Wh) { cudaFree(c->d_Wh); c->d_Wh = nullptr; c->wh_sym = -1; }
-  if (c->d_Wleft) { cudaFree(c->d_Wleft); c->d_Wleft = nullptr; }
+  if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copy
   c->sched_cells = 0;
-  // the mirror identities need the reference's own grids (src/initializer.c:66-82): v_j = -L_v + j dv, eta_{N/2} = 0 and
-  // dv * deta = 2 pi / N, i.e. L_eta * dv = pi; any other grid keeps the ordinary kernels
-  c->grid_mirror_ok = fabs(c->v[0] + c->L_v) <= 1e-12 * c->L_v && fabs(c->L_eta * c->dv - M_PI) <= 1e-12 * M_PI &&
-                      fabs(c->dv * c->deta * c->N - 2.0 * M_PI) <= 1e-12 * 2.0 * M_PI;
   if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
   if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
   c->tmap_ok = true;
-  if (qhat_mirror_enabled(c->N) && c->grid_mirror_ok) {
-    if (encode_weight_map(c, c->d_W, &c->tmapM, 1)) return 1;
-    if (!c->d_mtiles) {
-      const std::vector<MirrorTile> mt = build_mirror_tiles(c->N, qhat_mirror_pairs(c->N));
-      CK(cudaMalloc(&c->d_mtiles, mt.size() * sizeof(MirrorTile)));
-      CK(cudaMemcpy(c->d_mtiles, mt.data(), mt.size() * sizeof(MirrorTile), cudaMemcpyHostToDevice));
-      c->n_mtiles = (int)mt.size();
-    }
-    c->mirror_ok = true;
-  }
   return 0;
 }
 
 static int release_weights(sbte_ctx* c) {
   invalidate_graphs(c);
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }
-  if (c->d_Ws2) { cudaFree(c->d_Ws2); c->d_Ws2 = nullptr; }
-  if (c->d_Wh) { cudaFree(c->d_Wh); c->d_Wh = nullptr; c->wh_sym = -1; }
-  if (c->d_Wleft) { cudaFree(c->d_Wleft); c->d_Wleft = nullptr; }
-  c->mirror_ok = false;
   if (c->owns_W && c->d_W) cudaFree((void*)c->d_W);
   c->d_W = nullptr; c->owns_W = false; c->host_key = nullptr; c->tmap_ok = false;
   return 0;
@@ -236,19 +213,17 @@ struct HostSchedule {
 };
 
 // Pure host arithmetic (no CUDA call): also exported as sbte_batch_schedule_host for the CPU tests.
-// `mirror` != null: the row-blocks are the column-pair tiles of the mirror kernel (mirror.cuh) instead.
-static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out,
-                                 const std::vector<MirrorTile>* mirror = nullptr) {
+static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out) {
   const int cols = qhat_batch_cols(N);
   // row-blocks never straddle a zeta_x plane: bpx blocks of `cols` zeta_y columns per plane, the last one
   // partly empty when cols does not divide N (N = 20, 22)
   const int bpx = (N + cols - 1) / cols;
-  const int G = (cells + 31) / 32, RB = mirror ? (int)mirror->size() : N * bpx, T = G * RB;
+  const int G = (cells + 31) / 32, RB = N * bpx, T = G * RB;
   // tile t = (row-block rb = t / G, cell group cg = t % G); its length is (visited xi_x planes) * N steps
   std::vector<long long>& tbegin = out->tbegin;
   tbegin.assign(T + 1, 0);
   for (int t = 0; t < T; t++) {
-    const int zx = mirror ? (*mirror)[t / G].zx : (t / G) / bpx;
+    const int zx = (t / G) / bpx;
     tbegin[t + 1] = tbegin[t] + (long long)(sym ? sym_nrep(N, zx) : N) * N;
   }
   const long long total = tbegin[T];
@@ -257,7 +232,7 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
   std::vector<long long>& begin = out->begin;
   begin.assign(P + 1, 0);
-  const long long align = mirror ? qhat_mirror_align(N) : qhat_batch_align(N);   // the line-ring kernels work on whole xi_x chunks
+  const long long align = qhat_batch_align(N);   // the line-ring kernels work on whole xi_x chunks
   for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * (total / align)) / P) * align;
   auto owner = [&](long long g) {   // last CTA whose range starts at or before g
     int lo = 0, hi = P - 1;
@@ -285,20 +260,10 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   for (int p = 0; p < P; p++) ctile[p] = tile_of(std::min(begin[p], total - 1));
   // the inverse transform looks the part count up as np[(column / np_cols) * G + cell group]; with partly
   // empty row-blocks that table is kept per zeta column
-  const bool per_column = mirror != nullptr || (N % cols) != 0;
+  const bool per_column = (N % cols) != 0;
   if (per_column) {
     std::vector<int> col_rb((size_t)N * N, 0);   // row-block that writes zeta column q
-    if (mirror) {
-      for (int rb = 0; rb < RB; rb++) {
-        const MirrorTile& mt = (*mirror)[rb];
-        for (int p = 0; p < 4; p++) {
-          if (mt.zyA[p] >= 0) col_rb[(size_t)mt.zx * N + mt.zyA[p]] = rb;
-          if (mt.zyB[p] >= 0) col_rb[(size_t)mirror_nu(mt.zx, N) * N + mt.zyB[p]] = rb;
-        }
-      }
-    } else {
-      for (int q = 0; q < N * N; q++) col_rb[q] = (q / N) * bpx + (q % N) / cols;
-    }
+    for (int q = 0; q < N * N; q++) col_rb[q] = (q / N) * bpx + (q % N) / cols;
     std::vector<unsigned char> npc((size_t)N * N * G);
     for (int q = 0; q < N * N; q++)
       for (int g = 0; g < G; g++) npc[(size_t)q * G + g] = np[(size_t)col_rb[q] * G + g];
@@ -317,12 +282,7 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   const char* pe = getenv("SBTE_BATCH_CTAS");
   if (pe && atoi(pe) > 0) ctas = atoi(pe);
   HostSchedule h;
-  if (c->mirror_ok) {
-    const std::vector<MirrorTile> mt = build_mirror_tiles(c->N, qhat_mirror_pairs(c->N));
-    build_batch_schedule(c->N, cells, sym, ctas, &h, &mt);
-  } else {
-    build_batch_schedule(c->N, cells, sym, ctas, &h);
-  }
+  build_batch_schedule(c->N, cells, sym, ctas, &h);
   const int G = h.G, T = h.T, P = h.P, kmax = h.kmax;
   const size_t o1 = (size_t)(P + 1) * sizeof(long long);
   const size_t o2 = o1 + (size_t)(T + 1) * sizeof(long long);
@@ -355,55 +315,12 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
 }
 
 // Symmetrised weights for f == g (see common.cuh): built lazily, once per bound tensor.
-static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out, int box_columns);
-static int ensure_sym_mirror(sbte_ctx* c) {
-  if (c->d_Ws2) return 0;
-  c->graph_gen++;
-  CK(cudaMalloc(&c->d_Ws2, (size_t)c->n3 * c->n3 * sizeof(double)));
-  launch_symmetrize_weights_mirror(c, c->d_W, c->d_Ws2);
-  return encode_weight_map(c, c->d_Ws2, &c->tmapMs, 1);
-}
-// folded tensor of the mirror kernels for the current symmetrisation setting (on the way to Q only)
-static int ensure_fold_mirror(sbte_ctx* c, bool sym) {
-  if (c->d_Wh && c->wh_sym == (int)sym) return 0;
-  c->graph_gen++;
-  if (!c->d_Wh) CK(cudaMalloc(&c->d_Wh, (size_t)c->n3 * c->n3 * sizeof(double)));
-  launch_fold_weights_mirror(c, c->d_W, c->d_Wh, sym);
-  c->wh_sym = (int)sym;
-  if (c->d_Wleft) { cudaFree(c->d_Wleft); c->d_Wleft = nullptr; }   // packed from the previous folded tensor
-  return encode_weight_map(c, c->d_Wh, &c->tmapMh, 1);
-}
-// tensors of the 0D half-spectrum path (qhat_half.cu): the folded symmetrised tensor and, unless SBTE_HALF0D_NOPACK is
-// set (the leftover kernel then gathers from the folded tensor), the compact leftover tensor packed from it
-static int ensure_half0d_tensors(sbte_ctx* c) {
-  if (ensure_fold_mirror(c, true)) return 1;
-  static const bool no_pack = getenv("SBTE_HALF0D_NOPACK") != nullptr;
-  if (!no_pack && !c->d_Wleft) {
-    CK(cudaMalloc(&c->d_Wleft, qhat_half_leftover_doubles(c->N) * sizeof(double)));
-    launch_half_pack_leftover(c, c->d_Wh, c->d_Wleft);
-  }
-  return 0;
-}
 static int ensure_sym(sbte_ctx* c) {
   if (c->d_Ws) return 0;
   c->graph_gen++;
   CK(cudaMalloc(&c->d_Ws, (size_t)c->n3 * c->n3 * sizeof(double)));
   launch_symmetrize_weights(c, c->d_W, c->d_Ws);
   if (qhat_batch_supported(c->N)) return encode_weight_map(c, c->d_Ws, &c->tmapWs, 0);
-  return 0;
-}
-// the batched convolution and the symmetrised tensor of whichever batched kernel is active for this N
-static int ensure_sym_batched(sbte_ctx* c) { return c->mirror_ok ? ensure_sym_mirror(c) : ensure_sym(c); }
-// to_q: the spectrum only feeds Re(fft3D^-1(.)) -- the mirror kernels may then stream the folded tensor
-static int launch_batched_conv(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
-                               const BatchSched& sch, bool to_q) {
-  if (c->mirror_ok) {
-    const bool fold = to_q && qhat_mirror_fold_enabled(c->N);
-    if (fold && ensure_fold_mirror(c, sch.sym != 0)) return 1;
-    launch_qhat_mirror(c, spec, parts, part_stride, cells, sch, fold);
-  } else {
-    launch_qhat_batch2(c, spec, parts, part_stride, cells, sch);
-  }
   return 0;
 }
 static bool want_sym(sbte_ctx* c, bool same) {
@@ -448,10 +365,10 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
   if (k2 == SBTE_K2_BATCH) {
     if (!same) { set_error("batched convolution requires f == g (single species)"); return 1; }
     const bool sym = want_sym(c, true);
-    if (sym && ensure_sym_batched(c)) return 1;
+    if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    if (launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched, false)) return 1;
+    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
     launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
   } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
     if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
@@ -487,27 +404,14 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
 
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2) {
   if (ensure_capacity(c, batch)) return 1;  // before c->d_qhat is read: growth reallocates the scratch
-  if (batch == 1 && d_f == d_g && qhat_half0d_enabled(c->N) && c->grid_mirror_ok && want_sym(c, true) &&
-      resolve_k2(c, 1, k2) == SBTE_K2_STREAM && fft_cluster_supported(c->N)) {
-    // opt-in: half of the zeta rows (qhat_half.cu).  The partial spectra do not add up to the reference's Q^, only to a
-    // spectrum with the same real inverse transform -- which is all ComputeQ returns (src/collisions.c:212-221)
-    if (!c->d_W) { set_error("no weights bound"); return 1; }
-    if (ensure_half0d_tensors(c)) return 1;
-    launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
-    const int ns = (c->N == 32) ? 2 : 1;   // as the full stream kernel: two CTAs per column shorten the tail at N = 32
-    const QhatPair pr = {c->d_lay[0], c->d_lay[0]};
-    launch_qhat_stream_half(c, c->d_Wh, c->d_Wleft, 1, &pr, c->d_qhat, ns);
-    if (!launch_fft3d_inverse_sum(c, c->d_qhat, ns + 1, d_Q)) { set_error("half-spectrum path: no summing inverse transform for this N"); return 1; }
-    return check_launch("half-spectrum compute_q");
-  }
   if (resolve_k2(c, batch, k2) == SBTE_K2_BATCH && d_f == d_g && qhat_batch_supported(c->N)) {
     // fast path: forward transform -> stream-K convolution -> inverse transform summing the partial sums
     if (!c->d_W) { set_error("no weights bound"); return 1; }
     const bool sym = want_sym(c, true);
-    if (sym && ensure_sym_batched(c)) return 1;
+    if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    if (launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched, true)) return 1;
+    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
     launch_fft3d_parts(c, c->d_parts, c->parts_stride, c->sched, 1, batch, nullptr, d_Q);
     return check_launch("batched compute_q");
   }
@@ -529,10 +433,10 @@ int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, 
     if (ensure_capacity(c, batch)) return 1;
     if (!c->d_W) { set_error("no weights bound"); return 1; }
     const bool sym = want_sym(c, true);
-    if (sym && ensure_sym_batched(c)) return 1;
+    if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_src, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    if (launch_batched_conv(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched, true)) return 1;
+    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
     CellEpi epi = {};
     epi.mode = 1; epi.v = c->d_v; epi.wt = c->d_wt; epi.dv3 = c->dv * c->dv * c->dv; epi.lu = c->lu;
     epi.a = a; epi.x = x; epi.b = b; epi.y = y; epi.s = s; epi.Kn = Kn; epi.out = out;
@@ -569,13 +473,6 @@ int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g,
   }
   const double2* gjhat = same ? c->d_lay[1] : c->d_specB;
   QhatPair pairs[2] = {{gjhat, c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]}};
-  if (stream && same && qhat_half0d_enabled(c->N) && c->grid_mirror_ok && want_sym(c, true) && fft_cluster_supported(c->N)) {
-    // opt-in: half of the zeta rows (qhat_half.cu); the summed product of the two pairs obeys the same mirror relation
-    if (ensure_half0d_tensors(c)) return 1;
-    launch_qhat_stream_half(c, c->d_Wh, c->d_Wleft, 2, pairs, c->d_qhat, 1);
-    if (!launch_fft3d_inverse_sum(c, c->d_qhat, 2, d_Q)) { set_error("half-spectrum path: no summing inverse transform for this N"); return 1; }
-    return check_launch("half-spectrum maxpreserve");
-  }
   const bool sym = stream && want_sym(c, same);   // for f == g the three-product summand is symmetric as a whole
   if (sym && ensure_sym(c)) return 1;
   // splitting the columns between CTAs (as the one-pair kernel does at N = 32) does not pay here: N = 32 already runs
@@ -667,31 +564,20 @@ int sbte_destroy(sbte_ctx* c) {
   for (cudaEvent_t e : c->k2_ev) cudaEventDestroy(e);
   if (c->d_sched_mem) cudaFree(c->d_sched_mem);
   if (c->d_parts) cudaFree(c->d_parts);
-  if (c->d_mtiles) cudaFree(c->d_mtiles);
   cudaStreamDestroy(c->stream);
   delete c;
   return 0;
 }
 
 // The stream-K schedule ensure_batch_schedule() would upload for (N, cells, sym) on a device with `ctas` SMs.
-// Pure host arithmetic: works without a GPU (CPU tests, sizing).  mirror != 0: the layout of the mirror-paired
-// kernel (column-pair tiles, mirror.cuh).  dims = {G, T, P, np_cols, kmax, np_len};
+// Pure host arithmetic: works without a GPU (CPU tests, sizing).  dims = {G, T, P, np_cols, kmax, np_len};
 // any array pointer may be null (query dims first, then call again with arrays of P+1, T+1, P, T, np_len entries).
-int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int mirror, long long* cta_begin, long long* tile_begin,
+int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long* cta_begin, long long* tile_begin,
                              int* cta_tile, int* tile_first, unsigned char* np, int* dims) {
   if (N < 2 || N > 32 || (N % 2) != 0 || cells < 1 || ctas < 1) { set_error("batch schedule: bad arguments"); return 1; }
   if (!qhat_batch_supported(N)) { set_error("batch schedule: this N runs the any-N kernel (no schedule)"); return 1; }
-  if (mirror && N != 8 && N != 16 && N != 20 && N != 22 && N != 24) {
-    set_error("batch schedule: the mirror-paired kernels exist for N = 8, 16, 20, 22, 24");
-    return 1;
-  }
   HostSchedule h;
-  if (mirror) {
-    const std::vector<MirrorTile> mt = build_mirror_tiles(N, qhat_mirror_pairs(N));
-    build_batch_schedule(N, cells, sym != 0, ctas, &h, &mt);
-  } else {
-    build_batch_schedule(N, cells, sym != 0, ctas, &h);
-  }
+  build_batch_schedule(N, cells, sym != 0, ctas, &h);
   if (dims) { dims[0] = h.G; dims[1] = h.T; dims[2] = h.P; dims[3] = h.np_cols; dims[4] = h.kmax; dims[5] = (int)h.np.size(); }
   if (cta_begin) memcpy(cta_begin, h.begin.data(), h.begin.size() * sizeof(long long));
   if (tile_begin) memcpy(tile_begin, h.tbegin.data(), h.tbegin.size() * sizeof(long long));

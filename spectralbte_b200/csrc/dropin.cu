@@ -21,7 +21,7 @@ bool g_cons_ready = false;
 struct TransportState {
   bool ready = false;
   int N = 0, nX = 0, ic = 0;
-  double dt = 0;
+  double dt = 0, TWall_in = 1.0;
   std::vector<double> x, dx;       // as handed to initialize_transport (length unknown: kept as pointers too)
   const double* xp = nullptr;
   const double* dxp = nullptr;
@@ -56,9 +56,32 @@ void need_ctx(const char* who) {
   }
 }
 
+// The device copy is keyed on the identity of the caller's row-pointer array AND on a fingerprint of sampled
+// entries (64 rows x 16 entries, a few microseconds): weights regenerated in place, or freed and reallocated at the
+// same address, are uploaded again instead of silently streaming the stale copy (the reference reads the host rows
+// on every call, src/collisions.c:146).
+unsigned long long g_wfp = 0;
+unsigned long long weight_fingerprint(double** rows) {
+  const long n3 = g_ctx->n3;
+  unsigned long long h = 0x9E3779B97F4A7C15ull;
+  for (int r = 0; r < 64; r++) {
+    const long i = (n3 - 1) * r / 63;
+    const double* row = rows[i];
+    h ^= (unsigned long long)(size_t)row + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    for (int e = 0; e < 16; e++) {
+      unsigned long long bits;
+      memcpy(&bits, &row[(n3 - 1) * e / 15], sizeof bits);
+      h ^= bits + 0x9E3779B97F4A7C15ull + (h << 6) + (h >> 2);
+    }
+  }
+  return h;
+}
+
 void sync_weights(double** conv_weights) {
-  if (g_ctx->host_key != (const void*)conv_weights || !g_ctx->d_W) {
+  const unsigned long long fp = weight_fingerprint(conv_weights);
+  if (g_ctx->host_key != (const void*)conv_weights || !g_ctx->d_W || fp != g_wfp) {
     if (sbte_weights_upload_rows(g_ctx, conv_weights)) die("weight upload");
+    g_wfp = fp;
   }
 }
 
@@ -72,6 +95,7 @@ sbte_slab* slab_for(int order) {
     // the caller's x/dx arrays have nX + 2*order entries (src/mesh_setup.c:78-79)
     if (sbte_slab_create(g_ctx, &g_tr.slab, g_tr.nX, order, g_tr.xp, g_tr.dxp, g_tr.ic, g_tr.dt, 0, 1))
       die("slab creation");
+    if (sbte_slab_set_twall_in(g_tr.slab, g_tr.TWall_in)) die("slab wall temperature");
     g_tr.slab_order = order;
   }
   return g_tr.slab;
@@ -169,7 +193,23 @@ void dealloc_conservation(void) { g_cons_ready = false; }
 
 void initialize_transport(int numV, int numX, double lv, double* xnodes, double* dxnodes, double* vel, int IC,
                           double timestep, double TWall_in, sbte_species* mix) {
-  (void)lv; (void)vel; (void)TWall_in; (void)mix;
+  (void)lv; (void)vel; (void)mix;
+  // advectOne / advectTwo here own the whole mesh (rank 0 of 1): under an MPI launch with more than one rank every
+  // rank would silently apply walls / extrapolation at both ends of its sub-domain, so refuse instead (multi-GPU runs
+  // go through the sbte_slab_* interface)
+  {
+    const char* names[] = {"OMPI_COMM_WORLD_SIZE", "PMI_SIZE", "MV2_COMM_WORLD_SIZE", "WORLD_SIZE"};
+    for (const char* n : names) {
+      const char* v = getenv(n);
+      if (v && atoi(v) > 1) {
+        printf("libsbte_b200: the drop-in advectOne/advectTwo are single-rank (%s = %s); keep the reference's "
+               "transportroutines.c for multi-rank transport or use the sbte_slab_* interface\n", n, v);
+        fflush(stdout);
+        exit(1);
+      }
+    }
+  }
+  g_tr.TWall_in = TWall_in;
   g_tr.ready = true;
   g_tr.N = numV; g_tr.nX = numX; g_tr.ic = IC; g_tr.dt = timestep;
   g_tr.xp = xnodes; g_tr.dxp = dxnodes;   // retained like the reference (src/transportroutines.c:31-32)

@@ -7,7 +7,6 @@
 #include <vector>
 
 struct sbte_slab;
-namespace sbte { struct MirrorTile; }
 
 // Conservation data handed to kernels by value: the factored Gram matrix of the five moment
 // functionals and its pivots (reference: src/conserve.c:89-168,268-317).
@@ -68,17 +67,6 @@ struct sbte_ctx {
   bool sym_enabled = true;
   double* d_Ws = nullptr;
   CUtensorMap tmapWs;
-  // mirror-paired batched convolution (qhat_mirror.cu, opt-in): one-column tensor maps, its own symmetrised tensor
-  // (mirror.cuh: mirror_sym_weight) and the table of column-pair tiles
-  CUtensorMap tmapM, tmapMs, tmapMh;
-  double* d_Ws2 = nullptr;
-  double* d_Wh = nullptr;           // folded tensor (mirror_fold_weight), built for wh_sym
-  int wh_sym = -1;
-  double* d_Wleft = nullptr;        // compact leftover tensor of the 0D half-spectrum path (from d_Wh with wh_sym = 1)
-  sbte::MirrorTile* d_mtiles = nullptr;
-  int n_mtiles = 0;
-  bool mirror_ok = false;
-  bool grid_mirror_ok = false;      // v_j = -L_v + j dv, L_eta dv = pi: the grids the mirror / half-spectrum identities need
 
   // scratch, sized for `cap` cells
   int cap = 0;
@@ -156,14 +144,6 @@ struct QhatPair {
   const double2* xi_side;    // g^[xi]
   const double2* dif_side;   // f^[zeta - xi]
 };
-// qhat_half.cu -- 0D (one cell, f == g) on half of the zeta rows: folded tensor, mirror columns skip the folded steps
-// (N in {16,32}, SBTE_HALF0D=1).  qhat receives nsplit + 1 partial spectra whose sum has the same Re(fft3D^-1(.)) as Q^.
-bool qhat_half0d_enabled(int N);
-size_t qhat_half_leftover_doubles(int N);
-void launch_half_pack_leftover(sbte_ctx* c, const double* Wh, double* Wl);
-void launch_qhat_stream_half(sbte_ctx* c, const double* Wh, const double* Wl, int npairs, const QhatPair* pairs_parity,
-                             double2* qhat, int nsplit);
-
 // generic: natural-layout operands, any N, any batch (one CTA per (zeta, cell))
 void launch_qhat_generic(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int batch);
 // stream kernel (N in {16,24,32}, batch 1): parity-layout operands
@@ -182,16 +162,6 @@ void launch_qhat_batch_any(sbte_ctx* c, const double2* spec_cellminor, double2* 
 int qhat_batch_align(int N);
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);
-
-// qhat_mirror.cu -- mirror-paired batched kernel (N in {8,16}, SBTE_MIRROR=1)
-bool qhat_mirror_enabled(int N);
-int qhat_mirror_pairs(int N);
-int qhat_mirror_align(int N);
-bool qhat_mirror_fold_enabled(int N);
-void launch_symmetrize_weights_mirror(sbte_ctx* c, const double* W, double* Ws2);
-void launch_fold_weights_mirror(sbte_ctx* c, const double* W, double* Wh, bool sym);
-void launch_qhat_mirror(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
-                        const BatchSched& sch, bool fold);
 
 // conserve.cu -- K4 / K5 / moments
 void launch_conserve(sbte_ctx* c, double* Q, int batch);

@@ -183,7 +183,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   }
   // the weights above do not depend on the forward transform; the operand planes below do
   pdl_wait();
-  if (tid == 0) {
+  if (tid == 0 && nchunk > 0) {   // a CTA with no xi_x planes (nsplit > planes of this column) writes a zero partial sum
     issue_chunk(0);
     if (nchunk > 1) issue_chunk(1);
   }
@@ -318,6 +318,8 @@ static void launch_stream_n(sbte_ctx* c, const double* W, int npairs, const Qhat
 // nsplit: partial spectra qhat[0..nsplit) of n3 elements each, to be added by the caller
 void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, int depth, bool sym, int nsplit) {
   const double* W = sym ? c->d_Ws : c->d_W;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > c->N / 2) nsplit = c->N / 2;   // every column has at least N/2 representative planes: no CTA stays empty
   switch (c->N) {
     case 16: sym ? launch_stream_n<16, true>(c, W, npairs, pairs, qhat, depth, nsplit) : launch_stream_n<16, false>(c, W, npairs, pairs, qhat, depth, nsplit); break;
     case 24: sym ? launch_stream_n<24, true>(c, W, npairs, pairs, qhat, depth, nsplit) : launch_stream_n<24, false>(c, W, npairs, pairs, qhat, depth, nsplit); break;

@@ -124,12 +124,6 @@ static bool batch3_general(int N) {
   static const bool on = getenv("SBTE_NO_BATCH3G") == nullptr;
   return on && (N == 20 || N == 22);
 }
-// N = 24: xi_z loop rolled in three blocks of eight columns, N = 22: eleven blocks of two (SBTE_ROLL=1; unmeasured,
-// off by default)
-static bool batch3_rolled() {
-  static const bool on = getenv("SBTE_ROLL") != nullptr && atoi(getenv("SBTE_ROLL")) != 0;
-  return on;
-}
 bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24 || batch3_general(N); }
 int qhat_batch_align(int N) { return (N == 24 || batch3_general(N)) ? N : 1; }  // stream-K granularity in steps
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
@@ -375,10 +369,7 @@ struct Batch3Cfg {
   static_assert(SMEM <= 227 * 1024, "line ring + stages must fit in shared memory");
 };
 
-// ROLL > 1: the xi_z loop is kept rolled in ROLL blocks of N/ROLL columns (the operand registers are rotated
-// between blocks), which divides the size of the unrolled step -- 45-75 KB of SASS at N = 22/24, where ncu shows
-// instruction-fetch stalls -- by ROLL.  Same products in the same order per row: bit-identical results.
-template <int N, int ROLL>
+template <int N>
 __global__ void __launch_bounds__(Batch3Cfg<N>::THREADS, 1)
 qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
                    double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch) {
@@ -502,47 +493,16 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
         double2 fr[N];
 #pragma unroll
         for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
-        if constexpr (ROLL == 1) {
 #pragma unroll
-          for (int c = 0; c < N; c += 2) {
-            const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
+        for (int c = 0; c < N; c += 2) {
+          const double2 g0v = gl[c * 32], g1v = gl[(c + 1) * 32];
 #pragma unroll
-            for (int r = 0; r < N; r++) {
-              const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
-              const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
-              const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
-              cmac(acc[r], w2.x, p0);
-              cmac(acc[r], w2.y, p1);
-            }
-          }
-        } else {
-          constexpr int CB = N / ROLL;   // columns per block (even)
-          static_assert(N % ROLL == 0 && CB % 2 == 0, "blocks of whole column pairs");
-#pragma unroll 1
-          for (int cb = 0; cb < ROLL; cb++) {
-            const double2* gb = gl + cb * CB * 32;
-            const double* wb = wt + cb * CB;
-#pragma unroll
-            for (int c = 0; c < CB; c += 2) {
-              const double2 g0v = gb[c * 32], g1v = gb[(c + 1) * 32];
-#pragma unroll
-              for (int r = 0; r < N; r++) {
-                const double2 w2 = *reinterpret_cast<const double2*>(wb + r * N + c);
-                const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
-                const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
-                cmac(acc[r], w2.x, p0);
-                cmac(acc[r], w2.y, p1);
-              }
-            }
-            // next block: column c + CB reads operand index - CB, i.e. fr'[i] = fr[i - CB]; rotated in place along
-            // the CB cycles {s, s + CB, ..., s + (ROLL-1) CB} of length ROLL
-#pragma unroll
-            for (int s0 = 0; s0 < CB; s0++) {
-              const double2 top = fr[s0 + (ROLL - 1) * CB];
-#pragma unroll
-              for (int q = ROLL - 1; q >= 1; q--) fr[s0 + q * CB] = fr[s0 + (q - 1) * CB];
-              fr[s0] = top;
-            }
+          for (int r = 0; r < N; r++) {
+            const double2 w2 = *reinterpret_cast<const double2*>(wt + r * N + c);
+            const double2 p0 = cmul(g0v, fr[(r + N / 2 - c + N) % N]);
+            const double2 p1 = cmul(g1v, fr[(r + N / 2 - c - 1 + N) % N]);
+            cmac(acc[r], w2.x, p0);
+            cmac(acc[r], w2.y, p1);
           }
         }
       }
@@ -562,11 +522,11 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
 }
 
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
-template <int N, int ROLL = 1>
+template <int N>
 static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                             const BatchSched& sch) {
   using C = Batch3Cfg<N>;
-  auto kern = qhat_batch3_kernel<N, ROLL>;
+  auto kern = qhat_batch3_kernel<N>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
   if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -587,14 +547,8 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t
     case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
     case 16: launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch); break;
     case 20: launch_batch3_n<20>(c, spec, parts, part_stride, cells, sch); break;
-    case 22:   // rolled: eleven blocks of one column pair (the operand registers rotate by two between blocks)
-      if (batch3_rolled()) launch_batch3_n<22, 11>(c, spec, parts, part_stride, cells, sch);
-      else launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch);
-      break;
-    case 24:
-      if (batch3_rolled()) launch_batch3_n<24, 3>(c, spec, parts, part_stride, cells, sch);
-      else launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch);
-      break;
+    case 22: launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch); break;
+    case 24: launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch); break;
     default: set_error("qhat_batch: unsupported N"); break;
   }
 }

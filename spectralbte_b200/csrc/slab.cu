@@ -25,6 +25,7 @@ struct sbte_slab {
   sbte_ctx* c = nullptr;
   int nX = 0, order = 1, ic = 0, rank = 0, nranks = 1, ncell = 0;
   double dt = 0;
+  double TWall_in = 1.0;   // Init_field 1 wall parameter (src/initializer.c:275, src/transportroutines.c:57)
   double *d_x = nullptr, *d_dx = nullptr;
   double *d_f = nullptr, *d_fc = nullptr, *d_f1 = nullptr, *d_ft = nullptr;  // f, f_conv, f_1, f_tmp
   double *d_fl = nullptr, *d_fr = nullptr;                                   // wall faces
@@ -39,6 +40,8 @@ struct sbte_slab {
   } nb[2];
   int* d_flags = nullptr;   // my {ready, done, epoch}; the pass counter lives on the device (graph replay)
   int p2p = 0;              // 1: stencils read the neighbours' boundary cells over NVLink
+  long long halo_timeout = 0;   // bound of every device-side wait for a neighbour, in SM clock cycles (0 = none)
+  double halo_timeout_s = 0;
   // CUDA graph of one whole time step (single rank or peer halos: nothing but launches on one stream)
   struct StepGraph {
     cudaGraphExec_t exec = nullptr;
@@ -66,9 +69,30 @@ static int launch_ok(const char* what) {
 }
 
 static const double T0_WALL = 1.0, T1_WALL = 2.0;  // src/transportroutines.c:46-47
-static const double TWALL_IN = 1.0;                // src/initializer.c:275
 
 static inline double* cell(double* base, long n3, int l) { return base + (long)l * n3; }
+
+// seconds -> SM clock cycles at the device's maximum clock (clock64 never runs faster, so the wait lasts at least
+// `seconds`); seconds <= 0: unbounded
+static long long timeout_cycles(int device, double seconds) {
+  if (!(seconds > 0)) return 0;
+  int khz = 0;
+  if (cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device) != cudaSuccess || khz <= 0) khz = 2000000;
+  return (long long)(seconds * 1e3 * (double)khz);
+}
+
+// the error word of the peer halo (a wait for a neighbour ran out of time): checked where the host synchronises anyway
+static int peer_halo_failed(sbte_slab* s) {
+  if (!s->p2p || !s->d_flags) return 0;
+  int err = 0;
+  if (cudaMemcpy(&err, s->d_flags + 3, sizeof(int), cudaMemcpyDeviceToHost) != cudaSuccess) return 0;
+  if (!err) return 0;
+  char msg[256];
+  snprintf(msg, sizeof msg, "peer halo: a neighbouring rank did not arrive within %g s (SBTE_HALO_TIMEOUT_S / "
+           "sbte_slab_set_halo_timeout; 0 = wait for ever); the slab contents are invalid from that pass on", s->halo_timeout_s);
+  set_error(msg);
+  return 1;
+}
 
 // ghost cells owned by the physical boundaries, order 1 (src/transportroutines.c:116-137,156-172)
 static void fill_ghosts_one(sbte_slab* s, double* f) {
@@ -80,7 +104,7 @@ static void fill_ghosts_one(sbte_slab* s, double* f) {
   const bool first = s->rank == 0, last = s->rank == s->nranks - 1;
   if (first) {
     if (ic == 3 || ic == 5) { launch_diffuse_bc(st, cell(f, n3, 1), cell(f, n3, 0), c->d_v, c->d_wt, c->N, c->dv, T0_WALL, 0); c->launches++; }
-    else if (ic == 1) { launch_diffuse_bc(st, cell(f, n3, 1), cell(f, n3, 0), c->d_v, c->d_wt, c->N, c->dv, 2.0 * TWALL_IN, 0); c->launches++; }
+    else if (ic == 1) { launch_diffuse_bc(st, cell(f, n3, 1), cell(f, n3, 0), c->d_v, c->d_wt, c->N, c->dv, 2.0 * s->TWall_in, 0); c->launches++; }
     else if (ic != 6) cudaMemcpyAsync(cell(f, n3, 0), cell(f, n3, 1), cb, cudaMemcpyDeviceToDevice, st);
   }
   if (last) {
@@ -109,7 +133,8 @@ static void peer_begin(sbte_slab* s, const double* src, const double** peerL, co
   sbte_ctx* c = s->c;
   const long n3 = c->n3;
   const int id = array_id(s, src);
-  launch_halo_begin(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr);
+  launch_halo_begin(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr,
+                    s->halo_timeout);
   c->launches += 1;
   if (s->nb[0].on) *peerL = s->nb[0].arr[id] + (long)s->nb[0].cells * n3;   // their last `order` owned cells
   if (s->nb[1].on) *peerR = s->nb[1].arr[id] + (long)s->order * n3;         // their first `order` owned cells
@@ -132,7 +157,7 @@ static void upwind_two_pass(sbte_slab* s, double* src, double* dst) {
     const bool wall = (ic == 3 || ic == 5 || ic == 1);
     launch_wall_face(st, src, s->d_fl, s->d_x, s->d_dx, N, 2, 0, wall ? 0 : 1); c->launches++;
     if (wall) {
-      launch_diffuse_bc(st, s->d_fl, s->d_fl, c->d_v, c->d_wt, N, c->dv, (ic == 1) ? 2.0 * TWALL_IN : T0_WALL, 0);
+      launch_diffuse_bc(st, s->d_fl, s->d_fl, c->d_v, c->d_wt, N, c->dv, (ic == 1) ? 2.0 * s->TWall_in : T0_WALL, 0);
       c->launches++;
     }
   }
@@ -169,6 +194,11 @@ int sbte_slab_create(sbte_ctx* c, sbte_slab** out, int cells_local, int order, c
   sbte_slab* s = new sbte_slab();
   s->c = c; s->nX = cells_local; s->order = order; s->ic = init_field; s->dt = dt; s->rank = rank; s->nranks = nranks;
   s->ncell = cells_local + 2 * order;
+  {
+    const char* e = getenv("SBTE_HALO_TIMEOUT_S");
+    s->halo_timeout_s = (e && *e) ? atof(e) : 120.0;
+    s->halo_timeout = timeout_cycles(c->device, s->halo_timeout_s);
+  }
   const long n3 = c->n3;
   const size_t sb = (size_t)s->ncell * n3 * sizeof(double);
   std::vector<double> hx(x, x + s->ncell), hdx(dx, dx + s->ncell);
@@ -276,12 +306,26 @@ int sbte_slab_peer_attach(sbte_slab* s, int side, sbte_slab* other) {
   return 0;
 }
 
-// diagnostic: this rank's {ready, done, epoch} counters (synchronous copy on a side stream-less path)
-int sbte_slab_halo_state(sbte_slab* s, int* state3) {
+// diagnostic: this rank's {ready, done, epoch, error} words (synchronous copy)
+int sbte_slab_halo_state(sbte_slab* s, int* state4) {
   cudaSetDevice(s->c->device);
-  state3[0] = state3[1] = state3[2] = 0;
+  state4[0] = state4[1] = state4[2] = state4[3] = 0;
   if (!s->d_flags) return 0;
-  CKS(cudaMemcpy(state3, s->d_flags, 3 * sizeof(int), cudaMemcpyDeviceToHost));
+  CKS(cudaMemcpy(state4, s->d_flags, 4 * sizeof(int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
+// bound of the device-side waits for a neighbour; seconds <= 0: wait for ever.  A captured step graph carries the
+// old bound as a kernel argument, so it is dropped and re-captured.
+int sbte_slab_set_halo_timeout(sbte_slab* s, double seconds) {
+  cudaSetDevice(s->c->device);
+  s->halo_timeout_s = seconds > 0 ? seconds : 0;
+  s->halo_timeout = timeout_cycles(s->c->device, seconds);
+  if (s->graph.exec) {
+    cudaStreamSynchronize(s->c->stream);
+    cudaGraphExecDestroy(s->graph.exec);
+  }
+  s->graph = sbte_slab::StepGraph();
   return 0;
 }
 
@@ -290,6 +334,20 @@ int sbte_slab_set_peer_halo(sbte_slab* s, int enable) {
   if (enable && !s->d_flags) { set_error("export/import the IPC handles before enabling peer halos"); return 1; }
   if (enable && preload_transport_kernels()) { set_error("could not load the transport kernels"); return 1; }
   s->p2p = enable ? 1 : 0;
+  return 0;
+}
+
+// TWall_in of initialize_transport (src/transportroutines.c:57): the Init_field 1 left wall is a diffuse wall at
+// 2 * TWall_in (:120,:365).  Baked into a captured step graph as a kernel argument, so the graph is dropped.
+int sbte_slab_set_twall_in(sbte_slab* s, double TWall_in) {
+  cudaSetDevice(s->c->device);
+  if (!(TWall_in > 0)) { set_error("TWall_in must be positive"); return 1; }
+  s->TWall_in = TWall_in;
+  if (s->graph.exec) {
+    cudaStreamSynchronize(s->c->stream);
+    cudaGraphExecDestroy(s->graph.exec);
+  }
+  s->graph = sbte_slab::StepGraph();
   return 0;
 }
 
@@ -302,7 +360,8 @@ int sbte_slab_upload(sbte_slab* s, const double* f_host) {
 }
 int sbte_slab_download(sbte_slab* s, double* f_host) {
   cudaSetDevice(s->c->device);
-  return sbte_d2h(s->c, f_host, s->d_f, (size_t)s->ncell * s->c->n3 * sizeof(double));
+  if (sbte_d2h(s->c, f_host, s->d_f, (size_t)s->ncell * s->c->n3 * sizeof(double))) return 1;
+  return peer_halo_failed(s);
 }
 
 int sbte_slab_halo_regions(sbte_slab* s, int which, int stage, int side, double** d_send, double** d_recv,
@@ -373,7 +432,8 @@ int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
   double* fc = cell(s->d_fc, n3, o);
   double* f = cell(s->d_f, n3, o);
   if (s->p2p) {   // the update below overwrites cells the neighbours may still be reading in their last pass
-    launch_halo_quiesce(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr);
+    launch_halo_quiesce(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr,
+                        s->halo_timeout);
     c->launches++;
   }
   if (o == 1) {
@@ -443,7 +503,8 @@ int sbte_slab_moments(sbte_slab* s, double* mom_host) {
   sbte_ctx* c = s->c;
   launch_moments(c, cell(s->d_f, c->n3, s->order), s->d_mom, s->nX);
   if (launch_ok("moments")) return 1;
-  return sbte_d2h(c, mom_host, s->d_mom, (size_t)s->nX * 8 * sizeof(double));
+  if (sbte_d2h(c, mom_host, s->d_mom, (size_t)s->nX * 8 * sizeof(double))) return 1;
+  return peer_halo_failed(s);
 }
 
 }  // extern "C"

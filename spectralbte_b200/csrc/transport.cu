@@ -93,28 +93,36 @@ void launch_upwind_one(cudaStream_t st, const double* f, double* fc, const doubl
 // Each rank owns two counters in IPC-shared device memory: ready (source array of pass e is complete) and
 // done (my reads of the neighbours' arrays in pass e are complete).  Plain stream order on each GPU plus
 // these two tiny kernels replaces the host-synchronised message exchange.
-// Flags of one rank: {ready, done, epoch}.  epoch counts this rank's upwind passes ON THE DEVICE, so the same
+// Flags of one rank: {ready, done, epoch, error}.  epoch counts this rank's upwind passes ON THE DEVICE, so the same
 // launches can be replayed from a CUDA graph; every rank issues the same sequence of passes.
 //   begin: epoch++ ; ready = epoch ("my source array is complete") ; wait until each neighbour is ready for
 //          this pass and has finished reading my cells in the previous one (done >= epoch - 1)
 //   end:   done = epoch ("I no longer read my neighbours' source array of this pass")
 //   quiesce: wait until the neighbours' done reaches my epoch (before overwriting cells they may be reading)
-// Bounded spins: a lost neighbour becomes a launch error (~10 s at 2 GHz), not a hung GPU.
-__device__ __forceinline__ void spin_until(const volatile int* L, const volatile int* R, int vr, int vd) {
-  const long long t0 = clock64();
-  while ((L && (L[0] < vr || L[1] < vd)) || (R && (R[0] < vr || R[1] < vd))) {
-    if (clock64() - t0 > 20000000000LL) __trap();
+// Waits are bounded by `timeout` clock cycles (0 = wait for ever; the slab passes SBTE_HALO_TIMEOUT_S, default 120 s).
+// A rank may legitimately be late (writing files, instantiating a graph, stopped in a debugger), so running out of
+// time is NOT a trap: the waiting rank raises the error word flags[3], stops waiting -- every later wait of this slab
+// returns at once -- and the host reports the failure at its next synchronising call (sbte_slab_moments / _download /
+// _halo_state).  The CUDA context survives and no GPU hangs.
+__device__ __forceinline__ void spin_until(volatile int* my, const volatile int* L, const volatile int* R, int vr, int vd,
+                                           long long timeout) {
+  if (my[3] == 0) {
+    const long long t0 = clock64();
+    while ((L && (L[0] < vr || L[1] < vd)) || (R && (R[0] < vr || R[1] < vd))) {
+      if (timeout > 0 && clock64() - t0 > timeout) { my[3] = 1; break; }
+      __nanosleep(64);
+    }
   }
   __threadfence_system();
 }
-__global__ void halo_begin_kernel(int* my, const int* nbL, const int* nbR) {
+__global__ void halo_begin_kernel(int* my, const int* nbL, const int* nbR, long long timeout) {
   volatile int* m = reinterpret_cast<volatile int*>(my);
   const int e = m[2] + 1;
   m[2] = e;
   __threadfence_system();
   m[0] = e;
   __threadfence_system();
-  spin_until(reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), e, e - 1);
+  spin_until(m, reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), e, e - 1, timeout);
 }
 __global__ void halo_end_kernel(int* my) {
   __threadfence_system();
@@ -122,16 +130,16 @@ __global__ void halo_end_kernel(int* my) {
   m[1] = m[2];
   __threadfence_system();
 }
-__global__ void halo_quiesce_kernel(const int* my, const int* nbL, const int* nbR) {
-  const int e = reinterpret_cast<const volatile int*>(my)[2];
-  spin_until(reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), 0, e);
+__global__ void halo_quiesce_kernel(int* my, const int* nbL, const int* nbR, long long timeout) {
+  volatile int* m = reinterpret_cast<volatile int*>(my);
+  spin_until(m, reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), 0, m[2], timeout);
 }
-void launch_halo_begin(cudaStream_t st, int* my, const int* nbL, const int* nbR) {
-  halo_begin_kernel<<<1, 1, 0, st>>>(my, nbL, nbR);
+void launch_halo_begin(cudaStream_t st, int* my, const int* nbL, const int* nbR, long long timeout) {
+  halo_begin_kernel<<<1, 1, 0, st>>>(my, nbL, nbR, timeout);
 }
 void launch_halo_end(cudaStream_t st, int* my) { halo_end_kernel<<<1, 1, 0, st>>>(my); }
-void launch_halo_quiesce(cudaStream_t st, const int* my, const int* nbL, const int* nbR) {
-  halo_quiesce_kernel<<<1, 1, 0, st>>>(my, nbL, nbR);
+void launch_halo_quiesce(cudaStream_t st, int* my, const int* nbL, const int* nbR, long long timeout) {
+  halo_quiesce_kernel<<<1, 1, 0, st>>>(my, nbL, nbR, timeout);
 }
 
 // ---------------------------------------------------------------- second order (K6b)

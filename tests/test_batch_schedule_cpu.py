@@ -14,10 +14,10 @@ def _lib():
     return _lib.load()
 
 
-def schedule(N, cells, sym, ctas, mirror=False):
+def schedule(N, cells, sym, ctas):
     L = _lib()
     dims = (C.c_int * 6)()
-    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, int(mirror), None, None, None, None, None, dims) == 0
+    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, None, None, None, None, None, dims) == 0
     G, T, P, np_cols, kmax, np_len = list(dims)
     begin = np.zeros(P + 1, dtype=np.int64)
     tbegin = np.zeros(T + 1, dtype=np.int64)
@@ -25,7 +25,7 @@ def schedule(N, cells, sym, ctas, mirror=False):
     first = np.zeros(T, dtype=np.int32)
     npt = np.zeros(np_len, dtype=np.uint8)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
-    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, int(mirror), p(begin, C.c_longlong), p(tbegin, C.c_longlong),
+    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, p(begin, C.c_longlong), p(tbegin, C.c_longlong),
                                       p(ctile, C.c_int), p(first, C.c_int), p(npt, C.c_ubyte), dims) == 0
     return dict(G=G, T=T, P=P, np_cols=np_cols, kmax=kmax, begin=begin, tbegin=tbegin, ctile=ctile, first=first, np=npt)
 
@@ -111,9 +111,9 @@ def test_schedule_covers_every_step_once(N, cells, sym, ctas):
 def test_schedule_rejects_unscheduled_n():
     L = _lib()
     dims = (C.c_int * 6)()
-    assert L.sbte_batch_schedule_host(12, 40, 1, 148, 0, None, None, None, None, None, dims) != 0
+    assert L.sbte_batch_schedule_host(12, 40, 1, 148, None, None, None, None, None, dims) != 0
     assert b"any-N" in L.sbte_last_error()
-    assert L.sbte_batch_schedule_host(16, 0, 1, 148, 0, None, None, None, None, None, dims) != 0
+    assert L.sbte_batch_schedule_host(16, 0, 1, 148, None, None, None, None, None, dims) != 0
 
 
 @pytest.mark.parametrize("N", [20, 22, 24])
@@ -149,95 +149,3 @@ def test_line_ring_arrival_counts_complete_every_slot(N):
         newest = min(L - 1, COLS - 1 + ey)
         oldest = max(0, ey)          # warp COLS-1 reads line ey at step ey
         assert newest - oldest + 1 <= RING
-
-
-def mirror_tiles(N, pairs):
-    """build_mirror_tiles (csrc/mirror.cuh) restated: tiles of `pairs` column pairs of one zeta_x plane."""
-    nu = lambda i: (N - i) % N  # noqa: E731
-    tiles = []
-    for zx in range(N // 2 + 1):
-        groups = ([(list(range(1, N // 2)), True), ([0], False), ([N // 2], False)] if zx in (0, N // 2)
-                  else [(list(range(N)), True)])
-        for cols, paired in groups:
-            for i in range(0, len(cols), pairs):
-                tiles.append((zx, [(zy, nu(zy) if paired else -1) for zy in cols[i:i + pairs]]))
-    return tiles
-
-
-@pytest.mark.parametrize("N,cells,sym,ctas", [(16, 640, True, 148), (16, 33, False, 148), (8, 37, True, 148), (16, 80, True, 11),
-                                              (24, 250, True, 148), (22, 70, False, 148), (20, 33, True, 13)])
-def test_mirror_schedule_covers_every_step_once(N, cells, sym, ctas):
-    """Layout of the opt-in mirror-paired kernel (csrc/qhat_mirror.cu): a step (xi_x, xi_y) of an A column also serves
-    the step (nu xi_x, nu xi_y) of its mirror column."""
-    s = schedule(N, cells, sym, ctas, mirror=True)
-    pairs = 4 if N >= 16 else 2
-    tiles = mirror_tiles(N, pairs)
-    nu = lambda i: (N - i) % N  # noqa: E731
-    G, T, P = s["G"], s["T"], s["P"]
-    assert T == G * len(tiles) and s["np_cols"] == 1
-    begin, tbegin = s["begin"], s["tbegin"]
-    assert begin[0] == 0 and begin[-1] == tbegin[-1]
-    if N >= 20:                                      # line-ring variant: whole xi_x chunks, consecutive A columns per tile
-        assert np.all(begin % N == 0)
-        for zx, slots in tiles:
-            assert [zyA for zyA, _ in slots] == list(range(slots[0][0], slots[0][0] + len(slots)))
-    seen, writes = set(), {}
-    for p in range(P):
-        g0, n = int(begin[p]), int(begin[p + 1] - begin[p])
-        if n <= 0:
-            continue
-        t = int(s["ctile"][p])
-        te = int(tbegin[t + 1])
-        sl = g0 - int(tbegin[t])
-        for k in range(n):
-            if g0 + k == te:
-                t += 1
-                te = int(tbegin[t + 1])
-                sl = 0
-            rb, cg = divmod(t, G)
-            zx, slots = tiles[rb]
-            c, ey = divmod(sl, N)
-            ex = sym_rep(N, zx, c) if sym else c
-            part = p - int(s["first"][t])
-            writes.setdefault(t, set()).add(part)
-            for zyA, zyB in slots:
-                for key in [(zx, zyA, cg, ex, ey)] + ([(nu(zx), zyB, cg, nu(ex), nu(ey))] if zyB >= 0 else []):
-                    assert key not in seen
-                    seen.add(key)
-            sl += 1
-    # every zeta column visits its planes: A columns the representatives of zx, B columns their mirror images
-    want = 0
-    for zx in range(N):
-        for zy in range(N):
-            b_row = (zy > N // 2) if zx in (0, N // 2) else (zx > N // 2)
-            nplanes = (sym_nrep(N, nu(zx) if b_row else zx) if sym else N)
-            want += nplanes * N * G
-    assert len(seen) == want
-    for rb, (zx, slots) in enumerate(tiles):
-        for zyA, zyB in slots:
-            for cg in range(G):
-                t = rb * G + cg
-                for q in [zx * N + zyA] + ([nu(zx) * N + zyB] if zyB >= 0 else []):
-                    assert writes[t] == set(range(int(s["np"][q * G + cg])))
-
-
-@pytest.mark.parametrize("N", [20, 22, 24])
-def test_mirror_line_ring_arrival_counts(N):
-    """qhat_mirror_ring_kernel: PAIRS = 4 column slots, two warps each; both warps of the slot that reads a line last
-    also arrive for the slots that never read it, so every line's empty barrier sees 2 * PAIRS arrivals."""
-    PAIRS = 4
-    L = N + PAIRS - 1
-    arrivals = [0] * L
-    for ey in range(N):
-        for w in range(PAIRS):
-            jl = PAIRS - 1 + ey - w
-            cnt = 1
-            if jl < PAIRS - 1 and w == PAIRS - 1:
-                cnt = PAIRS - jl
-            if jl > N - 1 and w == N + PAIRS - 2 - jl:
-                cnt = jl - N + 2
-            arrivals[jl] += 2 * cnt                  # both halves
-    assert arrivals == [2 * PAIRS] * L
-    RING = 10
-    for ey in range(N):
-        assert min(L - 1, PAIRS - 1 + ey) - ey + 1 <= RING

@@ -4,8 +4,8 @@ per CUDA thread, emulated mbarriers / TMA copies / shared memory -- test infrast
 and runs them CTA by CTA on the stream-K schedule the library builds (sbte_batch_schedule_host).  The partial sums
 they write, combined the way the inverse transform combines them, must equal the oracle's convolution
 (src/collisions.c:127-165) for every cell.  This covers what arithmetic checks cannot: barrier counts (a wrong one
-hangs; the shim's bounded wait aborts), TMA coordinates, shared-memory offsets, tile switches, flushes -- for the
-GPU-verified kernels (as a check of the emulation itself) and for the opt-in kernels that have not run on a GPU yet."""
+hangs; the shim's bounded wait aborts), TMA coordinates, shared-memory offsets, tile switches, flushes -- so a
+change to the kernels' protocol is caught here before any GPU time is spent on it."""
 import ctypes as C
 import multiprocessing as mp
 import os
@@ -17,14 +17,13 @@ import pytest
 from conftest import relmax, seeded_f
 from oracle import oracle as orc
 from test_batch_schedule_cpu import schedule
-from test_mirror_emulation_cpu import _emul as _mirror_rule_lib
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 SRC = os.path.join(HERE, "emul", "kernel_emul.cpp")
 LIB = os.path.join(HERE, "emul", "libkernel_emul.so")
 DEPS = [SRC, os.path.join(HERE, "emul", "cuda_emul.h")] + [
-    os.path.join(ROOT, "spectralbte_b200", "csrc", f) for f in ("qhat_batch.cu", "qhat_mirror.cu", "mirror.cuh", "common.cuh", "internal.h")]
+    os.path.join(ROOT, "spectralbte_b200", "csrc", f) for f in ("qhat_batch.cu", "common.cuh", "internal.h")]
 
 
 def _lib():
@@ -55,20 +54,12 @@ def symmetrise_standard(W, N):
     return out.reshape(-1)
 
 
-# (0, 16, 3, True, 3) and (0, 22, 2, True, 3) -- the GPU-verified N=16 / N=22 kernels -- pass as well; left out to keep the
-# CPU suite short (same templates as the N=8 / N=20 cases)
 CASES = [  # kind, N, cells, sym, ctas
-    (0, 8, 37, True, 5), (0, 8, 5, False, 3),            # qhat_batch2_kernel<8>      (GPU-verified: checks the emulation)
-    (0, 20, 3, True, 4),                                   # qhat_batch3_kernel<20>     (GPU-verified, partly empty row-blocks)
-    (1, 8, 37, True, 5), (1, 8, 5, False, 3),             # qhat_mirror_kernel<8>
-    (1, 16, 3, True, 3),                                   # qhat_mirror_kernel<16>
-    (1, 20, 3, True, 4), (1, 20, 2, False, 3),            # qhat_mirror_ring_kernel<20>
-    (1, 22, 2, True, 3),                                   # qhat_mirror_ring_kernel<22> (odd N/2, padded box slots, partial tiles)
-    (1, 24, 1, True, 3),                                   # qhat_mirror_ring_kernel<24>
-    (2, 24, 1, True, 3),                                   # qhat_batch3_kernel<24, ROLL=3> (opt-in rolled xi_z loop)
-    (2, 22, 1, False, 3),                                  # qhat_batch3_kernel<22, ROLL=11>
-    (3, 8, 37, True, 5), (3, 8, 5, False, 3),             # qhat_mirror_kernel<8> on the folded tensor (combined body)
-    (3, 16, 3, True, 3),                                   # qhat_mirror_kernel<16> on the folded tensor
+    (0, 8, 37, True, 5), (0, 8, 5, False, 3),            # qhat_batch2_kernel<8>
+    (0, 16, 3, True, 3),                                   # qhat_batch2_kernel<16>
+    (0, 20, 3, True, 4),                                   # qhat_batch3_kernel<20> (partly empty row-blocks)
+    (0, 22, 2, False, 3),                                  # qhat_batch3_kernel<22>
+    (0, 24, 1, True, 3),                                   # qhat_batch3_kernel<24>
 ]
 
 
@@ -79,19 +70,11 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
     o = orc.Oracle(N, 9.0, 1)
     n3 = N ** 3
     W = np.random.default_rng(N).standard_normal(n3 * n3) if N <= 8 else orc.synthetic_weights(N)
-    if kind == 3:
-        Wk = np.empty_like(W)
-        R = _mirror_rule_lib()
-        assert R.mirror_emul_fold(N, W.ctypes.data_as(C.POINTER(C.c_double)), int(sym), Wk.ctypes.data_as(C.POINTER(C.c_double))) == 0
-    elif sym and kind == 1:
-        Wk = np.empty_like(W)
-        R = _mirror_rule_lib()
-        assert R.mirror_emul_symmetrize(N, W.ctypes.data_as(C.POINTER(C.c_double)), Wk.ctypes.data_as(C.POINTER(C.c_double))) == 0
-    elif sym:
+    if sym:
         Wk = symmetrise_standard(W, N)
     else:
         Wk = W
-    s = schedule(N, cells, sym, ctas, mirror=(kind in (1, 3)))
+    s = schedule(N, cells, sym, ctas)
     G, T, P, kmax = s["G"], s["T"], s["P"], s["kmax"]
     # spectra, cell-minor [G][n3][32]; padding cells are zero
     spec = np.zeros((G, n3, 32), dtype=complex)
@@ -132,62 +115,4 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
             seg = parts[:npc, b, col * N:(col + 1) * N]
             assert not np.isnan(seg.view(np.float64)).any(), (b, col)       # every part the table promises was written
             q[col * N:(col + 1) * N] = seg.sum(axis=0)
-        if kind == 3:   # the folded tensor does not give Q^ but a spectrum with the same Q = Re(fft3D^-1(.))
-            assert relmax(np.real(o.fft3d(q, invert=True)), o.compute_q(W, fs[b], fs[b])) < 1e-12, b
-        else:
-            assert relmax(q, o.qhat(W, F[b], F[b])) < 1e-12, b
-
-
-@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
-@pytest.mark.parametrize("N,nsplit,packed,npairs", [(16, 2, 1, 1), (16, 1, 1, 2)])   # (16, 1, 0, 1) -- leftovers gathered -- passes too
-def test_half_spectrum_0d_kernels_on_host(tmp_path, N, nsplit, packed, npairs):
-    """qhat_stream_half_kernel + qhat_half_leftover_kernel (csrc/qhat_half.cu, opt-in SBTE_HALF0D=1): the 0D stream kernel on the
-    folded tensor, mirror columns skipping the folded steps, leftovers added by the second kernel -- for ComputeQ(f, f) (one
-    operand pair) and ComputeQ_maxPreserve (two pairs sharing the weight pass, src/collisions.c:178-210).  The sum of the
-    partial spectra is not the reference's Q^, but Re(fft3D^-1(.)) must be the oracle's Q (src/collisions.c:212-221)."""
-    L = _lib()
-    dp = C.POINTER(C.c_double)
-    L.emul_half0d.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
-    o = orc.Oracle(N, 5.0, 0)
-    n3 = N ** 3
-    W = orc.synthetic_weights(N)
-    Wh = np.empty_like(W)
-    R = _mirror_rule_lib()
-    assert R.mirror_emul_fold(N, W.ctypes.data_as(dp), 1, Wh.ctypes.data_as(dp)) == 0
-    f = seeded_f(o.v, 41, noise=0.3)
-    z = np.arange(N)
-
-    def parity(x):   # spectrum of a real field in parity-split lines [x][y][z & 1][z >> 1] (LAY_PARITY, csrc/internal.h)
-        F = o.fft3d(np.asarray(x).astype(complex)).reshape(N, N, N)
-        out = np.empty((N, N, N), dtype=complex)
-        out[:, :, (z & 1) * (N // 2) + (z >> 1)] = F
-        return np.ascontiguousarray(out)
-
-    if npairs == 1:
-        xiA = dfA = parity(f)
-        xiB = dfB = xiA
-        want = o.compute_q(W, f, f)
-    else:                       # one species: M_i = M_j = M, g_i = g_j = f - M  (csrc/capi.cu: compute_q_maxpreserve_dev)
-        M, _ = o.find_maxwellian(f)
-        g = f - M
-        xiA, dfA = parity(g), parity(f)      # g_j^[xi] f^[zeta - xi]
-        xiB, dfB = parity(M), parity(g)      # M_j^[xi] g_i^[zeta - xi]
-        want = o.compute_q_maxpreserve(W, f, f)
-    parts = np.full((nsplit + 1) * n3, np.nan + 1j * np.nan, dtype=complex)
-    out = str(tmp_path / "parts.npy")
-    pd = lambda a: a.view(np.float64).ctypes.data_as(dp)  # noqa: E731
-
-    def child():
-        rc = L.emul_half0d(N, nsplit, packed, npairs, Wh.ctypes.data_as(dp), pd(xiA), pd(dfA), pd(xiB), pd(dfB), pd(parts))
-        if rc == 0:
-            np.save(out, parts)
-        os._exit(rc)
-
-    proc = mp.get_context("fork").Process(target=child)
-    proc.start()
-    proc.join(900)
-    assert proc.exitcode == 0, "kernel emulation failed or deadlocked (exit code %s)" % proc.exitcode
-    parts = np.load(out).reshape(nsplit + 1, n3)
-    assert not np.isnan(parts.view(np.float64)).any()
-    S = parts.sum(axis=0)
-    assert relmax(np.real(o.fft3d(S, invert=True)), want) < 1e-12
+        assert relmax(q, o.qhat(W, F[b], F[b])) < 1e-12, b

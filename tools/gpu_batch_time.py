@@ -1,5 +1,5 @@
 """Batched ComputeQ timing: `gpu_n22_time.py N [cells]` times one configuration under the current environment
-(SBTE_MIRROR, SBTE_ROLL, SBTE_NO_BATCH3G); without arguments, heatTrans-sized batches (250 cells) at N = 20, 22, 24:
+(SBTE_NO_BATCH3G, SBTE_BATCH_CTAS, ...); without arguments, heatTrans-sized batches (250 cells) at N = 20, 22, 24:
 line-ring kernel with partial row-blocks (default) against the any-N kernel (SBTE_NO_BATCH3G=1).
 numpy + ctypes only (no torch import), so it starts in a second on a fresh box."""
 import os
@@ -37,7 +37,7 @@ def run(N, cells=250, reps=10):
     nrep = sum((lambda a: a // 2 + 1 + (a + N) // 2 - a)((zx + N // 2) % N) for zx in range(N))
     flops = 10.0 * N ** 4 * nrep * cells
     print("N=%d cells=%d %s: %.3f ms/ComputeQ, convolution %.3f ms (%d launches) = %.2f TFLOP/s executed, checksum %.17g"
-          % (N, cells, "any-N kernel" if os.environ.get("SBTE_NO_BATCH3G") else "batched kernel (SBTE_MIRROR=%s SBTE_ROLL=%s)" % (os.environ.get("SBTE_MIRROR", "0"), os.environ.get("SBTE_ROLL", "0")), wall, k2ms / max(n, 1), n,
+          % (N, cells, "any-N kernel" if os.environ.get("SBTE_NO_BATCH3G") else "batched kernel", wall, k2ms / max(n, 1), n,
              flops / (k2ms / max(n, 1)) * 1e-9, float(np.abs(Q).sum())), flush=True)
 
 
