@@ -186,6 +186,9 @@ SBTE_API int sbte_slab_ipc_import(sbte_slab *s, int side, const unsigned char *h
 /* same-process form: `other` is a slab of another context (another stream or GPU with peer access enabled) */
 SBTE_API int sbte_slab_peer_attach(sbte_slab *s, int side, sbte_slab *other);
 SBTE_API int sbte_slab_set_peer_halo(sbte_slab *s, int enable);
+/* unmap the neighbours' slabs and leave the peer mode; with one process per GPU every rank detaches, the ranks
+ * synchronise, and only then are the slabs destroyed (exported memory must outlive its remote mappings) */
+SBTE_API int sbte_slab_peer_detach(sbte_slab *s);
 /* this rank's {ready, done, epoch, error} words.  error != 0: a device-side wait for a neighbour ran out of time
  * (the waiting kernels do not trap: they raise this word, stop waiting, and sbte_slab_moments / sbte_slab_download
  * then fail with a message). */

@@ -80,6 +80,7 @@ PROTOTYPES = {
     "sbte_slab_halo_state": (C.c_int, [_vp, C.POINTER(C.c_int)]),
     "sbte_slab_set_halo_timeout": (C.c_int, [_vp, C.c_double]),
     "sbte_slab_set_peer_halo": (C.c_int, [_vp, C.c_int]),
+    "sbte_slab_peer_detach": (C.c_int, [_vp]),
     "sbte_slab_collide": (C.c_int, [_vp, C.c_double, C.c_int]),
     "sbte_slab_step": (C.c_int, [_vp, C.c_double, C.c_int]),
     "sbte_slab_moments": (C.c_int, [_vp, _dp]),

@@ -318,6 +318,9 @@ class Slab:
     def set_peer_halo(self, enable=True):
         check(self.L.sbte_slab_set_peer_halo(self.h, int(bool(enable))))
 
+    def peer_detach(self):
+        check(self.L.sbte_slab_peer_detach(self.h))
+
     def collide(self, Kn, k2=K2_AUTO):
         check(self.L.sbte_slab_collide(self.h, float(Kn), int(k2)))
 

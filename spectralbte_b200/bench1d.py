@@ -207,6 +207,7 @@ class Runner:
                                                            else "NCCL batch_isend_irecv")
         halo_state = s.halo_state() if (self.world > 1 and halo.mode == "p2p") else None
         self.sync_all(c)
+        halo.close()
         s.close()
         if self.rank != 0:
             return None
@@ -257,6 +258,7 @@ class Runner:
         mode = halo.mode
         err = s.halo_state()[3] if mode == "p2p" else 0
         self.sync_all(c)
+        halo.close()
         s.close()
         digests = [None]
         if self.rank == 0:

@@ -251,11 +251,15 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   int kmax = 1;
   for (int t = 0; t < T; t++) {
     // CTAs with an empty range never write: pick owners among non-empty ranges
-    int a = owner(tbegin[t]);
-    const int b = owner(tbegin[t + 1] - 1);
+    const int a = owner(tbegin[t]);
     first[t] = a;
-    np[t] = (unsigned char)(b - a + 1);
-    kmax = std::max(kmax, b - a + 1);
+    // canonical summation (qhat_batch.cu chunk_end): the first CTA folds its e0 chunks into part 0, every chunk a later
+    // CTA computes is a part of its own
+    const long long e0 = (std::min(begin[a + 1], tbegin[t + 1]) - tbegin[t]) / align;
+    const long long nchunks = (tbegin[t + 1] - tbegin[t]) / align;
+    const int parts_t = 1 + (int)(nchunks - e0);
+    np[t] = (unsigned char)parts_t;
+    kmax = std::max(kmax, parts_t);
   }
   for (int p = 0; p < P; p++) ctile[p] = tile_of(std::min(begin[p], total - 1));
   // the inverse transform looks the part count up as np[(column / np_cols) * G + cell group]; with partly

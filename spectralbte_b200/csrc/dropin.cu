@@ -13,7 +13,28 @@
 #include "../../include/sbte_b200.h"
 #include "internal.h"
 
+#include <chrono>
+
 namespace {
+
+// SBTE_DROPIN_TIMING=1: wall time and call count per drop-in symbol, printed by dealloc_coll
+struct Tally { double s = 0; long n = 0; };
+Tally g_tally[6];
+const char* const g_tally_name[6] = {"ComputeQ", "ComputeQ_maxPreserve", "conserveAllMoments", "advectOne", "advectTwo", "weight upload"};
+bool timing_on() {
+  static const bool on = getenv("SBTE_DROPIN_TIMING") != nullptr;
+  return on;
+}
+struct Timed {
+  int id;
+  std::chrono::steady_clock::time_point t0;
+  explicit Timed(int i) : id(i) { if (timing_on()) t0 = std::chrono::steady_clock::now(); }
+  ~Timed() {
+    if (!timing_on()) return;
+    g_tally[id].s += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    g_tally[id].n++;
+  }
+};
 
 sbte_ctx* g_ctx = nullptr;
 bool g_cons_ready = false;
@@ -80,6 +101,7 @@ unsigned long long weight_fingerprint(double** rows) {
 void sync_weights(double** conv_weights) {
   const unsigned long long fp = weight_fingerprint(conv_weights);
   if (g_ctx->host_key != (const void*)conv_weights || !g_ctx->d_W || fp != g_wfp) {
+    Timed t(5);
     if (sbte_weights_upload_rows(g_ctx, conv_weights)) die("weight upload");
     g_wfp = fp;
   }
@@ -127,6 +149,12 @@ void initialize_coll(int nodes, double length, double* vel, double* zeta) {
 }
 
 void dealloc_coll(void) {
+  if (timing_on()) {
+    for (int i = 0; i < 6; i++)
+      if (g_tally[i].n) printf("libsbte_b200 timing: %-22s %8ld calls %10.4f s  (%.1f us per call)\n", g_tally_name[i], g_tally[i].n,
+                               g_tally[i].s, 1e6 * g_tally[i].s / g_tally[i].n);
+    fflush(stdout);
+  }
   if (g_tr.slab) { sbte_slab_destroy(g_tr.slab); g_tr.slab = nullptr; }
   if (g_ctx) { sbte_destroy(g_ctx); g_ctx = nullptr; }
 }
@@ -134,12 +162,14 @@ void dealloc_coll(void) {
 void ComputeQ(double* f, double* g, double* Q, double** conv_weights) {
   need_ctx("ComputeQ");
   sync_weights(conv_weights);
+  Timed t(0);
   if (sbte_compute_q_host(g_ctx, f, g, Q, SBTE_K2_AUTO)) die("ComputeQ");
 }
 
 void ComputeQ_maxPreserve(double* f, double* g, double* Q, double** conv_weights) {
   need_ctx("ComputeQ_maxPreserve");
   sync_weights(conv_weights);
+  Timed t(1);
   if (sbte_compute_q_maxpreserve_host(g_ctx, f, g, Q, SBTE_K2_AUTO)) die("ComputeQ_maxPreserve");
 }
 
@@ -182,6 +212,7 @@ void conserveAllMoments(double** Q) {
     printf("libsbte_b200: conserveAllMoments called before initialize_conservation\n");
     exit(1);
   }
+  Timed t(2);
   const size_t bytes = (size_t)g_ctx->n3 * sizeof(double);
   if (sbte::ensure_capacity(g_ctx, 1)) die("conserveAllMoments");
   if (sbte_h2d(g_ctx, g_ctx->d_Q, Q[0], bytes)) die("conserve h2d");
@@ -216,8 +247,8 @@ void initialize_transport(int numV, int numX, double lv, double* xnodes, double*
   if (g_tr.slab) { sbte_slab_destroy(g_tr.slab); g_tr.slab = nullptr; }
 }
 
-void advectOne(double** f, double** f_conv, int id) { (void)id; advect_host(f, f_conv, 1); }
-void advectTwo(double** f, double** f_conv, int id) { (void)id; advect_host(f, f_conv, 2); }
+void advectOne(double** f, double** f_conv, int id) { (void)id; Timed t(3); advect_host(f, f_conv, 1); }
+void advectTwo(double** f, double** f_conv, int id) { (void)id; Timed t(4); advect_host(f, f_conv, 2); }
 
 void dealloc_trans(void) {
   if (g_tr.slab) { sbte_slab_destroy(g_tr.slab); g_tr.slab = nullptr; }

@@ -125,7 +125,7 @@ static bool batch3_general(int N) {
   return on && (N == 20 || N == 22);
 }
 bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24 || batch3_general(N); }
-int qhat_batch_align(int N) { return (N == 24 || batch3_general(N)) ? N : 1; }  // stream-K granularity in steps
+int qhat_batch_align(int N) { return N; }  // stream-K granularity in steps: whole xi_x chunks (canonical summation order)
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
 
 // ------------------------------------------------------------------------------------------
@@ -245,15 +245,35 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   int cur_t = -1, cur_cg = -1, cur_X = -1, epoch = -1;
   int zx = 0, zy = 0;
 
-  auto flush = [&]() {
-    const int rb = cur_t / G, cg = cur_t - rb * G;
+  // Canonical summation order (independent of the schedule, hence of the SM count and of how many cells this rank
+  // holds): Q^ = ((C_0 + C_1) + C_2) + ..., C_c = the sum over the N steps of the c-th visited xi_x chunk started from
+  // zero.  CTA ranges are whole chunks.  The CTA that owns a tile's first chunk keeps the running fold in part 0 (a
+  // read-modify-write of its own 16 N bytes per thread at every chunk end, hidden behind the plane switch); a CTA that
+  // enters the tile later writes every chunk as its own part 1 + (c - e0), e0 = chunks held by the first CTA, and the
+  // inverse transform continues the same left fold over the parts.
+  auto chunk_end = [&](int c) {
+    const int cg = cur_t - (cur_t / G) * G;
     const long cell = (long)cg * 32 + lane;
     if (cell < cells) {
-      const int part = (int)blockIdx.x - sch.tile_first[cur_t];
-      double2* out = parts + (size_t)part * part_stride + cell * n3 + ((long)zx * N + zy) * N;
+      const int first = sch.tile_first[cur_t];
+      double2* out = parts + cell * n3 + ((long)zx * N + zy) * N;
+      if ((int)blockIdx.x == first) {
+        if (c > 0) {
+#pragma unroll
+          for (int r = 0; r < N; r++) {
+            const double2 tot = out[r];
+            acc[r] = make_double2(tot.x + acc[r].x, tot.y + acc[r].y);
+          }
+        }
+      } else {
+        const int e0 = (int)((sch.cta_begin[first + 1] - sch.tile_begin[cur_t]) / N);
+        out += (size_t)(1 + c - e0) * part_stride;
+      }
 #pragma unroll
       for (int r = 0; r < N; r++) out[r] = acc[r];
     }
+#pragma unroll
+    for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
   };
 
   int t = sch.cta_tile[blockIdx.x];
@@ -264,11 +284,6 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     int rb, cg, ex, ey, X;
     decode(t, sl, rb, cg, ex, ey, X);
     if (t != cur_t) {
-      if (cur_t >= 0) {
-        flush();
-#pragma unroll
-        for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
-      }
       cur_t = t;
       const int q0 = rb * C::COLS;
       zx = q0 / N;
@@ -317,8 +332,8 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       mbar_arrive(&empty[st]);
       if (plane_done) mbar_arrive(emptyPlane);
     }
+    if (ey == N - 1) chunk_end(sl / N);
   }
-  flush();
 }
 
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
@@ -451,27 +466,39 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   int k = 0;
   long qbase = 0;
 
-  auto flush = [&]() {
-    const int rb = cur_t / G, cg = cur_t - rb * G;
+  // canonical summation order, as in qhat_batch2_kernel: left fold over the chunk sums, part 0 kept by the CTA that owns
+  // the tile's first chunk, one part per chunk from every later CTA
+  auto chunk_end = [&](int c) {
+    const int cg = cur_t - (cur_t / G) * G;
     const long cell = (long)cg * 32 + lane;
     if (cell < cells && (!C::PARTIAL || zy < N)) {
-      const int part = (int)blockIdx.x - sch.tile_first[cur_t];
-      double2* out = parts + (size_t)part * part_stride + cell * n3 + ((long)zx * N + zy) * N;
+      const int first = sch.tile_first[cur_t];
+      double2* out = parts + cell * n3 + ((long)zx * N + zy) * N;
+      if ((int)blockIdx.x == first) {
+        if (c > 0) {
+#pragma unroll
+          for (int r = 0; r < N; r++) {
+            const double2 tot = out[r];
+            acc[r] = make_double2(tot.x + acc[r].x, tot.y + acc[r].y);
+          }
+        }
+      } else {
+        const int e0 = (int)((sch.cta_begin[first + 1] - sch.tile_begin[cur_t]) / N);
+        out += (size_t)(1 + c - e0) * part_stride;
+      }
 #pragma unroll
       for (int r = 0; r < N; r++) out[r] = acc[r];
     }
+#pragma unroll
+    for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
   };
 
   int t = sch.cta_tile[blockIdx.x];
   long long te = sch.tile_begin[t + 1];
-  for (int ch = 0; ch < nchunk; ch++, qbase += L) {
-    if (g0 + (long long)ch * N == te) { t++; te = sch.tile_begin[t + 1]; }
+  int cl = (int)((g0 - sch.tile_begin[t]) / N);   // chunk ordinal inside the tile
+  for (int ch = 0; ch < nchunk; ch++, qbase += L, cl++) {
+    if (g0 + (long long)ch * N == te) { t++; te = sch.tile_begin[t + 1]; cl = 0; }
     if (t != cur_t) {
-      if (cur_t >= 0) {
-        flush();
-#pragma unroll
-        for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
-      }
       cur_t = t;
       const int rb = t / G;
       zx = rb / C::BPX;
@@ -517,8 +544,8 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
         mbar_arrive_cnt(&emptyL[slot], cnt);
       }
     }
+    chunk_end(cl);
   }
-  flush();
 }
 
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
@@ -545,7 +572,13 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t
   if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
   switch (c->N) {
     case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
-    case 16: launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch); break;
+    case 16: {
+      // A/B switch: the line-ring kernel has no plane switch (no bubble at chunk ends) but streams N + 7 lines per chunk
+      static const bool ring16 = getenv("SBTE_N16_RING") != nullptr;
+      if (ring16) launch_batch3_n<16>(c, spec, parts, part_stride, cells, sch);
+      else launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch);
+      break;
+    }
     case 20: launch_batch3_n<20>(c, spec, parts, part_stride, cells, sch); break;
     case 22: launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch); break;
     case 24: launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch); break;

@@ -230,17 +230,33 @@ int sbte_slab_create(sbte_ctx* c, sbte_slab** out, int cells_local, int order, c
   return 0;
 }
 
+// Unmaps the neighbours' slabs (CUDA IPC) and switches the peer halo off.  Exported memory must not be freed while
+// another process still maps it, so multi-process callers detach on every rank, synchronise the ranks, and only then
+// destroy their slabs (spectralbte_b200/halo.py SlabHalo.close).
+int sbte_slab_peer_detach(sbte_slab* s) {
+  cudaSetDevice(s->c->device);
+  cudaStreamSynchronize(s->c->stream);
+  if (s->graph.exec) { cudaGraphExecDestroy(s->graph.exec); }   // the captured step references the mapped pointers
+  s->graph = sbte_slab::StepGraph();
+  for (int side = 0; side < 2; side++) {
+    sbte_slab::Peer& p = s->nb[side];
+    if (p.on && p.mapped) {
+      // (a closed ring of two ranks maps the same neighbour on both sides: mappings are reference-counted, one close each)
+      for (int a = 0; a < 3; a++)
+        if (p.arr[a]) cudaIpcCloseMemHandle(p.arr[a]);
+      if (p.flags) cudaIpcCloseMemHandle(p.flags);
+    }
+  }
+  for (int side = 0; side < 2; side++) s->nb[side] = sbte_slab::Peer();
+  s->p2p = 0;
+  cudaGetLastError();
+  return 0;
+}
+
 int sbte_slab_destroy(sbte_slab* s) {
   if (!s) return 0;
   cudaSetDevice(s->c->device);
-  cudaStreamSynchronize(s->c->stream);
-  if (s->graph.exec) cudaGraphExecDestroy(s->graph.exec);
-  for (int side = 0; side < 2; side++)
-    if (s->nb[side].on && s->nb[side].mapped) {
-      for (int a = 0; a < 3; a++)
-        if (s->nb[side].arr[a]) cudaIpcCloseMemHandle(s->nb[side].arr[a]);
-      if (s->nb[side].flags) cudaIpcCloseMemHandle(s->nb[side].flags);
-    }
+  sbte_slab_peer_detach(s);
   cudaFree(s->d_flags);
   cudaFree(s->d_x); cudaFree(s->d_dx); cudaFree(s->d_f); cudaFree(s->d_fc); cudaFree(s->d_f1); cudaFree(s->d_ft);
   cudaFree(s->d_fl); cudaFree(s->d_fr); cudaFree(s->d_Q); cudaFree(s->d_mom);

@@ -121,6 +121,15 @@ class SlabHalo:
             return False
         return True
 
+    def close(self):
+        """Collective: every rank unmaps its neighbours, then the ranks synchronise; after that the slabs may be
+        destroyed in any order (memory exported over CUDA IPC must not be freed while a peer still maps it)."""
+        if self.slab.nranks > 1:
+            self.slab.coll.sync()
+            if self.mode == "p2p":
+                self.slab.peer_detach()
+            dist.barrier()
+
     def _regions(self, which, stage):
         key = (which, stage)
         if key not in self._cache:

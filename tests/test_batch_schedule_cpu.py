@@ -49,7 +49,7 @@ def test_schedule_covers_every_step_once(N, cells, sym, ctas):
     s = schedule(N, cells, sym, ctas)
     cols = 8 if N >= 16 else 4                       # Batch2Cfg / Batch3Cfg::COLS
     bpx = -(-N // cols)                              # row-blocks per zeta_x plane
-    ring = N in (20, 22, 24)                         # line-ring kernel: whole xi_x chunks per CTA range
+    ring = True                                      # every kernel works on whole xi_x chunks (canonical summation order)
     G, T, P = s["G"], s["T"], s["P"]
     assert G == -(-cells // 32) and T == G * N * bpx and 1 <= P <= ctas
     begin, tbegin = s["begin"], s["tbegin"]
@@ -81,7 +81,16 @@ def test_schedule_covers_every_step_once(N, cells, sym, ctas):
             c, ey = divmod(sl, N)
             ex = sym_rep(N, zx, c) if sym else c
             assert 0 <= ex < N
-            part = p - int(s["first"][t])
+            # chunk_end() of the kernels: the CTA owning the tile's first chunk folds into part 0, a later CTA writes
+            # every chunk as part 1 + (c - e0), e0 = chunks held by the first CTA
+            first = int(s["first"][t])
+            if p == first:
+                assert sl == k if t == int(s["ctile"][p]) and g0 == tbegin[t] else True
+                part = 0
+            else:
+                assert p > first
+                e0 = (int(begin[first + 1]) - int(tbegin[t])) // N
+                part = 1 + c - e0
             assert 0 <= part < s["kmax"]
             writes.setdefault(t, set()).add(part)
             for w in range(cols):

@@ -63,34 +63,29 @@ CASES = [  # kind, N, cells, sym, ctas
 ]
 
 
-@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")   # the oracle's OpenMP pool; the child only runs the emulation
-@pytest.mark.parametrize("kind,N,cells,sym,ctas", CASES)
-def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
+def run_emulation(tmp_path, kind, N, cells, sym, ctas, tag=""):
+    """Runs the kernels CTA by CTA on the library's schedule; returns (combined Q^ per cell, oracle, W, spectra)."""
     L = _lib()
     o = orc.Oracle(N, 9.0, 1)
     n3 = N ** 3
     W = np.random.default_rng(N).standard_normal(n3 * n3) if N <= 8 else orc.synthetic_weights(N)
-    if sym:
-        Wk = symmetrise_standard(W, N)
-    else:
-        Wk = W
+    Wk = symmetrise_standard(W, N) if sym else W
     s = schedule(N, cells, sym, ctas)
     G, T, P, kmax = s["G"], s["T"], s["P"], s["kmax"]
     # spectra, cell-minor [G][n3][32]; padding cells are zero
     spec = np.zeros((G, n3, 32), dtype=complex)
-    F, fs = [], []
+    F = []
     for b in range(cells):
         f = seeded_f(o.v, 700 + b, noise=0.3) * (1.0 + 0.05 * b)
         Fb = o.fft3d(f.astype(complex))
         F.append(Fb)
-        fs.append(f)
         spec[b // 32, :, b % 32] = Fb
     stride = G * 32 * n3
     parts = np.full(kmax * stride, np.nan + 1j * np.nan, dtype=complex)
     dv = o.v[1] - o.v[0]
     L_eta = 0.5 * N * (2.0 * np.pi / (N * dv))
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
-    out = str(tmp_path / "parts.npy")
+    out = str(tmp_path / ("parts%s.npy" % tag))
 
     def child():   # a deadlocked protocol ends the emulation with _Exit: keep that out of the test runner
         rc = L.emul_batched(kind, N, cells, int(sym), P, p(s["begin"], C.c_longlong), p(s["tbegin"], C.c_longlong), p(s["ctile"], C.c_int),
@@ -105,8 +100,10 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
     proc.join(900)
     assert proc.exitcode == 0, "kernel emulation failed or deadlocked (exit code %s)" % proc.exitcode
     parts = np.load(out)
-    # combine the partial sums the way the inverse transform does: np[(column / np_cols) * G + cell group] parts per column
+    # combine the partial sums the way the inverse transform does: a left fold over np[(column / np_cols) * G + cell group]
+    # parts per column, starting from zero (csrc/fft.cu)
     parts = parts.reshape(kmax, G * 32, n3)
+    Q = []
     for b in range(cells):
         q = np.zeros(n3, dtype=complex)
         for col in range(N * N):
@@ -114,5 +111,30 @@ def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
             assert npc >= 1
             seg = parts[:npc, b, col * N:(col + 1) * N]
             assert not np.isnan(seg.view(np.float64)).any(), (b, col)       # every part the table promises was written
-            q[col * N:(col + 1) * N] = seg.sum(axis=0)
-        assert relmax(q, o.qhat(W, F[b], F[b])) < 1e-12, b
+            acc = np.zeros(N, dtype=complex)
+            for m in range(npc):
+                acc = acc + seg[m]
+            q[col * N:(col + 1) * N] = acc
+        Q.append(q)
+    return Q, o, W, F
+
+
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")   # the oracle's OpenMP pool; the child only runs the emulation
+@pytest.mark.parametrize("kind,N,cells,sym,ctas", CASES)
+def test_kernel_control_flow_on_host(tmp_path, kind, N, cells, sym, ctas):
+    Q, o, W, F = run_emulation(tmp_path, kind, N, cells, sym, ctas)
+    for b in range(cells):
+        assert relmax(Q[b], o.qhat(W, F[b], F[b])) < 1e-12, b
+
+
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
+@pytest.mark.parametrize("N,sym,a,b", [(8, True, (37, 5), (37, 3)), (8, True, (37, 5), (5, 4)), (8, False, (40, 7), (9, 2)),
+                                       (20, True, (3, 4), (2, 7))])
+def test_summation_order_is_independent_of_the_schedule(tmp_path, N, sym, a, b):
+    """Rank-count invariance at the source: the same cell gives the same BITS whatever the number of CTAs and however
+    many other cells share the launch (the reference's per-cell loop, exec/boltz.c:285-345, has that property by
+    construction).  The kernels get it from a canonical order -- left fold over xi_x chunk sums -- in chunk_end()."""
+    Qa, *_ = run_emulation(tmp_path, 0, N, a[0], sym, a[1], "a")
+    Qb, *_ = run_emulation(tmp_path, 0, N, b[0], sym, b[1], "b")
+    for cell in range(min(a[0], b[0])):
+        assert np.array_equal(Qa[cell].view(np.float64), Qb[cell].view(np.float64)), cell
