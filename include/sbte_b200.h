@@ -123,10 +123,11 @@ SBTE_API int sbte_set_symmetrize(sbte_ctx *c, int enable);
 
 /* The stream-K schedule of the batched convolution for `cells` cells on a device with `ctas` SMs (what the
  * library uploads before a batched ComputeQ; exec/boltz.c:285-345 has no counterpart -- its cells are a plain loop).
- * Pure host arithmetic, no device needed.
+ * Pure host arithmetic, no device needed.  split != 0: the second launch that serves a last cell group with at most
+ * 16 live cells at N = 16 on tiles of 16 zeta_y columns x 16 cells (two columns per warp).
  * dims = {G, T, P, np_cols, kmax, np_len}; array pointers may be null:
  * query dims first, then pass arrays of P+1, T+1, P, T and np_len entries.  Fails for N without a scheduled kernel. */
-SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long *cta_begin, long long *tile_begin,
+SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int split, long long *cta_begin, long long *tile_begin,
                                       int *cta_tile, int *tile_first, unsigned char *np, int *dims);
 
 /* kernel selection for the convolution */

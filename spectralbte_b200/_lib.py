@@ -36,7 +36,7 @@ PROTOTYPES = {
     "sbte_launch_count": (C.c_ulonglong, [_vp]),
     "sbte_reserve": (C.c_int, [_vp, C.c_int]),
     "sbte_set_symmetrize": (C.c_int, [_vp, C.c_int]),
-    "sbte_batch_schedule_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
+    "sbte_batch_schedule_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_ubyte), C.POINTER(C.c_int)]),
     "sbte_k2_profile": (C.c_int, [_vp, C.c_int]),
     "sbte_k2_profile_read": (C.c_int, [_vp, C.POINTER(C.c_double), C.POINTER(C.c_int)]),

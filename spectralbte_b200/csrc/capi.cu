@@ -172,6 +172,7 @@ static int make_tensor_map(sbte_ctx* c) {
   c->sched_cells = 0;
   if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
   if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
+  if (qhat_batch_split_supported(c->N) && encode_weight_map(c, c->d_W, &c->tmapW16, 16)) return 1;
   c->tmap_ok = true;
   return 0;
 }
@@ -213,8 +214,10 @@ struct HostSchedule {
 };
 
 // Pure host arithmetic (no CUDA call): also exported as sbte_batch_schedule_host for the CPU tests.
-static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out) {
-  const int cols = qhat_batch_cols(N);
+// split: the schedule of one remainder group on split tiles (qhat_batch.cu Batch3Cfg<N, true>: 16 columns per tile); its
+// CTAs may be as short as one chunk, so that the launch adds about one chunk time after the main launch.
+static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out, bool split = false) {
+  const int cols = split ? 16 : qhat_batch_cols(N);
   // row-blocks never straddle a zeta_x plane: bpx blocks of `cols` zeta_y columns per plane, the last one
   // partly empty when cols does not divide N (N = 20, 22)
   const int bpx = (N + cols - 1) / cols;
@@ -228,7 +231,7 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   }
   const long long total = tbegin[T];
   int P = ctas;
-  const long long min_steps = 4 * (long long)N;  // at least a few xi_x chunks per CTA
+  const long long min_steps = (split ? 1 : 4) * (long long)N;  // at least a few xi_x chunks per CTA
   if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
   std::vector<long long>& begin = out->begin;
   begin.assign(P + 1, 0);
@@ -276,34 +279,87 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
   out->G = G; out->T = T; out->P = P; out->np_cols = per_column ? 1 : cols; out->kmax = kmax;
 }
 
-static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
-  if (c->sched_cells == cells && c->sched_sym == (int)sym && c->d_sched_mem) return 0;
-  c->graph_gen++;   // the schedule tables move: captured slab steps must be rebuilt
-  CK(cudaStreamSynchronize(c->stream));
-  if (c->d_sched_mem) { cudaFree(c->d_sched_mem); c->d_sched_mem = nullptr; }
-  if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
-  int ctas = c->sm_count;
-  const char* pe = getenv("SBTE_BATCH_CTAS");
-  if (pe && atoi(pe) > 0) ctas = atoi(pe);
-  HostSchedule h;
-  build_batch_schedule(c->N, cells, sym, ctas, &h);
-  const int G = h.G, T = h.T, P = h.P, kmax = h.kmax;
+// uploads one host schedule; returns the device view through *dev (tables live in *mem)
+static int upload_schedule(const HostSchedule& h, bool sym, void** mem, BatchSched* dev) {
+  const int T = h.T, P = h.P;
   const size_t o1 = (size_t)(P + 1) * sizeof(long long);
   const size_t o2 = o1 + (size_t)(T + 1) * sizeof(long long);
   const size_t o3 = o2 + (size_t)P * sizeof(int);
   const size_t o4 = o3 + (size_t)T * sizeof(int);
   const size_t bytes = o4 + h.np.size();
-  CK(cudaMalloc(&c->d_sched_mem, bytes));
+  CK(cudaMalloc(mem, bytes));
   std::vector<unsigned char> blob(bytes);
   memcpy(blob.data(), h.begin.data(), o1);
   memcpy(blob.data() + o1, h.tbegin.data(), o2 - o1);
   memcpy(blob.data() + o2, h.ctile.data(), o3 - o2);
   memcpy(blob.data() + o3, h.first.data(), o4 - o3);
   memcpy(blob.data() + o4, h.np.data(), h.np.size());
-  CK(cudaMemcpy(c->d_sched_mem, blob.data(), bytes, cudaMemcpyHostToDevice));
-  unsigned char* base = (unsigned char*)c->d_sched_mem;
-  c->sched = {(const long long*)base, (const long long*)(base + o1), (const int*)(base + o2), (const int*)(base + o3),
-              base + o4, G, T, P, h.np_cols, kmax, sym ? 1 : 0};
+  CK(cudaMemcpy(*mem, blob.data(), bytes, cudaMemcpyHostToDevice));
+  unsigned char* base = (unsigned char*)*mem;
+  *dev = {(const long long*)base, (const long long*)(base + o1), (const int*)(base + o2), (const int*)(base + o3),
+          base + o4, h.G, T, P, h.np_cols, h.kmax, sym ? 1 : 0};
+  return 0;
+}
+
+// Schedules of a batched ComputeQ over `cells` cells.  Ordinarily one launch (c->sched_main == c->sched).  At N = 16 a
+// last cell group with at most 16 live cells runs on split tiles in a second launch (c->sched_split, group c->split_cg):
+// c->sched is then only the view the inverse transform needs -- part counts per zeta column for every group.
+static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
+  if (c->sched_cells == cells && c->sched_sym == (int)sym && (c->d_sched_mem || c->d_sched_mem2)) return 0;
+  c->graph_gen++;   // the schedule tables move: captured slab steps must be rebuilt
+  CK(cudaStreamSynchronize(c->stream));
+  for (void** m : {&c->d_sched_mem, &c->d_sched_mem2, &c->d_sched_mem3})
+    if (*m) { cudaFree(*m); *m = nullptr; }
+  if (c->sm_count == 0) CK(cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device));
+  int ctas = c->sm_count;
+  const char* pe = getenv("SBTE_BATCH_CTAS");
+  if (pe && atoi(pe) > 0) ctas = atoi(pe);
+  const int N = c->N, rem = cells % 32, G = (cells + 31) / 32;
+  static const bool plane16 = getenv("SBTE_N16_PLANE") != nullptr;
+  auto longest = [&](const HostSchedule& hs) {   // chunks of the busiest CTA = duration of the launch in chunk times
+    long long m = 0;
+    for (int p = 0; p < hs.P; p++) m = std::max(m, (hs.begin[p + 1] - hs.begin[p]) / N);
+    return (double)m;
+  };
+  // The split launch follows the main one, so it pays only where dropping the padded group shortens the main launch
+  // by more than the split launch lasts (80 cells: 6 -> 4 + 1 chunk times; 44 cells: 4 -> 4 + 1, not used).
+  bool split = qhat_batch_split_supported(N) && !plane16 && rem >= 1 && rem <= 16;
+  HostSchedule h, h2;
+  if (split) {
+    HostSchedule h0;
+    build_batch_schedule(N, cells, sym, ctas, &h0);
+    build_batch_schedule(N, 16, sym, ctas, &h2, true);
+    double t_split = longest(h2) + 0.5;   // + launch gap and pipeline fill
+    if (cells - rem > 0) {
+      build_batch_schedule(N, cells - rem, sym, ctas, &h);
+      t_split += longest(h);
+    }
+    if (t_split >= longest(h0)) { split = false; h = h0; }
+  } else {
+    build_batch_schedule(N, cells, sym, ctas, &h);
+  }
+  c->cells_main = split ? cells - rem : cells;
+  c->split_on = split;
+  c->split_cg = G - 1;
+  int kmax = 1;
+  if (c->cells_main > 0) {
+    if (upload_schedule(h, sym, &c->d_sched_mem, &c->sched_main)) return 1;
+    kmax = h.kmax;
+  }
+  c->sched = c->sched_main;
+  if (split) {
+    if (upload_schedule(h2, sym, &c->d_sched_mem2, &c->sched_split)) return 1;
+    kmax = std::max(kmax, h2.kmax);
+    // part counts per zeta column and cell group, main groups first, the split group last
+    std::vector<unsigned char> npc((size_t)N * N * G);
+    for (int q = 0; q < N * N; q++) {
+      for (int g = 0; g < G - 1; g++) npc[(size_t)q * G + g] = h.np[(size_t)(q / h.np_cols) * h.G + g];
+      npc[(size_t)q * G + (G - 1)] = h2.np[(size_t)(q / h2.np_cols) * h2.G];
+    }
+    CK(cudaMalloc(&c->d_sched_mem3, npc.size()));
+    CK(cudaMemcpy(c->d_sched_mem3, npc.data(), npc.size(), cudaMemcpyHostToDevice));
+    c->sched = {nullptr, nullptr, nullptr, nullptr, (const unsigned char*)c->d_sched_mem3, G, 0, 0, 1, kmax, sym ? 1 : 0};
+  }
   c->sched_cells = cells;
   c->sched_sym = (int)sym;
   // partial-sum workspace: kmax parts of (padded cells) x n3 complex
@@ -318,13 +374,22 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   return 0;
 }
 
+// the convolution launches of one batched ComputeQ: the main tiles, then the split tiles of the remainder group
+static void launch_batched_conv(sbte_ctx* c, const double2* spec, int batch) {
+  if (c->cells_main > 0) launch_qhat_batch2(c, spec, c->d_parts, c->parts_stride, c->cells_main, c->sched_main);
+  if (c->split_on) launch_qhat_batch_split(c, spec, c->d_parts, c->parts_stride, batch, c->sched_split, c->split_cg);
+}
+
 // Symmetrised weights for f == g (see common.cuh): built lazily, once per bound tensor.
 static int ensure_sym(sbte_ctx* c) {
   if (c->d_Ws) return 0;
   c->graph_gen++;
   CK(cudaMalloc(&c->d_Ws, (size_t)c->n3 * c->n3 * sizeof(double)));
   launch_symmetrize_weights(c, c->d_W, c->d_Ws);
-  if (qhat_batch_supported(c->N)) return encode_weight_map(c, c->d_Ws, &c->tmapWs, 0);
+  if (qhat_batch_supported(c->N)) {
+    if (encode_weight_map(c, c->d_Ws, &c->tmapWs, 0)) return 1;
+    if (qhat_batch_split_supported(c->N) && encode_weight_map(c, c->d_Ws, &c->tmapWs16, 16)) return 1;
+  }
   return 0;
 }
 static bool want_sym(sbte_ctx* c, bool same) {
@@ -372,7 +437,7 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_batched_conv(c, c->d_lay[0], batch);
     launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
   } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
     if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
@@ -415,7 +480,7 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
     if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_f, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_batched_conv(c, c->d_lay[0], batch);
     launch_fft3d_parts(c, c->d_parts, c->parts_stride, c->sched, 1, batch, nullptr, d_Q);
     return check_launch("batched compute_q");
   }
@@ -440,7 +505,7 @@ int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, 
     if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
     launch_fft3d(c, d_src, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
-    launch_qhat_batch2(c, c->d_lay[0], c->d_parts, c->parts_stride, batch, c->sched);
+    launch_batched_conv(c, c->d_lay[0], batch);
     CellEpi epi = {};
     epi.mode = 1; epi.v = c->d_v; epi.wt = c->d_wt; epi.dv3 = c->dv * c->dv * c->dv; epi.lu = c->lu;
     epi.a = a; epi.x = x; epi.b = b; epi.y = y; epi.s = s; epi.Kn = Kn; epi.out = out;
@@ -567,6 +632,8 @@ int sbte_destroy(sbte_ctx* c) {
   if (c->h_pin) cudaFreeHost(c->h_pin);
   for (cudaEvent_t e : c->k2_ev) cudaEventDestroy(e);
   if (c->d_sched_mem) cudaFree(c->d_sched_mem);
+  if (c->d_sched_mem2) cudaFree(c->d_sched_mem2);
+  if (c->d_sched_mem3) cudaFree(c->d_sched_mem3);
   if (c->d_parts) cudaFree(c->d_parts);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -574,14 +641,16 @@ int sbte_destroy(sbte_ctx* c) {
 }
 
 // The stream-K schedule ensure_batch_schedule() would upload for (N, cells, sym) on a device with `ctas` SMs.
-// Pure host arithmetic: works without a GPU (CPU tests, sizing).  dims = {G, T, P, np_cols, kmax, np_len};
+// Pure host arithmetic: works without a GPU (CPU tests, sizing).  split != 0: the schedule of the split-tile launch that
+// serves a remainder group of at most 16 cells at N = 16.  dims = {G, T, P, np_cols, kmax, np_len};
 // any array pointer may be null (query dims first, then call again with arrays of P+1, T+1, P, T, np_len entries).
-int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, long long* cta_begin, long long* tile_begin,
+int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int split, long long* cta_begin, long long* tile_begin,
                              int* cta_tile, int* tile_first, unsigned char* np, int* dims) {
   if (N < 2 || N > 32 || (N % 2) != 0 || cells < 1 || ctas < 1) { set_error("batch schedule: bad arguments"); return 1; }
   if (!qhat_batch_supported(N)) { set_error("batch schedule: this N runs the any-N kernel (no schedule)"); return 1; }
+  if (split && (N != 16 || cells > 16)) { set_error("batch schedule: split tiles serve one group of at most 16 cells at N = 16"); return 1; }
   HostSchedule h;
-  build_batch_schedule(N, cells, sym != 0, ctas, &h);
+  build_batch_schedule(N, split ? 16 : cells, sym != 0, ctas, &h, split != 0);
   if (dims) { dims[0] = h.G; dims[1] = h.T; dims[2] = h.P; dims[3] = h.np_cols; dims[4] = h.kmax; dims[5] = (int)h.np.size(); }
   if (cta_begin) memcpy(cta_begin, h.begin.data(), h.begin.size() * sizeof(long long));
   if (tile_begin) memcpy(tile_begin, h.tbegin.data(), h.tbegin.size() * sizeof(long long));

@@ -67,6 +67,7 @@ struct sbte_ctx {
   bool sym_enabled = true;
   double* d_Ws = nullptr;
   CUtensorMap tmapWs;
+  CUtensorMap tmapW16, tmapWs16;   // boxes of 16 zeta_y columns: split tiles of the N = 16 remainder group
 
   // scratch, sized for `cap` cells
   int cap = 0;
@@ -85,8 +86,14 @@ struct sbte_ctx {
   // batched-convolution schedule + partial-sum workspace (valid for sched_cells cells)
   int sched_cells = 0;
   int sched_sym = -1;
-  BatchSched sched = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};
+  BatchSched sched = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};        // what the inverse transform reads
+  BatchSched sched_main = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};   // main convolution launch
+  BatchSched sched_split = {nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, 0, 0, 0, 0};  // split tiles of the remainder group
+  bool split_on = false;
+  int split_cg = 0, cells_main = 0;
   void* d_sched_mem = nullptr;
+  void* d_sched_mem2 = nullptr;
+  void* d_sched_mem3 = nullptr;
   double2* d_parts = nullptr;
   size_t parts_stride = 0;          // double2 elements per part
   int parts_cap = 0;                // parts allocated
@@ -162,6 +169,9 @@ void launch_qhat_batch_any(sbte_ctx* c, const double2* spec_cellminor, double2* 
 int qhat_batch_align(int N);
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);
+bool qhat_batch_split_supported(int N);
+void launch_qhat_batch_split(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
+                             const BatchSched& sch, int cg_base);
 
 // conserve.cu -- K4 / K5 / moments
 void launch_conserve(sbte_ctx* c, double* Q, int batch);

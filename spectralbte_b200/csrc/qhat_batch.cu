@@ -366,29 +366,37 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
 // When COLS does not divide N (N = 20, 22) the last row-block of every zeta_x plane is partly empty: its surplus
 // warps keep the barrier protocol going (waits and arrivals) but neither multiply nor write, and the weight
 // tile's surplus rows are the next plane's (or, past the end of the tensor, TMA zero fill).
-template <int N>
+// SPLIT (N = 16): the tile of a cell group with at most 16 live cells.  A warp then serves TWO zeta_y columns with 16
+// cells each (lanes 0-15: column 2w, lanes 16-31: column 2w+1), the CTA all 16 columns of a zeta_x plane: half the work
+// of the two ordinary tiles the padded group would need.  Same per-lane arithmetic in the same order, hence the same bits.
+template <int N, bool SPLIT = false>
 struct Batch3Cfg {
-  static constexpr int COLS = 8;
+  static constexpr int WARPS = 8;                    // compute warps
+  static constexpr int COLS = SPLIT ? 16 : 8;        // zeta_y columns per CTA
   static constexpr int BPX = (N + COLS - 1) / COLS;  // row-blocks per zeta_x plane
   static constexpr bool PARTIAL = (N % COLS) != 0;
-  static constexpr int CONSUMERS = COLS * 32;
+  static constexpr int CONSUMERS = WARPS * 32;
   static constexpr int THREADS = CONSUMERS + 128;
   static constexpr int ROWS = COLS * N;
   static constexpr int LINE = N * 32;
-  static constexpr int RING = 10;
-  static constexpr int STAGES = 2;
+  // stages of (xi-side line, weight tile) the producer may run ahead, and a line ring deep enough for that lookahead
+  // (the COLS lines being read + one per stage): N = 16: 4 / 12 (split: 2 / 18), N = 20: 3 / 11, N = 22, 24: 2 / 10
+  static constexpr int STAGES = SPLIT ? 2 : (N <= 16) ? 4 : (N <= 20) ? 3 : 2;
+  static constexpr int RING = COLS + STAGES;
   static constexpr int LPC = N + COLS - 1;          // lines streamed per chunk
   static constexpr size_t LINE_BYTES = (size_t)LINE * 16;
   static constexpr size_t STAGE_BYTES = LINE_BYTES + (size_t)ROWS * N * 8;
   static constexpr size_t SMEM = RING * LINE_BYTES + STAGES * STAGE_BYTES + 512;
   static_assert(SMEM <= 227 * 1024, "line ring + stages must fit in shared memory");
+  static_assert(!SPLIT || (N % 16 == 0 && ROWS <= 256), "split tiles: whole zeta_x planes of 16 columns, TMA box <= 256 rows");
 };
 
-template <int N>
-__global__ void __launch_bounds__(Batch3Cfg<N>::THREADS, 1)
+// cg_base: cell group the (single-group) schedule of a SPLIT launch refers to; 0 otherwise
+template <int N, bool SPLIT>
+__global__ void __launch_bounds__(Batch3Cfg<N, SPLIT>::THREADS, 1)
 qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
-                   double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch) {
-  using C = Batch3Cfg<N>;
+                   double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch, int cg_base) {
+  using C = Batch3Cfg<N, SPLIT>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES, R = C::RING, L = C::LPC;
   SBTE_DYN_SMEM(smraw);
@@ -411,15 +419,15 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   const bool sym = sch.sym != 0;
 
   if (tid == 0) {
-    for (int b = 0; b < S; b++) { mbar_init(&fullS[b], 1); mbar_init(&emptyS[b], C::COLS); }
+    for (int b = 0; b < S; b++) { mbar_init(&fullS[b], 1); mbar_init(&emptyS[b], C::WARPS); }
     for (int b = 0; b < R; b++) { mbar_init(&fullL[b], 1); mbar_init(&emptyL[b], C::COLS); }
     mbar_fence_init();
   }
   __syncthreads();
 
-  if (warp >= C::COLS) {
+  if (warp >= C::WARPS) {
     SBTE_SETMAXNREG_DEC(24);
-    if (warp == C::COLS && lane == 0) {
+    if (warp == C::WARPS && lane == 0) {
       int k = 0;          // local step counter (stage ring)
       long q = 0;         // line sequence number (line ring)
       int t = sch.cta_tile[blockIdx.x];
@@ -432,7 +440,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
         const int ex = sym ? sym_rep(N, zx, cl) : cl;
         int X = zx + N / 2 - ex;
         if (X < 0) X += N; else if (X > N - 1) X -= N;
-        const double2* gs = spec + (size_t)cg * n3 * 32;
+        const double2* gs = spec + (size_t)(cg_base + cg) * n3 * 32;
         int issued = 0;   // lines of this chunk issued so far
         for (int ey = 0; ey < N; ey++, k++) {
           // lines needed by step ey: j' <= COLS-1 + ey
@@ -459,6 +467,9 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   }
 
   SBTE_SETMAXNREG_INC(240);
+  // this lane's zeta_y column inside the CTA's row-block and its cell inside the group
+  const int col = SPLIT ? 2 * warp + (lane >> 4) : warp;
+  const int clane = SPLIT ? (lane & 15) : lane;
   double2 acc[N];
 #pragma unroll
   for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
@@ -470,7 +481,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   // the tile's first chunk, one part per chunk from every later CTA
   auto chunk_end = [&](int c) {
     const int cg = cur_t - (cur_t / G) * G;
-    const long cell = (long)cg * 32 + lane;
+    const long cell = (long)(cg_base + cg) * 32 + clane;
     if (cell < cells && (!C::PARTIAL || zy < N)) {
       const int first = sch.tile_first[cur_t];
       double2* out = parts + cell * n3 + ((long)zx * N + zy) * N;
@@ -502,21 +513,21 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       cur_t = t;
       const int rb = t / G;
       zx = rb / C::BPX;
-      zy = (rb % C::BPX) * C::COLS + warp;
+      zy = (rb % C::BPX) * C::COLS + col;
     }
     const bool live = !C::PARTIAL || zy < N;
     for (int ey = 0; ey < N; ey++, k++) {
       const int st = k % S;
-      const int jl = C::COLS - 1 + ey - warp;          // this warp's line within the chunk
+      const int jl = C::COLS - 1 + ey - col;           // this column's line within the chunk
       const long q = qbase + jl;
       const int slot = (int)(q % R);
       mbar_wait(&fullS[st], (uint32_t)((k / S) & 1));
       mbar_wait(&fullL[slot], (uint32_t)((q / R) & 1));
 
       if (live) {
-        const double2* fl = ring + (size_t)slot * C::LINE + lane;
-        const double2* gl = stage_line(st) + lane;
-        const double* wt = stage_w(st) + warp * N * N;
+        const double2* fl = ring + (size_t)slot * C::LINE + clane;
+        const double2* gl = stage_line(st) + clane;
+        const double* wt = stage_w(st) + col * N * N;
         double2 fr[N];
 #pragma unroll
         for (int z = 0; z < N; z++) fr[z] = fl[z * 32];
@@ -534,13 +545,13 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
         }
       }
       __syncwarp();
-      if (lane == 0) {
-        mbar_arrive(&emptyS[st]);
-        // readers of line jl are the warps with 0 <= jl - (COLS-1) + w' < N; the last one in step order
-        // also arrives for the warps that never read it
+      if (lane == 0) mbar_arrive(&emptyS[st]);
+      if (clane == 0) {
+        // readers of line jl are the columns with 0 <= jl - (COLS-1) + col' < N; the last one in step order
+        // also arrives for the columns that never read it
         uint32_t cnt = 1;
-        if (jl < C::COLS - 1 && warp == C::COLS - 1) cnt = (uint32_t)(C::COLS - jl);
-        if (jl > N - 1 && warp == N + C::COLS - 2 - jl) cnt = (uint32_t)(jl - N + 2);
+        if (jl < C::COLS - 1 && col == C::COLS - 1) cnt = (uint32_t)(C::COLS - jl);
+        if (jl > N - 1 && col == N + C::COLS - 2 - jl) cnt = (uint32_t)(jl - N + 2);
         mbar_arrive_cnt(&emptyL[slot], cnt);
       }
     }
@@ -549,18 +560,18 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
 }
 
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
-template <int N>
-static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
-                            const BatchSched& sch) {
-  using C = Batch3Cfg<N>;
-  auto kern = qhat_batch3_kernel<N>;
+template <int N, bool SPLIT = false>
+static void launch_batch3_n(sbte_ctx* c, const CUtensorMap& tmap, const double2* spec, double2* parts, size_t part_stride, int cells,
+                            const BatchSched& sch, int cg_base = 0) {
+  using C = Batch3Cfg<N, SPLIT>;
+  auto kern = qhat_batch3_kernel<N, SPLIT>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
   if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
     configured.fetch_or(1u << c->device);
   }
   k2_mark(c);
-  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(sch.sym ? c->tmapWs : c->tmapW, spec, parts, part_stride, cells, sch);
+  kern<<<sch.P, C::THREADS, C::SMEM, c->stream>>>(tmap, spec, parts, part_stride, cells, sch, cg_base);
   k2_mark(c);
   c->launches += 1;
 }
@@ -570,20 +581,34 @@ static void launch_batch3_n(sbte_ctx* c, const double2* spec, double2* parts, si
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch) {
   if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
+  const CUtensorMap& tm = sch.sym ? c->tmapWs : c->tmapW;
   switch (c->N) {
     case 8: launch_batch2_n<8>(c, spec, parts, part_stride, cells, sch); break;
     case 16: {
-      // A/B switch: the line-ring kernel has no plane switch (no bubble at chunk ends) but streams N + 7 lines per chunk
-      static const bool ring16 = getenv("SBTE_N16_RING") != nullptr;
-      if (ring16) launch_batch3_n<16>(c, spec, parts, part_stride, cells, sch);
+      // The line-ring kernel has no plane switch (no bubble at chunk ends) although it streams N + 7 lines per chunk;
+      // SBTE_N16_PLANE=1 keeps the resident-plane kernel for A/B runs
+      static const bool ring16 = getenv("SBTE_N16_PLANE") == nullptr;   // default: line ring (2.47 vs 2.69 ms at 640 cells)
+      if (ring16) launch_batch3_n<16>(c, tm, spec, parts, part_stride, cells, sch);
       else launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch);
       break;
     }
-    case 20: launch_batch3_n<20>(c, spec, parts, part_stride, cells, sch); break;
-    case 22: launch_batch3_n<22>(c, spec, parts, part_stride, cells, sch); break;
-    case 24: launch_batch3_n<24>(c, spec, parts, part_stride, cells, sch); break;
+    case 20: launch_batch3_n<20>(c, tm, spec, parts, part_stride, cells, sch); break;
+    case 22: launch_batch3_n<22>(c, tm, spec, parts, part_stride, cells, sch); break;
+    case 24: launch_batch3_n<24>(c, tm, spec, parts, part_stride, cells, sch); break;
     default: set_error("qhat_batch: unsupported N"); break;
   }
+}
+
+// the remainder group (at most 16 live cells) of an N = 16 slab: two columns per warp (Batch3Cfg<16, true>)
+bool qhat_batch_split_supported(int N) {
+  static const bool off = getenv("SBTE_NO_SPLIT16") != nullptr;
+  return N == 16 && !off;
+}
+void launch_qhat_batch_split(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
+                             const BatchSched& sch, int cg_base) {
+  if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
+  if (c->N != 16) { set_error("qhat_batch: split tiles exist for N = 16 only"); return; }
+  launch_batch3_n<16, true>(c, sch.sym ? c->tmapWs16 : c->tmapW16, spec, parts, part_stride, cells, sch, cg_base);
 }
 #endif
 

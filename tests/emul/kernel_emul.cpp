@@ -46,13 +46,22 @@ void run_batch3(const Args& a) {
   const CUtensorMap tm = fake_map(a.W, (long long)N * N * N, N, C::COLS * N);
   for (int p = 0; p < a.P; p++)
     emul::run_cta(p, a.P, C::THREADS, C::SMEM,
-                  [&](int) { qhat_batch3_kernel<N>(tm, a.spec, a.parts, a.stride, a.cells, a.sch); });
+                  [&](int) { qhat_batch3_kernel<N, false>(tm, a.spec, a.parts, a.stride, a.cells, a.sch, 0); });
+}
+// split tiles: the remainder group `cg_base` (at most 16 live cells), two zeta_y columns per warp
+template <int N>
+void run_batch3_split(const Args& a, int cg_base) {
+  using C = Batch3Cfg<N, true>;
+  const CUtensorMap tm = fake_map(a.W, (long long)N * N * N, N, C::COLS * N);
+  for (int p = 0; p < a.P; p++)
+    emul::run_cta(p, a.P, C::THREADS, C::SMEM,
+                  [&](int) { qhat_batch3_kernel<N, true>(tm, a.spec, a.parts, a.stride, a.cells, a.sch, cg_base); });
 }
 }  // namespace
 
 extern "C" {
 
-// kind: 0 = the library's kernels (qhat_batch2 / qhat_batch3).
+// kind: 0 = qhat_batch2 (N = 8, 16) / qhat_batch3 (N = 20, 22, 24); 1 = qhat_batch3<16>; 100 + g = qhat_batch3<16, split> on group g.
 // Schedule tables as returned by sbte_batch_schedule_host (host pointers); W = the tensor the kernel streams
 // (plain or symmetrised, matching `sym`); spec = cell-minor spectra [G][n3][32] complex;
 // parts = kmax * stride complex, pre-filled by the caller.
@@ -63,7 +72,8 @@ int emul_batched(int kind, int N, int cells, int sym, int P, const long long* ct
   a.N = N; a.cells = cells; a.P = P;
   a.sch = {cta_begin, tile_begin, cta_tile, tile_first, np, G, T, P, np_cols, kmax, sym};
   a.W = W; a.spec = (const double2*)spec; a.parts = (double2*)parts;
-  a.stride = (size_t)G * 32 * (size_t)N * N * N;
+  // parts are laid out for ALL cell groups of the batch; a split launch (kind = 100 + g) serves the last group g only
+  a.stride = (size_t)(kind >= 100 ? kind - 100 + 1 : G) * 32 * (size_t)N * N * N;
   a.L_eta = L_eta; a.L_v = L_v;
   if (kind == 0) {
     if (N == 8) run_batch2<8>(a);
@@ -71,6 +81,12 @@ int emul_batched(int kind, int N, int cells, int sym, int P, const long long* ct
     else if (N == 20) run_batch3<20>(a);
     else if (N == 22) run_batch3<22>(a);
     else if (N == 24) run_batch3<24>(a);
+    else return 1;
+  } else if (kind == 1) {   // N = 16 on the line-ring kernel (the library's default for N = 16)
+    if (N == 16) run_batch3<16>(a);
+    else return 1;
+  } else if (kind >= 100) {   // N = 16 split tiles; kind - 100 = the cell group they serve (schedule built with split = 1)
+    if (N == 16) run_batch3_split<16>(a, kind - 100);
     else return 1;
   } else {
     return 1;

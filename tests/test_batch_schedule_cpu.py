@@ -14,10 +14,10 @@ def _lib():
     return _lib.load()
 
 
-def schedule(N, cells, sym, ctas):
+def schedule(N, cells, sym, ctas, split=False):
     L = _lib()
     dims = (C.c_int * 6)()
-    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, None, None, None, None, None, dims) == 0
+    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, int(split), None, None, None, None, None, dims) == 0
     G, T, P, np_cols, kmax, np_len = list(dims)
     begin = np.zeros(P + 1, dtype=np.int64)
     tbegin = np.zeros(T + 1, dtype=np.int64)
@@ -25,7 +25,7 @@ def schedule(N, cells, sym, ctas):
     first = np.zeros(T, dtype=np.int32)
     npt = np.zeros(np_len, dtype=np.uint8)
     p = lambda a, t: a.ctypes.data_as(C.POINTER(t))  # noqa: E731
-    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, p(begin, C.c_longlong), p(tbegin, C.c_longlong),
+    assert L.sbte_batch_schedule_host(N, cells, int(sym), ctas, int(split), p(begin, C.c_longlong), p(tbegin, C.c_longlong),
                                       p(ctile, C.c_int), p(first, C.c_int), p(npt, C.c_ubyte), dims) == 0
     return dict(G=G, T=T, P=P, np_cols=np_cols, kmax=kmax, begin=begin, tbegin=tbegin, ctile=ctile, first=first, np=npt)
 
@@ -120,12 +120,12 @@ def test_schedule_covers_every_step_once(N, cells, sym, ctas):
 def test_schedule_rejects_unscheduled_n():
     L = _lib()
     dims = (C.c_int * 6)()
-    assert L.sbte_batch_schedule_host(12, 40, 1, 148, None, None, None, None, None, dims) != 0
+    assert L.sbte_batch_schedule_host(12, 40, 1, 148, 0, None, None, None, None, None, dims) != 0
     assert b"any-N" in L.sbte_last_error()
-    assert L.sbte_batch_schedule_host(16, 0, 1, 148, None, None, None, None, None, dims) != 0
+    assert L.sbte_batch_schedule_host(16, 0, 1, 148, 0, None, None, None, None, None, dims) != 0
 
 
-@pytest.mark.parametrize("N", [20, 22, 24])
+@pytest.mark.parametrize("N", [16, 20, 22, 24])
 def test_line_ring_arrival_counts_complete_every_slot(N):
     """qhat_batch3_kernel: each of the L = N + COLS - 1 lines of a chunk is read by the warps w with
     0 <= jl - (COLS-1) + w < N; the reader that comes last in step order also arrives for the warps that never
@@ -153,7 +153,7 @@ def test_line_ring_arrival_counts_complete_every_slot(N):
     assert all(1 <= r <= COLS for r in readers)
     # the producer needs line j' <= COLS-1 + ey before step ey: never more than COLS + 1 lines ahead of the oldest
     # line still being read, which must fit the ring
-    RING = 10
+    RING = 8 + (4 if N <= 16 else 3 if N <= 20 else 2)   # Batch3Cfg::RING = COLS + STAGES
     for ey in range(N):
         newest = min(L - 1, COLS - 1 + ey)
         oldest = max(0, ey)          # warp COLS-1 reads line ey at step ey

@@ -280,6 +280,32 @@ def test_batched_computeq_matches_oracle(sb, N, cells, k2):
         assert relmax(Q[b], Qo) < TOL_QHAT
 
 
+@pytest.mark.parametrize("cells", [12, 44, 80])
+def test_split_tiles_of_the_remainder_group_n16(sb, cells):
+    """N = 16: a last cell group with at most 16 live cells runs on split tiles (two zeta_y columns per warp) in a second
+    launch.  Every cell against the generic kernel and three against the oracle; and the cells of the split group must
+    carry the same BITS as when they sit in a full group on ordinary tiles (rank-count invariance: which tile shape
+    serves a cell depends on how many cells the rank holds)."""
+    N = 16
+    o = orc.Oracle(N, 9.0, 1)
+    c = sb.Collisions(N, 9.0, inhomogeneous=True)
+    c.synthetic_weights(11)
+    W = c.weights_to_host()
+    full = -(-cells // 32) * 32
+    f = np.stack([seeded_f(o.v, 300 + b, noise=0.2) * (1.0 + 0.01 * b) for b in range(full)])
+    for sym in (True, False):
+        c.set_symmetrize(sym)
+        qh = c.Qhat(f[:cells], k2=sb.K2_BATCH).reshape(cells, -1)
+        qg = c.Qhat(f[:cells], k2=sb.K2_GENERIC).reshape(cells, -1)
+        for b in range(cells):
+            assert relmax(qh[b], qg[b]) < TOL_QHAT, (sym, b)
+        Qs = c.ComputeQ(f[:cells], k2=sb.K2_BATCH).reshape(cells, -1)
+        Qf = c.ComputeQ(f, k2=sb.K2_BATCH).reshape(full, -1)          # the same cells inside a full last group
+        assert np.array_equal(Qs, Qf[:cells]), sym
+    for b in (0, cells - 1):
+        assert relmax(Qs[b], o.compute_q(W, f[b], f[b])) < TOL_QHAT   # Qs: the unsymmetrised pass
+
+
 @pytest.mark.parametrize("N,cells", [(22, 70), (20, 33), (22, 250)])
 def test_line_ring_with_partial_row_blocks(sb, N, cells):
     """N = 20, 22: 8 zeta_y columns per CTA do not tile a zeta_x plane, so every third row-block is partly

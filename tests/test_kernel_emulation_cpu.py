@@ -56,31 +56,42 @@ def symmetrise_standard(W, N):
 
 CASES = [  # kind, N, cells, sym, ctas
     (0, 8, 37, True, 5), (0, 8, 5, False, 3),            # qhat_batch2_kernel<8>
-    (0, 16, 3, True, 3),                                   # qhat_batch2_kernel<16>
+    (0, 16, 3, True, 3),                                   # qhat_batch2_kernel<16> (SBTE_N16_PLANE=1)
+    (1, 16, 3, True, 3),                                   # qhat_batch3_kernel<16> (the default at N = 16)
     (0, 20, 3, True, 4),                                   # qhat_batch3_kernel<20> (partly empty row-blocks)
     (0, 22, 2, False, 3),                                  # qhat_batch3_kernel<22>
     (0, 24, 1, True, 3),                                   # qhat_batch3_kernel<24>
 ]
 
 
-def run_emulation(tmp_path, kind, N, cells, sym, ctas, tag=""):
-    """Runs the kernels CTA by CTA on the library's schedule; returns (combined Q^ per cell, oracle, W, spectra)."""
+def run_emulation(tmp_path, kind, N, cells, sym, ctas, tag="", split_group=None):
+    """Runs the kernels CTA by CTA on the library's schedule; returns (combined Q^ per cell, oracle, W, spectra).
+    split_group = g: only the split-tile launch that serves the last cell group g (at most 16 live cells) is run; the
+    result list then holds None for the cells of the other groups."""
     L = _lib()
     o = orc.Oracle(N, 9.0, 1)
     n3 = N ** 3
     W = np.random.default_rng(N).standard_normal(n3 * n3) if N <= 8 else orc.synthetic_weights(N)
     Wk = symmetrise_standard(W, N) if sym else W
-    s = schedule(N, cells, sym, ctas)
+    Gtot = -(-cells // 32)
+    if split_group is None:
+        s = schedule(N, cells, sym, ctas)
+        assert s["G"] == Gtot
+    else:
+        assert split_group == Gtot - 1 and 1 <= cells - 32 * split_group <= 16
+        s = schedule(N, cells - 32 * split_group, sym, ctas, split=True)
+        assert s["G"] == 1
+        kind = 100 + split_group
     G, T, P, kmax = s["G"], s["T"], s["P"], s["kmax"]
-    # spectra, cell-minor [G][n3][32]; padding cells are zero
-    spec = np.zeros((G, n3, 32), dtype=complex)
+    # spectra, cell-minor [Gtot][n3][32]; padding cells are zero
+    spec = np.zeros((Gtot, n3, 32), dtype=complex)
     F = []
     for b in range(cells):
         f = seeded_f(o.v, 700 + b, noise=0.3) * (1.0 + 0.05 * b)
         Fb = o.fft3d(f.astype(complex))
         F.append(Fb)
         spec[b // 32, :, b % 32] = Fb
-    stride = G * 32 * n3
+    stride = Gtot * 32 * n3
     parts = np.full(kmax * stride, np.nan + 1j * np.nan, dtype=complex)
     dv = o.v[1] - o.v[0]
     L_eta = 0.5 * N * (2.0 * np.pi / (N * dv))
@@ -102,12 +113,16 @@ def run_emulation(tmp_path, kind, N, cells, sym, ctas, tag=""):
     parts = np.load(out)
     # combine the partial sums the way the inverse transform does: a left fold over np[(column / np_cols) * G + cell group]
     # parts per column, starting from zero (csrc/fft.cu)
-    parts = parts.reshape(kmax, G * 32, n3)
+    parts = parts.reshape(kmax, Gtot * 32, n3)
     Q = []
     for b in range(cells):
+        if split_group is not None and b // 32 != split_group:
+            Q.append(None)
+            continue
+        g = 0 if split_group is not None else b // 32
         q = np.zeros(n3, dtype=complex)
         for col in range(N * N):
-            npc = int(s["np"][(col // s["np_cols"]) * G + b // 32])
+            npc = int(s["np"][(col // s["np_cols"]) * G + g])
             assert npc >= 1
             seg = parts[:npc, b, col * N:(col + 1) * N]
             assert not np.isnan(seg.view(np.float64)).any(), (b, col)       # every part the table promises was written
@@ -138,3 +153,17 @@ def test_summation_order_is_independent_of_the_schedule(tmp_path, N, sym, a, b):
     Qb, *_ = run_emulation(tmp_path, 0, N, b[0], sym, b[1], "b")
     for cell in range(min(a[0], b[0])):
         assert np.array_equal(Qa[cell].view(np.float64), Qb[cell].view(np.float64)), cell
+
+
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
+@pytest.mark.parametrize("sym,cells,ctas_split", [(True, 35, 40), (False, 44, 7)])
+def test_split_tiles_give_the_bits_of_ordinary_tiles(tmp_path, sym, cells, ctas_split):
+    """N = 16: a last cell group with at most 16 live cells runs on split tiles (two zeta_y columns per warp, 16 cells each,
+    Batch3Cfg<16, true>).  Same per-lane arithmetic in the same canonical order: its cells must come out bit-identical to
+    the ordinary line-ring tiles (kind 1) serving the padded group -- and both must equal the oracle to 1e-12."""
+    g = (cells - 1) // 32
+    Qs, o, W, F = run_emulation(tmp_path, 0, 16, cells, sym, ctas_split, "s", split_group=g)
+    Qr, *_ = run_emulation(tmp_path, 1, 16, cells, sym, 5, "r")
+    for b in range(32 * g, cells):
+        assert relmax(Qs[b], o.qhat(W, F[b], F[b])) < 1e-12, b
+        assert np.array_equal(Qs[b].view(np.float64), Qr[b].view(np.float64)), b
