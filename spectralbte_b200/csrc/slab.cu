@@ -125,56 +125,47 @@ static int array_id(const sbte_slab* s, const double* p) {
   return -1;
 }
 
-// peer-halo prologue of an upwind pass reading `src`: publish "src complete", wait for the neighbours' src and
-// for their reads of the previous pass, and return the mapped boundary cells (null where there is no peer)
-static void peer_begin(sbte_slab* s, const double* src, const double** peerL, const double** peerR) {
+// peer-memory halo of an upwind pass reading `src`: the mapped boundary cells of the neighbours (null where there is
+// no peer) and the flag words the stencil kernel orders itself with
+static HaloSync peer_halo(sbte_slab* s, const double* src, const double** peerL, const double** peerR) {
   *peerL = *peerR = nullptr;
-  if (!s->p2p) return;
-  sbte_ctx* c = s->c;
-  const long n3 = c->n3;
+  HaloSync hs = {nullptr, nullptr, nullptr, 0};
+  if (!s->p2p) return hs;
+  const long n3 = s->c->n3;
   const int id = array_id(s, src);
-  launch_halo_begin(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr,
-                    s->halo_timeout);
-  c->launches += 1;
   if (s->nb[0].on) *peerL = s->nb[0].arr[id] + (long)s->nb[0].cells * n3;   // their last `order` owned cells
   if (s->nb[1].on) *peerR = s->nb[1].arr[id] + (long)s->order * n3;         // their first `order` owned cells
-}
-static void peer_end(sbte_slab* s) {
-  if (!s->p2p) return;
-  launch_halo_end(s->c->stream, s->d_flags);
-  s->c->launches += 1;
+  hs.my = s->d_flags;
+  hs.nbL = s->nb[0].on ? s->nb[0].flags : nullptr;
+  hs.nbR = s->nb[1].on ? s->nb[1].flags : nullptr;
+  hs.timeout = s->halo_timeout;
+  return hs;
 }
 
-// one upwindTwo pass src -> dst (src/transportroutines.c:241-470); ghosts from neighbours must be in place
-static void upwind_two_pass(sbte_slab* s, double* src, double* dst) {
+// one upwindTwo pass src -> dst (src/transportroutines.c:241-470); ghosts from neighbours must be in place.
+// avg != null: dst = (avg + pass result) / 2, the closing average of advectTwo (:487-491) folded into its second pass.
+static void upwind_two_pass(sbte_slab* s, double* src, double* dst, const double* avg) {
   sbte_ctx* c = s->c;
-  const long n3 = c->n3;
   const int nX = s->nX, ic = s->ic, N = c->N;
   cudaStream_t st = c->stream;
   const bool first = s->rank == 0, last = s->rank == s->nranks - 1;
-  if (first) {
-    launch_extrapolate(st, src, n3, 1, 2, 3); c->launches++;
-    const bool wall = (ic == 3 || ic == 5 || ic == 1);
-    launch_wall_face(st, src, s->d_fl, s->d_x, s->d_dx, N, 2, 0, wall ? 0 : 1); c->launches++;
-    if (wall) {
-      launch_diffuse_bc(st, s->d_fl, s->d_fl, c->d_v, c->d_wt, N, c->dv, (ic == 1) ? 2.0 * s->TWall_in : T0_WALL, 0);
-      c->launches++;
-    }
+  const bool wallL = (ic == 3 || ic == 5 || ic == 1), wallR = (ic == 3 || ic == 5);
+  if (first || last) {   // extrapolated ghost + wall face of each physical end this rank holds: one launch
+    launch_edge_prep(st, src, s->d_fl, s->d_fr, s->d_x, s->d_dx, N, nX, first ? 1 : 0, last ? 1 : 0, wallL ? 0 : 1, wallR ? 0 : 1);
+    c->launches++;
   }
-  if (last) {
-    launch_extrapolate(st, src, n3, nX + 2, nX + 1, nX); c->launches++;
-    const bool wall = (ic == 3 || ic == 5);
-    launch_wall_face(st, src, s->d_fr, s->d_x, s->d_dx, N, nX + 1, 1, wall ? 0 : 1); c->launches++;
-    if (wall) { launch_diffuse_bc(st, s->d_fr, s->d_fr, c->d_v, c->d_wt, N, c->dv, T1_WALL, 1); c->launches++; }
+  if (first && wallL) {
+    launch_diffuse_bc(st, s->d_fl, s->d_fl, c->d_v, c->d_wt, N, c->dv, (ic == 1) ? 2.0 * s->TWall_in : T0_WALL, 0);
+    c->launches++;
   }
+  if (last && wallR) { launch_diffuse_bc(st, s->d_fr, s->d_fr, c->d_v, c->d_wt, N, c->dv, T1_WALL, 1); c->launches++; }
   const double *peerL, *peerR;
-  peer_begin(s, src, &peerL, &peerR);
+  const HaloSync hs = peer_halo(s, src, &peerL, &peerR);
   // Poiseuille forcing coefficient Ma*0.5*dt/(2*h_v), Ma = 1, h_v = 2 L_v/(N-1) (src/transportroutines.c:37,255,431)
   const double force = (ic == 5) ? 1.0 * 0.5 * s->dt / (2 * (2 * c->L_v / (N - 1))) : 0.0;
   launch_upwind_two(st, src, dst, s->d_fl, s->d_fr, c->d_v, s->d_x, s->d_dx, N, nX, s->dt, first ? 1 : 0, last ? 1 : 0,
-                    peerL, peerR, force);
+                    peerL, peerR, force, avg, hs);
   c->launches++;
-  peer_end(s);
 }
 
 static void pick(sbte_slab* s, int which, double*& A, double*& B) {
@@ -406,26 +397,21 @@ int sbte_slab_upwind_stage(sbte_slab* s, int which, int stage) {
   if (s->order == 1) {
     fill_ghosts_one(s, A);
     const double *peerL, *peerR;
-    peer_begin(s, A, &peerL, &peerR);
-    launch_upwind_one(c->stream, A, B, c->d_v, s->d_dx, c->N, s->nX, s->dt, peerL, peerR);
+    const HaloSync hs = peer_halo(s, A, &peerL, &peerR);
+    launch_upwind_one(c->stream, A, B, c->d_v, s->d_dx, c->N, s->nX, s->dt, peerL, peerR, hs);
     c->launches++;
-    peer_end(s);
   } else {
-    if (stage == 0) upwind_two_pass(s, A, s->d_ft);
-    else upwind_two_pass(s, s->d_ft, B);
+    if (stage == 0) upwind_two_pass(s, A, s->d_ft, nullptr);
+    else upwind_two_pass(s, s->d_ft, B, A);   // with the closing average (A + pass) / 2
   }
   return launch_ok("upwind");
 }
 
+// kept for callers of the staged interface: the average of advectTwo (src/transportroutines.c:487-491) is now part of
+// the second upwind stage, so there is nothing left to do here
 int sbte_slab_advect_finish(sbte_slab* s, int which) {
-  cudaSetDevice(s->c->device);
-  if (s->order == 1) return 0;
-  double *A, *B;
-  pick(s, which, A, B);
-  const long n3 = s->c->n3;
-  launch_average(s->c->stream, cell(A, n3, 2), cell(B, n3, 2), (long)s->nX * n3);
-  s->c->launches++;
-  return launch_ok("advect average");
+  (void)s; (void)which;
+  return 0;
 }
 
 int sbte_slab_advect(sbte_slab* s, int which) {
@@ -447,7 +433,7 @@ int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
   const int o = s->order, nX = s->nX;
   double* fc = cell(s->d_fc, n3, o);
   double* f = cell(s->d_f, n3, o);
-  if (s->p2p) {   // the update below overwrites cells the neighbours may still be reading in their last pass
+  if (s->p2p && o == 1) {   // first order: the update below overwrites f, which the neighbours read in the same pass
     launch_halo_quiesce(c->stream, s->d_flags, s->nb[0].on ? s->nb[0].flags : nullptr, s->nb[1].on ? s->nb[1].flags : nullptr,
                         s->halo_timeout);
     c->launches++;

@@ -63,42 +63,20 @@ __device__ __forceinline__ const double* cell_src(const double* __restrict__ f, 
   return f + (long)l * n3;
 }
 
-__global__ void __launch_bounds__(256)
-upwind_one_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ v,
-                  const double* __restrict__ dx, int N, int nX, double dt, const double* __restrict__ peerL,
-                  const double* __restrict__ peerR) {
-  const long n3 = (long)N * N * N;
-  const int l = blockIdx.y + 1;
-  const double* fl = f + (long)l * n3;
-  const double* fm = cell_src<1>(f, peerL, peerR, n3, nX, l - 1);
-  const double* fp = cell_src<1>(f, peerL, peerR, n3, nX, l + 1);
-  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
-    const int i = (int)(p / (N * N));
-    const double cfl = dt * v[i] / dx[l];
-    double r;
-    if (i < N / 2) r = (1.0 + cfl) * fl[p] - cfl * fp[p];
-    else r = (1.0 - cfl) * fl[p] + cfl * fm[p];
-    fc[(long)l * n3 + p] = r;
-  }
-}
-
-void launch_upwind_one(cudaStream_t st, const double* f, double* fc, const double* v, const double* dx, int N, int nX,
-                       double dt, const double* peerL, const double* peerR) {
-  const long n3 = (long)N * N * N;
-  dim3 grid((unsigned)((n3 + 255) / 256), nX);
-  upwind_one_kernel<<<grid, 256, 0, st>>>(f, fc, v, dx, N, nX, dt, peerL, peerR);
-}
-
 // ---------------------------------------------------------------- cross-GPU ordering for peer halos
-// Each rank owns two counters in IPC-shared device memory: ready (source array of pass e is complete) and
-// done (my reads of the neighbours' arrays in pass e are complete).  Plain stream order on each GPU plus
-// these two tiny kernels replaces the host-synchronised message exchange.
-// Flags of one rank: {ready, done, epoch, error}.  epoch counts this rank's upwind passes ON THE DEVICE, so the same
-// launches can be replayed from a CUDA graph; every rank issues the same sequence of passes.
-//   begin: epoch++ ; ready = epoch ("my source array is complete") ; wait until each neighbour is ready for
-//          this pass and has finished reading my cells in the previous one (done >= epoch - 1)
-//   end:   done = epoch ("I no longer read my neighbours' source array of this pass")
-//   quiesce: wait until the neighbours' done reaches my epoch (before overwriting cells they may be reading)
+// Each rank owns a few words in IPC-shared device memory -- flags {ready, done, epoch, error, blocks} -- and the
+// stencil kernels themselves keep the ranks in step (no separate flag kernels, no host involvement, so a whole time
+// step is one CUDA-graph replay):
+//   entering pass e = epoch + 1 (epoch counts this rank's completed passes ON THE DEVICE; every rank issues the same
+//   sequence of passes): block (0,0) publishes ready = e -- the source array is complete, stream order guarantees it;
+//   only the blocks that touch the slab's ends wait: the first block row until the LEFT neighbour is ready for pass e
+//   and has finished reading my cells in pass e-1 (its done >= e-1: this pass may overwrite what it read), the last
+//   block row likewise on the RIGHT neighbour; interior blocks never wait;
+//   leaving: the last block of the grid to finish publishes done = e (my reads of the neighbours' arrays are
+//   complete) and epoch = e.
+//   quiesce (first order only): wait until the neighbours' done reaches my epoch before the collision update
+//   overwrites f, which they read in the same pass.  At second order the update writes f_1 and f_conv, neither of
+//   which a neighbour reads before my next pass publishes ready, and the waits above cover every other overwrite.
 // Waits are bounded by `timeout` clock cycles (0 = wait for ever; the slab passes SBTE_HALO_TIMEOUT_S, default 120 s).
 // A rank may legitimately be late (writing files, instantiating a graph, stopped in a debugger), so running out of
 // time is NOT a trap: the waiting rank raises the error word flags[3], stops waiting -- every later wait of this slab
@@ -110,73 +88,122 @@ __device__ __forceinline__ void spin_until(volatile int* my, const volatile int*
     const long long t0 = clock64();
     while ((L && (L[0] < vr || L[1] < vd)) || (R && (R[0] < vr || R[1] < vd))) {
       if (timeout > 0 && clock64() - t0 > timeout) { my[3] = 1; break; }
-      __nanosleep(64);
+      __nanosleep(32);
     }
   }
   __threadfence_system();
 }
-__global__ void halo_begin_kernel(int* my, const int* nbL, const int* nbR, long long timeout) {
-  volatile int* m = reinterpret_cast<volatile int*>(my);
-  const int e = m[2] + 1;
-  m[2] = e;
-  __threadfence_system();
-  m[0] = e;
-  __threadfence_system();
-  spin_until(m, reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), e, e - 1, timeout);
+// all threads of the block; returns the pass number.  needL / needR: this block reads the left / right neighbour's
+// cells or writes cells that neighbour reads.
+__device__ __forceinline__ int halo_enter(const HaloSync& h, bool needL, bool needR) {
+  if (!h.my) return 0;
+  __shared__ int s_pass;
+  if (threadIdx.x == 0) {
+    volatile int* m = reinterpret_cast<volatile int*>(h.my);
+    const int e = m[2] + 1;
+    if (blockIdx.x == 0 && blockIdx.y == 0) {
+      __threadfence_system();
+      m[0] = e;
+      __threadfence_system();
+    }
+    const volatile int* L = (needL && h.nbL) ? reinterpret_cast<const volatile int*>(h.nbL) : nullptr;
+    const volatile int* R = (needR && h.nbR) ? reinterpret_cast<const volatile int*>(h.nbR) : nullptr;
+    if (L || R) spin_until(m, L, R, e, e - 1, h.timeout);
+    s_pass = e;
+  }
+  __syncthreads();
+  return s_pass;
 }
-__global__ void halo_end_kernel(int* my) {
-  __threadfence_system();
-  volatile int* m = reinterpret_cast<volatile int*>(my);
-  m[1] = m[2];
-  __threadfence_system();
+__device__ __forceinline__ void halo_leave(const HaloSync& h, int e) {
+  if (!h.my) return;
+  __syncthreads();   // every load of this block has been consumed
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    const int total = (int)(gridDim.x * gridDim.y);
+    if (atomicAdd(h.my + 4, 1) == total - 1) {
+      volatile int* m = reinterpret_cast<volatile int*>(h.my);
+      m[4] = 0;
+      __threadfence_system();
+      m[1] = e;
+      m[2] = e;
+      __threadfence_system();
+    }
+  }
 }
+
+__global__ void __launch_bounds__(256)
+upwind_one_kernel(const double* __restrict__ f, double* __restrict__ fc, const double* __restrict__ v,
+                  const double* __restrict__ dx, int N, int nX, double dt, const double* __restrict__ peerL,
+                  const double* __restrict__ peerR, HaloSync hs) {
+  const long n3 = (long)N * N * N;
+  const int l = blockIdx.y + 1;
+  const int pass = halo_enter(hs, l == 1, l == nX);
+  const double* fl = f + (long)l * n3;
+  const double* fm = cell_src<1>(f, peerL, peerR, n3, nX, l - 1);
+  const double* fp = cell_src<1>(f, peerL, peerR, n3, nX, l + 1);
+  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
+    const int i = (int)(p / (N * N));
+    const double cfl = dt * v[i] / dx[l];
+    double r;
+    if (i < N / 2) r = (1.0 + cfl) * fl[p] - cfl * __ldcg(fp + p);
+    else r = (1.0 - cfl) * fl[p] + cfl * __ldcg(fm + p);
+    fc[(long)l * n3 + p] = r;
+  }
+  halo_leave(hs, pass);
+}
+
+void launch_upwind_one(cudaStream_t st, const double* f, double* fc, const double* v, const double* dx, int N, int nX,
+                       double dt, const double* peerL, const double* peerR, const HaloSync& hs) {
+  const long n3 = (long)N * N * N;
+  dim3 grid((unsigned)((n3 + 255) / 256), nX);
+  upwind_one_kernel<<<grid, 256, 0, st>>>(f, fc, v, dx, N, nX, dt, peerL, peerR, hs);
+}
+
 __global__ void halo_quiesce_kernel(int* my, const int* nbL, const int* nbR, long long timeout) {
   volatile int* m = reinterpret_cast<volatile int*>(my);
   spin_until(m, reinterpret_cast<const volatile int*>(nbL), reinterpret_cast<const volatile int*>(nbR), 0, m[2], timeout);
 }
-void launch_halo_begin(cudaStream_t st, int* my, const int* nbL, const int* nbR, long long timeout) {
-  halo_begin_kernel<<<1, 1, 0, st>>>(my, nbL, nbR, timeout);
-}
-void launch_halo_end(cudaStream_t st, int* my) { halo_end_kernel<<<1, 1, 0, st>>>(my); }
 void launch_halo_quiesce(cudaStream_t st, int* my, const int* nbL, const int* nbR, long long timeout) {
   halo_quiesce_kernel<<<1, 1, 0, st>>>(my, nbL, nbR, timeout);
 }
 
 // ---------------------------------------------------------------- second order (K6b)
-// ghost by linear extrapolation: f[dst] = 2 f[a] - f[b]
-__global__ void extrapolate_kernel(double* __restrict__ f, long n3, int dst, int a, int b) {
-  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x)
-    f[dst * n3 + p] = 2 * f[a * n3 + p] - f[b * n3 + p];
-}
-void launch_extrapolate(cudaStream_t st, double* f, long n3, int dst, int a, int b) {
-  extrapolate_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(f, n3, dst, a, b);
-}
-
-// wall face values from the limited slope in the wall cell `l` (2 on the left, nX+1 on the right):
-//   left  wall: outgoing half (i <  N/2): face = f_l - dx/2 * s ; no-flux fill (i >= N/2): f_l + dx/2 * s
-//   right wall: outgoing half (i >= N/2): face = f_l + dx/2 * s ; no-flux fill (i <  N/2): f_l - dx/2 * s
-// `fill_noflux` = 1 writes both halves (no wall model); 0 writes only the outgoing half (the diffuse
-// kernel then fills the incoming half).
-__global__ void wall_face_kernel(const double* __restrict__ f, double* __restrict__ face, const double* __restrict__ x,
-                                 const double* __restrict__ dx, int N, int l, int right, int fill_noflux) {
+// Physical ends of the slab at second order (src/transportroutines.c:271-297 ghosts, :351-404 wall faces), one launch for
+// both ends (blockIdx.y: 0 = left, 1 = right, when both are requested):
+//   ghost cell by linear extrapolation, f[g] = 2 f[l] - f[in2];
+//   wall face from the limited slope s of the wall cell l (2 on the left, nX+1 on the right), which reads the ghost value
+//   just formed:  lower half (i < N/2): face = f_l - dx/2 s ; upper half: f_l + dx/2 s.
+// fill_* = 1 writes both halves (no wall model: no-flux fill); 0 writes only the outgoing half (the diffuse kernel then
+// fills the incoming half).
+__global__ void edge_prep_kernel(double* __restrict__ f, double* __restrict__ fl, double* __restrict__ fr,
+                                 const double* __restrict__ x, const double* __restrict__ dx, int N, int nX, int do_left,
+                                 int do_right, int fill_left, int fill_right) {
   const long n3 = (long)N * N * N;
   const long half = (long)(N / 2) * N * N;
+  const int right = (do_left && do_right) ? (int)blockIdx.y : (do_right ? 1 : 0);
+  const int l = right ? nX + 1 : 2;                 // the wall cell
+  const int g = right ? nX + 2 : 1;                 // the ghost cell next to it
+  const int in2 = right ? nX : 3;                   // second cell inward
+  double* face = right ? fr : fl;
+  const int fill_noflux = right ? fill_right : fill_left;
   for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
-    const bool lower = p < half;                 // i < N/2
+    const double f0 = f[(long)l * n3 + p], fi = f[(long)in2 * n3 + p];
+    const double fg = 2 * f0 - fi;                  // extrapolate_kernel: f[g] = 2 f[l] - f[in2]
+    f[(long)g * n3 + p] = fg;
+    const bool lower = p < half;                    // i < N/2
     const bool outgoing = right ? !lower : lower;
     if (!outgoing && !fill_noflux) continue;
-    const double fm = f[(long)(l - 1) * n3 + p], f0 = f[(long)l * n3 + p], fp = f[(long)(l + 1) * n3 + p];
+    const double fm = right ? fi : fg, fp = right ? fg : fi;   // cells l-1 and l+1
     const double s = minmod3((f0 - fm) / (x[l] - x[l - 1]), (fp - f0) / (x[l + 1] - x[l]),
                              (fp - fm) / (x[l + 1] - x[l - 1]));
-    // both walls: lower half (i < N/2) takes f0 - dx/2 s, upper half takes f0 + dx/2 s
-    const double val = lower ? f0 - 0.5 * dx[l] * s : f0 + 0.5 * dx[l] * s;
-    face[p] = val;
+    face[p] = lower ? f0 - 0.5 * dx[l] * s : f0 + 0.5 * dx[l] * s;
   }
 }
-void launch_wall_face(cudaStream_t st, const double* f, double* face, const double* x, const double* dx, int N, int l,
-                      int right, int fill_noflux) {
+void launch_edge_prep(cudaStream_t st, double* f, double* fl, double* fr, const double* x, const double* dx, int N, int nX,
+                      int do_left, int do_right, int fill_left, int fill_right) {
   const long n3 = (long)N * N * N;
-  wall_face_kernel<<<(unsigned)((n3 + 255) / 256), 256, 0, st>>>(f, face, x, dx, N, l, right, fill_noflux);
+  dim3 grid((unsigned)((n3 + 255) / 256), (do_left && do_right) ? 2 : 1);
+  edge_prep_kernel<<<grid, 256, 0, st>>>(f, fl, fr, x, dx, N, nX, do_left, do_right, fill_left, fill_right);
 }
 
 // MUSCL / minmod stencil for the owned cells l = 2 .. nX+1. left_wall / right_wall: this rank holds
@@ -196,23 +223,31 @@ __global__ void __launch_bounds__(256)
 upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __restrict__ fl,
                   const double* __restrict__ fr, const double* __restrict__ v, const double* __restrict__ x,
                   const double* __restrict__ dx, int N, int nX, double dt, int left_wall, int right_wall,
-                  const double* peerL, const double* peerR, double force) {
+                  const double* peerL, const double* peerR, double force, const double* __restrict__ avg, HaloSync hs) {
   const long n3 = (long)N * N * N;
   const int h = N / 2;
   const int l0 = 2 + blockIdx.y * UP_CH;
   const int l1 = min(l0 + UP_CH, nX + 2);
+  // the first block row reads the left ghosts and writes the cells the left neighbour reads; the last one likewise
+  const int pass = halo_enter(hs, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
   const long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
-  if (p >= n3) return;
+  if (p < n3) {
   const int i = (int)(p / (N * N));
   const int j = (int)((p / N) % N);
   const double hv = 0.5 * dt * v[i];
   auto F = [&](int l) { return __ldcg(cell_src<2>(f, peerL, peerR, n3, nX, l) + p); };
-  auto forced = [&](double r, int l) {   // Poiseuille forcing (:428-436,457-465): d/dv_y of the pass input
+  auto forced0 = [&](double r, int l) {   // Poiseuille forcing (:428-436,457-465): d/dv_y of the pass input
     if (force == 0.0) return r;
     const double* c0 = f + (long)l * n3;
     if (j == 0) return r - force * c0[p + N];
     if (j == N - 1) return r - force * c0[p - N];
     return r - force * (c0[p + N] - c0[p - N]);
+  };
+  // avg != null: the second pass of advectTwo ends with f_conv = (f + f_conv) / 2 (src/transportroutines.c:487-491);
+  // the pass result goes through the same rounding as when it was stored first and averaged by a second kernel
+  auto forced = [&](double r, int l) {
+    const double v = forced0(r, l);
+    return avg ? 0.5 * (avg[(long)l * n3 + p] + v) : v;
   };
   if (i >= h) {   // information travels to the right: face value of cell l-1 is the upwind one
     double fm = F(l0 - 1), f0 = F(l0);
@@ -250,25 +285,17 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
       fm = f0; f0 = fp; fp = fpp; s1 = s2;
     }
   }
+  }
+  halo_leave(hs, pass);
 }
 void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const double* fl, const double* fr,
                        const double* v, const double* x, const double* dx, int N, int nX, double dt, int left_wall,
-                       int right_wall, const double* peerL, const double* peerR, double force) {
+                       int right_wall, const double* peerL, const double* peerR, double force, const double* avg,
+                       const HaloSync& hs) {
   const long n3 = (long)N * N * N;
   dim3 grid((unsigned)((n3 + 255) / 256), (unsigned)((nX + UP_CH - 1) / UP_CH));
   upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall, peerL, peerR,
-                                          force);
-}
-
-// fc = 0.5 * (f + fc) on n contiguous doubles (src/transportroutines.c:487-491)
-__global__ void average_kernel(const double* __restrict__ f, double* __restrict__ fc, long n) {
-  for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n; p += (long)gridDim.x * blockDim.x)
-    fc[p] = 0.5 * (f[p] + fc[p]);
-}
-void launch_average(cudaStream_t st, const double* f, double* fc, long n) {
-  long blocks = (n + 255) / 256;
-  if (blocks > 148 * 16) blocks = 148 * 16;
-  average_kernel<<<(unsigned)blocks, 256, 0, st>>>(f, fc, n);
+                                          force, avg, hs);
 }
 
 // With lazy module loading (the CUDA default) the first launch of a kernel loads it, and the driver cannot do that
@@ -278,8 +305,8 @@ void launch_average(cudaStream_t st, const double* f, double* fc, long n) {
 int preload_transport_kernels() {
   cudaFuncAttributes a;
   const void* fns[] = {(const void*)diffuse_bc_kernel, (const void*)upwind_one_kernel, (const void*)upwind_two_kernel,
-                       (const void*)halo_begin_kernel, (const void*)halo_end_kernel, (const void*)halo_quiesce_kernel,
-                       (const void*)extrapolate_kernel, (const void*)wall_face_kernel, (const void*)average_kernel};
+                       (const void*)halo_quiesce_kernel,
+                       (const void*)edge_prep_kernel};
   for (const void* f : fns)
     if (cudaFuncGetAttributes(&a, f) != cudaSuccess) return 1;
   return 0;
