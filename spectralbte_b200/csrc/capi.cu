@@ -494,21 +494,35 @@ int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q
 // One collision stage of the 1D step for a slab: out = a x + b y + s conserve(Q(src, src)) / Kn.
 // Fast path (batched kernels with a whole-cell inverse transform): conservation and update run as the
 // epilogue of the inverse transform; otherwise the three separate kernels.
+// chain: bit 0 = the cell-minor spectrum of d_src is already in d_lay[0] (the previous stage left it there),
+//        bit 1 = leave the spectrum of `out` there for the next stage (the inverse transform's kernel goes on with the
+//        forward transform of the updated cell).  Both only on the fused path; *chained tells the caller what happened.
 int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, int k2, double* out, double a,
-                      const double* x, double b, const double* y, double s, double Kn) {
+                      const double* x, double b, const double* y, double s, double Kn, int chain, int* chained) {
   static const bool no_fuse = getenv("SBTE_NO_FUSE") != nullptr;
+  static const bool no_chain = getenv("SBTE_NO_CHAIN") != nullptr;
+  if (chained) *chained = 0;
+  struct Scope {   // the same transform kernel for every slab size (see sbte_ctx::cell_fft_any)
+    sbte_ctx* c; bool old;
+    explicit Scope(sbte_ctx* c_) : c(c_), old(c_->cell_fft_any) { c->cell_fft_any = true; }
+    ~Scope() { c->cell_fft_any = old; }
+  } scope(c);
   if (!no_fuse && resolve_k2(c, batch, k2) == SBTE_K2_BATCH && qhat_batch_supported(c->N) &&
-      batch >= 8 && (c->N == 8 || c->N == 16)) {
+      batch >= 2 && (c->N == 8 || c->N == 16)) {
     if (ensure_capacity(c, batch)) return 1;
     if (!c->d_W) { set_error("no weights bound"); return 1; }
     const bool sym = want_sym(c, true);
     if (sym && ensure_sym(c)) return 1;
     if (ensure_batch_schedule(c, batch, sym)) return 1;
-    launch_fft3d(c, d_src, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
+    if (!(chain & 1)) launch_fft3d(c, d_src, nullptr, 0, batch, nullptr, c->d_lay[0], LAY_CELLMINOR, nullptr, false);
     launch_batched_conv(c, c->d_lay[0], batch);
     CellEpi epi = {};
     epi.mode = 1; epi.v = c->d_v; epi.wt = c->d_wt; epi.dv3 = c->dv * c->dv * c->dv; epi.lu = c->lu;
     epi.a = a; epi.x = x; epi.b = b; epi.y = y; epi.s = s; epi.Kn = Kn; epi.out = out;
+    if ((chain & 2) && !no_chain) {
+      epi.next_lay = c->d_lay[0]; epi.next_pre = c->d_pre[0]; epi.next_post = c->d_post[0]; epi.next_pref = c->pref[0];
+      if (chained) *chained = 1;
+    }
     if (launch_fft3d_parts_update(c, c->d_parts, c->parts_stride, c->sched, batch, epi)) return check_launch("fused collision stage");
     set_error("fused collision stage: no whole-cell transform for this N");
     return 1;

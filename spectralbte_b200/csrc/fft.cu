@@ -355,7 +355,38 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
       const long g = cell * n3 + idx;
       double basev = (epi.a == 1.0) ? epi.x[g] : epi.a * epi.x[g];
       if (epi.y) basev = basev + epi.b * epi.y[g];
-      epi.out[g] = basev + epi.s * q / epi.Kn;
+      const double fnew = basev + epi.s * q / epi.Kn;
+      epi.out[g] = fnew;
+      if (epi.next_lay) {
+        // chained forward transform of the updated cell (the next Heun stage starts from it): same pre-twiddle and
+        // trapezoid factor as the stand-alone forward pass above, imaginary input 0
+        const double2 cs = __ldg(epi.next_pre + i + j + k);
+        const double factor = epi.next_pref * __ldg(epi.wt + i) * __ldg(epi.wt + j) * __ldg(epi.wt + k);
+        const double xr = fnew, xi = 0.0;
+        cellsm[(i * N + j) * P + k] = make_double2(factor * (cs.x * xr - cs.y * xi), factor * (cs.x * xi + cs.y * xr));
+      }
+    }
+    if (!epi.next_lay) return;
+    __syncthreads();
+    for (int l = threadIdx.x; l < N * N; l += blockDim.x)            // along z
+      dft_line<N>(cellsm + l * P, 1, -1.0);
+    __syncthreads();
+    for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along y
+      const int i = l / N, k = l % N;
+      dft_line<N>(cellsm + (i * N) * P + k, P, -1.0);
+    }
+    __syncthreads();
+    for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along x
+      const int j = l / N, k = l % N;
+      dft_line<N>(cellsm + j * P + k, N * P, -1.0);
+    }
+    __syncthreads();
+    for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {       // post-twiddle, cell-minor layout for the convolution
+      const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
+      const double2 cs = __ldg(epi.next_post + idx);
+      const double2 z = cellsm[(i * N + j) * P + k];
+      epi.next_lay[((cell >> 5) * n3 + idx) * 32 + (cell & 31)] =
+          make_double2(cs.x * z.x - cs.y * z.y, cs.x * z.y + cs.y * z.x);
     }
     return;
   }
@@ -404,7 +435,7 @@ static void launch_cell_n(sbte_ctx* c, const double* in_real, const double2* in_
 static bool try_cell_fft(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,
                          double2* out_nat, double2* out_lay, int layout, double* out_real, bool accumulate_real,
                          const CellEpi* epi_in = nullptr) {
-  if (batch < 8 || accumulate_real) return false;
+  if ((batch < 8 && !c->cell_fft_any) || accumulate_real) return false;
   CellEpi epi = {};
   if (epi_in) epi = *epi_in;
   switch (c->N) {

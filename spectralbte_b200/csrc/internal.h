@@ -28,6 +28,12 @@ struct CellEpi {
   double b; const double* y;   // y may be null
   double s, Kn;
   double* out;
+  // chained forward transform of `out` (null: none): cell-minor spectrum for the next stage's convolution, written by the
+  // same kernel while the updated cell is still in shared memory -- one launch and one trip through global memory less
+  double2* next_lay;
+  const double2* next_pre;    // forward pre-twiddles [3N-2]
+  const double2* next_post;   // forward post-twiddles [N^3]
+  double next_pref;           // forward prefactor (2 pi)^-3/2 dv^3
 };
 
 // stream-K schedule of the batched convolution (device tables, see qhat_batch.cu)
@@ -110,6 +116,9 @@ struct sbte_ctx {
   std::vector<StepGraph> step_graphs;
   unsigned long long graph_gen = 1;   // bumped whenever a buffer a captured graph may reference is replaced
   unsigned long long launches = 0;  // kernels launched through this context
+  // slab collisions take the whole-cell transform at ANY batch size: which kernel transforms a cell must not depend on
+  // how many cells the rank holds (rank-count invariance, bit for bit); other callers keep it for batches >= 8
+  bool cell_fft_any = false;
   bool k2_prof = false;             // bracket every K2 launch with CUDA events
   std::vector<cudaEvent_t> k2_ev;   // [2*i], [2*i+1] = start/stop of launch i
   size_t k2_ev_used = 0;

@@ -18,7 +18,7 @@
 namespace sbte {
 int compute_q_dev(sbte_ctx* c, const double* d_f, const double* d_g, double* d_Q, int batch, int k2);
 int collide_stage_dev(sbte_ctx* c, const double* d_src, double* d_Q, int batch, int k2, double* out, double a,
-                      const double* x, double b, const double* y, double s, double Kn);
+                      const double* x, double b, const double* y, double s, double Kn, int chain, int* chained);
 }
 
 struct sbte_slab {
@@ -440,12 +440,14 @@ int sbte_slab_collide(sbte_slab* s, double Kn, int k2) {
   }
   if (o == 1) {
     // f = f_conv + dt Q / Kn
-    if (collide_stage_dev(c, fc, s->d_Q, nX, k2, f, 1.0, fc, 0.0, nullptr, s->dt, Kn)) return 1;
+    if (collide_stage_dev(c, fc, s->d_Q, nX, k2, f, 1.0, fc, 0.0, nullptr, s->dt, Kn, 0, nullptr)) return 1;
   } else {
     double* f1 = cell(s->d_f1, n3, o);
     // f_1 = f_conv + dt Q(f_conv) / Kn ;  f_conv = (f_conv + f_1)/2 + dt/2 Q(f_1) / Kn  (Heun)
-    if (collide_stage_dev(c, fc, s->d_Q, nX, k2, f1, 1.0, fc, 0.0, nullptr, s->dt, Kn)) return 1;
-    if (collide_stage_dev(c, f1, s->d_Q, nX, k2, fc, 0.5, fc, 0.5, f1, 0.5 * s->dt, Kn)) return 1;
+    // the first stage's closing kernel goes on with the forward transform of f_1, which the second stage starts from
+    int chained = 0;
+    if (collide_stage_dev(c, fc, s->d_Q, nX, k2, f1, 1.0, fc, 0.0, nullptr, s->dt, Kn, 2, &chained)) return 1;
+    if (collide_stage_dev(c, f1, s->d_Q, nX, k2, fc, 0.5, fc, 0.5, f1, 0.5 * s->dt, Kn, chained ? 1 : 0, nullptr)) return 1;
   }
   return launch_ok("collide");
 }

@@ -235,7 +235,19 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
   const int i = (int)(p / (N * N));
   const int j = (int)((p / N) % N);
   const double hv = 0.5 * dt * v[i];
-  auto F = [&](int l) { return __ldcg(cell_src<2>(f, peerL, peerR, n3, nX, l) + p); };
+  // the whole window this thread marches through, cells l0-2 .. l0+UP_CH+1, is requested before anything consumes it:
+  // one memory round trip per thread instead of one per cell (the kernel is latency-bound for small slabs)
+  double w[UP_CH + 4], av[UP_CH];
+#pragma unroll
+  for (int q = 0; q < UP_CH + 4; q++) {
+    const int l = l0 - 2 + q;
+    w[q] = (l <= l1 + 1) ? __ldcg(cell_src<2>(f, peerL, peerR, n3, nX, l) + p) : 0.0;
+  }
+  if (avg) {
+#pragma unroll
+    for (int q = 0; q < UP_CH; q++) av[q] = (l0 + q < l1) ? avg[(long)(l0 + q) * n3 + p] : 0.0;
+  }
+  auto F = [&](int l) { return w[l - l0 + 2]; };
   auto forced0 = [&](double r, int l) {   // Poiseuille forcing (:428-436,457-465): d/dv_y of the pass input
     if (force == 0.0) return r;
     const double* c0 = f + (long)l * n3;
@@ -245,9 +257,9 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
   };
   // avg != null: the second pass of advectTwo ends with f_conv = (f + f_conv) / 2 (src/transportroutines.c:487-491);
   // the pass result goes through the same rounding as when it was stored first and averaged by a second kernel
-  auto forced = [&](double r, int l) {
+  auto forced = [&](double r, int l, int q) {
     const double v = forced0(r, l);
-    return avg ? 0.5 * (avg[(long)l * n3 + p] + v) : v;
+    return avg ? 0.5 * (av[q] + v) : v;
   };
   if (i >= h) {   // information travels to the right: face value of cell l-1 is the upwind one
     double fm = F(l0 - 1), f0 = F(l0);
@@ -263,7 +275,7 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
       double r;
       if (l == 2 && left_wall) r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - fl[p]);
       else r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - (fm + 0.5 * dx[l - 1] * sprev));
-      fc[(long)l * n3 + p] = forced(r, l);
+      fc[(long)l * n3 + p] = forced(r, l, q);
       fm = f0; f0 = fp; sprev = s1;
     }
   } else {        // information travels to the left: face value of cell l+1 is the upwind one
@@ -281,7 +293,7 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
         s2 = slope_at(f0, fp, fpp, x, l + 1);
         r = f0 - cfl * (fp - 0.5 * dx[l + 1] * s2 - (f0 - 0.5 * dx[l] * s1));
       }
-      fc[(long)l * n3 + p] = forced(r, l);
+      fc[(long)l * n3 + p] = forced(r, l, q);
       fm = f0; f0 = fp; fp = fpp; s1 = s2;
     }
   }

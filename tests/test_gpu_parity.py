@@ -54,6 +54,38 @@ def test_fft3d_whole_cell_kernel_matches_oracle(sb, N):
         assert relmax(got[:3], small) < 1e-13
 
 
+@pytest.mark.parametrize("N,batch,rule", [(16, 1, 0), (32, 1, 0), (16, 12, 1), (24, 3, 1), (22, 9, 1)])
+def test_fft3d_matches_cufft(sb, N, batch, rule):
+    """cuFFT (torch.fft on the device) as a second, independent validation of the hand-written transforms -- the cluster
+    kernel (batch 1, N = 16 / 32), the whole-cell kernel (N = 16, batch >= 8) and the plane-parallel pair: fft3D is a
+    trapezoid-weighted, shifted DFT (src/collisions.c:232-283),
+        out[a] = post[a] * sum_b exp(-+ 2 pi i a.b / N) * pre[b] * w[b] * in[b] * (2 pi)^(-3/2) delta^3,
+    pre[b] = exp(s i (b_x+b_y+b_z) L_start delta), post[a] = exp(s i L_end (g_ax+g_ay+g_az)), s = +1 forward, -1 inverse."""
+    import torch
+    o = orc.Oracle(N, 7.0, rule)
+    c = sb.Collisions(N, 7.0, inhomogeneous=bool(rule))
+    dev = torch.device("cuda", 0)
+    rng = np.random.default_rng(7 * N + batch)
+    dv, deta = c.v[1] - c.v[0], c.eta[1] - c.eta[0]
+    L_v, L_eta = -c.v[0], -c.eta[0]
+    wt = np.ones(N)
+    wt[0] = wt[-1] = 0.5
+    idx = np.arange(N)
+    for inv in (False, True):
+        z = rng.standard_normal((batch, N, N, N)) + 1j * rng.standard_normal((batch, N, N, N))
+        got = c.fft3D(z.reshape(batch, -1), inv).reshape(batch, N, N, N)
+        sign, delta, L_start, L_end, grid = (-1.0, deta, L_v, L_eta, c.v) if inv else (1.0, dv, L_eta, L_v, c.eta)
+        s3 = idx[:, None, None] + idx[None, :, None] + idx[None, None, :]
+        pre = np.exp(1j * sign * s3 * L_start * delta)
+        post = np.exp(1j * sign * L_end * (grid[:, None, None] + grid[None, :, None] + grid[None, None, :]))
+        w3 = wt[:, None, None] * wt[None, :, None] * wt[None, None, :]
+        x = torch.from_numpy(z * (pre * w3 * (2.0 * np.pi) ** -1.5 * delta ** 3)).to(dev)
+        y = torch.fft.ifftn(x, dim=(1, 2, 3), norm="forward") if inv else torch.fft.fftn(x, dim=(1, 2, 3))
+        want = y.cpu().numpy() * post
+        assert relmax(got, want) < 1e-13
+        assert relmax(want[0].reshape(-1), o.fft3d(z[0].reshape(-1), inv)) < 1e-13   # and cuFFT agrees with the oracle
+
+
 # ---------------------------------------------------------------- the convolution
 def _weights(name, N, W_bkw8, W_heat8):
     if name == "bkw":
@@ -421,11 +453,13 @@ def test_peer_memory_halo_equals_single_rank(sb, W_heat8, order, ic):
     assert np.array_equal(got, want)
 
 
-@pytest.mark.parametrize("order,ic,nX", [(1, 3, 16), (2, 3, 16), (1, 6, 16), (2, 6, 16), (2, 6, 80), (1, 3, 70)])
-def test_two_rank_split_equals_single_rank(sb, W_heat8, order, ic, nX):
+@pytest.mark.parametrize("order,ic,nX,h", [(1, 3, 16, 8), (2, 3, 16, 8), (1, 6, 16, 8), (2, 6, 16, 8), (2, 6, 80, 40), (1, 3, 70, 35),
+                                            (2, 6, 16, 5), (1, 3, 44, 4)])
+def test_two_rank_split_equals_single_rank(sb, W_heat8, order, ic, nX, h):
     """Rank-count invariance: two slabs exchanging halos through the regions
     reported by the library reproduce the single-slab run bit for bit -- also when the halves form a different number
-    of 32-cell groups than the whole (nX = 80, 70: another stream-K schedule, same canonical summation order)."""
+    of 32-cell groups than the whole (nX = 80, 70: another stream-K schedule, same canonical summation order) and when
+    one rank holds only h = 4 or 5 cells (the same transform kernels at every slab size)."""
     N, dt, Kn = 8, 2e-3, 1.52
     o = orc.Oracle(N, 9.0, 1)
     _, x, dx = orc.make_mesh([nX], [0.05 * nX], order)
@@ -436,13 +470,11 @@ def test_two_rank_split_equals_single_rank(sb, W_heat8, order, ic, nX):
     f0[order:nX + order] *= 1.0 + 0.1 * rng.standard_normal((nX, o.n3))
     one = sb.Slab(c, nX, order, x, dx, ic, dt)
     one.upload(f0)
-    h = nX // 2
     parts = []
-    for r in range(2):
-        lo = r * h
-        xs, dxs = x[lo:lo + h + 2 * order].copy(), dx[lo:lo + h + 2 * order].copy()
-        p = sb.Slab(c, h, order, xs, dxs, ic, dt, rank=r, nranks=2)
-        p.upload(f0[lo:lo + h + 2 * order].copy())
+    for r, (lo, n) in enumerate(((0, h), (h, nX - h))):     # rank 0 holds the first h cells
+        xs, dxs = x[lo:lo + n + 2 * order].copy(), dx[lo:lo + n + 2 * order].copy()
+        p = sb.Slab(c, n, order, xs, dxs, ic, dt, rank=r, nranks=2)
+        p.upload(f0[lo:lo + n + 2 * order].copy())
         parts.append(p)
 
     def exchange(which, stage):
@@ -473,7 +505,7 @@ def test_two_rank_split_equals_single_rank(sb, W_heat8, order, ic, nX):
         if order == 2:
             advect(1)
     whole = one.download()[order:nX + order]
-    split = np.concatenate([p.download()[order:h + order] for p in parts])
+    split = np.concatenate([p.download()[order:p.nX + order] for p in parts])
     assert np.array_equal(whole, split)
 
 
@@ -612,6 +644,68 @@ def test_config_n32_hard_spheres_real_weights_vs_oracle(sb):
     Qc = c.conserveAllMoments(Q)
     assert np.abs(c.moment_functionals(Qc)).max() < 1e-13
     assert relmax(c.ComputeQ_maxPreserve(f), o.compute_q_maxpreserve(W, f, f)) < TOL_QHAT
+    # two different distributions (the f != g entry of the mixture-shaped interface, src/collisions.c:178-210): the BKW
+    # data against the shifted-isotropic one, both orders, plain ComputeQ and maxPreserve with its g - M_i quirk (:104)
+    g = o.init_hom(2)
+    assert relmax(c.ComputeQ(f, g), o.compute_q(W, f, g)) < TOL_QHAT
+    assert relmax(c.ComputeQ_maxPreserve(f, g), o.compute_q_maxpreserve(W, f, g)) < TOL_QHAT
+    assert relmax(c.ComputeQ_maxPreserve(g, f), o.compute_q_maxpreserve(W, g, f)) < TOL_QHAT
+
+
+def test_n32_weight_file_round_trip_is_bit_exact(sb, tmp_path):
+    """The 8.59 GB Weights/N32_isotropic_L_v5_lambda1.wts in the reference's format (headerless native doubles, row by
+    row: src/weights.c:78-88 load, :100-103 store): save from one context, load into another, and the convolution on
+    the loaded tensor must give the bits of the convolution on the original (plain and symmetrised stream)."""
+    import shutil
+    N, L_v = 32, 5.0
+    if shutil.disk_usage(tmp_path).free < 10 * 2 ** 30:
+        pytest.skip("less than 10 GiB free for the 8.59 GB weight file")
+    a = sb.Collisions(N, L_v)
+    a.generate_weights(1.0)
+    path = str(tmp_path / "N32_isotropic_L_v5_lambda1.wts")
+    a.save_weights(path)
+    assert os.path.getsize(path) == 8 * N ** 6
+    b = sb.Collisions(N, L_v)
+    b.load_weights(path)
+    os.remove(path)
+    f = orc.Oracle(N, L_v, 0).init_hom(0)
+    for sym in (True, False):
+        a.set_symmetrize(sym)
+        b.set_symmetrize(sym)
+        assert np.array_equal(a.Qhat(f, k2=sb.K2_STREAM).view(np.float64), b.Qhat(f, k2=sb.K2_STREAM).view(np.float64)), sym
+    # a few rows of the tensors themselves, bit for bit, through the device pointers
+    import ctypes as C
+    n3 = N ** 3
+    for row in (0, n3 // 2 + 17, n3 - 1):
+        ra, rb = np.empty(n3), np.empty(n3)
+        for ctx, out in ((a, ra), (b, rb)):
+            sb._lib.check(ctx.L.sbte_d2h(ctx.h, out.ctypes.data, C.c_void_p(ctx.L.sbte_weights_device(ctx.h) + row * n3 * 8), out.nbytes))
+        assert np.array_equal(ra, rb), row
+
+
+@pytest.mark.parametrize("N", [22, 24])
+def test_config_heattrans_full_step_matches_oracle(sb, N):
+    """BASELINE config 5 (input_examples/heatTrans.long.in: N = 22 as shipped, 24 as BASELINE states): L_v=9, Kn=0.3,
+    lambda=1, Init_field 3 (diffuse walls), Space_order 1, dt=1e-4, dx=1/250 -- a 40-cell slab between the walls, 3 full
+    time steps (exec/boltz.c:264-353) with device-generated weights against the oracle reading the same tensor."""
+    L_v, Kn, order, ic, dt, nX = 9.0, 0.3, 1, 3, 1e-4, 40
+    c = sb.Collisions(N, L_v, inhomogeneous=True)
+    c.generate_weights(1.0)
+    W = c.weights_to_host()
+    o = orc.Oracle(N, L_v, 1)
+    _, x, dx = orc.make_mesh([nX], [nX / 250.0], order)
+    f = o.init_inhom(ic, nX, order)
+    s = sb.Slab(c, nX, order, x, dx, ic, dt)
+    s.upload(f)
+    fc, f1, ft = np.zeros_like(f), np.zeros_like(f), np.zeros_like(f)
+    for _ in range(3):
+        s.step(Kn)
+        o.step_1d(W, nX, x, dx, dt, Kn, order, ic, f, fc, f1, ft)
+    got = s.download()[order:nX + order]
+    assert relmax(got, f[order:nX + order]) < 1e-11
+    mom = s.moments()
+    for l in (0, 1, nX // 2, nX - 1):
+        np.testing.assert_allclose(mom[l, [0, 1, 4, 7]], o.row_1d(f[l + order]), rtol=1e-10, atol=1e-13)
 
 
 def test_config_shock1p2_derived_matches_oracle(sb):
