@@ -97,8 +97,12 @@ def load():
             raise RuntimeError(
                 "libsbte_b200.so is missing (%s): build it with `python -m spectralbte_b200.build`; "
                 "there is no CPU fallback" % LIB_PATH)
-        L = C.CDLL(LIB_PATH)  # RTLD_LOCAL: the drop-in symbol names stay private to this handle
+        # SBTE_LIB_PATH: another build of the library for A/B timing (tools/); symbols it lacks are skipped there only
+        override = os.environ.get("SBTE_LIB_PATH")
+        L = C.CDLL(override or LIB_PATH)  # RTLD_LOCAL: the drop-in symbol names stay private to this handle
         for name, (res, args) in PROTOTYPES.items():
+            if override and not hasattr(L, name):
+                continue
             fn = getattr(L, name)  # AttributeError if the library does not export a declared symbol
             fn.restype = res
             fn.argtypes = args

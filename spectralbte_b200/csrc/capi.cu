@@ -798,19 +798,40 @@ int sbte_weights_load_file(sbte_ctx* c, const char* path) {
   if (alloc_weights(c)) { fclose(fp); return 1; }
   const size_t total = (size_t)c->n3 * c->n3;
   const size_t chunk = (size_t)(64u << 20) / sizeof(double);
-  double* pin = nullptr;
-  CK(cudaMallocHost(&pin, chunk * sizeof(double)));
-  for (size_t off = 0; off < total; off += chunk) {
+  // two pinned buffers: the read of one chunk overlaps the upload of the previous one; every failure path releases the
+  // file, the buffers and the half-filled tensor
+  double* pin[2] = {nullptr, nullptr};
+  cudaEvent_t done[2] = {nullptr, nullptr};
+  auto cleanup = [&](bool failed) {
+    fclose(fp);
+    for (int b = 0; b < 2; b++) {
+      if (done[b]) { cudaEventSynchronize(done[b]); cudaEventDestroy(done[b]); }
+      if (pin[b]) cudaFreeHost(pin[b]);
+    }
+    if (failed) release_weights(c);
+  };
+  cudaError_t e = cudaSuccess;
+  for (int b = 0; b < 2 && e == cudaSuccess; b++) {
+    e = cudaMallocHost(&pin[b], chunk * sizeof(double));
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&done[b], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { cleanup(true); set_error(std::string("weight file staging buffers: ") + cudaGetErrorString(e)); return 1; }
+  int b = 0;
+  for (size_t off = 0; off < total; off += chunk, b ^= 1) {
     const size_t n = std::min(chunk, total - off);
-    if (fread(pin, sizeof(double), n, fp) != n) {   // src/weights.c:82-86
-      fclose(fp); cudaFreeHost(pin); release_weights(c);
+    cudaEventSynchronize(done[b]);                  // the previous upload from this buffer has finished
+    if (fread(pin[b], sizeof(double), n, fp) != n) {   // src/weights.c:82-86
+      cleanup(true);
       set_error("Error reading weight file");
       return 1;
     }
-    CK(cudaMemcpy((double*)c->d_W + off, pin, n * sizeof(double), cudaMemcpyHostToDevice));
+    e = cudaMemcpyAsync((double*)c->d_W + off, pin[b], n * sizeof(double), cudaMemcpyHostToDevice, c->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(done[b], c->stream);
+    if (e != cudaSuccess) { cleanup(true); set_error(std::string("weight upload: ") + cudaGetErrorString(e)); return 1; }
   }
-  fclose(fp);
-  cudaFreeHost(pin);
+  e = cudaStreamSynchronize(c->stream);
+  cleanup(e != cudaSuccess);
+  if (e != cudaSuccess) { set_error(std::string("weight upload: ") + cudaGetErrorString(e)); return 1; }
   return make_tensor_map(c);
 }
 
@@ -848,19 +869,22 @@ int sbte_weights_save_file(sbte_ctx* c, const char* path) {
   const size_t total = (size_t)c->n3 * c->n3;
   const size_t chunk = (size_t)(64u << 20) / sizeof(double);
   double* pin = nullptr;
-  CK(cudaMallocHost(&pin, chunk * sizeof(double)));
-  CK(cudaStreamSynchronize(c->stream));
-  for (size_t off = 0; off < total; off += chunk) {
+  cudaError_t e = cudaMallocHost(&pin, chunk * sizeof(double));
+  if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+  for (size_t off = 0; off < total && e == cudaSuccess; off += chunk) {
     const size_t n = std::min(chunk, total - off);
-    CK(cudaMemcpy(pin, c->d_W + off, n * sizeof(double), cudaMemcpyDeviceToHost));
-    if (fwrite(pin, sizeof(double), n, fp) != n) {
-      fclose(fp); cudaFreeHost(pin);
+    e = cudaMemcpy(pin, c->d_W + off, n * sizeof(double), cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && fwrite(pin, sizeof(double), n, fp) != n) {
+      fclose(fp);
+      cudaFreeHost(pin);
       set_error("Something is wrong with storing the weights");   // src/weights.c:104-107
       return 1;
     }
   }
-  fclose(fp);
-  cudaFreeHost(pin);
+  const bool closed = fclose(fp) == 0;
+  if (pin) cudaFreeHost(pin);
+  if (e != cudaSuccess) { set_error(std::string("weight file: ") + cudaGetErrorString(e)); return 1; }
+  if (!closed) { set_error("Something is wrong with storing the weights"); return 1; }
   return 0;
 }
 

@@ -117,6 +117,14 @@ __device__ __forceinline__ double2 ldg_stream_f64x2(const double* p) {
   return r;
 }
 
+// ---------------------------------------------------------------- fire-and-forget accumulation in L2
+// p[0] += v without waiting for the old value (SASS RED.E.ADD.F64): an IEEE double add performed at the L2 slice.  Used
+// where exactly ONE thread ever updates the location, in program order, so the result is the same left fold -- bit for
+// bit -- as a load / add / store by that thread would give, without its round trip.
+__device__ __forceinline__ void red_add_f64(double* p, double v) {
+  asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
+}
+
 // ---------------------------------------------------------------- deterministic block reduction
 // Sums `NV` doubles per thread over the whole block in a fixed tree order; result valid in all
 // threads. `scratch` needs NV * 32 doubles. Block size must be a multiple of 32, <= 1024.

@@ -119,6 +119,7 @@ struct sbte_ctx {
   // slab collisions take the whole-cell transform at ANY batch size: which kernel transforms a cell must not depend on
   // how many cells the rank holds (rank-count invariance, bit for bit); other callers keep it for batches >= 8
   bool cell_fft_any = false;
+  int wg_nonconverged = 0, wg_classes = 0;   // last device weight generation: integrals that ended abnormally (QUADPACK)
   bool k2_prof = false;             // bracket every K2 launch with CUDA events
   std::vector<cudaEvent_t> k2_ev;   // [2*i], [2*i+1] = start/stop of launch i
   size_t k2_ev_used = 0;

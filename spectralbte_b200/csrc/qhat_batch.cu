@@ -248,29 +248,32 @@ qhat_batch2_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   // Canonical summation order (independent of the schedule, hence of the SM count and of how many cells this rank
   // holds): Q^ = ((C_0 + C_1) + C_2) + ..., C_c = the sum over the N steps of the c-th visited xi_x chunk started from
   // zero.  CTA ranges are whole chunks.  The CTA that owns a tile's first chunk keeps the running fold in part 0 (a
-  // read-modify-write of its own 16 N bytes per thread at every chunk end, hidden behind the plane switch); a CTA that
+  // reduction into its own 16 N bytes per thread at every chunk end); a CTA that
   // enters the tile later writes every chunk as its own part 1 + (c - e0), e0 = chunks held by the first CTA, and the
-  // inverse transform continues the same left fold over the parts.
+  // inverse transform continues the same left fold over the parts.  The fold into part 0 is a fire-and-forget
+  // red.global.add.f64 per component (one writer per location, program order): a load/add/store there cost 8 % at
+  // N = 24 (profiles/r02_canonical_fold_ab.txt), the reduction in L2 costs nothing measurable.
   auto chunk_end = [&](int c) {
     const int cg = cur_t - (cur_t / G) * G;
     const long cell = (long)cg * 32 + lane;
     if (cell < cells) {
       const int first = sch.tile_first[cur_t];
       double2* out = parts + cell * n3 + ((long)zx * N + zy) * N;
+      bool fold = false;
       if ((int)blockIdx.x == first) {
-        if (c > 0) {
-#pragma unroll
-          for (int r = 0; r < N; r++) {
-            const double2 tot = out[r];
-            acc[r] = make_double2(tot.x + acc[r].x, tot.y + acc[r].y);
-          }
-        }
+        fold = c > 0;
       } else {
         const int e0 = (int)((sch.cta_begin[first + 1] - sch.tile_begin[cur_t]) / N);
         out += (size_t)(1 + c - e0) * part_stride;
       }
+      if (fold) {   // part 0 += C_c in L2, no round trip: this thread is the only writer of these locations
+        double* o = reinterpret_cast<double*>(out);
 #pragma unroll
-      for (int r = 0; r < N; r++) out[r] = acc[r];
+        for (int r = 0; r < N; r++) { red_add_f64(o + 2 * r, acc[r].x); red_add_f64(o + 2 * r + 1, acc[r].y); }
+      } else {
+#pragma unroll
+        for (int r = 0; r < N; r++) out[r] = acc[r];
+      }
     }
 #pragma unroll
     for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
@@ -485,20 +488,21 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     if (cell < cells && (!C::PARTIAL || zy < N)) {
       const int first = sch.tile_first[cur_t];
       double2* out = parts + cell * n3 + ((long)zx * N + zy) * N;
+      bool fold = false;
       if ((int)blockIdx.x == first) {
-        if (c > 0) {
-#pragma unroll
-          for (int r = 0; r < N; r++) {
-            const double2 tot = out[r];
-            acc[r] = make_double2(tot.x + acc[r].x, tot.y + acc[r].y);
-          }
-        }
+        fold = c > 0;
       } else {
         const int e0 = (int)((sch.cta_begin[first + 1] - sch.tile_begin[cur_t]) / N);
         out += (size_t)(1 + c - e0) * part_stride;
       }
+      if (fold) {   // part 0 += C_c in L2, no round trip: this thread is the only writer of these locations
+        double* o = reinterpret_cast<double*>(out);
 #pragma unroll
-      for (int r = 0; r < N; r++) out[r] = acc[r];
+        for (int r = 0; r < N; r++) { red_add_f64(o + 2 * r, acc[r].x); red_add_f64(o + 2 * r + 1, acc[r].y); }
+      } else {
+#pragma unroll
+        for (int r = 0; r < N; r++) out[r] = acc[r];
+      }
     }
 #pragma unroll
     for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);

@@ -180,6 +180,7 @@ inline void tma_tensor2d_g2s(void* smem_dst, const void* tmap, int c0, int c1, u
   mbar_complete_tx(bar, (long long)t->box0 * t->box1 * 8);
 }
 inline double2 ldg_stream_f64x2(const double* p) { return make_double2(p[0], p[1]); }
+inline void red_add_f64(double* p, double v) { *p += v; }   // single writer per location (see common.cuh)
 inline void pdl_wait() {}
 inline void pdl_launch_dependents() {}
 
