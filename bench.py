@@ -394,21 +394,32 @@ def run_0d_n32(args):
     launches = c.launches - l0
     ms = max_over_ranks(ms, world)
 
-    # the same evaluation with the symmetrised stream switched off: the reference's own 8*N^6-byte formulation
-    plain = None
-    if not os.environ.get("SBTE_NO_SYM"):
-        c.set_symmetrize(False)
+    # the same evaluation (i) without the transposed pairing: the symmetrised stream over every zeta column, and
+    # (ii) with both switched off: the reference's own 8*N^6-byte formulation
+    from spectralbte_b200 import bench1d
+    xy_state, xy_dev = c.xy_pairing_state()
+    plain = sym_only = None
+
+    def variant(nbytes):
         for _ in range(3):
             step()
         c.sync()
         c.k2_profile(True)
-        p_ms = timed(step, args.steps)
-        pk_ms, pk_n = c.k2_profile_read()
+        v_ms = timed(step, args.steps)
+        vk_ms, vk_n = c.k2_profile_read()
         c.k2_profile(False)
+        rec = {"evals_per_s": args.steps / (v_ms * 1e-3), "kernel_ms": vk_ms / max(1, vk_n), "bytes_per_launch": nbytes}
+        rec["achieved_GBs"] = nbytes / (rec["kernel_ms"] * 1e-3) / 1e9
+        return rec
+
+    if not os.environ.get("SBTE_NO_SYM"):
+        c.set_xy_pairing(False)
+        if xy_state == 1 and not os.environ.get("SBTE_NO_XYSYM"):
+            sym_only = variant(8.0 * float(N) ** 4 * bench1d.nrep_sum(N))
+        c.set_symmetrize(False)
+        plain = variant(8.0 * float(N) ** 6)
         c.set_symmetrize(True)
-        plain = {"evals_per_s": args.steps / (p_ms * 1e-3), "kernel_ms": pk_ms / max(1, pk_n),
-                 "bytes_per_launch": 8.0 * float(N) ** 6}
-        plain["achieved_GBs"] = plain["bytes_per_launch"] / (plain["kernel_ms"] * 1e-3) / 1e9
+        c.set_xy_pairing(True)
 
     # the 0D driver's call: ComputeQ_maxPreserve = three reference evaluations folded into one weight pass
     for _ in range(3):
@@ -456,15 +467,18 @@ def run_0d_n32(args):
     peak, peak_src = peaks()
     sym = not os.environ.get("SBTE_NO_SYM")
     ref_bytes = 8.0 * float(N) ** 6
-    # symmetrised stream (f == g): rows zeta read nrep(zeta_x) of their N xi_x planes, nrep = N/2+1 | N/2
-    from spectralbte_b200 import bench1d
-    wbytes = 8.0 * float(N) ** 4 * bench1d.nrep_sum(N) if sym else ref_bytes
+    # symmetrised stream (f == g): rows zeta read nrep(zeta_x) of their N xi_x planes, nrep = N/2+1 | N/2;
+    # transposed pairing: only the zeta columns zx >= zy are streamed ((zx + 1) columns per zx)
+    pairing = xy_state == 1 and not os.environ.get("SBTE_NO_XYSYM") and args.k2 in ("auto", "stream")
+    planes = [(bench1d.sym_nrep(N, zx) if sym else N) for zx in range(N)]
+    wbytes = 8.0 * float(N) ** 3 * sum((zx + 1 if pairing else N) * planes[zx] for zx in range(N))
     k2_avg_ms = k2_ms / max(1, k2_n)
     achieved = wbytes / (k2_avg_ms * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tp = os.path.join(ROOT, "profiles", "k2_stream_traffic.json")
     if os.path.exists(tp):
-        traffic = json.load(open(tp)).get("dram_bytes_per_launch_sym" if sym else "dram_bytes_per_launch")
+        key = "dram_bytes_per_launch_pairing" if pairing else ("dram_bytes_per_launch_sym" if sym else "dram_bytes_per_launch")
+        traffic = json.load(open(tp)).get(key)
         traffic_src = "static: profiles/k2_stream_traffic.json (one ncu --set full capture, dram__bytes_read.sum + dram__bytes_write.sum per launch; not measured in this run)"
     value = world * args.steps / (ms * 1e-3)
     line = None
@@ -477,13 +491,21 @@ def run_0d_n32(args):
                        "note": "0D does not shard: N GPUs = N independent replicas; the sharded 1D cases are under `oned`"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": traffic, "traffic_source": traffic_src,
-                         "kernel": "qhat_stream_kernel<32,1,2,%s>" % ("sym" if sym else "plain"),
+                         "kernel": ("qhat_stream_kernel<32,2,2,%s,16 warps,transposed pairing>" if pairing else
+                                    "qhat_stream_kernel<32,1,2,%s>") % ("sym" if sym else "plain"),
                          "kernel_ms": k2_avg_ms, "kernel_share_of_step": k2_ms / ms, "algorithmic_bytes_per_launch": wbytes,
                          "reference_formulation_bytes": ref_bytes,
                          "note": ("f == g: the summand is symmetric under xi <-> zeta-xi, so the kernel streams the symmetrised "
                                   "tensor Ws = W + W o sigma over nrep(zeta_x) of N xi_x planes (4.43 GB at N=32) instead of the "
-                                  "reference's 8*N^6 = 8.59 GB; `plain_kernel` times the unsymmetrised stream") if sym else
-                                 "unsymmetrised stream (SBTE_NO_SYM): 8*N^6 bytes per evaluation as in the reference",
+                                  "reference's 8*N^6 = 8.59 GB" +
+                                  ("; and the bound tensor was checked to be invariant under x <-> y of both indices (relative "
+                                   "deviation %.1e), so only the zeta columns zx >= zy are streamed (2.29 GB) and every weight "
+                                   "serves column (zx,zy) with the spectrum and column (zy,zx) with the transposed spectrum" % xy_dev
+                                   if pairing else "") +
+                                  "; `sym_kernel` times the symmetrised stream over all columns, `plain_kernel` the unsymmetrised one")
+                                 if sym else "unsymmetrised stream (SBTE_NO_SYM): 8*N^6 bytes per evaluation as in the reference",
+                         "xy_pairing": {"state": xy_state, "relative_deviation": xy_dev, "in_use": bool(pairing)},
+                         "sym_kernel": (dict(sym_only, frac=sym_only["achieved_GBs"] / peak) if sym_only else None),
                          "plain_kernel": (dict(plain, frac=plain["achieved_GBs"] / peak) if plain else None),
                          "peak_source": peak_src},
             "e2e": {"value": world * args.steps / e2e_s, "unit": "evals/s", "h2d_bytes_per_step": n3 * 8,
@@ -499,7 +521,7 @@ def run_0d_n32(args):
             line["sustained"] = sustained
     n32_dir = n32_info = None
     if rank == 0 and world == 1 and not args.no_dropin and not args.no_dropin_n32:
-        from spectralbte_b200 import bench_dropin
+        import bench_dropin
         n32_dir, n32_info = bench_dropin.stage_n32(c)   # the bound weights as the reference's own .wts file
     # free the 17 GB of N=32 tensors before the 1D cases build theirs
     df.free()
@@ -516,7 +538,7 @@ def run_0d_n32(args):
     if rank != 0:
         return
     if world == 1 and not args.no_dropin:
-        from spectralbte_b200 import bench_dropin
+        import bench_dropin
         line["dropin"] = bench_dropin.run(ROOT, local, n32_dir=n32_dir, n32_info=n32_info)
     if world == 1 and not args.no_cpu:
         cb = cpu_computeq_n32(args.cpu_steps, 1)

@@ -8,8 +8,8 @@ process start, CUDA context creation and the one-time upload of the weight rows.
 `step_s_median` (0D runs only) is the median of the driver's own "Time elapsed" prints (:203-204, wall clock of one
 ComputeQ_maxPreserve + conserveAllMoments; the 1D branch prints clock() differences per cell, which are not comparable).
 
-Both executables are test infrastructure built by oracle/build_ref.sh; this module only starts them (bench.py's
-cpu_baseline / reference leg is one of the places allowed to execute oracle/)."""
+Both executables are test infrastructure built by oracle/build_ref.sh; this module is part of bench.py (its reference /
+cpu_baseline legs are the one place outside tests/ allowed to execute oracle/) and lives beside it, not in the package."""
 import lzma
 import os
 import re
@@ -89,7 +89,7 @@ def _prepare(tmp, golden, name, wts):
 def stage_n32(coll):
     """Scratch run directory holding the bound N=32 weights of `coll` as Weights/N32_isotropic_L_v5_lambda1.wts (the
     reference's format, src/weights.c:100-103); returns (dir, seconds) or (None, reason)."""
-    from .api import weights_filename
+    from spectralbte_b200.api import weights_filename
     tmp = tempfile.mkdtemp(prefix="sbte_dropin_n32_", dir=os.environ.get("SBTE_SCRATCH", "/tmp"))
     if shutil.disk_usage(tmp).free < 10 * 2 ** 30:
         shutil.rmtree(tmp, ignore_errors=True)

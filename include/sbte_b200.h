@@ -120,6 +120,14 @@ SBTE_API int sbte_weights_save_file(sbte_ctx *c, const char *path);
  * streams a symmetrised copy Ws = W + W o sigma over half of the xi_x planes (built lazily on the device;
  * costs one extra N^6 tensor). On by default; disable to stream the tensor exactly as the reference does. */
 SBTE_API int sbte_set_symmetrize(sbte_ctx *c, int enable);
+/* Isotropic weights (src/weights.c:265-281) are invariant under swapping the x and y axes of both indices, so for f == g
+ * the rows of zeta column (zy, zx) are the rows of column (zx, zy) read against the x<->y transposed spectrum: the 0D
+ * stream then reads only the columns zx >= zy (51.6 % of them at N = 32) and forms two outputs per weight.  Used only
+ * after the bound tensor has been CHECKED (one pass, once) to have that invariance to 1e-14 of its largest entry; any other
+ * tensor keeps the full stream.  On by default; sbte_xy_pairing_state reports -1 not examined / 0 not invariant / 1 in
+ * use, and the measured relative deviation. */
+SBTE_API int sbte_set_xy_pairing(sbte_ctx *c, int enable);
+SBTE_API int sbte_xy_pairing_state(sbte_ctx *c, int *state, double *deviation);
 
 /* The stream-K schedule of the batched convolution for `cells` cells on a device with `ctas` SMs (what the
  * library uploads before a batched ComputeQ; exec/boltz.c:285-345 has no counterpart -- its cells are a plain loop).

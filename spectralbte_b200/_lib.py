@@ -36,6 +36,8 @@ PROTOTYPES = {
     "sbte_launch_count": (C.c_ulonglong, [_vp]),
     "sbte_reserve": (C.c_int, [_vp, C.c_int]),
     "sbte_set_symmetrize": (C.c_int, [_vp, C.c_int]),
+    "sbte_set_xy_pairing": (C.c_int, [_vp, C.c_int]),
+    "sbte_xy_pairing_state": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_double)]),
     "sbte_batch_schedule_host": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_longlong), C.POINTER(C.c_longlong),
                                            C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_ubyte), C.POINTER(C.c_int)]),
     "sbte_k2_profile": (C.c_int, [_vp, C.c_int]),

@@ -149,6 +149,16 @@ class Collisions:
         """Toggle the symmetrised weight stream used when f == g (default on)."""
         check(self.L.sbte_set_symmetrize(self.h, int(bool(enable))))
 
+    def set_xy_pairing(self, enable=True):
+        """Toggle the transposed pairing of the 0D stream (half of the zeta columns; needs an x<->y invariant tensor)."""
+        check(self.L.sbte_set_xy_pairing(self.h, int(bool(enable))))
+
+    def xy_pairing_state(self):
+        """(state, deviation): -1 not examined, 0 tensor not invariant, 1 in use; relative deviation found by the check."""
+        st, dev = C.c_int(), C.c_double()
+        check(self.L.sbte_xy_pairing_state(self.h, C.byref(st), C.byref(dev)))
+        return st.value, dev.value
+
     def k2_profile(self, enable=True):
         check(self.L.sbte_k2_profile(self.h, int(bool(enable))))
 

@@ -51,6 +51,12 @@ def k2_name(N):
     return "qhat_batch_any_kernel"
 
 
+def sym_nrep(N, zx):
+    """Representative xi_x planes of the symmetrised tensor for rows with this zeta_x (csrc/common.cuh sym_nrep)."""
+    a = (zx + N // 2) % N
+    return a // 2 + 1 + (a + N) // 2 - a
+
+
 def nrep_sum(N):
     """Sum over zeta_x of the representative xi_x planes the symmetrised tensor keeps (csrc/common.cuh sym_nrep)."""
     return sum(((zx + N // 2) % N) // 2 + 1 + (((zx + N // 2) % N) + N) // 2 - ((zx + N // 2) % N) for zx in range(N))

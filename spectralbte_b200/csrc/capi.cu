@@ -169,6 +169,7 @@ static int encode_weight_map(sbte_ctx* c, const double* W, CUtensorMap* out, int
 static int make_tensor_map(sbte_ctx* c) {
   c->tmap_ok = false;
   if (c->d_Ws) { cudaFree(c->d_Ws); c->d_Ws = nullptr; }   // a new tensor invalidates the symmetrised copy
+  c->xy_sym = -1;
   c->sched_cells = 0;
   if (!qhat_batch_supported(c->N) || !c->d_W) return 0;
   if (encode_weight_map(c, c->d_W, &c->tmapW)) return 1;
@@ -392,6 +393,21 @@ static int ensure_sym(sbte_ctx* c) {
   }
   return 0;
 }
+// Transposed pairing of the 0D stream (qhat.cu, TP): only for f == g, for the N it is built for, and only after the bound
+// tensor has been checked -- once, one pass over it -- to be invariant under x <-> y of both indices to 1e-14 of its
+// largest entry (isotropic weights are, to round-off; an arbitrary file need not be and then keeps the full stream).
+static bool want_xy(sbte_ctx* c, bool same) {
+  static int env = -1;
+  if (env < 0) { const char* e = getenv("SBTE_NO_XYSYM"); env = (e && atoi(e) != 0) ? 0 : 1; }
+  if (!same || !c->xy_enabled || env != 1 || !qhat_stream_tp_supported(c->N) || !c->d_W) return false;
+  if (c->xy_sym < 0) {
+    double d = 0.0, a = 0.0;
+    if (weights_xy_symmetry(c, c->d_W, &d, &a)) { c->xy_sym = 0; return false; }
+    c->xy_sym_dev = a > 0.0 ? d / a : 0.0;
+    c->xy_sym = (a > 0.0 && d <= 1e-14 * a) ? 1 : 0;
+  }
+  return c->xy_sym == 1;
+}
 static bool want_sym(sbte_ctx* c, bool same) {
   static int env = -1;
   if (env < 0) { const char* e = getenv("SBTE_NO_SYM"); env = (e && atoi(e) != 0) ? 0 : 1; }
@@ -455,7 +471,18 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     static const int want = getenv("SBTE_NO_SPLIT") ? 1 : (getenv("SBTE_SPLIT") ? atoi(getenv("SBTE_SPLIT")) : 2);
     static const bool all_n = getenv("SBTE_SPLIT_ALL") != nullptr;   // testing: split the smaller grids too
     const int ns = ((c->N == 32 || all_n) && want >= 1 && want <= max_split) ? want : 1;
-    launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym, ns);
+    if (want_xy(c, same) && k2 == SBTE_K2_STREAM) {
+      // half of the zeta columns, each weight against the spectrum and against its x <-> y transpose
+      launch_transpose_xy(c, c->d_lay[0], c->d_lay[1]);
+      const QhatPair tp[2] = {{c->d_lay[0], c->d_lay[0]}, {c->d_lay[1], c->d_lay[1]}};
+      // one CTA per streamed column: splitting the columns (as the one-pair kernel does) only loses here -- 0.449 ms
+      // against 0.479 / 0.467 / 0.490 ms with 2 / 3 / 4 parts, sustained (profiles/r02_tp_tune.txt)
+      launch_qhat_stream_tp(c, tp, d_qhat, sym, 1);
+      if (nsplit) *nsplit = 1;
+      return check_launch("qhat");
+    } else {
+      launch_qhat_stream(c, 1, &p, d_qhat, k2 == SBTE_K2_STREAM_DEEP ? 4 : 2, sym, ns);
+    }
     if (nsplit) *nsplit = ns;
   } else {
     if (!same && batch > 4) { set_error("generic convolution with f != g is limited to 4 cells"); return 1; }
@@ -711,6 +738,19 @@ int sbte_reserve(sbte_ctx* c, int cells) {
 int sbte_set_symmetrize(sbte_ctx* c, int enable) {
   if (c->sym_enabled != (enable != 0)) c->graph_gen++;
   c->sym_enabled = enable != 0;
+  return 0;
+}
+
+// transposed pairing of the 0D stream: switch, and what the check of the bound tensor found
+int sbte_set_xy_pairing(sbte_ctx* c, int enable) {
+  c->xy_enabled = enable != 0;
+  return 0;
+}
+int sbte_xy_pairing_state(sbte_ctx* c, int* state, double* deviation) {
+  cudaSetDevice(c->device);
+  if (c->xy_sym < 0 && c->d_W && qhat_stream_tp_supported(c->N)) (void)want_xy(c, true);   // examine the tensor now
+  if (state) *state = c->xy_sym;
+  if (deviation) *deviation = c->xy_sym_dev;
   return 0;
 }
 

@@ -71,6 +71,10 @@ struct sbte_ctx {
   bool tmap_ok = false;
   // symmetrised copy for f == g (Ws[zeta][xi] = W[zeta][xi] + W[zeta][sigma_zeta(xi)], see common.cuh)
   bool sym_enabled = true;
+  // x <-> y invariance of the bound tensor: -1 not examined yet, 0 no, 1 yes (|W[t zeta][t xi] - W[zeta][xi]| <= 1e-14 max|W|)
+  int xy_sym = -1;
+  double xy_sym_dev = 0.0;            // the measured relative deviation
+  bool xy_enabled = true;
   double* d_Ws = nullptr;
   CUtensorMap tmapWs;
   CUtensorMap tmapW16, tmapWs16;   // boxes of 16 zeta_y columns: split tiles of the N = 16 remainder group
@@ -172,6 +176,11 @@ void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2*
 bool fft_cluster_supported(int N);
 bool launch_fft3d_inverse_sum(sbte_ctx* c, const double2* parts, int nparts, double* out_real);
 void launch_symmetrize_weights(sbte_ctx* c, const double* W, double* Ws);
+// transposed pairing (f == g, tensor invariant under x <-> y of both indices): half of the zeta columns are streamed
+bool qhat_stream_tp_supported(int N);
+void launch_qhat_stream_tp(sbte_ctx* c, const QhatPair* pairs, double2* qhat, bool sym, int nsplit);
+void launch_transpose_xy(sbte_ctx* c, const double2* src, double2* dst);
+int weights_xy_symmetry(sbte_ctx* c, const double* W, double* max_diff, double* max_abs);
 // batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32
 bool qhat_batch_supported(int N);
 int qhat_batch_cols(int N);

@@ -15,6 +15,7 @@
 //                  zeta (x,y) column, the whole N x N (zeta_z, xi_z) Toeplitz tile in registers.
 //                  (qhat_batch.cu)
 #include <stdlib.h>
+#include <string.h>
 
 #include <atomic>
 
@@ -105,11 +106,20 @@ struct StreamCfg {
 };
 
 // SYM: W is the symmetrised tensor Ws and only the representative xi_x planes are visited (f == g only).
-template <int N, int NP, int DEPTH, bool SYM, int WT>
+// TP ("transposed pairing", NP = 2, f == g): for a tensor that is invariant under swapping the x and y axes of both
+// indices -- W[(zy,zx,zz)][(ey,ex,ez)] = W[(zx,zy,zz)][(ex,ey,ez)], which isotropic weights are (src/weights.c:265-281:
+// they depend on |zeta|, |xi|, |xi - zeta/2| and a product of per-axis trapezoid factors) -- the rows of column (zy, zx)
+// are the rows of column (zx, zy) read against the x<->y transposed spectrum:
+//     Q^(zy,zx,zz) = sum_xi W[(zx,zy,zz)][xi] F(xi) F(sigma(xi)),   F(ex,ey,ez) = f^(ey,ex,ez).
+// Only the columns zx >= zy are streamed (N(N+1)/2 of N^2: 51.6 % of the bytes at N = 32); pair A is the spectrum itself
+// and accumulates column (zx,zy), pair B is the transposed spectrum and accumulates column (zy,zx): two outputs from one
+// weight, 12 FP64 instructions per weight.  The library verifies the invariance of the bound tensor before using it.
+template <int N, int NP, int DEPTH, bool SYM, int WT, bool TP>
 __global__ void __launch_bounds__(StreamCfg<N, WT>::THREADS, (N == 32 && NP == 1 && DEPTH <= 2) ? 2 : 1)
 qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
                    const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat,
                    int nsplit) {
+  static_assert(!TP || NP == 2, "transposed pairing streams two operand pairs");
   using C = StreamCfg<N, WT>;
   constexpr int HALF = C::HALF, PLANE = C::PLANE;
   constexpr long n3 = (long)N * N * N;
@@ -124,8 +134,18 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   const bool active = rgw < C::RGW;
   // nsplit > 1: the xi_x planes of a column are shared between nsplit CTAs, each writing its own partial
   // spectrum qhat[part]; the inverse transform adds the parts in order.  More, shorter CTAs = a shorter tail.
-  const int part = blockIdx.x / (N * N), colid = blockIdx.x - part * (N * N);
-  const int zx = colid / N, zy = colid % N;
+  constexpr int NCOL = TP ? N * (N + 1) / 2 : N * N;   // columns streamed
+  const int part = blockIdx.x / NCOL, cidx = blockIdx.x - part * NCOL;
+  int zx, zy;
+  if (TP) {   // cidx enumerates the columns zx >= zy: cidx = zx (zx + 1) / 2 + zy
+    zx = (int)((sqrtf(8.0f * (float)cidx + 1.0f) - 1.0f) * 0.5f);
+    while ((zx + 1) * (zx + 2) / 2 <= cidx) zx++;
+    while (zx * (zx + 1) / 2 > cidx) zx--;
+    zy = cidx - zx * (zx + 1) / 2;
+  } else {
+    zx = cidx / N; zy = cidx % N;
+  }
+  const int colid = zx * N + zy;
   const int nchunk_all = SYM ? sym_nrep(N, zx) : N;
   const int cbeg = part * nchunk_all / nsplit;
   const int nchunk = (part + 1) * nchunk_all / nsplit - cbeg;   // xi_x planes visited by this CTA
@@ -188,9 +208,11 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
     if (nchunk > 1) issue_chunk(1);
   }
 
-  double2 acc[4];
+  double2 acc[4], accB[TP ? 4 : 1];
 #pragma unroll
   for (int j = 0; j < 4; j++) acc[j] = make_double2(0.0, 0.0);
+#pragma unroll
+  for (int j = 0; j < (TP ? 4 : 1); j++) accB[j] = make_double2(0.0, 0.0);
 
   for (int it0 = 0; it0 < NIT; it0 += DEPTH) {
 #pragma unroll
@@ -219,7 +241,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
             p[j][1] = cmul(g1, fw[j]);
           }
         }
-        if (NP > 1) {
+        if (NP > 1 && !TP) {
           const double2* gl = st + 2 * PLANE + ey * N;
           const double2* fl = st + 3 * PLANE + Y * N;
           const double2 g0 = gl[offg0], g1 = gl[offg1];
@@ -239,6 +261,19 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
           cmac(acc[j], wb[d][j].x, p[j][0]);
           cmac(acc[j], wb[d][j].y, p[j][1]);
         }
+        if (TP && zx != zy) {   // the same weights against the transposed spectrum: the rows of column (zy, zx)
+          const double2* gl = st + 2 * PLANE + ey * N;
+          const double2* fl = st + 3 * PLANE + Y * N;
+          const double2 g0 = gl[offg0], g1 = gl[offg1];
+          double2 fw[5];
+#pragma unroll
+          for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
+#pragma unroll
+          for (int j = 0; j < 4; j++) {
+            cmac(accB[j], wb[d][j].x, cmul(g0, fw[j + 1]));
+            cmac(accB[j], wb[d][j].y, cmul(g1, fw[j]));
+          }
+        }
         if (it + DEPTH < NIT) load_w(it + DEPTH, wb[d]);
       }
       if (step == C::SPC - 1) {
@@ -253,30 +288,39 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   // the trailing __syncthreads of the last chunk guarantees nobody still reads it)
   double2* red = planes;
 #pragma unroll
-  for (int j = 0; j < 4; j++) red[tid * 4 + j] = active ? acc[j] : make_double2(0.0, 0.0);
-  __syncthreads();
-  if (tid < N) {
-    const int r = tid;
-    const int rbr = r / C::ROWS_W, rg = (r % C::ROWS_W) / 4, j = r % 4;
-    double sr = 0.0, si = 0.0;
-    for (int p = 0; p < C::PH; p++) {
-      const int w = p * C::RB + rbr;
-      for (int q = 0; q < HALF; q++) {
-        const double2 v = red[((w * 32) + rg * HALF + q) * 4 + j];
-        sr += v.x; si += v.y;
-      }
+  for (int round = 0; round < (TP ? 2 : 1); round++) {
+    if (round == 1) {
+      if (zx == zy) break;   // a diagonal column is its own transpose: pair B would rewrite the rows pair A wrote
+      __syncthreads();
     }
-    qhat[(long)part * n3 + (long)colid * N + r] = make_double2(sr, si);
+#pragma unroll
+    for (int j = 0; j < 4; j++)
+      red[tid * 4 + j] = active ? (round == 0 ? acc[j] : accB[TP ? j : 0]) : make_double2(0.0, 0.0);
+    __syncthreads();
+    if (tid < N) {
+      const int r = tid;
+      const int rbr = r / C::ROWS_W, rg = (r % C::ROWS_W) / 4, j = r % 4;
+      double sr = 0.0, si = 0.0;
+      for (int p = 0; p < C::PH; p++) {
+        const int w = p * C::RB + rbr;
+        for (int q = 0; q < HALF; q++) {
+          const double2 v = red[((w * 32) + rg * HALF + q) * 4 + j];
+          sr += v.x; si += v.y;
+        }
+      }
+      const int out_col = round == 0 ? colid : zy * N + zx;
+      qhat[(long)part * n3 + (long)out_col * N + r] = make_double2(sr, si);
+    }
   }
 }
 
 bool qhat_stream_supported(int N) { return N == 16 || N == 24 || N == 32; }
 
-template <int N, int NP, int DEPTH, bool SYM, int WT = 8>
+template <int N, int NP, int DEPTH, bool SYM, int WT = 8, bool TP = false>
 static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pairs, double2* qhat, int nsplit = 1) {
   using C = StreamCfg<N, WT>;
   const size_t smem = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2) + 64;
-  auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM, WT>;
+  auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM, WT, TP>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
   if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -284,7 +328,7 @@ static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pai
   }
   k2_mark(c);
   cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = dim3(N * N * nsplit);
+  cfg.gridDim = dim3((TP ? N * (N + 1) / 2 : N * N) * nsplit);
   cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = c->stream;
@@ -326,6 +370,74 @@ void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2*
     case 32: sym ? launch_stream_n<32, true>(c, W, npairs, pairs, qhat, depth, nsplit) : launch_stream_n<32, false>(c, W, npairs, pairs, qhat, depth, nsplit); break;
     default: set_error("qhat_stream: unsupported N"); break;
   }
+}
+
+// transposed pairing (TP): pairs[0] = the spectrum (both sides), pairs[1] = its x<->y transpose (both sides); f == g only
+bool qhat_stream_tp_supported(int N) { return N == 32 || N == 16; }
+void launch_qhat_stream_tp(sbte_ctx* c, const QhatPair* pairs, double2* qhat, bool sym, int nsplit) {
+  const double* W = sym ? c->d_Ws : c->d_W;
+  if (nsplit < 1) nsplit = 1;
+  if (nsplit > c->N / 2) nsplit = c->N / 2;
+  // 16 warps with two weight tiles in flight per thread; 8 warps with four were 15 % slower (profiles/r02_tp_tune.txt)
+  switch (c->N) {
+    case 16: sym ? launch_stream_inst<16, 2, 2, true, 16, true>(c, W, pairs, qhat, nsplit) : launch_stream_inst<16, 2, 2, false, 16, true>(c, W, pairs, qhat, nsplit); break;
+    case 32: sym ? launch_stream_inst<32, 2, 2, true, 16, true>(c, W, pairs, qhat, nsplit) : launch_stream_inst<32, 2, 2, false, 16, true>(c, W, pairs, qhat, nsplit); break;
+    default: set_error("qhat_stream (transposed pairing): unsupported N"); break;
+  }
+}
+
+// dst(x, y, .) = src(y, x, .) for a parity-split (or natural) spectrum: lines of N complex values move as a whole
+__global__ void transpose_xy_kernel(const double2* __restrict__ src, double2* __restrict__ dst, int N) {
+  const int line = blockIdx.x;                 // destination line (x, y)
+  const int x = line / N, y = line - x * N;
+  const double2* s = src + ((size_t)y * N + x) * N;
+  double2* d = dst + (size_t)line * N;
+  for (int k = threadIdx.x; k < N; k += blockDim.x) d[k] = s[k];
+}
+void launch_transpose_xy(sbte_ctx* c, const double2* src, double2* dst) {
+  transpose_xy_kernel<<<c->N * c->N, 32, 0, c->stream>>>(src, dst, c->N);
+  c->launches += 1;
+}
+
+// max |W[(zx,zy,zz)][(ex,ey,ez)] - W[(zy,zx,zz)][(ey,ex,ez)]| and max |W| over the tensor, as bit patterns of
+// non-negative doubles (atomicMax on unsigned long long orders them correctly); out[0] = difference, out[1] = magnitude
+__global__ void xy_symmetry_kernel(const double* __restrict__ W, unsigned long long* __restrict__ out, int N) {
+  const size_t n3 = (size_t)N * N * N, total = n3 * n3;
+  double dmax = 0.0, amax = 0.0;
+  for (size_t e = blockIdx.x * (size_t)blockDim.x + threadIdx.x; e < total; e += (size_t)gridDim.x * blockDim.x) {
+    const int zeta = (int)(e / n3), xi = (int)(e - (size_t)zeta * n3);
+    const int zx = zeta / (N * N), zy = (zeta / N) % N, zz = zeta % N;
+    if (zx < zy) continue;                     // every unordered pair once
+    const int ex = xi / (N * N), ey = (xi / N) % N, ez = xi % N;
+    const double a = W[e];
+    const double b = W[(((size_t)zy * N + zx) * N + zz) * n3 + ((size_t)ey * N + ex) * N + ez];
+    dmax = fmax(dmax, fabs(a - b));
+    amax = fmax(amax, fmax(fabs(a), fabs(b)));
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    dmax = fmax(dmax, __shfl_xor_sync(0xffffffffu, dmax, o));
+    amax = fmax(amax, __shfl_xor_sync(0xffffffffu, amax, o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMax(out, (unsigned long long)__double_as_longlong(dmax));
+    atomicMax(out + 1, (unsigned long long)__double_as_longlong(amax));
+  }
+}
+// returns 0 and the two maxima; synchronises the context's stream
+int weights_xy_symmetry(sbte_ctx* c, const double* W, double* max_diff, double* max_abs) {
+  unsigned long long* d = nullptr;
+  if (cudaMalloc(&d, 16) != cudaSuccess) return 1;
+  cudaMemsetAsync(d, 0, 16, c->stream);
+  xy_symmetry_kernel<<<148 * 16, 256, 0, c->stream>>>(W, d, c->N);
+  c->launches += 1;
+  unsigned long long h[2] = {0, 0};
+  cudaMemcpyAsync(h, d, 16, cudaMemcpyDeviceToHost, c->stream);
+  const cudaError_t e = cudaStreamSynchronize(c->stream);
+  cudaFree(d);
+  if (e != cudaSuccess) return 1;
+  memcpy(max_diff, &h[0], 8);
+  memcpy(max_abs, &h[1], 8);
+  return 0;
 }
 
 // Ws[zeta][xi] = W[zeta][xi] + W[zeta][sigma(xi)] on representative planes, W on self-paired planes, 0 elsewhere

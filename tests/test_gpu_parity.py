@@ -778,6 +778,41 @@ def test_symmetrised_stream_equals_plain_stream(sb, N, k2, cells):
         assert relmax(ma, mb) < 1e-13
 
 
+@pytest.mark.parametrize("N,L_v,lam", [(16, 5.0, 0.0), (16, 9.0, 1.0), (32, 5.0, 1.0)])
+def test_transposed_pairing_of_the_0d_stream(sb, N, L_v, lam):
+    """Isotropic weights are invariant under x <-> y of both indices, so the 0D stream reads only the zeta columns
+    zx >= zy and forms column (zy, zx) from the same weights against the transposed spectrum (csrc/qhat.cu, TP).  The
+    library must (i) find the generated tensor invariant, (ii) reproduce the full stream's Q^ far inside the 1e-12
+    tolerance, plain and symmetrised, (iii) refuse a tensor that is not invariant (synthetic weights) and give the very
+    bits of the full stream there."""
+    rule = 0
+    c = sb.Collisions(N, L_v)
+    c.generate_weights(lam)
+    state, dev = c.xy_pairing_state()
+    assert state == 1 and dev <= 1e-14, (state, dev)
+    o = orc.Oracle(N, L_v, rule)
+    f = seeded_f(o.v, 77, noise=0.2)
+    for sym in (True, False):
+        c.set_symmetrize(sym)
+        c.set_xy_pairing(True)
+        qa, Qa = c.Qhat(f, k2=sb.K2_STREAM), c.ComputeQ(f, k2=sb.K2_STREAM)
+        c.set_xy_pairing(False)
+        qb, Qb = c.Qhat(f, k2=sb.K2_STREAM), c.ComputeQ(f, k2=sb.K2_STREAM)
+        assert not np.array_equal(qa, qb)                 # two different kernels really ran
+        assert relmax(qa, qb) < 1e-13 and relmax(Qa, Qb) < 1e-13, sym
+    c.set_xy_pairing(True)
+    if N == 16:
+        W = c.weights_to_host()
+        assert relmax(qa, o.qhat(W, o.fft3d(f.astype(complex)), o.fft3d(f.astype(complex)))) < TOL_QHAT
+    # a tensor without the invariance keeps the full stream
+    c.synthetic_weights(5)
+    state, dev = c.xy_pairing_state()
+    assert state == 0 and dev > 1e-3
+    qa = c.Qhat(f, k2=sb.K2_STREAM)
+    c.set_xy_pairing(False)
+    assert np.array_equal(qa, c.Qhat(f, k2=sb.K2_STREAM))
+
+
 def test_symmetrised_representatives_cover_every_pair_once():
     """Host-side check of the xi_x representative rule used by the kernels (common.cuh sym_nrep/sym_rep)."""
     for N in (8, 16, 22, 24, 32):
