@@ -457,7 +457,11 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     launch_combine_parts(c, c->d_parts, c->parts_stride, c->sched, batch, d_qhat);
   } else if (k2 == SBTE_K2_STREAM || k2 == SBTE_K2_STREAM_DEEP) {
     if (batch != 1 || !qhat_stream_supported(c->N)) { set_error("stream convolution: batch must be 1, N in {16,24,32}"); return 1; }
+    const bool tp = want_xy(c, same) && k2 == SBTE_K2_STREAM;
+    c->fft_layT = tp ? c->d_lay[1] : nullptr;   // the cluster transform writes the transposed copy along with the spectrum
+    c->fft_layT_done = false;
     launch_fft3d(c, d_f, nullptr, 0, 1, nullptr, c->d_lay[0], LAY_PARITY, nullptr, false);
+    c->fft_layT = nullptr;
     const double2* gl = c->d_lay[0];
     if (!same) {
       launch_fft3d(c, d_g, nullptr, 0, 1, nullptr, c->d_lay[1], LAY_PARITY, nullptr, false);
@@ -471,9 +475,9 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
     static const int want = getenv("SBTE_NO_SPLIT") ? 1 : (getenv("SBTE_SPLIT") ? atoi(getenv("SBTE_SPLIT")) : 2);
     static const bool all_n = getenv("SBTE_SPLIT_ALL") != nullptr;   // testing: split the smaller grids too
     const int ns = ((c->N == 32 || all_n) && want >= 1 && want <= max_split) ? want : 1;
-    if (want_xy(c, same) && k2 == SBTE_K2_STREAM) {
+    if (tp) {
       // half of the zeta columns, each weight against the spectrum and against its x <-> y transpose
-      launch_transpose_xy(c, c->d_lay[0], c->d_lay[1]);
+      if (!c->fft_layT_done) launch_transpose_xy(c, c->d_lay[0], c->d_lay[1]);
       const QhatPair tp[2] = {{c->d_lay[0], c->d_lay[0]}, {c->d_lay[1], c->d_lay[1]}};
       // one CTA per streamed column: splitting the columns (as the one-pair kernel does) only loses here -- 0.449 ms
       // against 0.479 / 0.467 / 0.490 ms with 2 / 3 / 4 parts, sustained (profiles/r02_tp_tune.txt)

@@ -61,6 +61,7 @@ struct FftJob {
   double2* out_nat;
   double2* out_lay;
   double* out_real;
+  double2* out_layT;         // optional second copy of a parity-layout spectrum with x and y swapped (transposed pairing)
 };
 struct FftJobs {
   FftJob j[4];
@@ -547,6 +548,7 @@ fft3d_cluster_kernel(FftJobs jobs, PartsIn pin, const double2* __restrict__ pre,
   cluster.sync();
   double2* out_nat = jobs.j[job].out_nat;
   double2* out_lay = jobs.j[job].out_lay;
+  double2* out_layT = jobs.j[job].out_layT;
   double* out_real = jobs.j[job].out_real;
   const int layout = jobs.layout, accumulate = jobs.accumulate_real;
   for (int l = threadIdx.x; l < PL * N; l += blockDim.x) {          // along x: line (j, k), gathered over DSMEM
@@ -571,6 +573,7 @@ fft3d_cluster_kernel(FftJobs jobs, PartsIn pin, const double2* __restrict__ pre,
         else if (layout == LAY_CELLMINOR) out_lay[((cell >> 5) * n3 + loc) * 32 + (cell & 31)] = o;
         else out_lay[coff + loc] = o;
       }
+      if (out_layT) out_layT[coff + ((long)j * N + ip) * N + (k & 1) * (N / 2) + (k >> 1)] = o;   // element (ip, j, k) at (j, ip, k)
     };
     if constexpr ((N & (N - 1)) == 0) {
       constexpr int LG = ilog2(N);
@@ -654,10 +657,15 @@ static bool try_cluster_fft(sbte_ctx* c, const double* in_real, const double2* i
   FftJobs jobs = {};
   jobs.j[0].in_real = in_real; jobs.j[0].in_cplx = in_cplx;
   jobs.j[0].out_nat = out_nat; jobs.j[0].out_lay = out_lay; jobs.j[0].out_real = out_real;
+  // a caller that wants the x<->y transposed parity-layout copy as well leaves its address in the context
+  const bool want_T = c->fft_layT != nullptr && batch == 1 && layout == LAY_PARITY && out_lay != nullptr && !invert;
+  jobs.j[0].out_layT = want_T ? c->fft_layT : nullptr;
   jobs.cells_per_job = batch;
   jobs.layout = layout;
   jobs.accumulate_real = accumulate_real ? 1 : 0;
-  return launch_cluster(c, jobs, pin, invert, batch);
+  const bool ok = launch_cluster(c, jobs, pin, invert, batch);
+  if (ok && want_T) c->fft_layT_done = true;
+  return ok;
 }
 
 void launch_fft3d(sbte_ctx* c, const double* in_real, const double2* in_cplx, int invert, int batch,

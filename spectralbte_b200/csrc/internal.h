@@ -75,6 +75,8 @@ struct sbte_ctx {
   int xy_sym = -1;
   double xy_sym_dev = 0.0;            // the measured relative deviation
   bool xy_enabled = true;
+  double2* fft_layT = nullptr;        // set around a forward transform: also write the x<->y transposed parity-layout copy here
+  bool fft_layT_done = false;         // ... and whether the kernel that ran could do it (else launch_transpose_xy)
   double* d_Ws = nullptr;
   CUtensorMap tmapWs;
   CUtensorMap tmapW16, tmapWs16;   // boxes of 16 zeta_y columns: split tiles of the N = 16 remainder group

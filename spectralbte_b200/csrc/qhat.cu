@@ -127,6 +127,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   extern __shared__ __align__(128) unsigned char smraw[];
   double2* planes = reinterpret_cast<double2*>(smraw);                       // [2][NP][2][PLANE]
   uint64_t* full = reinterpret_cast<uint64_t*>(smraw + 2 * STAGE_ELEMS * sizeof(double2));
+  int* done_cnt = reinterpret_cast<int*>(full + 2);   // [2] warps that have finished reading a stage
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int rb = warp % C::RB, ph = warp / C::RB;
@@ -181,6 +182,8 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   if (tid == 0) {
     mbar_init(&full[0], 1);
     mbar_init(&full[1], 1);
+    done_cnt[0] = 0;
+    done_cnt[1] = 0;
     mbar_fence_init();
   }
   __syncthreads();
@@ -277,16 +280,25 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
         if (it + DEPTH < NIT) load_w(it + DEPTH, wb[d]);
       }
       if (step == C::SPC - 1) {
-        // every warp is done with stage s: refill it with the planes of chunk + 2
-        __syncthreads();
-        if (tid == 0 && chunk + 2 < nchunk) issue_chunk(chunk + 2);
+        // No CTA-wide barrier at the chunk end: the LAST warp to finish reading stage s refills it with the planes of
+        // chunk + 2 (its full barrier cannot complete that phase before every warp has passed this point, so a fast
+        // warp simply waits there).  With one CTA per SM a __syncthreads here idled every warp once per chunk.
+        __syncwarp();
+        if (lane == 0) {
+          __threadfence_block();
+          if (atomicAdd(&done_cnt[s], 1) == C::NWARP - 1) {
+            __threadfence_block();
+            done_cnt[s] = 0;
+            if (chunk + 2 < nchunk) issue_chunk(chunk + 2);
+          }
+        }
       }
     }
   }
 
-  // deterministic cross-thread reduction: [thread][4] partial sums -> N rows (reuses the plane ring;
-  // the trailing __syncthreads of the last chunk guarantees nobody still reads it)
+  // deterministic cross-thread reduction: [thread][4] partial sums -> N rows (reuses the plane ring)
   double2* red = planes;
+  __syncthreads();   // every warp has left the main loop: the plane ring is free
 #pragma unroll
   for (int round = 0; round < (TP ? 2 : 1); round++) {
     if (round == 1) {
