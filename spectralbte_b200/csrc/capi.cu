@@ -109,7 +109,7 @@ static void invalidate_graphs(sbte_ctx* c) {
 static void free_scratch(sbte_ctx* c) {
   invalidate_graphs(c);
   cudaFree(c->d_tmp); cudaFree(c->d_specA); cudaFree(c->d_specB); cudaFree(c->d_specC);
-  for (int i = 0; i < 3; i++) cudaFree(c->d_lay[i]);
+  for (int i = 0; i < 3; i++) { cudaFree(c->d_lay[i]); cudaFree(c->d_layT[i]); c->d_layT[i] = nullptr; }
   cudaFree(c->d_qhat); cudaFree(c->d_Q); cudaFree(c->d_f); cudaFree(c->d_g); cudaFree(c->d_M); cudaFree(c->d_mom);
   c->d_tmp = c->d_specA = c->d_specB = c->d_specC = c->d_qhat = nullptr;
   c->d_lay[0] = c->d_lay[1] = c->d_lay[2] = nullptr;
@@ -141,6 +141,7 @@ int ensure_capacity(sbte_ctx* c, int cells) {
   CK(cudaMalloc(&c->d_lay[1], cb32));
   CK(cudaMalloc(&c->d_lay[2], cb32));
   CK(cudaMalloc(&c->d_M, 4 * (size_t)c->n3 * sizeof(double)));
+  for (int i = 0; i < 3; i++) CK(cudaMalloc(&c->d_layT[i], (size_t)c->n3 * sizeof(double2)));
   c->cap = cells;
   return 0;
 }
@@ -481,7 +482,7 @@ int qhat_from_real(sbte_ctx* c, const double* d_f, const double* d_g, double2* d
       const QhatPair tp[2] = {{c->d_lay[0], c->d_lay[0]}, {c->d_lay[1], c->d_lay[1]}};
       // one CTA per streamed column: splitting the columns (as the one-pair kernel does) only loses here -- 0.449 ms
       // against 0.479 / 0.467 / 0.490 ms with 2 / 3 / 4 parts, sustained (profiles/r02_tp_tune.txt)
-      launch_qhat_stream_tp(c, tp, d_qhat, sym, 1);
+      launch_qhat_stream_tp(c, 2, tp, d_qhat, sym, 1);
       if (nsplit) *nsplit = 1;
       return check_launch("qhat");
     } else {
@@ -582,11 +583,29 @@ int compute_q_maxpreserve_dev(sbte_ctx* c, const double* d_f, const double* d_g,
   // three spectra: f^ (A), g_i^ (B), M_j^ (C); g_j^ == g_i^ for one species (f == g)
   const double* ins[4] = {d_f, gi, Mj, gj};
   double2* outs[4] = {c->d_lay[0], c->d_lay[1], c->d_lay[2], c->d_specB};
-  if (!launch_fft3d_multi(c, same ? 3 : 4, ins, outs, lay)) {   // one launch where the cluster kernel exists
+  const bool tp = stream && k2 == SBTE_K2_STREAM && want_xy(c, same);
+  c->fft_layT_multi = tp ? c->d_layT : nullptr;   // the cluster transform writes the transposed copies along with the spectra
+  c->fft_layT_done = false;
+  const bool multi = launch_fft3d_multi(c, same ? 3 : 4, ins, outs, lay);
+  c->fft_layT_multi = nullptr;
+  if (!multi) {   // one launch where the cluster kernel exists
     for (int q = 0; q < (same ? 3 : 4); q++) launch_fft3d(c, ins[q], nullptr, 0, 1, nullptr, outs[q], lay, nullptr, false);
   }
   const double2* gjhat = same ? c->d_lay[1] : c->d_specB;
   QhatPair pairs[2] = {{gjhat, c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]}};
+  if (tp) {
+    // transposed pairing: half of the zeta columns; the two summed products against the spectra give column (zx, zy),
+    // against the transposed spectra column (zy, zx)
+    if (!c->fft_layT_done)
+      for (int q = 0; q < 3; q++) launch_transpose_xy(c, c->d_lay[q], c->d_layT[q]);
+    const QhatPair p4[4] = {{c->d_lay[1], c->d_lay[0]}, {c->d_lay[2], c->d_lay[1]},
+                            {c->d_layT[1], c->d_layT[0]}, {c->d_layT[2], c->d_layT[1]}};
+    const bool symt = want_sym(c, true);
+    if (symt && ensure_sym(c)) return 1;
+    launch_qhat_stream_tp(c, 4, p4, c->d_qhat, symt, 1);
+    launch_fft3d(c, nullptr, c->d_qhat, 1, 1, nullptr, nullptr, 0, d_Q, false);
+    return check_launch("maxpreserve (transposed pairing)");
+  }
   const bool sym = stream && want_sym(c, same);   // for f == g the three-product summand is symmetric as a whole
   if (sym && ensure_sym(c)) return 1;
   // splitting the columns between CTAs (as the one-pair kernel does at N = 32) does not pay here: N = 32 already runs

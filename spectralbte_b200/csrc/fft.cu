@@ -635,11 +635,16 @@ bool launch_fft3d_multi(sbte_ctx* c, int njobs, const double* const* in_real, do
   if (!fft_cluster_supported(c->N) || njobs > 4 || getenv("SBTE_NO_CLUSTER_FFT")) return false;
   FftJobs jobs = {};
   for (int q = 0; q < njobs; q++) { jobs.j[q].in_real = in_real[q]; jobs.j[q].out_lay = out_lay[q]; }
+  const bool want_T = c->fft_layT_multi != nullptr && layout == LAY_PARITY && njobs <= 3;
+  if (want_T)
+    for (int q = 0; q < njobs; q++) jobs.j[q].out_layT = c->fft_layT_multi[q];
   if (layout == LAY_CELLMINOR) return false;   // the cell-minor interleave belongs to one batched job
   jobs.cells_per_job = 1;
   jobs.layout = layout;
   PartsIn nopart = {nullptr, 0, nullptr, 0, 0};
-  return launch_cluster(c, jobs, nopart, 0, njobs);
+  const bool ok = launch_cluster(c, jobs, nopart, 0, njobs);
+  if (ok && want_T) c->fft_layT_done = true;
+  return ok;
 }
 
 bool launch_fft3d_inverse_sum(sbte_ctx* c, const double2* parts, int nparts, double* out_real) {

@@ -76,6 +76,7 @@ struct sbte_ctx {
   double xy_sym_dev = 0.0;            // the measured relative deviation
   bool xy_enabled = true;
   double2* fft_layT = nullptr;        // set around a forward transform: also write the x<->y transposed parity-layout copy here
+  double2* const* fft_layT_multi = nullptr;   // the same for launch_fft3d_multi: one destination per job
   bool fft_layT_done = false;         // ... and whether the kernel that ran could do it (else launch_transpose_xy)
   double* d_Ws = nullptr;
   CUtensorMap tmapWs;
@@ -88,6 +89,7 @@ struct sbte_ctx {
   double2* d_specB = nullptr;    //                             [cap][n3]  (operand "g": xi side)
   double2* d_specC = nullptr;    // third spectrum (maxPreserve: Maxwellian)
   double2* d_lay[3] = {nullptr, nullptr, nullptr};  // kernel-specific operand layouts of A, B, C
+  double2* d_layT[3] = {nullptr, nullptr, nullptr}; // their x<->y transposes (one cell each; transposed pairing of maxPreserve)
   double2* d_qhat = nullptr;     // [cap][n3]
   double* d_Q = nullptr;         // [cap][n3]
   double* d_f = nullptr;         // staging for host-pointer entry points [cap][n3]
@@ -180,7 +182,7 @@ bool launch_fft3d_inverse_sum(sbte_ctx* c, const double2* parts, int nparts, dou
 void launch_symmetrize_weights(sbte_ctx* c, const double* W, double* Ws);
 // transposed pairing (f == g, tensor invariant under x <-> y of both indices): half of the zeta columns are streamed
 bool qhat_stream_tp_supported(int N);
-void launch_qhat_stream_tp(sbte_ctx* c, const QhatPair* pairs, double2* qhat, bool sym, int nsplit);
+void launch_qhat_stream_tp(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, bool sym, int nsplit);
 void launch_transpose_xy(sbte_ctx* c, const double2* src, double2* dst);
 int weights_xy_symmetry(sbte_ctx* c, const double* W, double* max_diff, double* max_abs);
 // batched kernel (N in {8,16}): cell-minor operand layout, cells padded to a multiple of 32

@@ -105,6 +105,12 @@ struct StreamCfg {
   static_assert(N % PH == 0, "phases must tile");
 };
 
+// operand pairs of one weight pass: xi-side spectrum g^[xi] and dif-side spectrum f^[zeta - xi] of up to four products
+struct StreamOperands {
+  const double2* xi[4];
+  const double2* df[4];
+};
+
 // SYM: W is the symmetrised tensor Ws and only the representative xi_x planes are visited (f == g only).
 // TP ("transposed pairing", NP = 2, f == g): for a tensor that is invariant under swapping the x and y axes of both
 // indices -- W[(zy,zx,zz)][(ey,ex,ez)] = W[(zx,zy,zz)][(ex,ey,ez)], which isotropic weights are (src/weights.c:265-281:
@@ -116,16 +122,24 @@ struct StreamCfg {
 // weight, 12 FP64 instructions per weight.  The library verifies the invariance of the bound tensor before using it.
 template <int N, int NP, int DEPTH, bool SYM, int WT, bool TP>
 __global__ void __launch_bounds__(StreamCfg<N, WT>::THREADS, (N == 32 && NP == 1 && DEPTH <= 2) ? 2 : 1)
-qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA, const double2* __restrict__ dfA,
-                   const double2* __restrict__ xiB, const double2* __restrict__ dfB, double2* __restrict__ qhat,
-                   int nsplit) {
-  static_assert(!TP || NP == 2, "transposed pairing streams two operand pairs");
+qhat_stream_kernel(const double* __restrict__ W, StreamOperands ops, double2* __restrict__ qhat, int nsplit) {
+  // NP = 2 with TP: one pair per orientation (ComputeQ).  NP = 4 with TP: two summed pairs per orientation
+  // (ComputeQ_maxPreserve): pairs 0,1 against the spectra, pairs 2,3 against their x<->y transposes.
+  static_assert(!TP || NP == 2 || NP == 4, "transposed pairing streams two or four operand pairs");
+  static_assert(NP != 4 || TP, "four pairs only as two orientations of two");
   using C = StreamCfg<N, WT>;
   constexpr int HALF = C::HALF, PLANE = C::PLANE;
   constexpr long n3 = (long)N * N * N;
-  constexpr uint32_t STAGE_ELEMS = 2 * NP * PLANE;  // per stage: NP x (xi-side plane, dif-side plane)
+  // Eight planes of 16 KB do not fit twice: with four pairs a stage holds HALF a chunk -- the xi_y lines
+  // [sub N/2, (sub+1) N/2) of every xi-side plane and the N/2 dif-side lines they meet (contiguous modulo N).
+  constexpr int SUB = (NP == 4 && (size_t)4 * NP * PLANE * sizeof(double2) > 200 * 1024) ? 2 : 1;   // staged sub-chunks per xi_x chunk
+  constexpr int LPS = N / SUB;                      // lines per staged plane
+  constexpr int SPLANE = LPS * N;                   // complex elements per staged plane
+  constexpr int SPS = C::SPC / SUB;                 // steps per sub-chunk
+  static_assert(C::SPC % SUB == 0 && (SUB == 1 || C::PH * SPS == LPS), "a sub-chunk covers a contiguous range of xi_y");
+  constexpr uint32_t STAGE_ELEMS = 2 * NP * SPLANE;  // per stage: NP x (xi-side plane, dif-side plane)
   extern __shared__ __align__(128) unsigned char smraw[];
-  double2* planes = reinterpret_cast<double2*>(smraw);                       // [2][NP][2][PLANE]
+  double2* planes = reinterpret_cast<double2*>(smraw);                       // [2][NP][2][SPLANE]
   uint64_t* full = reinterpret_cast<uint64_t*>(smraw + 2 * STAGE_ELEMS * sizeof(double2));
   int* done_cnt = reinterpret_cast<int*>(full + 2);   // [2] warps that have finished reading a stage
 
@@ -164,18 +178,31 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   }
   const int offg0 = cp, offg1 = HALF + cp;
 
-  auto issue_chunk = [&](int chunk) {  // one thread: stage the operand planes of the chunk-th visited xi_x
-    const int s = chunk & 1;
+  // first dif-side line of a sub-chunk in ascending order: the lines Y = zy + N/2 - ey, ey in [sub LPS, (sub+1) LPS)
+  auto sub_ylo = [&](int sub) {
+    if (SUB == 1) return 0;
+    int y = zy + N / 2 - (sub * LPS + LPS - 1);
+    y %= N;
+    return y < 0 ? y + N : y;
+  };
+  auto issue_chunk = [&](int q) {  // one thread: stage the operand planes of sub-chunk q = chunk * SUB + sub
+    const int s = q & 1;
+    const int chunk = q / SUB, sub = q - chunk * SUB;
     const int ex = chunk_ex(chunk);
     int X = zx + N / 2 - ex;
     if (X < 0) X += N; else if (X > N - 1) X -= N;
     double2* dst = planes + (size_t)s * STAGE_ELEMS;
     mbar_arrive_expect_tx(&full[s], STAGE_ELEMS * (uint32_t)sizeof(double2));
-    tma_bulk_g2s(dst, xiA + (size_t)ex * PLANE, PLANE * sizeof(double2), &full[s]);
-    tma_bulk_g2s(dst + PLANE, dfA + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
-    if (NP > 1) {
-      tma_bulk_g2s(dst + 2 * PLANE, xiB + (size_t)ex * PLANE, PLANE * sizeof(double2), &full[s]);
-      tma_bulk_g2s(dst + 3 * PLANE, dfB + (size_t)X * PLANE, PLANE * sizeof(double2), &full[s]);
+    const int ylo = sub_ylo(sub);
+    const int n1 = (SUB == 1) ? N : min(LPS, N - ylo);      // lines before the wrap
+#pragma unroll
+    for (int p = 0; p < NP; p++) {
+      tma_bulk_g2s(dst + (2 * p) * SPLANE, ops.xi[p] + (size_t)ex * PLANE + (size_t)sub * SPLANE, SPLANE * sizeof(double2),
+                   &full[s]);
+      const double2* dsrc = ops.df[p] + (size_t)X * PLANE;
+      tma_bulk_g2s(dst + (2 * p + 1) * SPLANE, dsrc + (size_t)ylo * N, (uint32_t)(n1 * N * sizeof(double2)), &full[s]);
+      if (SUB > 1 && n1 < LPS)
+        tma_bulk_g2s(dst + (2 * p + 1) * SPLANE + n1 * N, dsrc, (uint32_t)((LPS - n1) * N * sizeof(double2)), &full[s]);
     }
   };
 
@@ -208,7 +235,7 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
   pdl_wait();
   if (tid == 0 && nchunk > 0) {   // a CTA with no xi_x planes (nsplit > planes of this column) writes a zero partial sum
     issue_chunk(0);
-    if (nchunk > 1) issue_chunk(1);
+    if (nchunk * SUB > 1) issue_chunk(1);
   }
 
   double2 acc[4], accB[TP ? 4 : 1];
@@ -223,17 +250,21 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
       const int it = it0 + d;
       if (it >= NIT) break;   // block-uniform (NIT need not be a multiple of DEPTH)
       const int chunk = it / C::SPC, step = it % C::SPC;
-      const int s = chunk & 1;
-      if (step == 0) mbar_wait(&full[s], (chunk >> 1) & 1);
+      const int sub = step / SPS, q = chunk * SUB + sub;      // staged sub-chunk this step reads
+      const int s = q & 1;
+      if (step % SPS == 0) mbar_wait(&full[s], (q >> 1) & 1);
       const int ey = ph + step * C::PH;
       int Y = zy + N / 2 - ey;
       if (Y < 0) Y += N; else if (Y > N - 1) Y -= N;
+      int yl = Y - sub_ylo(sub);                               // line of the staged dif-side plane
+      if (yl < 0) yl += N;
+      const int el = ey - sub * LPS;                           // line of the staged xi-side plane
       const double2* st = planes + (size_t)s * STAGE_ELEMS;
-      if (active) {
-        double2 p[4][2];
+      // sum of the products of operand pairs p0 and (if p1 >= 0) p1 for this thread's 4 x 2 tile
+      auto products = [&](int p0, int p1, double2 (&p)[4][2]) {
         {
-          const double2* gl = st + ey * N;
-          const double2* fl = st + PLANE + Y * N;
+          const double2* gl = st + (2 * p0) * SPLANE + el * N;
+          const double2* fl = st + (2 * p0 + 1) * SPLANE + yl * N;
           const double2 g0 = gl[offg0], g1 = gl[offg1];
           double2 fw[5];
 #pragma unroll
@@ -244,9 +275,9 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
             p[j][1] = cmul(g1, fw[j]);
           }
         }
-        if (NP > 1 && !TP) {
-          const double2* gl = st + 2 * PLANE + ey * N;
-          const double2* fl = st + 3 * PLANE + Y * N;
+        if (p1 >= 0) {
+          const double2* gl = st + (2 * p1) * SPLANE + el * N;
+          const double2* fl = st + (2 * p1 + 1) * SPLANE + yl * N;
           const double2 g0 = gl[offg0], g1 = gl[offg1];
           double2 fw[5];
 #pragma unroll
@@ -259,37 +290,37 @@ qhat_stream_kernel(const double* __restrict__ W, const double2* __restrict__ xiA
             p[j][1].y = fma(g1.x, fw[j].y, fma(g1.y, fw[j].x, p[j][1].y));
           }
         }
+      };
+      if (active) {
+        double2 p[4][2];
+        // orientation e: one pair (NP = 1, or NP = 2 with TP) or two summed pairs (maxPreserve: NP = 2 without TP, NP = 4)
+        products(0, (NP == 4 || (NP == 2 && !TP)) ? 1 : -1, p);
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           cmac(acc[j], wb[d][j].x, p[j][0]);
           cmac(acc[j], wb[d][j].y, p[j][1]);
         }
-        if (TP && zx != zy) {   // the same weights against the transposed spectrum: the rows of column (zy, zx)
-          const double2* gl = st + 2 * PLANE + ey * N;
-          const double2* fl = st + 3 * PLANE + Y * N;
-          const double2 g0 = gl[offg0], g1 = gl[offg1];
-          double2 fw[5];
-#pragma unroll
-          for (int k = 0; k < 5; k++) fw[k] = fl[offw[k]];
+        if (TP && zx != zy) {   // the same weights against the transposed spectra: the rows of column (zy, zx)
+          products(NP == 4 ? 2 : 1, NP == 4 ? 3 : -1, p);
 #pragma unroll
           for (int j = 0; j < 4; j++) {
-            cmac(accB[j], wb[d][j].x, cmul(g0, fw[j + 1]));
-            cmac(accB[j], wb[d][j].y, cmul(g1, fw[j]));
+            cmac(accB[j], wb[d][j].x, p[j][0]);
+            cmac(accB[j], wb[d][j].y, p[j][1]);
           }
         }
         if (it + DEPTH < NIT) load_w(it + DEPTH, wb[d]);
       }
-      if (step == C::SPC - 1) {
-        // No CTA-wide barrier at the chunk end: the LAST warp to finish reading stage s refills it with the planes of
-        // chunk + 2 (its full barrier cannot complete that phase before every warp has passed this point, so a fast
-        // warp simply waits there).  With one CTA per SM a __syncthreads here idled every warp once per chunk.
+      if (step % SPS == SPS - 1) {
+        // No CTA-wide barrier at the end of a (sub-)chunk: the LAST warp to finish reading stage s refills it with the
+        // planes of sub-chunk q + 2 (its full barrier cannot complete that phase before every warp has passed this
+        // point, so a fast warp simply waits there).  With one CTA per SM a __syncthreads here idled every warp.
         __syncwarp();
         if (lane == 0) {
           __threadfence_block();
           if (atomicAdd(&done_cnt[s], 1) == C::NWARP - 1) {
             __threadfence_block();
             done_cnt[s] = 0;
-            if (chunk + 2 < nchunk) issue_chunk(chunk + 2);
+            if (q + 2 < nchunk * SUB) issue_chunk(q + 2);
           }
         }
       }
@@ -331,8 +362,11 @@ bool qhat_stream_supported(int N) { return N == 16 || N == 24 || N == 32; }
 template <int N, int NP, int DEPTH, bool SYM, int WT = 8, bool TP = false>
 static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pairs, double2* qhat, int nsplit = 1) {
   using C = StreamCfg<N, WT>;
-  const size_t smem = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2) + 64;
+  const size_t full2 = (size_t)2 * 2 * NP * C::PLANE * sizeof(double2);   // two stages of whole planes
+  const size_t smem = ((NP == 4 && full2 > 200 * 1024) ? full2 / 2 : full2) + 64;
   auto kern = qhat_stream_kernel<N, NP, DEPTH, SYM, WT, TP>;
+  StreamOperands ops = {};
+  for (int q = 0; q < NP; q++) { ops.xi[q] = pairs[q].xi_side; ops.df[q] = pairs[q].dif_side; }
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
   if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -349,8 +383,7 @@ static void launch_stream_inst(sbte_ctx* c, const double* W, const QhatPair* pai
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = use_pdl() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kern, W, pairs[0].xi_side, pairs[0].dif_side, NP > 1 ? pairs[1].xi_side : (const double2*)nullptr,
-                     NP > 1 ? pairs[1].dif_side : (const double2*)nullptr, qhat, nsplit);
+  cudaLaunchKernelEx(&cfg, kern, W, ops, qhat, nsplit);
   k2_mark(c);
   c->launches += 1;
 }
@@ -386,10 +419,20 @@ void launch_qhat_stream(sbte_ctx* c, int npairs, const QhatPair* pairs, double2*
 
 // transposed pairing (TP): pairs[0] = the spectrum (both sides), pairs[1] = its x<->y transpose (both sides); f == g only
 bool qhat_stream_tp_supported(int N) { return N == 32 || N == 16; }
-void launch_qhat_stream_tp(sbte_ctx* c, const QhatPair* pairs, double2* qhat, bool sym, int nsplit) {
+// npairs = 2: ComputeQ (pairs[0] spectrum, pairs[1] transposed spectrum); npairs = 4: ComputeQ_maxPreserve (pairs[0..1]
+// its two summed products, pairs[2..3] the same against the transposed spectra)
+void launch_qhat_stream_tp(sbte_ctx* c, int npairs, const QhatPair* pairs, double2* qhat, bool sym, int nsplit) {
   const double* W = sym ? c->d_Ws : c->d_W;
   if (nsplit < 1) nsplit = 1;
   if (nsplit > c->N / 2) nsplit = c->N / 2;
+  if (npairs == 4) {
+    switch (c->N) {
+      case 16: sym ? launch_stream_inst<16, 4, 2, true, 16, true>(c, W, pairs, qhat, nsplit) : launch_stream_inst<16, 4, 2, false, 16, true>(c, W, pairs, qhat, nsplit); break;
+      case 32: sym ? launch_stream_inst<32, 4, 2, true, 16, true>(c, W, pairs, qhat, nsplit) : launch_stream_inst<32, 4, 2, false, 16, true>(c, W, pairs, qhat, nsplit); break;
+      default: set_error("qhat_stream (transposed pairing): unsupported N"); break;
+    }
+    return;
+  }
   // 16 warps with two weight tiles in flight per thread; 8 warps with four were 15 % slower (profiles/r02_tp_tune.txt)
   switch (c->N) {
     case 16: sym ? launch_stream_inst<16, 2, 2, true, 16, true>(c, W, pairs, qhat, nsplit) : launch_stream_inst<16, 2, 2, false, 16, true>(c, W, pairs, qhat, nsplit); break;

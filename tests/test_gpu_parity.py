@@ -795,15 +795,18 @@ def test_transposed_pairing_of_the_0d_stream(sb, N, L_v, lam):
     for sym in (True, False):
         c.set_symmetrize(sym)
         c.set_xy_pairing(True)
-        qa, Qa = c.Qhat(f, k2=sb.K2_STREAM), c.ComputeQ(f, k2=sb.K2_STREAM)
+        qa, Qa, Ma = c.Qhat(f, k2=sb.K2_STREAM), c.ComputeQ(f, k2=sb.K2_STREAM), c.ComputeQ_maxPreserve(f)
         c.set_xy_pairing(False)
-        qb, Qb = c.Qhat(f, k2=sb.K2_STREAM), c.ComputeQ(f, k2=sb.K2_STREAM)
-        assert not np.array_equal(qa, qb)                 # two different kernels really ran
+        qb, Qb, Mb = c.Qhat(f, k2=sb.K2_STREAM), c.ComputeQ(f, k2=sb.K2_STREAM), c.ComputeQ_maxPreserve(f)
+        assert not np.array_equal(qa, qb) and not np.array_equal(Ma, Mb)   # different kernels really ran
         assert relmax(qa, qb) < 1e-13 and relmax(Qa, Qb) < 1e-13, sym
+        # ComputeQ_maxPreserve: its two summed products in both orientations (four operand pairs, half-chunk staging at N = 32)
+        assert relmax(Ma, Mb) < 1e-13, sym
     c.set_xy_pairing(True)
     if N == 16:
         W = c.weights_to_host()
         assert relmax(qa, o.qhat(W, o.fft3d(f.astype(complex)), o.fft3d(f.astype(complex)))) < TOL_QHAT
+        assert relmax(Ma, o.compute_q_maxpreserve(W, f, f)) < TOL_QHAT
     # a tensor without the invariance keeps the full stream
     c.synthetic_weights(5)
     state, dev = c.xy_pairing_state()

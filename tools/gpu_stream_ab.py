@@ -34,4 +34,7 @@ run("ComputeQ sym", cq)
 c.set_symmetrize(False)
 run("ComputeQ plain", cq, 150)
 c.set_symmetrize(True)
-run("maxPreserve", mp)
+run("maxPreserve sym", mp)
+if has_xy:
+    c.set_xy_pairing(True)
+    run("maxPreserve default", mp)
