@@ -1,4 +1,6 @@
 #!/bin/bash
+# (tools/ab/ is not tracked: build the old library with `git worktree add /tmp/wt 2d82f08 && (cd /tmp/wt && python -m spectralbte_b200.build)`
+#  and copy /tmp/wt/spectralbte_b200/libsbte_b200.so to tools/ab/libsbte_precanon.so first.)
 # Same-box A/B of the batched convolution: the current library (canonical summation order, fold into part 0 by
 # red.global.add.f64) against the library before the canonical order (tools/ab/libsbte_precanon.so, commit 2d82f08).
 mkdir -p gpurun_out
