@@ -252,7 +252,11 @@ __device__ __forceinline__ void dft_line(double2* __restrict__ base, int stride,
   }
 }
 
-template <int N>
+// SPEC: 0 = every input / output / epilogue variant decided at run time; 1 = the slab step's forward transform (real
+// input, cell-minor spectrum out); 2 = its inverse transform of the convolution's partial sums with the conservation /
+// update epilogue (and the chained forward transform).  The specialised instances carry a fraction of the code: with one
+// cell per SM (small slabs) every CTA runs through the kernel exactly once and instruction fetch is what it waits for.
+template <int N, int SPEC>
 __global__ void __launch_bounds__(256, ((N & (N - 1)) == 0) ? 2 : 1)
 fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict__ in_cplx, PartsIn pin,
                   const double2* __restrict__ pre, const double2* __restrict__ post, const double* __restrict__ wt,
@@ -272,8 +276,8 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
       xr[q] = 0.0; xi[q] = 0.0;
       if (idx < n3) {
         const long g = cell * n3 + idx;
-        if (in_real) xr[q] = __ldg(in_real + g);
-        else if (pin.parts) {
+        if (SPEC == 1 || (SPEC == 0 && in_real)) xr[q] = __ldg(in_real + g);
+        else if (SPEC == 2 || pin.parts) {
           const int tile = ((idx / N) / pin.cols) * pin.G + (int)(cell >> 5);
           const int np = pin.tile_np[tile];
           for (int m = 0; m < np; m++) {
@@ -295,21 +299,29 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
       }
     }
   }
+  // The three axis passes are ONE piece of code run once, or -- when the epilogue chains the next stage's forward
+  // transform -- twice (rolled loop: the second transform does not double the kernel's instruction footprint).
+  int rep = 0;
+  double sg = sgn;
+#pragma unroll 1
+  for (;;) {
   __syncthreads();
   for (int l = threadIdx.x; l < N * N; l += blockDim.x)            // along z: line (i, j)
-    dft_line<N>(cellsm + l * P, 1, sgn);
+    dft_line<N>(cellsm + l * P, 1, sg);
   __syncthreads();
   for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along y: line (i, k)
     const int i = l / N, k = l % N;
-    dft_line<N>(cellsm + (i * N) * P + k, P, sgn);
+    dft_line<N>(cellsm + (i * N) * P + k, P, sg);
   }
   __syncthreads();
   for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along x: line (j, k)
     const int j = l / N, k = l % N;
-    dft_line<N>(cellsm + j * P + k, N * P, sgn);
+    dft_line<N>(cellsm + j * P + k, N * P, sg);
   }
   __syncthreads();
-  if (epi.mode == 1) {
+  if (rep == 1) break;                                             // that was the chained forward transform
+  if (!(SPEC == 2 || (SPEC == 0 && epi.mode == 1))) break;         // plain transform: on to the outputs
+  {
     // Q = Re(post * z) stays in shared memory; moments -> multipliers -> corrected Q -> update, all here
     __shared__ double red[5 * 32];
     __shared__ double lam[5];
@@ -368,20 +380,11 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
       }
     }
     if (!epi.next_lay) return;
-    __syncthreads();
-    for (int l = threadIdx.x; l < N * N; l += blockDim.x)            // along z
-      dft_line<N>(cellsm + l * P, 1, -1.0);
-    __syncthreads();
-    for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along y
-      const int i = l / N, k = l % N;
-      dft_line<N>(cellsm + (i * N) * P + k, P, -1.0);
-    }
-    __syncthreads();
-    for (int l = threadIdx.x; l < N * N; l += blockDim.x) {          // along x
-      const int j = l / N, k = l % N;
-      dft_line<N>(cellsm + j * P + k, N * P, -1.0);
-    }
-    __syncthreads();
+  }
+  rep = 1;
+  sg = -1.0;
+  }
+  if (rep == 1) {
     for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {       // post-twiddle, cell-minor layout for the convolution
       const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
       const double2 cs = __ldg(epi.next_post + idx);
@@ -405,6 +408,10 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
       const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
       const double2 z = cellsm[(i * N + j) * P + k];
       const double2 o = make_double2(cs[q].x * z.x - cs[q].y * z.y, cs[q].x * z.y + cs[q].y * z.x);
+      if (SPEC == 1) {
+        out_lay[((cell >> 5) * n3 + idx) * 32 + (cell & 31)] = o;
+        continue;
+      }
       if (out_nat) out_nat[cell * n3 + idx] = o;
       if (out_real) out_real[cell * n3 + idx] = o.x;
       if (out_lay) {
@@ -420,11 +427,17 @@ template <int N>
 static void launch_cell_n(sbte_ctx* c, const double* in_real, const double2* in_cplx, PartsIn pin, int invert, int batch,
                           double2* out_nat, double2* out_lay, int layout, double* out_real, const CellEpi& epi) {
   const size_t smem = (size_t)N * N * (N + 1) * sizeof(double2);
-  auto kern = fft3d_cell_kernel<N>;
-  static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
-  if (!((configured.load() >> c->device) & 1u)) {
+  static const bool generic_only = getenv("SBTE_CELL_FFT_GENERIC") != nullptr;
+  int spec = 0;
+  if (!generic_only) {
+    if (!invert && in_real && !out_nat && !out_real && out_lay && layout == LAY_CELLMINOR && epi.mode == 0) spec = 1;
+    else if (invert && pin.parts && epi.mode == 1) spec = 2;
+  }
+  auto kern = spec == 1 ? fft3d_cell_kernel<N, 1> : (spec == 2 ? fft3d_cell_kernel<N, 2> : fft3d_cell_kernel<N, 0>);
+  static std::atomic<unsigned> configured[3];   // per device: function attributes belong to the device context
+  if (!((configured[spec].load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    configured.fetch_or(1u << c->device);
+    configured[spec].fetch_or(1u << c->device);
   }
   const int d = invert ? 1 : 0;
   kern<<<batch, 256, smem, c->stream>>>(in_real, in_cplx, pin, c->d_pre[d], c->d_post[d], c->d_wt, c->pref[d],
