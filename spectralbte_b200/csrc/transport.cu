@@ -188,7 +188,7 @@ __global__ void edge_prep_kernel(double* __restrict__ f, double* __restrict__ fl
   const int fill_noflux = right ? fill_right : fill_left;
   for (long p = blockIdx.x * (long)blockDim.x + threadIdx.x; p < n3; p += (long)gridDim.x * blockDim.x) {
     const double f0 = f[(long)l * n3 + p], fi = f[(long)in2 * n3 + p];
-    const double fg = 2 * f0 - fi;                  // extrapolate_kernel: f[g] = 2 f[l] - f[in2]
+    const double fg = 2 * f0 - fi;                  // ghost by linear extrapolation: f[g] = 2 f[l] - f[in2]
     f[(long)g * n3 + p] = fg;
     const bool lower = p < half;                    // i < N/2
     const bool outgoing = right ? !lower : lower;

@@ -1,4 +1,4 @@
-"""Batched ComputeQ timing: `gpu_n22_time.py N [cells]` times one configuration under the current environment
+"""Batched ComputeQ timing: `gpu_batch_time.py N [cells]` times one configuration under the current environment
 (SBTE_NO_BATCH3G, SBTE_BATCH_CTAS, ...); without arguments, heatTrans-sized batches (250 cells) at N = 20, 22, 24:
 line-ring kernel with partial row-blocks (default) against the any-N kernel (SBTE_NO_BATCH3G=1).
 numpy + ctypes only (no torch import), so it starts in a second on a fresh box."""
