@@ -180,6 +180,8 @@ SBTE_API int sbte_slab_download(sbte_slab *s, double *f_host);
 SBTE_API int sbte_slab_advect(sbte_slab *s, int which);
 /* stage = 0,1 for the two upwindTwo passes inside advectTwo (halo needed before each) */
 SBTE_API int sbte_slab_upwind_stage(sbte_slab *s, int which, int stage);
+/* kept for callers of the staged interface; the closing average of advectTwo (src/transportroutines.c:487-491) is part
+ * of the second upwind stage, so this does nothing */
 SBTE_API int sbte_slab_advect_finish(sbte_slab *s, int which);
 /* device pointers + element counts of the boundary cells to send / ghost cells to receive for the
  * array the next upwind pass reads. side 0 = left neighbour, 1 = right neighbour */

@@ -3,8 +3,10 @@
 //
 // Mirrors the 1D branch of the reference driver (/root/reference/exec/boltz.c:264-353) and the
 // ghost-cell logic of src/transportroutines.c:107-172 (order 1) and :261-404 (order 2), with the
-// blocking MPI halo replaced by "ghost cells are filled by the caller" (NCCL / peer copies between
-// the regions reported by sbte_slab_halo_regions) so f never leaves the device.
+// blocking MPI halo replaced either by peer memory (the stencil kernels read the neighbour GPU's boundary cells and
+// order themselves with device-side counters: sbte_slab_ipc_* / peer_attach, transport.cu halo_enter / halo_leave)
+// or by "ghost cells are filled by the caller" (NCCL between the regions reported by sbte_slab_halo_regions);
+// either way f never leaves the device.
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
