@@ -453,6 +453,44 @@ def test_peer_memory_halo_equals_single_rank(sb, W_heat8, order, ic):
     assert np.array_equal(got, want)
 
 
+def test_peer_halo_wait_times_out_without_killing_the_context(sb, W_heat8):
+    """A neighbour that never arrives (it may be writing files, or gone): the waiting stencil kernels must not trap.
+    They raise the slab's error word after the configured bound and stop waiting; the host learns it from the next
+    synchronising call; the CUDA context -- and every other slab in it -- keeps working."""
+    N, nX, order, ic, dt, Kn = 8, 16, 2, 6, 2e-3, 1.52
+    o = orc.Oracle(N, 9.0, 1)
+    _, x, dx = orc.make_mesh([nX], [0.8], order)
+    f0 = o.init_inhom(ic, nX, order)
+    ctxs = [sb.Collisions(N, 9.0, inhomogeneous=True) for _ in range(2)]
+    for c in ctxs:
+        c.set_weights(W_heat8)
+    h = nX // 2
+    parts = []
+    for r in range(2):
+        lo = r * h
+        p = sb.Slab(ctxs[r], h, order, x[lo:lo + h + 2 * order].copy(), dx[lo:lo + h + 2 * order].copy(), ic, dt, rank=r, nranks=2)
+        p.upload(f0[lo:lo + h + 2 * order].copy())
+        parts.append(p)
+    parts[0].peer_attach(1, parts[1])
+    parts[1].peer_attach(0, parts[0])
+    for p in parts:
+        p.set_peer_halo(True)
+        p.set_halo_timeout(0.05)
+    parts[0].upwind_stage(0, 0)          # rank 1 never issues its pass: rank 0 waits 50 ms, then gives up
+    ctxs[0].sync()
+    assert parts[0].halo_state()[3] == 1
+    with pytest.raises(sb._lib.SbteError, match="did not arrive"):
+        parts[0].moments()
+    # the context is alive: an ordinary single-rank slab on the same context steps and reproduces the oracle
+    one = sb.Slab(ctxs[0], nX, order, x, dx, ic, dt)
+    one.upload(f0)
+    f = f0.copy()
+    fc, f1, ft = np.zeros_like(f), np.zeros_like(f), np.zeros_like(f)
+    one.step(Kn)
+    o.step_1d(W_heat8, nX, x, dx, dt, Kn, order, ic, f, fc, f1, ft)
+    assert relmax(one.download()[order:nX + order], f[order:nX + order]) < 1e-11
+
+
 @pytest.mark.parametrize("order,ic,nX,h", [(1, 3, 16, 8), (2, 3, 16, 8), (1, 6, 16, 8), (2, 6, 16, 8), (2, 6, 80, 40), (1, 3, 70, 35),
                                             (2, 6, 16, 5), (1, 3, 44, 4)])
 def test_two_rank_split_equals_single_rank(sb, W_heat8, order, ic, nX, h):
