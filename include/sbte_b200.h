@@ -131,8 +131,10 @@ SBTE_API int sbte_xy_pairing_state(sbte_ctx *c, int *state, double *deviation);
 
 /* The stream-K schedule of the batched convolution for `cells` cells on a device with `ctas` SMs (what the
  * library uploads before a batched ComputeQ; exec/boltz.c:285-345 has no counterpart -- its cells are a plain loop).
- * Pure host arithmetic, no device needed.  split != 0: the second launch that serves a last cell group with at most
- * 16 live cells at N = 16 on tiles of 16 zeta_y columns x 16 cells (two columns per warp).
+ * Pure host arithmetic, no device needed.  split bit 0: the second launch that serves a last cell group with at most
+ * 16 live cells at N = 16 on tiles of 16 zeta_y columns x 16 cells (two columns per warp); bit 1: ranges cut at whole
+ * xi_x chunks only (the library's schedule under SBTE_CHUNK_CUTS=1); bit 2: ranges cut at any step wherever the kernel
+ * takes that (SBTE_CHUNK_CUTS=0); neither: the library's own choice between the two (the better predicted duration).
  * dims = {G, T, P, np_cols, kmax, np_len}; array pointers may be null:
  * query dims first, then pass arrays of P+1, T+1, P, T and np_len entries.  Fails for N without a scheduled kernel. */
 SBTE_API int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int split, long long *cta_begin, long long *tile_begin,

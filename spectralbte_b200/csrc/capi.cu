@@ -213,12 +213,14 @@ struct HostSchedule {
   std::vector<int> ctile, first;          // [P], [T]
   std::vector<unsigned char> np;          // [T], or [N*N*G] when kept per zeta column
   int G = 0, T = 0, P = 0, np_cols = 0, kmax = 1;
+  bool cuts = false;   // ranges may end inside a chunk
 };
 
 // Pure host arithmetic (no CUDA call): also exported as sbte_batch_schedule_host for the CPU tests.
 // split: the schedule of one remainder group on split tiles (qhat_batch.cu Batch3Cfg<N, true>: 16 columns per tile); its
 // CTAs may be as short as one chunk, so that the launch adds about one chunk time after the main launch.
-static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out, bool split = false) {
+static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSchedule* out, bool split = false,
+                                 int cuts = -1) {   // cuts: -1 = qhat_batch_cut_mode(N), else that mode
   const int cols = split ? 16 : qhat_batch_cols(N);
   // row-blocks never straddle a zeta_x plane: bpx blocks of `cols` zeta_y columns per plane, the last one
   // partly empty when cols does not divide N (N = 20, 22)
@@ -232,12 +234,24 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
     tbegin[t + 1] = tbegin[t] + (long long)(sym ? sym_nrep(N, zx) : N) * N;
   }
   const long long total = tbegin[T];
-  int P = ctas;
-  const long long min_steps = (split ? 1 : 4) * (long long)N;  // at least a few xi_x chunks per CTA
-  if (total / P < min_steps) P = (int)std::max<long long>(1, total / min_steps);
+  // Cut granularity.  Whole xi_x chunks: the resident-plane kernel cannot do otherwise, and the busiest CTA then sets the
+  // duration (ceil(chunks / P) chunk times).  Any step (line-ring kernels: a cut chunk's running sum passes from CTA p to
+  // p + 1): equal shares, at the price qhat_batch_cut_cost(N).  Every CTA needs at least one chunk's worth of steps, so
+  // that the chunks it shares with its two neighbours are different chunks.
+  int mode = cuts >= 0 ? cuts : qhat_batch_cut_mode(N);
+  if (mode != 0 && qhat_batch_cut_mode(N) == 0) mode = 0;
+  const long long chunks = total / N;
+  const int P_whole = (int)std::max<long long>(1, std::min<long long>(ctas, chunks / (split ? 1 : 4)));   // a few chunks per CTA
+  const int P_any = (int)std::max<long long>(1, std::min<long long>(ctas, chunks));
+  if (mode == 1) {
+    const double t_whole = (double)((chunks + P_whole - 1) / P_whole);
+    const double t_any = (double)chunks / P_any * (1.0 + qhat_batch_cut_cost(N));
+    mode = t_any < t_whole ? 2 : 0;
+  }
+  const long long align = mode == 2 ? 1 : N;
+  const int P = mode == 2 ? P_any : P_whole;
   std::vector<long long>& begin = out->begin;
   begin.assign(P + 1, 0);
-  const long long align = qhat_batch_align(N);   // the line-ring kernels work on whole xi_x chunks
   for (int p = 0; p <= P; p++) begin[p] = (long long)(((__int128)p * (total / align)) / P) * align;
   auto owner = [&](long long g) {   // last CTA whose range starts at or before g
     int lo = 0, hi = P - 1;
@@ -258,11 +272,11 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
     // CTAs with an empty range never write: pick owners among non-empty ranges
     const int a = owner(tbegin[t]);
     first[t] = a;
-    // canonical summation (qhat_batch.cu chunk_end): the first CTA folds its e0 chunks into part 0, every chunk a later
-    // CTA computes is a part of its own
-    const long long e0 = (std::min(begin[a + 1], tbegin[t + 1]) - tbegin[t]) / align;
-    const long long nchunks = (tbegin[t + 1] - tbegin[t]) / align;
-    const int parts_t = 1 + (int)(nchunks - e0);
+    // canonical summation (qhat_batch.cu chunk_end): the first CTA folds the e0 chunks it completes into part 0, every
+    // chunk a later CTA completes is a part of its own (a cut chunk is completed by the later of its two CTAs)
+    const long long e0 = (std::min(begin[a + 1], tbegin[t + 1]) - tbegin[t]) / N;
+    const long long nchunks = (tbegin[t + 1] - tbegin[t]) / N;
+    const int parts_t = (e0 > 0 ? 1 : 0) + (int)(nchunks - e0);
     np[t] = (unsigned char)parts_t;
     kmax = std::max(kmax, parts_t);
   }
@@ -279,6 +293,7 @@ static void build_batch_schedule(int N, int cells, bool sym, int ctas, HostSched
     np.swap(npc);
   }
   out->G = G; out->T = T; out->P = P; out->np_cols = per_column ? 1 : cols; out->kmax = kmax;
+  out->cuts = mode == 2;
 }
 
 // uploads one host schedule; returns the device view through *dev (tables live in *mem)
@@ -300,6 +315,7 @@ static int upload_schedule(const HostSchedule& h, bool sym, void** mem, BatchSch
   unsigned char* base = (unsigned char*)*mem;
   *dev = {(const long long*)base, (const long long*)(base + o1), (const int*)(base + o2), (const int*)(base + o3),
           base + o4, h.G, T, P, h.np_cols, h.kmax, sym ? 1 : 0};
+  dev->cuts = h.cuts ? 1 : 0;
   return 0;
 }
 
@@ -320,8 +336,8 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
   static const bool plane16 = getenv("SBTE_N16_PLANE") != nullptr;
   auto longest = [&](const HostSchedule& hs) {   // chunks of the busiest CTA = duration of the launch in chunk times
     long long m = 0;
-    for (int p = 0; p < hs.P; p++) m = std::max(m, (hs.begin[p + 1] - hs.begin[p]) / N);
-    return (double)m;
+    for (int p = 0; p < hs.P; p++) m = std::max(m, hs.begin[p + 1] - hs.begin[p]);
+    return (double)m / N;
   };
   // The split launch follows the main one, so it pays only where dropping the padded group shortens the main launch
   // by more than the split launch lasts (80 cells: 6 -> 4 + 1 chunk times; 44 cells: 4 -> 4 + 1, not used).
@@ -361,6 +377,24 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
     CK(cudaMalloc(&c->d_sched_mem3, npc.size()));
     CK(cudaMemcpy(c->d_sched_mem3, npc.data(), npc.size(), cudaMemcpyHostToDevice));
     c->sched = {nullptr, nullptr, nullptr, nullptr, (const unsigned char*)c->d_sched_mem3, G, 0, 0, 1, kmax, sym ? 1 : 0};
+  }
+  {
+    // hand-over buffers for cut chunks (BatchSched::carry): one accumulator set per compute warp and CTA and a flag word
+    // each; the main and the split launch run one after the other and share them
+    const size_t Pmax = (size_t)std::max(c->cells_main > 0 ? h.P : 0, split ? h2.P : 0);
+    const size_t acc_bytes = Pmax * kBatchWarps * (size_t)N * 32 * sizeof(double2);
+    const size_t flag_bytes = Pmax * kBatchWarps * sizeof(int);
+    if (c->carry_bytes < acc_bytes + flag_bytes) {
+      if (c->d_carry) cudaFree(c->d_carry);
+      c->d_carry = nullptr;
+      c->carry_bytes = 0;
+      CK(cudaMalloc(&c->d_carry, acc_bytes + flag_bytes));
+      c->carry_bytes = acc_bytes + flag_bytes;
+    }
+    int* flags = (int*)((unsigned char*)c->d_carry + acc_bytes);
+    CK(cudaMemset(flags, 0, flag_bytes));
+    c->sched_main.carry = c->sched_split.carry = (double2*)c->d_carry;
+    c->sched_main.carry_flag = c->sched_split.carry_flag = flags;
   }
   c->sched_cells = cells;
   c->sched_sym = (int)sym;
@@ -698,6 +732,7 @@ int sbte_destroy(sbte_ctx* c) {
   if (c->d_sched_mem) cudaFree(c->d_sched_mem);
   if (c->d_sched_mem2) cudaFree(c->d_sched_mem2);
   if (c->d_sched_mem3) cudaFree(c->d_sched_mem3);
+  if (c->d_carry) cudaFree(c->d_carry);
   if (c->d_parts) cudaFree(c->d_parts);
   cudaStreamDestroy(c->stream);
   delete c;
@@ -705,16 +740,17 @@ int sbte_destroy(sbte_ctx* c) {
 }
 
 // The stream-K schedule ensure_batch_schedule() would upload for (N, cells, sym) on a device with `ctas` SMs.
-// Pure host arithmetic: works without a GPU (CPU tests, sizing).  split != 0: the schedule of the split-tile launch that
-// serves a remainder group of at most 16 cells at N = 16.  dims = {G, T, P, np_cols, kmax, np_len};
+// Pure host arithmetic: works without a GPU (CPU tests, sizing).  split bit 0: the schedule of the split-tile launch that
+// serves a remainder group of at most 16 cells at N = 16; bit 1: cuts at whole xi_x chunks only (what SBTE_CHUNK_CUTS=1
+// makes the library use); bit 2: cuts at any step wherever the kernel takes them (SBTE_CHUNK_CUTS=0); neither: the library's choice.  dims = {G, T, P, np_cols, kmax, np_len};
 // any array pointer may be null (query dims first, then call again with arrays of P+1, T+1, P, T, np_len entries).
 int sbte_batch_schedule_host(int N, int cells, int sym, int ctas, int split, long long* cta_begin, long long* tile_begin,
                              int* cta_tile, int* tile_first, unsigned char* np, int* dims) {
   if (N < 2 || N > 32 || (N % 2) != 0 || cells < 1 || ctas < 1) { set_error("batch schedule: bad arguments"); return 1; }
   if (!qhat_batch_supported(N)) { set_error("batch schedule: this N runs the any-N kernel (no schedule)"); return 1; }
-  if (split && (N != 16 || cells > 16)) { set_error("batch schedule: split tiles serve one group of at most 16 cells at N = 16"); return 1; }
+  if ((split & 1) && (N != 16 || cells > 16)) { set_error("batch schedule: split tiles serve one group of at most 16 cells at N = 16"); return 1; }
   HostSchedule h;
-  build_batch_schedule(N, split ? 16 : cells, sym != 0, ctas, &h, split != 0);
+  build_batch_schedule(N, (split & 1) ? 16 : cells, sym != 0, ctas, &h, (split & 1) != 0, (split & 2) ? 0 : (split & 4) ? 2 : -1);
   if (dims) { dims[0] = h.G; dims[1] = h.T; dims[2] = h.P; dims[3] = h.np_cols; dims[4] = h.kmax; dims[5] = (int)h.np.size(); }
   if (cta_begin) memcpy(cta_begin, h.begin.data(), h.begin.size() * sizeof(long long));
   if (tile_begin) memcpy(tile_begin, h.tbegin.data(), h.tbegin.size() * sizeof(long long));

@@ -125,6 +125,26 @@ __device__ __forceinline__ void red_add_f64(double* p, double v) {
   asm volatile("red.global.add.f64 [%0], %1;" ::"l"(p), "d"(v) : "memory");
 }
 
+// ---------------------------------------------------------------- hand-over of a running sum between two CTAs of a launch
+// One word per (producer CTA, warp): the producer stores its data, fences, and publishes 1; the consumer waits for the 1
+// (bounded: a lost publication traps instead of hanging the GPU), reads the data past L1 and re-arms the word with 0 for
+// the next launch in the stream.  Used by the batched convolution where a stream-K cut falls inside a xi_x chunk.
+__device__ __forceinline__ void carry_publish(int* flag) {
+  asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
+}
+__device__ __forceinline__ void carry_await(const int* flag) {
+  int v = 0;
+  unsigned spins = 0;
+  for (;;) {
+    asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
+    if (v != 0) break;
+    __nanosleep(64);
+    if (++spins > (1u << 25)) __trap();   // seconds: the producer publishes at the very start of its range
+  }
+}
+__device__ __forceinline__ void carry_rearm(int* flag) { *reinterpret_cast<volatile int*>(flag) = 0; }
+__device__ __forceinline__ double2 carry_load(const double2* p) { return __ldcg(p); }
+
 // ---------------------------------------------------------------- deterministic block reduction
 // Sums `NV` doubles per thread over the whole block in a fixed tree order; result valid in all
 // threads. `scratch` needs NV * 32 doubles. Block size must be a multiple of 32, <= 1024.

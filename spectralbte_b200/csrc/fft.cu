@@ -326,6 +326,9 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
     __shared__ double red[5 * 32];
     __shared__ double lam[5];
     double bsum[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+    // (both element loops of this epilogue: unrolled so that the global loads of several elements are in flight at once
+    // -- a CTA that runs alone on its SM is latency-bound; the sums keep their order)
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
       const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
       const double2 cs = __ldg(post + idx);
@@ -358,6 +361,7 @@ fft3d_cell_kernel(const double* __restrict__ in_real, const double2* __restrict_
     }
     __syncthreads();
     const double l0 = lam[0], l1 = lam[1], l2 = lam[2], l3 = lam[3], l4 = lam[4];
+#pragma unroll 4
     for (int idx = threadIdx.x; idx < n3; idx += blockDim.x) {
       const int i = idx / (N * N), j = (idx / N) % N, k = idx % N;
       const double vi = __ldg(epi.v + i), vj = __ldg(epi.v + j), vk = __ldg(epi.v + k);

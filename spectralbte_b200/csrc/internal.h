@@ -37,6 +37,8 @@ struct CellEpi {
 };
 
 // stream-K schedule of the batched convolution (device tables, see qhat_batch.cu)
+constexpr int kBatchWarps = 8;   // compute warps per CTA of the batched convolution kernels (one carry slot each)
+
 struct BatchSched {
   const long long* cta_begin;   // [P+1] first global step of every CTA
   const long long* tile_begin;  // [T+1] first global step of every tile (tile lengths vary when symmetrised)
@@ -44,6 +46,11 @@ struct BatchSched {
   const int* tile_first;        // [T] first CTA that touches tile t
   const unsigned char* tile_np; // number of partial sums, indexed [(zeta column / cols) * G + cell group]
   int G, T, P, cols, kmax, sym; // cols: zeta columns per tile_np entry (the tile width, or 1: table kept per column)
+  // hand-over of the running sum of a xi_x chunk that a stream-K cut divides between CTA p and p + 1 (line-ring kernels):
+  // carry[p] = one accumulator set per compute warp, carry_flag[p * warps + w] = published
+  double2* carry = nullptr;
+  int* carry_flag = nullptr;
+  int cuts = 0;                 // 1: some range ends inside a chunk (the kernel instance that hands running sums over)
 };
 
 struct sbte_ctx {
@@ -108,6 +115,8 @@ struct sbte_ctx {
   void* d_sched_mem = nullptr;
   void* d_sched_mem2 = nullptr;
   void* d_sched_mem3 = nullptr;
+  void* d_carry = nullptr;          // carry + flags of the batched convolution (see BatchSched)
+  size_t carry_bytes = 0;
   double2* d_parts = nullptr;
   size_t parts_stride = 0;          // double2 elements per part
   int parts_cap = 0;                // parts allocated
@@ -189,7 +198,8 @@ int weights_xy_symmetry(sbte_ctx* c, const double* W, double* max_diff, double* 
 bool qhat_batch_supported(int N);
 int qhat_batch_cols(int N);
 void launch_qhat_batch_any(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells, bool sym);
-int qhat_batch_align(int N);
+int qhat_batch_cut_mode(int N);      // 0 = stream-K cuts at whole xi_x chunks only, 1 = builder's choice, 2 = at any step
+double qhat_batch_cut_cost(int N);   // measured price of cutting anywhere (fraction of the launch)
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch);
 bool qhat_batch_split_supported(int N);

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 
 #include <atomic>
+#include <type_traits>
 
 #include "common.cuh"
 #include "internal.h"
@@ -125,7 +126,24 @@ static bool batch3_general(int N) {
   return on && (N == 20 || N == 22);
 }
 bool qhat_batch_supported(int N) { return N == 8 || N == 16 || N == 24 || batch3_general(N); }
-int qhat_batch_align(int N) { return N; }  // stream-K granularity in steps: whole xi_x chunks (canonical summation order)
+// Where a stream-K range may end.  The line-ring kernels take a cut at any step (a cut xi_x chunk's running sum is handed
+// from one CTA to the next, so the canonical summation order is kept); the resident-plane kernel (N = 8, and N = 16 under
+// SBTE_N16_PLANE) needs whole chunks.  0 = whole chunks only, 1 = the schedule builder chooses (see qhat_batch_cut_cost),
+// 2 = any step.  SBTE_CHUNK_CUTS=1 forces whole chunks, =0 forces cuts at any step (A/B runs).
+int qhat_batch_cut_mode(int N) {
+  static const char* env = getenv("SBTE_CHUNK_CUTS");
+  static const bool plane16 = getenv("SBTE_N16_PLANE") != nullptr;
+  if (N == 8 || (N == 16 && plane16)) return 0;
+  if (env) return atoi(env) != 0 ? 0 : 2;
+  return 1;
+}
+// Measured price of cutting anywhere, as a fraction of the launch: with whole-chunk cuts every CTA reaches its chunk ends
+// at the same moments and the SMs run the (45-75 KB, fully unrolled) step body in lockstep, which the instruction caches
+// they share reward; ranges of unequal phase lose that (ncu, N = 24, 250 cells: stall_no_instruction 0.29 -> 0.45 per
+// issue, 12.11 -> 12.46 ms).  N = 16's body fits the per-SM cache; there the price is that of the step loop with run-time
+// bounds (the instance for whole-chunk schedules, CUTS = false, has them at compile time: 2.487 against 2.505 ms at 640
+// cells).  The builder cuts anywhere only where the better balance is worth more than this.
+double qhat_batch_cut_cost(int N) { return N <= 16 ? 0.012 : N <= 20 ? 0.015 : N <= 22 ? 0.03 : 0.035; }
 int qhat_batch_cols(int N) { return (N >= 16) ? 8 : 4; }
 
 // ------------------------------------------------------------------------------------------
@@ -365,7 +383,7 @@ static void launch_batch2_n(sbte_ctx* c, const double2* spec, double2* parts, si
 // Y = zeta_y0 + N/2 + COLS-1 - j'; warp w reads line j' = COLS-1 + xi_y - w at step xi_y).  Every slot
 // has a full (TMA) and an empty mbarrier of COLS arrivals; lines at the chunk edges have fewer than COLS
 // readers, so their last reader arrives for the absent ones (mbarrier.arrive with a count).
-// Stream-K ranges are aligned to whole chunks.
+// Stream-K ranges may be cut anywhere (qhat_batch_cut_mode): a cut chunk's running sum passes from one CTA to the next.
 // When COLS does not divide N (N = 20, 22) the last row-block of every zeta_x plane is partly empty: its surplus
 // warps keep the barrier protocol going (waits and arrivals) but neither multiply nor write, and the weight
 // tile's surplus rows are the next plane's (or, past the end of the tensor, TMA zero fill).
@@ -391,17 +409,19 @@ struct Batch3Cfg {
   static constexpr size_t STAGE_BYTES = LINE_BYTES + (size_t)ROWS * N * 8;
   static constexpr size_t SMEM = RING * LINE_BYTES + STAGES * STAGE_BYTES + 512;
   static_assert(SMEM <= 227 * 1024, "line ring + stages must fit in shared memory");
+  static_assert(WARPS == kBatchWarps, "carry slots are sized for kBatchWarps warps per CTA");
   static_assert(!SPLIT || (N % 16 == 0 && ROWS <= 256), "split tiles: whole zeta_x planes of 16 columns, TMA box <= 256 rows");
 };
 
 // cg_base: cell group the (single-group) schedule of a SPLIT launch refers to; 0 otherwise
-template <int N, bool SPLIT>
+// CUTS = false: the instance for schedules cut at whole chunks only (no hand-over code, step loop with compile-time bounds)
+template <int N, bool SPLIT, bool CUTS = true>
 __global__ void __launch_bounds__(Batch3Cfg<N, SPLIT>::THREADS, 1)
 qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
                    double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch, int cg_base) {
   using C = Batch3Cfg<N, SPLIT>;
   constexpr long n3 = (long)N * N * N;
-  constexpr int S = C::STAGES, R = C::RING, L = C::LPC;
+  constexpr int S = C::STAGES, R = C::RING;
   SBTE_DYN_SMEM(smraw);
   double2* ring = reinterpret_cast<double2*>(smraw);
   unsigned char* stage0 = smraw + R * C::LINE_BYTES;
@@ -414,12 +434,48 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   auto stage_w = [&](int s) { return reinterpret_cast<double*>(stage0 + (size_t)s * C::STAGE_BYTES + C::LINE_BYTES); };
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const long long g0 = sch.cta_begin[blockIdx.x];
-  const int n = (int)(sch.cta_begin[blockIdx.x + 1] - g0);   // multiple of N (whole chunks)
-  if (n <= 0) return;
   const int G = sch.G;
-  const int nchunk = n / N;
   const bool sym = sch.sym != 0;
+  // The range [g0, g1) in segments of one xi_x chunk each (chunk boundaries are the multiples of N): a cut may fall
+  // inside a chunk, whose running sum then passes from this CTA's predecessor to it (or from it to its successor)
+  // through sch.carry.  Order: the head of the chunk cut by g1 FIRST (published at once: the successor needs it only at
+  // the very end of its own range, so nobody waits), the whole chunks, the tail of the chunk cut by g0 LAST.
+  // The host schedule gives every CTA at least N steps, so the two cut chunks are different chunks.
+  // Positions are kept relative to g0 (32 bits): h0 = steps of the cut chunk at the start, n1 = steps of the one at the end.
+  int h0, n1, nwhole, tb, te;
+  const int t0 = sch.cta_tile[blockIdx.x];
+  {
+    const long long g0 = sch.cta_begin[blockIdx.x], g1 = sch.cta_begin[blockIdx.x + 1];
+    if (g1 <= g0) return;
+    const long long w0 = ((g0 + N - 1) / N) * N, w1 = (g1 / N) * N;
+    h0 = (int)(w0 - g0);
+    n1 = (int)(g1 - w1);
+    nwhole = (int)((w1 - w0) / N);
+    tb = (int)(sch.tile_begin[t0] - g0);       // bounds of the tile the whole chunks are in, cached
+    te = (int)(sch.tile_begin[t0 + 1] - g0);
+  }
+  const int seg_pre = n1 > 0 ? 1 : 0, seg_post = h0 > 0 ? 1 : 0;
+  const int nseg = seg_pre + nwhole + seg_post;
+  // segment i -> its tile, its chunk's ordinal in the tile and the xi_y range [ey0, ey1) this CTA computes of it
+  int tw = t0;
+  auto segment = [&](int i, int& t, int& cl, int& ey0, int& ey1) {
+    if (i >= seg_pre && i - seg_pre < nwhole) {
+      const int rc = h0 + (i - seg_pre) * N;
+      if (rc >= te) {   // tiles are whole chunks: one switch at most
+        tw++; tb = te;
+        te = (int)(sch.tile_begin[tw + 1] - sch.cta_begin[blockIdx.x]);
+      }
+      t = tw; cl = (rc - tb) / N; ey0 = 0; ey1 = N;
+    } else if (i < seg_pre) {   // at most once, before any whole chunk
+      const long long w1 = sch.cta_begin[blockIdx.x + 1] - n1;
+      t = t0;
+      while (w1 >= sch.tile_begin[t + 1]) t++;
+      cl = (int)((w1 - sch.tile_begin[t]) / N); ey0 = 0; ey1 = n1;
+    } else {                    // at most once, after the whole chunks
+      t = t0;
+      cl = (int)((sch.cta_begin[blockIdx.x] + h0 - N - sch.tile_begin[t0]) / N); ey0 = N - h0; ey1 = N;
+    }
+  };
 
   if (tid == 0) {
     for (int b = 0; b < S; b++) { mbar_init(&fullS[b], 1); mbar_init(&emptyS[b], C::WARPS); }
@@ -433,22 +489,21 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     if (warp == C::WARPS && lane == 0) {
       int k = 0;          // local step counter (stage ring)
       long q = 0;         // line sequence number (line ring)
-      int t = sch.cta_tile[blockIdx.x];
-      long long te = sch.tile_begin[t + 1];
-      int cl = (int)((g0 - sch.tile_begin[t]) / N);   // chunk ordinal inside the tile
-      for (int ch = 0; ch < nchunk; ch++, cl++) {
-        if (g0 + (long long)ch * N == te) { t++; te = sch.tile_begin[t + 1]; cl = 0; }
+      for (int i = 0; i < nseg; i++) {
+        int t, cl, ey0, ey1;
+        segment(i, t, cl, ey0, ey1);
         const int rb = t / G, cg = t - rb * G;
         const int zx = rb / C::BPX, zy0 = (rb % C::BPX) * C::COLS;
         const int ex = sym ? sym_rep(N, zx, cl) : cl;
         int X = zx + N / 2 - ex;
         if (X < 0) X += N; else if (X > N - 1) X -= N;
         const double2* gs = spec + (size_t)(cg_base + cg) * n3 * 32;
-        int issued = 0;   // lines of this chunk issued so far
-        for (int ey = 0; ey < N; ey++, k++) {
+        int issued = ey0;                      // next line j' of this chunk to issue: the segment needs [ey0, lend)
+        const int lend = C::COLS - 1 + ey1;
+        for (int ey = ey0; ey < ey1; ey++, k++) {
           // lines needed by step ey: j' <= COLS-1 + ey
           const int need = C::COLS + ey;
-          for (; issued < need && issued < L; issued++, q++) {
+          for (; issued < need && issued < lend; issued++, q++) {
             const int slot = (int)(q % R);
             if (q >= R) mbar_wait(&emptyL[slot], (uint32_t)(((q / R) - 1) & 1));
             int Y = (zy0 + N / 2 + C::COLS - 1 - issued) % N;
@@ -478,10 +533,12 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
   int cur_t = -1, zx = 0, zy = 0;
   int k = 0;
-  long qbase = 0;
+  using QT = std::conditional_t<(N <= 16), int, long>;   // line sequence numbers (32 bits are plenty; N = 16 runs faster with them)
+  QT qbase = 0;
 
   // canonical summation order, as in qhat_batch2_kernel: left fold over the chunk sums, part 0 kept by the CTA that owns
-  // the tile's first chunk, one part per chunk from every later CTA
+  // the tile's first step (it folds the chunks it completes), one part per chunk from every later CTA.  A chunk cut by
+  // a range boundary is completed -- and written -- by the later of its two CTAs.
   auto chunk_end = [&](int c) {
     const int cg = cur_t - (cur_t / G) * G;
     const long cell = (long)(cg_base + cg) * 32 + clane;
@@ -492,8 +549,8 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       if ((int)blockIdx.x == first) {
         fold = c > 0;
       } else {
-        const int e0 = (int)((sch.cta_begin[first + 1] - sch.tile_begin[cur_t]) / N);
-        out += (size_t)(1 + c - e0) * part_stride;
+        const int e0 = (int)((sch.cta_begin[first + 1] - sch.tile_begin[cur_t]) / N);   // chunks the first CTA completes
+        out += (size_t)((e0 > 0 ? 1 : 0) + c - e0) * part_stride;
       }
       if (fold) {   // part 0 += C_c in L2, no round trip: this thread is the only writer of these locations
         double* o = reinterpret_cast<double*>(out);
@@ -508,22 +565,16 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
     for (int r = 0; r < N; r++) acc[r] = make_double2(0.0, 0.0);
   };
 
-  int t = sch.cta_tile[blockIdx.x];
-  long long te = sch.tile_begin[t + 1];
-  int cl = (int)((g0 - sch.tile_begin[t]) / N);   // chunk ordinal inside the tile
-  for (int ch = 0; ch < nchunk; ch++, qbase += L, cl++) {
-    if (g0 + (long long)ch * N == te) { t++; te = sch.tile_begin[t + 1]; cl = 0; }
-    if (t != cur_t) {
-      cur_t = t;
-      const int rb = t / G;
-      zx = rb / C::BPX;
-      zy = (rb % C::BPX) * C::COLS + col;
-    }
+  // The steps [ey0, ey1) of the current chunk: the general form, and (used for N > 16, see below) the form for whole
+  // chunks, ey0 = 0 and ey1 = N at compile time.
+  auto run_steps = [&](auto whole_tag, int ey0_, int ey1_) {
+    constexpr bool WHOLE = decltype(whole_tag)::value;
+    const int ey0 = WHOLE ? 0 : ey0_, ey1 = WHOLE ? N : ey1_;
     const bool live = !C::PARTIAL || zy < N;
-    for (int ey = 0; ey < N; ey++, k++) {
+    for (int ey = ey0; ey < ey1; ey++, k++) {
       const int st = k % S;
       const int jl = C::COLS - 1 + ey - col;           // this column's line within the chunk
-      const long q = qbase + jl;
+      const QT q = qbase + (jl - ey0);                 // the segment streams lines ey0 .. COLS-2 + ey1
       const int slot = (int)(q % R);
       mbar_wait(&fullS[st], (uint32_t)((k / S) & 1));
       mbar_wait(&fullL[slot], (uint32_t)((q / R) & 1));
@@ -551,24 +602,115 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       __syncwarp();
       if (lane == 0) mbar_arrive(&emptyS[st]);
       if (clane == 0) {
-        // readers of line jl are the columns with 0 <= jl - (COLS-1) + col' < N; the last one in step order
-        // also arrives for the columns that never read it
+        // readers of line jl in this segment are the columns col' with ey0 <= jl - (COLS-1) + col' < ey1; the one that
+        // comes last in step order (the largest) also arrives for the columns that never read the line
         uint32_t cnt = 1;
-        if (jl < C::COLS - 1 && col == C::COLS - 1) cnt = (uint32_t)(C::COLS - jl);
-        if (jl > N - 1 && col == N + C::COLS - 2 - jl) cnt = (uint32_t)(jl - N + 2);
+        if (WHOLE) {
+          if (jl < C::COLS - 1 && col == C::COLS - 1) cnt = (uint32_t)(C::COLS - jl);
+          if (jl > N - 1 && col == N + C::COLS - 2 - jl) cnt = (uint32_t)(jl - N + 2);
+        } else {
+          const int hi = ey1 - 1 - jl + C::COLS - 1, lo = ey0 - jl + C::COLS - 1;
+          const int cmax = hi < C::COLS - 1 ? hi : C::COLS - 1;
+          const int cmin = lo > 0 ? lo : 0;
+          if (col == cmax) cnt = (uint32_t)(C::COLS - (cmax - cmin));
+        }
         mbar_arrive_cnt(&emptyL[slot], cnt);
       }
     }
-    chunk_end(cl);
+    qbase += C::COLS - 1 + ey1 - ey0;
+  };
+  auto enter_tile = [&](int t) {
+    if (t != cur_t) {
+      cur_t = t;
+      const int rb = t / G;
+      zx = rb / C::BPX;
+      zy = (rb % C::BPX) * C::COLS + col;
+    }
+  };
+
+  // a chunk begun by the previous CTA: continue from its running sum (same operations in the same order as an uncut
+  // chunk, hence the same bits)
+  auto carry_in = [&]() {
+    int* flag = sch.carry_flag + ((size_t)blockIdx.x - 1) * C::WARPS + warp;
+    if (lane == 0) carry_await(flag);
+    __syncwarp();
+    const double2* in = sch.carry + (((size_t)blockIdx.x - 1) * C::WARPS + warp) * C::LINE + lane;
+#pragma unroll
+    for (int r = 0; r < N; r++) acc[r] = carry_load(in + r * 32);
+    __syncwarp();
+    if (lane == 0) carry_rearm(flag);
+  };
+  // a chunk the next CTA completes: hand the running sum over
+  auto carry_out = [&]() {
+    double2* out = sch.carry + ((size_t)blockIdx.x * C::WARPS + warp) * C::LINE + lane;
+#pragma unroll
+    for (int r = 0; r < N; r++) { out[r * 32] = acc[r]; acc[r] = make_double2(0.0, 0.0); }
+    __threadfence();
+    __syncwarp();
+    if (lane == 0) carry_publish(sch.carry_flag + (size_t)blockIdx.x * C::WARPS + warp);
+  };
+
+  if constexpr (!CUTS) {
+    // whole-chunk schedule: nothing but whole chunks, one instance of the step body, bounds known at compile time
+#pragma unroll 1
+    for (int i = 0; i < nwhole; i++) {
+      int t, cl, ey0, ey1;
+      segment(i, t, cl, ey0, ey1);
+      enter_tile(t);
+      run_steps(std::true_type{}, 0, N);
+      chunk_end(cl);
+    }
+  } else if constexpr (N <= 16) {
+    // One instance of the step body for every segment: two of them (2 x 27 KB) would not share the 32 KB instruction
+    // cache, and a small slab's CTA changes between them every few chunks (80 cells: 0.183 -> 0.173 ms per launch).
+#pragma unroll 1
+    for (int i = 0; i < nseg; i++) {
+      int t, cl, ey0, ey1;
+      segment(i, t, cl, ey0, ey1);
+      enter_tile(t);
+      if (ey0 > 0) carry_in();
+      run_steps(std::false_type{}, ey0, ey1);
+      if (ey1 == N) chunk_end(cl);
+      else carry_out();
+    }
+  } else {
+    // phase 0: the head of the chunk cut by g1 (handed to the next CTA); 1: the whole chunks; 2: the tail of the chunk
+    // cut by g0 (continued from the previous CTA's running sum).  The general form of the step loop exists once, for 0
+    // and 2; the whole chunks have the loop with compile-time bounds to themselves (N = 24 loses 2 % without).
+    int i = 0;
+#pragma unroll 1
+    for (int phase = 0; phase < 3; phase++) {
+      if (phase == 1) {
+#pragma unroll 1
+        for (int w = 0; w < nwhole; w++, i++) {
+          int t, cl, ey0, ey1;
+          segment(i, t, cl, ey0, ey1);
+          enter_tile(t);
+          run_steps(std::true_type{}, 0, N);
+          chunk_end(cl);
+        }
+        continue;
+      }
+      if (phase == 0 ? seg_pre == 0 : seg_post == 0) continue;
+      int t, cl, ey0, ey1;
+      segment(i, t, cl, ey0, ey1);
+      i++;
+      enter_tile(t);
+      if (phase == 2) carry_in();
+      run_steps(std::false_type{}, ey0, ey1);
+      if (phase == 2) chunk_end(cl);
+      else carry_out();
+    }
   }
 }
 
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
-template <int N, bool SPLIT = false>
+template <int N, bool SPLIT = false, bool CUTS = true>
 static void launch_batch3_n(sbte_ctx* c, const CUtensorMap& tmap, const double2* spec, double2* parts, size_t part_stride, int cells,
                             const BatchSched& sch, int cg_base = 0) {
   using C = Batch3Cfg<N, SPLIT>;
-  auto kern = qhat_batch3_kernel<N, SPLIT>;
+  if (!CUTS && sch.cuts) { set_error("qhat_batch: this kernel instance takes whole-chunk schedules only"); return; }
+  auto kern = qhat_batch3_kernel<N, SPLIT, CUTS>;
   static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
   if (!((configured.load() >> c->device) & 1u)) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::SMEM);
@@ -592,8 +734,9 @@ void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t
       // The line-ring kernel has no plane switch (no bubble at chunk ends) although it streams N + 7 lines per chunk;
       // SBTE_N16_PLANE=1 keeps the resident-plane kernel for A/B runs
       static const bool ring16 = getenv("SBTE_N16_PLANE") == nullptr;   // default: line ring (2.47 vs 2.69 ms at 640 cells)
-      if (ring16) launch_batch3_n<16>(c, tm, spec, parts, part_stride, cells, sch);
-      else launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch);
+      if (!ring16) launch_batch2_n<16>(c, spec, parts, part_stride, cells, sch);
+      else if (sch.cuts) launch_batch3_n<16>(c, tm, spec, parts, part_stride, cells, sch);
+      else launch_batch3_n<16, false, false>(c, tm, spec, parts, part_stride, cells, sch);
       break;
     }
     case 20: launch_batch3_n<20>(c, tm, spec, parts, part_stride, cells, sch); break;

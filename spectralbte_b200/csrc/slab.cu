@@ -152,8 +152,13 @@ static void upwind_two_pass(sbte_slab* s, double* src, double* dst, const double
   cudaStream_t st = c->stream;
   const bool first = s->rank == 0, last = s->rank == s->nranks - 1;
   const bool wallL = (ic == 3 || ic == 5 || ic == 1), wallR = (ic == 3 || ic == 5);
-  if (first || last) {   // extrapolated ghost + wall face of each physical end this rank holds: one launch
-    launch_edge_prep(st, src, s->d_fl, s->d_fr, s->d_x, s->d_dx, N, nX, first ? 1 : 0, last ? 1 : 0, wallL ? 0 : 1, wallR ? 0 : 1);
+  // Physical ends this rank holds.  With a wall model: extrapolated ghost + outgoing half of the wall face (one launch
+  // for both ends), then the diffuse kernel fills the incoming half.  Without one (no-flux fill) the stencil kernel forms
+  // ghost and face itself (SBTE_NO_EDGE_FUSE=1: the separate launch, for A/B runs).
+  static const bool fuse = getenv("SBTE_NO_EDGE_FUSE") == nullptr;
+  const bool prepL = first && (wallL || !fuse), prepR = last && (wallR || !fuse);
+  if (prepL || prepR) {
+    launch_edge_prep(st, src, s->d_fl, s->d_fr, s->d_x, s->d_dx, N, nX, prepL ? 1 : 0, prepR ? 1 : 0, wallL ? 0 : 1, wallR ? 0 : 1);
     c->launches++;
   }
   if (first && wallL) {
@@ -165,8 +170,8 @@ static void upwind_two_pass(sbte_slab* s, double* src, double* dst, const double
   const HaloSync hs = peer_halo(s, src, &peerL, &peerR);
   // Poiseuille forcing coefficient Ma*0.5*dt/(2*h_v), Ma = 1, h_v = 2 L_v/(N-1) (src/transportroutines.c:37,255,431)
   const double force = (ic == 5) ? 1.0 * 0.5 * s->dt / (2 * (2 * c->L_v / (N - 1))) : 0.0;
-  launch_upwind_two(st, src, dst, s->d_fl, s->d_fr, c->d_v, s->d_x, s->d_dx, N, nX, s->dt, first ? 1 : 0, last ? 1 : 0,
-                    peerL, peerR, force, avg, hs);
+  launch_upwind_two(st, src, dst, s->d_fl, s->d_fr, c->d_v, s->d_x, s->d_dx, N, nX, s->dt, first ? (prepL ? 1 : 2) : 0,
+                    last ? (prepR ? 1 : 2) : 0, peerL, peerR, force, avg, hs);
   c->launches++;
 }
 

@@ -207,18 +207,22 @@ void launch_edge_prep(cudaStream_t st, double* f, double* fl, double* fr, const 
 }
 
 // MUSCL / minmod stencil for the owned cells l = 2 .. nX+1. left_wall / right_wall: this rank holds
-// the physical boundary and uses the wall faces fl / fr instead of the neighbour reconstruction.
+// the physical boundary: 1 = the wall faces fl / fr (edge_prep_kernel, then the wall model) replace the neighbour
+// reconstruction; 2 = an end without wall model (no-flux fill): ghost and face are formed here, with edge_prep_kernel's
+// expressions, and that launch is not needed.
 //
 // Each thread marches one velocity node through UP_CH consecutive cells: the limited slope of cell l is the
 // "own" slope of cell l and the upwind-neighbour slope of cell l+1 (v_x > 0) or l-1 (v_x < 0), so carrying it
 // along the march computes every slope once (3 FP64 divisions per node and pass instead of 6) with exactly the
 // reference's expressions (src/transportroutines.c:411-416,441-446), i.e. the same bits as the per-cell form.
-constexpr int UP_CH = 8;
+// UP_CH is chosen per launch (launch_upwind_two): 8 for large slabs, fewer for small ones, where the kernel is one
+// wave of latency-bound blocks and a shorter march means more blocks and a shorter dependent chain per thread.
 
 __device__ __forceinline__ double slope_at(double fm, double f0, double fp, const double* __restrict__ x, int l) {
   return minmod3((f0 - fm) / (x[l] - x[l - 1]), (fp - f0) / (x[l + 1] - x[l]), (fp - fm) / (x[l + 1] - x[l - 1]));
 }
 
+template <int UP_CH>
 __global__ void __launch_bounds__(256)
 upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __restrict__ fl,
                   const double* __restrict__ fr, const double* __restrict__ v, const double* __restrict__ x,
@@ -247,6 +251,13 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
 #pragma unroll
     for (int q = 0; q < UP_CH; q++) av[q] = (l0 + q < l1) ? avg[(long)(l0 + q) * n3 + p] : 0.0;
   }
+  // ends without wall model: the ghost by linear extrapolation, f[g] = 2 f[l] - f[in2] (src/transportroutines.c:271-297)
+  if (left_wall == 2 && l0 == 2) w[1] = 2 * w[2] - w[3];
+  if (right_wall == 2) {
+#pragma unroll
+    for (int q = 2; q < UP_CH + 4; q++)
+      if (l0 - 2 + q == nX + 2) w[q] = 2 * w[q - 1] - w[q - 2];
+  }
   auto F = [&](int l) { return w[l - l0 + 2]; };
   auto forced0 = [&](double r, int l) {   // Poiseuille forcing (:428-436,457-465): d/dv_y of the pass input
     if (force == 0.0) return r;
@@ -273,7 +284,11 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
       const double s1 = slope_at(fm, f0, fp, x, l);
       const double cfl = hv / dx[l];
       double r;
-      if (l == 2 && left_wall) r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - fl[p]);
+      if (l == 2 && left_wall) {
+        // no wall model: the face edge_prep_kernel would store for this (upper) half, f_l + dx/2 s, s = this cell's slope
+        const double face = left_wall == 2 ? f0 + 0.5 * dx[l] * s1 : fl[p];
+        r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - face);
+      }
       else r = f0 - cfl * (f0 + 0.5 * dx[l] * s1 - (fm + 0.5 * dx[l - 1] * sprev));
       fc[(long)l * n3 + p] = forced(r, l, q);
       fm = f0; f0 = fp; sprev = s1;
@@ -287,7 +302,10 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
       if (l >= l1) break;
       const double cfl = hv / dx[l];
       double r, fpp = 0.0, s2 = 0.0;
-      if (l == nX + 1 && right_wall) r = f0 - cfl * (fr[p] - (f0 - 0.5 * dx[l] * s1));
+      if (l == nX + 1 && right_wall) {
+        const double face = right_wall == 2 ? f0 - 0.5 * dx[l] * s1 : fr[p];   // lower half: f_l - dx/2 s
+        r = f0 - cfl * (face - (f0 - 0.5 * dx[l] * s1));
+      }
       else {
         fpp = F(l + 2);
         s2 = slope_at(f0, fp, fpp, x, l + 1);
@@ -305,9 +323,27 @@ void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const doubl
                        int right_wall, const double* peerL, const double* peerR, double force, const double* avg,
                        const HaloSync& hs) {
   const long n3 = (long)N * N * N;
-  dim3 grid((unsigned)((n3 + 255) / 256), (unsigned)((nX + UP_CH - 1) / UP_CH));
-  upwind_two_kernel<<<grid, 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall, right_wall, peerL, peerR,
-                                          force, avg, hs);
+  const unsigned gx = (unsigned)((n3 + 255) / 256);
+  // the shortest march whose grid still fits the device in one wave (two blocks of 256 threads per SM)
+  static int slots = 0;
+  if (slots == 0) {
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    slots = 2 * (sms > 0 ? sms : 148);
+  }
+  auto blocks = [&](int ch) { return (long)gx * ((nX + ch - 1) / ch); };
+#define SBTE_UPWIND_TWO(CH)                                                                                           \
+  upwind_two_kernel<CH><<<dim3(gx, (unsigned)((nX + CH - 1) / CH)), 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt,   \
+                                                                                 left_wall, right_wall, peerL, peerR, \
+                                                                                 force, avg, hs)
+  if (blocks(2) <= slots) SBTE_UPWIND_TWO(2);
+  else if (blocks(3) <= slots) SBTE_UPWIND_TWO(3);
+  else if (blocks(4) <= slots) SBTE_UPWIND_TWO(4);
+  else if (blocks(5) <= slots) SBTE_UPWIND_TWO(5);
+  else if (blocks(6) <= slots) SBTE_UPWIND_TWO(6);
+  else SBTE_UPWIND_TWO(8);
+#undef SBTE_UPWIND_TWO
 }
 
 // With lazy module loading (the CUDA default) the first launch of a kernel loads it, and the driver cannot do that
@@ -316,7 +352,10 @@ void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const doubl
 // loaded.  Loading every transport / halo kernel up front removes that window.
 int preload_transport_kernels() {
   cudaFuncAttributes a;
-  const void* fns[] = {(const void*)diffuse_bc_kernel, (const void*)upwind_one_kernel, (const void*)upwind_two_kernel,
+  const void* fns[] = {(const void*)diffuse_bc_kernel, (const void*)upwind_one_kernel,
+                       (const void*)upwind_two_kernel<2>, (const void*)upwind_two_kernel<3>,
+                       (const void*)upwind_two_kernel<4>, (const void*)upwind_two_kernel<5>,
+                       (const void*)upwind_two_kernel<6>, (const void*)upwind_two_kernel<8>,
                        (const void*)halo_quiesce_kernel,
                        (const void*)edge_prep_kernel};
   for (const void* f : fns)

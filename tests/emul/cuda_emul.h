@@ -102,6 +102,7 @@ static thread_local dim3 blockDim, gridDim;
 
 inline void __syncthreads() { emul::cta->all.wait(); }
 inline void __syncwarp() { emul::cta->warps[emul::warp_id].wait(); }
+inline void __threadfence() { __atomic_thread_fence(__ATOMIC_SEQ_CST); }
 [[noreturn]] inline void __trap() {
   fprintf(stderr, "emul: __trap() in block %u thread %u (bounded wait expired: lost arrival / transaction)\n", blockIdx.x, threadIdx.x);
   fflush(stderr);
@@ -181,6 +182,18 @@ inline void tma_tensor2d_g2s(void* smem_dst, const void* tmap, int c0, int c1, u
 }
 inline double2 ldg_stream_f64x2(const double* p) { return make_double2(p[0], p[1]); }
 inline void red_add_f64(double* p, double v) { *p += v; }   // single writer per location (see common.cuh)
+// hand-over of a running sum between two CTAs (common.cuh carry_*): CTAs run one after the other here, in launch order, so
+// a consumer always finds the word published; anything else is a protocol error (wrong slot, missing publication)
+inline void carry_publish(int* flag) { __atomic_store_n(flag, 1, __ATOMIC_RELEASE); }
+inline void carry_await(const int* flag) {
+  if (__atomic_load_n(flag, __ATOMIC_ACQUIRE) == 0) {
+    fprintf(stderr, "emul: block %u warp %d waits for a running sum nobody published\n", blockIdx.x, emul::warp_id);
+    fflush(stderr);
+    _Exit(6);
+  }
+}
+inline void carry_rearm(int* flag) { __atomic_store_n(flag, 0, __ATOMIC_RELAXED); }
+inline double2 carry_load(const double2* p) { return *p; }
 inline void pdl_wait() {}
 inline void pdl_launch_dependents() {}
 

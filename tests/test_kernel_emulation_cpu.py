@@ -58,28 +58,33 @@ CASES = [  # kind, N, cells, sym, ctas
     (0, 8, 37, True, 5), (0, 8, 5, False, 3),            # qhat_batch2_kernel<8>
     (0, 16, 3, True, 3),                                   # qhat_batch2_kernel<16> (SBTE_N16_PLANE=1)
     (1, 16, 3, True, 3),                                   # qhat_batch3_kernel<16> (the default at N = 16)
+    (2, 16, 3, True, 3),                                   # its instance for schedules cut at whole chunks only
     (0, 20, 3, True, 4),                                   # qhat_batch3_kernel<20> (partly empty row-blocks)
     (0, 22, 2, False, 3),                                  # qhat_batch3_kernel<22>
     (0, 24, 1, True, 3),                                   # qhat_batch3_kernel<24>
 ]
 
 
-def run_emulation(tmp_path, kind, N, cells, sym, ctas, tag="", split_group=None):
+def run_emulation(tmp_path, kind, N, cells, sym, ctas, tag="", split_group=None, whole=False, anywhere=False):
     """Runs the kernels CTA by CTA on the library's schedule; returns (combined Q^ per cell, oracle, W, spectra).
     split_group = g: only the split-tile launch that serves the last cell group g (at most 16 live cells) is run; the
-    result list then holds None for the cells of the other groups."""
+    result list then holds None for the cells of the other groups.  whole / anywhere: stream-K cuts at whole xi_x chunks only / at any step (default: the library's choice)."""
     L = _lib()
     o = orc.Oracle(N, 9.0, 1)
     n3 = N ** 3
     W = np.random.default_rng(N).standard_normal(n3 * n3) if N <= 8 else orc.synthetic_weights(N)
     Wk = symmetrise_standard(W, N) if sym else W
     Gtot = -(-cells // 32)
+    if kind in (0, 2) and N == 16 and split_group is None:
+        whole = True   # (kind 2: the line-ring instance without hand-over code)
+    if kind == 0 and N == 16 and split_group is None:
+        whole = True   # the resident-plane kernel (what SBTE_N16_PLANE=1 selects, with whole-chunk cuts) cannot take a cut chunk
     if split_group is None:
-        s = schedule(N, cells, sym, ctas)
+        s = schedule(N, cells, sym, ctas, whole=whole, anywhere=anywhere and not whole)
         assert s["G"] == Gtot
     else:
         assert split_group == Gtot - 1 and 1 <= cells - 32 * split_group <= 16
-        s = schedule(N, cells - 32 * split_group, sym, ctas, split=True)
+        s = schedule(N, cells - 32 * split_group, sym, ctas, split=True, whole=whole, anywhere=anywhere)
         assert s["G"] == 1
         kind = 100 + split_group
     G, T, P, kmax = s["G"], s["T"], s["P"], s["kmax"]
@@ -167,3 +172,36 @@ def test_split_tiles_give_the_bits_of_ordinary_tiles(tmp_path, sym, cells, ctas_
     for b in range(32 * g, cells):
         assert relmax(Qs[b], o.qhat(W, F[b], F[b])) < 1e-12, b
         assert np.array_equal(Qs[b].view(np.float64), Qr[b].view(np.float64)), b
+
+
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
+@pytest.mark.parametrize("kind,N,cells,sym,ctas,split", [(1, 16, 3, True, 7, None), (0, 20, 2, False, 9, None), (0, 24, 1, True, 11, None),
+                                                         (0, 16, 35, True, 13, 1)])
+def test_cuts_inside_a_chunk_give_the_bits_of_whole_chunk_cuts(tmp_path, kind, N, cells, sym, ctas, split):
+    _cuts_vs_whole(tmp_path, kind, N, cells, sym, ctas, split)
+
+
+@pytest.mark.filterwarnings("ignore:This process.*is multi-threaded:DeprecationWarning")
+def test_whole_chunk_instance_gives_the_same_bits(tmp_path):
+    """N = 16 has two instances of the line-ring kernel: the general one and, for schedules cut at whole chunks, one
+    without hand-over code.  Same chunk sums, same fold: same bits."""
+    Qg, *_ = run_emulation(tmp_path, 1, 16, 3, True, 7, "g", anywhere=True)
+    Qw, *_ = run_emulation(tmp_path, 2, 16, 3, True, 7, "w")
+    for b in range(3):
+        assert np.array_equal(Qg[b].view(np.float64), Qw[b].view(np.float64)), b
+
+
+def _cuts_vs_whole(tmp_path, kind, N, cells, sym, ctas, split):
+    """Line-ring kernels: a stream-K range may end inside a xi_x chunk.  The CTA that begins the chunk hands its running
+    sum to the next one (BatchSched::carry), which continues with the same operations in the same order -- so the chunk
+    sum, and with it every cell, has the BITS of a schedule cut at whole chunks (and of the oracle to 1e-12).  The
+    emulation also fails if a running sum is awaited that nobody published, or published and never taken."""
+    Qc, o, W, F = run_emulation(tmp_path, kind, N, cells, sym, ctas, "c", split_group=split, anywhere=True)
+    Qw, *_ = run_emulation(tmp_path, kind, N, cells, sym, ctas, "w", split_group=split, whole=True)
+    s = schedule(N, cells - 32 * split if split is not None else cells, sym, ctas, split=split is not None, anywhere=True)
+    assert np.any(s["begin"][1:-1] % N != 0)          # the case does cut chunks
+    for b in range(cells):
+        if Qc[b] is None:
+            continue
+        assert relmax(Qc[b], o.qhat(W, F[b], F[b])) < 1e-12, b
+        assert np.array_equal(Qc[b].view(np.float64), Qw[b].view(np.float64)), b
