@@ -86,12 +86,21 @@ __device__ __forceinline__ void spin_until(volatile int* my, const volatile int*
                                            long long timeout) {
   if (my[3] == 0) {
     const long long t0 = clock64();
-    while ((L && (L[0] < vr || L[1] < vd)) || (R && (R[0] < vr || R[1] < vd))) {
+    // {ready, done} of a neighbour are adjacent words, 8-byte aligned: one load -- one NVLink round trip -- per look
+    // The load is an acquire at system scope: what the neighbour wrote before it published is visible to this thread's
+    // later loads (and, through the block barrier that follows, to the block's) -- no separate fence, which with peer
+    // mappings in place costs microseconds on the path every boundary block takes.
+    auto behind = [&](const volatile int* nb) {
+      if (!nb) return false;
+      long long w;
+      asm volatile("ld.acquire.sys.global.b64 %0, [%1];" : "=l"(w) : "l"(nb) : "memory");
+      return (int)(w & 0xffffffffLL) < vr || (int)(w >> 32) < vd;
+    };
+    while (behind(L) || behind(R)) {
       if (timeout > 0 && clock64() - t0 > timeout) { my[3] = 1; break; }
       __nanosleep(32);
     }
   }
-  __threadfence_system();
 }
 // all threads of the block; returns the pass number.  needL / needR: this block reads the left / right neighbour's
 // cells or writes cells that neighbour reads.
@@ -102,9 +111,8 @@ __device__ __forceinline__ int halo_enter(const HaloSync& h, bool needL, bool ne
     volatile int* m = reinterpret_cast<volatile int*>(h.my);
     const int e = m[2] + 1;
     if (blockIdx.x == 0 && blockIdx.y == 0) {
-      __threadfence_system();
+      __threadfence_system();   // everything earlier kernels wrote (stream order) before the word that announces it
       m[0] = e;
-      __threadfence_system();
     }
     const volatile int* L = (needL && h.nbL) ? reinterpret_cast<const volatile int*>(h.nbL) : nullptr;
     const volatile int* R = (needR && h.nbR) ? reinterpret_cast<const volatile int*>(h.nbR) : nullptr;
@@ -118,7 +126,9 @@ __device__ __forceinline__ void halo_leave(const HaloSync& h, int e) {
   if (!h.my) return;
   __syncthreads();   // every load of this block has been consumed
   if (threadIdx.x == 0) {
-    __threadfence_system();
+    // device scope is enough to count the blocks; the one system-scope fence of the pass is the last block's, and it is
+    // cumulative over what the counter ordered before it
+    __threadfence();
     const int total = (int)(gridDim.x * gridDim.y);
     if (atomicAdd(h.my + 4, 1) == total - 1) {
       volatile int* m = reinterpret_cast<volatile int*>(h.my);
@@ -126,7 +136,6 @@ __device__ __forceinline__ void halo_leave(const HaloSync& h, int e) {
       __threadfence_system();
       m[1] = e;
       m[2] = e;
-      __threadfence_system();
     }
   }
 }
@@ -215,7 +224,7 @@ void launch_edge_prep(cudaStream_t st, double* f, double* fl, double* fr, const 
 // "own" slope of cell l and the upwind-neighbour slope of cell l+1 (v_x > 0) or l-1 (v_x < 0), so carrying it
 // along the march computes every slope once (3 FP64 divisions per node and pass instead of 6) with exactly the
 // reference's expressions (src/transportroutines.c:411-416,441-446), i.e. the same bits as the per-cell form.
-// UP_CH is chosen per launch (launch_upwind_two): 8 for large slabs, fewer for small ones, where the kernel is one
+// UP_CH is chosen per launch (launch_upwind_two): 8 for large slabs, fewer (or, to stay within one wave, a few more) for small ones, where the kernel is one
 // wave of latency-bound blocks and a shorter march means more blocks and a shorter dependent chain per thread.
 
 __device__ __forceinline__ double slope_at(double fm, double f0, double fp, const double* __restrict__ x, int l) {
@@ -230,9 +239,13 @@ upwind_two_kernel(const double* f, double* __restrict__ fc, const double* __rest
                   const double* peerL, const double* peerR, double force, const double* __restrict__ avg, HaloSync hs) {
   const long n3 = (long)N * N * N;
   const int h = N / 2;
-  const int l0 = 2 + blockIdx.y * UP_CH;
-  const int l1 = min(l0 + UP_CH, nX + 2);
-  // the first block row reads the left ghosts and writes the cells the left neighbour reads; the last one likewise
+  // Block rows: the first and the last hold just the two cells at each end of the slab -- the only ones whose stencil
+  // reaches a neighbour's cells and the only ones a neighbour reads -- so that the rows that may have to wait for a
+  // neighbour have the shortest march; the rows between them march UP_CH cells each and never wait.
+  int l0, l1;
+  if (blockIdx.y == 0) { l0 = 2; l1 = 4; }
+  else if (blockIdx.y == gridDim.y - 1) { l0 = nX; l1 = nX + 2; }
+  else { l0 = 4 + ((int)blockIdx.y - 1) * UP_CH; l1 = min(l0 + UP_CH, nX); }
   const int pass = halo_enter(hs, blockIdx.y == 0, blockIdx.y == gridDim.y - 1);
   const long p = blockIdx.x * (long)blockDim.x + threadIdx.x;
   if (p < n3) {
@@ -332,16 +345,20 @@ void launch_upwind_two(cudaStream_t st, const double* f, double* fc, const doubl
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     slots = 2 * (sms > 0 ? sms : 148);
   }
-  auto blocks = [&](int ch) { return (long)gx * ((nX + ch - 1) / ch); };
+  // rows: the two cells at either end of the slab, and the nX - 4 cells between them in marches of `ch`
+  auto rows = [&](int ch) { return 2 + (nX - 4 + ch - 1) / ch; };
+  auto blocks = [&](int ch) { return (long)gx * rows(ch); };
 #define SBTE_UPWIND_TWO(CH)                                                                                           \
-  upwind_two_kernel<CH><<<dim3(gx, (unsigned)((nX + CH - 1) / CH)), 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt,   \
-                                                                                 left_wall, right_wall, peerL, peerR, \
-                                                                                 force, avg, hs)
+  upwind_two_kernel<CH><<<dim3(gx, (unsigned)rows(CH)), 256, 0, st>>>(f, fc, fl, fr, v, x, dx, N, nX, dt, left_wall,      \
+                                                                     right_wall, peerL, peerR, force, avg, hs)
   if (blocks(2) <= slots) SBTE_UPWIND_TWO(2);
   else if (blocks(3) <= slots) SBTE_UPWIND_TWO(3);
   else if (blocks(4) <= slots) SBTE_UPWIND_TWO(4);
   else if (blocks(5) <= slots) SBTE_UPWIND_TWO(5);
   else if (blocks(6) <= slots) SBTE_UPWIND_TWO(6);
+  else if (blocks(8) <= slots) SBTE_UPWIND_TWO(8);
+  else if (blocks(10) <= slots) SBTE_UPWIND_TWO(10);   // one wave of longer marches beats two waves of short ones
+  else if (blocks(12) <= slots) SBTE_UPWIND_TWO(12);
   else SBTE_UPWIND_TWO(8);
 #undef SBTE_UPWIND_TWO
 }
@@ -356,6 +373,7 @@ int preload_transport_kernels() {
                        (const void*)upwind_two_kernel<2>, (const void*)upwind_two_kernel<3>,
                        (const void*)upwind_two_kernel<4>, (const void*)upwind_two_kernel<5>,
                        (const void*)upwind_two_kernel<6>, (const void*)upwind_two_kernel<8>,
+                       (const void*)upwind_two_kernel<10>, (const void*)upwind_two_kernel<12>,
                        (const void*)halo_quiesce_kernel,
                        (const void*)edge_prep_kernel};
   for (const void* f : fns)
