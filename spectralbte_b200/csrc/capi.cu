@@ -392,7 +392,7 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
       c->carry_bytes = acc_bytes + flag_bytes;
     }
     int* flags = (int*)((unsigned char*)c->d_carry + acc_bytes);
-    CK(cudaMemset(flags, 0, flag_bytes));
+    CK(cudaMemsetAsync(flags, 0, flag_bytes, c->stream));   // on the stream the kernels run on (it does not wait for the null stream)
     c->sched_main.carry = c->sched_split.carry = (double2*)c->d_carry;
     c->sched_main.carry_flag = c->sched_split.carry_flag = flags;
   }
