@@ -338,6 +338,42 @@ def test_split_tiles_of_the_remainder_group_n16(sb, cells):
         assert relmax(Qs[b], o.compute_q(W, f[b], f[b])) < TOL_QHAT   # Qs: the unsymmetrised pass
 
 
+_CUT_SNIPPET = """
+import hashlib, sys
+import numpy as np
+sys.path.insert(0, %(root)r)
+import spectralbte_b200 as sb
+N, cells = %(N)d, %(cells)d
+c = sb.Collisions(N, 9.0, inhomogeneous=True)
+c.synthetic_weights(11)
+v = np.linspace(-9.0, 9.0, N)
+X, Y, Z = np.meshgrid(v, v, v, indexing="ij")
+f = np.stack([np.exp(-((X - 0.1 * b) ** 2 + Y ** 2 + (Z + 0.05 * b) ** 2) / (1.0 + 0.01 * b)) for b in range(cells)])
+Q = c.ComputeQ(f, k2=sb.K2_BATCH)
+print("DIGEST", hashlib.sha256(np.ascontiguousarray(Q).tobytes()).hexdigest(), float(np.abs(Q).max()))
+"""
+
+
+@pytest.mark.parametrize("N,cells", [(16, 70), (16, 160), (20, 40), (24, 33)])
+def test_cuts_inside_chunks_give_whole_chunk_bits(N, cells):
+    """Line-ring kernels: a stream-K range may end inside a xi_x chunk, the running sum then passes from one CTA to the
+    next through global memory (flag word per warp, release / acquire).  The same batch computed by a process that cuts
+    at any step (SBTE_CHUNK_CUTS=0) and by one that cuts at whole chunks only (=1) must agree bit for bit -- on the
+    hardware, where the hand-over is a real inter-CTA exchange (the CPU emulation runs the CTAs one after the other)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    digests = {}
+    for mode in ("0", "1"):
+        r = subprocess.run([sys.executable, "-c", _CUT_SNIPPET % dict(root=root, N=N, cells=cells)], capture_output=True, text=True,
+                           timeout=600, env=dict(os.environ, SBTE_CHUNK_CUTS=mode))
+        assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+        line = [ln for ln in r.stdout.splitlines() if ln.startswith("DIGEST")][-1].split()
+        assert float(line[2]) > 0.0
+        digests[mode] = line[1]
+    assert digests["0"] == digests["1"]
+
+
 @pytest.mark.parametrize("N,cells", [(22, 70), (20, 33), (22, 250)])
 def test_line_ring_with_partial_row_blocks(sb, N, cells):
     """N = 20, 22: 8 zeta_y columns per CTA do not tile a zeta_x plane, so every third row-block is partly
