@@ -379,9 +379,10 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
     c->sched = {nullptr, nullptr, nullptr, nullptr, (const unsigned char*)c->d_sched_mem3, G, 0, 0, 1, kmax, sym ? 1 : 0};
   }
   {
-    // hand-over buffers for cut chunks (BatchSched::carry): one accumulator set per compute warp and CTA and a flag word
-    // each; the main and the split launch run one after the other and share them
-    const size_t Pmax = (size_t)std::max(c->cells_main > 0 ? h.P : 0, split ? h2.P : 0);
+    // hand-over buffers for cut chunks (BatchSched::carry): one accumulator set per compute warp and CTA and a flag word each
+    // (the main and the split schedule each have their own slots: the two may share one launch)
+    const size_t Pm = c->cells_main > 0 ? (size_t)h.P : 0, Ps = split ? (size_t)h2.P : 0;
+    const size_t Pmax = Pm + Ps;
     const size_t acc_bytes = Pmax * kBatchWarps * (size_t)N * 32 * sizeof(double2);
     const size_t flag_bytes = Pmax * kBatchWarps * sizeof(int);
     if (c->carry_bytes < acc_bytes + flag_bytes) {
@@ -393,8 +394,10 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
     }
     int* flags = (int*)((unsigned char*)c->d_carry + acc_bytes);
     CK(cudaMemsetAsync(flags, 0, flag_bytes, c->stream));   // on the stream the kernels run on (it does not wait for the null stream)
-    c->sched_main.carry = c->sched_split.carry = (double2*)c->d_carry;
-    c->sched_main.carry_flag = c->sched_split.carry_flag = flags;
+    c->sched_main.carry = (double2*)c->d_carry;
+    c->sched_main.carry_flag = flags;
+    c->sched_split.carry = (double2*)c->d_carry + Pm * kBatchWarps * (size_t)N * 32;
+    c->sched_split.carry_flag = flags + Pm * kBatchWarps;
   }
   c->sched_cells = cells;
   c->sched_sym = (int)sym;
@@ -412,6 +415,10 @@ static int ensure_batch_schedule(sbte_ctx* c, int cells, bool sym) {
 
 // the convolution launches of one batched ComputeQ: the main tiles, then the split tiles of the remainder group
 static void launch_batched_conv(sbte_ctx* c, const double2* spec, int batch) {
+  if (c->cells_main > 0 && c->split_on && c->sched_main.cuts && qhat_batch_pair_supported(c->N)) {
+    launch_qhat_batch_pair(c, spec, c->d_parts, c->parts_stride, c->cells_main, batch, c->sched_main, c->sched_split, c->split_cg);
+    return;
+  }
   if (c->cells_main > 0) launch_qhat_batch2(c, spec, c->d_parts, c->parts_stride, c->cells_main, c->sched_main);
   if (c->split_on) launch_qhat_batch_split(c, spec, c->d_parts, c->parts_stride, batch, c->sched_split, c->split_cg);
 }

@@ -198,6 +198,9 @@ int weights_xy_symmetry(sbte_ctx* c, const double* W, double* max_diff, double* 
 bool qhat_batch_supported(int N);
 int qhat_batch_cols(int N);
 void launch_qhat_batch_any(sbte_ctx* c, const double2* spec_cellminor, double2* qhat, int cells, bool sym);
+bool qhat_batch_pair_supported(int N);   // main + split tiles in one launch
+void launch_qhat_batch_pair(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells_main, int cells_all,
+                            const BatchSched& schM, const BatchSched& schS, int cg_split);
 int qhat_batch_cut_mode(int N);      // 0 = stream-K cuts at whole xi_x chunks only, 1 = builder's choice, 2 = at any step
 double qhat_batch_cut_cost(int N);   // measured price of cutting anywhere (fraction of the launch)
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec_cellminor, double2* parts, size_t part_stride, int cells,

@@ -415,10 +415,11 @@ struct Batch3Cfg {
 
 // cg_base: cell group the (single-group) schedule of a SPLIT launch refers to; 0 otherwise
 // CUTS = false: the instance for schedules cut at whole chunks only (no hand-over code, step loop with compile-time bounds)
-template <int N, bool SPLIT, bool CUTS = true>
-__global__ void __launch_bounds__(Batch3Cfg<N, SPLIT>::THREADS, 1)
-qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
-                   double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch, int cg_base) {
+// cta: this CTA's index in the schedule (the block index, except in the paired launch below)
+template <int N, bool SPLIT, bool CUTS>
+__device__ __forceinline__ void qhat_batch3_body(const CUtensorMap& tmapW, const double2* __restrict__ spec,
+                                                 double2* __restrict__ parts, size_t part_stride, int cells,
+                                                 const BatchSched& sch, int cg_base, const unsigned cta) {
   using C = Batch3Cfg<N, SPLIT>;
   constexpr long n3 = (long)N * N * N;
   constexpr int S = C::STAGES, R = C::RING;
@@ -443,9 +444,9 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   // The host schedule gives every CTA at least N steps, so the two cut chunks are different chunks.
   // Positions are kept relative to g0 (32 bits): h0 = steps of the cut chunk at the start, n1 = steps of the one at the end.
   int h0, n1, nwhole, tb, te;
-  const int t0 = sch.cta_tile[blockIdx.x];
+  const int t0 = sch.cta_tile[cta];
   {
-    const long long g0 = sch.cta_begin[blockIdx.x], g1 = sch.cta_begin[blockIdx.x + 1];
+    const long long g0 = sch.cta_begin[cta], g1 = sch.cta_begin[cta + 1];
     if (g1 <= g0) return;
     const long long w0 = ((g0 + N - 1) / N) * N, w1 = (g1 / N) * N;
     h0 = (int)(w0 - g0);
@@ -463,17 +464,17 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       const int rc = h0 + (i - seg_pre) * N;
       if (rc >= te) {   // tiles are whole chunks: one switch at most
         tw++; tb = te;
-        te = (int)(sch.tile_begin[tw + 1] - sch.cta_begin[blockIdx.x]);
+        te = (int)(sch.tile_begin[tw + 1] - sch.cta_begin[cta]);
       }
       t = tw; cl = (rc - tb) / N; ey0 = 0; ey1 = N;
     } else if (i < seg_pre) {   // at most once, before any whole chunk
-      const long long w1 = sch.cta_begin[blockIdx.x + 1] - n1;
+      const long long w1 = sch.cta_begin[cta + 1] - n1;
       t = t0;
       while (w1 >= sch.tile_begin[t + 1]) t++;
       cl = (int)((w1 - sch.tile_begin[t]) / N); ey0 = 0; ey1 = n1;
     } else {                    // at most once, after the whole chunks
       t = t0;
-      cl = (int)((sch.cta_begin[blockIdx.x] + h0 - N - sch.tile_begin[t0]) / N); ey0 = N - h0; ey1 = N;
+      cl = (int)((sch.cta_begin[cta] + h0 - N - sch.tile_begin[t0]) / N); ey0 = N - h0; ey1 = N;
     }
   };
 
@@ -546,7 +547,7 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
       const int first = sch.tile_first[cur_t];
       double2* out = parts + cell * n3 + ((long)zx * N + zy) * N;
       bool fold = false;
-      if ((int)blockIdx.x == first) {
+      if ((int)cta == first) {
         fold = c > 0;
       } else {
         const int e0 = (int)((sch.cta_begin[first + 1] - sch.tile_begin[cur_t]) / N);   // chunks the first CTA completes
@@ -631,10 +632,10 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   // a chunk begun by the previous CTA: continue from its running sum (same operations in the same order as an uncut
   // chunk, hence the same bits)
   auto carry_in = [&]() {
-    int* flag = sch.carry_flag + ((size_t)blockIdx.x - 1) * C::WARPS + warp;
+    int* flag = sch.carry_flag + ((size_t)cta - 1) * C::WARPS + warp;
     if (lane == 0) carry_await(flag);
     __syncwarp();
-    const double2* in = sch.carry + (((size_t)blockIdx.x - 1) * C::WARPS + warp) * C::LINE + lane;
+    const double2* in = sch.carry + (((size_t)cta - 1) * C::WARPS + warp) * C::LINE + lane;
 #pragma unroll
     for (int r = 0; r < N; r++) acc[r] = carry_load(in + r * 32);
     __syncwarp();
@@ -642,12 +643,12 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   };
   // a chunk the next CTA completes: hand the running sum over
   auto carry_out = [&]() {
-    double2* out = sch.carry + ((size_t)blockIdx.x * C::WARPS + warp) * C::LINE + lane;
+    double2* out = sch.carry + ((size_t)cta * C::WARPS + warp) * C::LINE + lane;
 #pragma unroll
     for (int r = 0; r < N; r++) { out[r * 32] = acc[r]; acc[r] = make_double2(0.0, 0.0); }
     __threadfence();
     __syncwarp();
-    if (lane == 0) carry_publish(sch.carry_flag + (size_t)blockIdx.x * C::WARPS + warp);
+    if (lane == 0) carry_publish(sch.carry_flag + (size_t)cta * C::WARPS + warp);
   };
 
   if constexpr (!CUTS) {
@@ -704,6 +705,28 @@ qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __r
   }
 }
 
+template <int N, bool SPLIT, bool CUTS = true>
+__global__ void __launch_bounds__(Batch3Cfg<N, SPLIT>::THREADS, 1)
+qhat_batch3_kernel(const __grid_constant__ CUtensorMap tmapW, const double2* __restrict__ spec,
+                   double2* __restrict__ parts, size_t part_stride, int cells, BatchSched sch, int cg_base) {
+  qhat_batch3_body<N, SPLIT, CUTS>(tmapW, spec, parts, part_stride, cells, sch, cg_base, blockIdx.x);
+}
+
+// The main tiles and the split tiles of the remainder group in ONE launch: CTAs [0, schM.P) run the ordinary-tile code on
+// schM, the rest the split-tile code on schS (group cg_split).  One CTA per SM either way, so an SM that is through with
+// its ordinary share takes a split CTA at once -- no drain and refill of the whole device between two launches.
+template <int N>
+__global__ void __launch_bounds__(Batch3Cfg<N, false>::THREADS, 1)
+qhat_batch3_pair_kernel(const __grid_constant__ CUtensorMap tmapM, const __grid_constant__ CUtensorMap tmapS,
+                        const double2* __restrict__ spec, double2* __restrict__ parts, size_t part_stride, int cells_main,
+                        int cells_all, BatchSched schM, BatchSched schS, int cg_split) {
+  static_assert(Batch3Cfg<N, false>::THREADS == Batch3Cfg<N, true>::THREADS, "one block shape for both tile kinds");
+  if (blockIdx.x < (unsigned)schM.P)
+    qhat_batch3_body<N, false, true>(tmapM, spec, parts, part_stride, cells_main, schM, 0, blockIdx.x);
+  else
+    qhat_batch3_body<N, true, true>(tmapS, spec, parts, part_stride, cells_all, schS, cg_split, blockIdx.x - (unsigned)schM.P);
+}
+
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
 template <int N, bool SPLIT = false, bool CUTS = true>
 static void launch_batch3_n(sbte_ctx* c, const CUtensorMap& tmap, const double2* spec, double2* parts, size_t part_stride, int cells,
@@ -724,6 +747,29 @@ static void launch_batch3_n(sbte_ctx* c, const CUtensorMap& tmap, const double2*
 #endif
 
 #ifndef SBTE_HOST_EMUL   // host launch code: not part of the host emulation
+// main + split tiles of an N = 16 slab in one launch (both schedules of the general, cut-anywhere kind)
+bool qhat_batch_pair_supported(int N) {
+  static const bool off = getenv("SBTE_NO_PAIR_LAUNCH") != nullptr;
+  return N == 16 && !off;
+}
+void launch_qhat_batch_pair(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells_main, int cells_all,
+                            const BatchSched& schM, const BatchSched& schS, int cg_split) {
+  if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
+  if (c->N != 16) { set_error("qhat_batch: the paired launch exists for N = 16 only"); return; }
+  constexpr size_t smem = Batch3Cfg<16, false>::SMEM > Batch3Cfg<16, true>::SMEM ? Batch3Cfg<16, false>::SMEM : Batch3Cfg<16, true>::SMEM;
+  auto kern = qhat_batch3_pair_kernel<16>;
+  static std::atomic<unsigned> configured{0};   // per device: function attributes belong to the device context
+  if (!((configured.load() >> c->device) & 1u)) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    configured.fetch_or(1u << c->device);
+  }
+  k2_mark(c);
+  kern<<<schM.P + schS.P, Batch3Cfg<16, false>::THREADS, smem, c->stream>>>(schM.sym ? c->tmapWs : c->tmapW, schS.sym ? c->tmapWs16 : c->tmapW16,
+                                                                           spec, parts, part_stride, cells_main, cells_all, schM, schS, cg_split);
+  k2_mark(c);
+  c->launches += 1;
+}
+
 void launch_qhat_batch2(sbte_ctx* c, const double2* spec, double2* parts, size_t part_stride, int cells,
                         const BatchSched& sch) {
   if (!c->tmap_ok) { set_error("qhat_batch: weight tensor map not initialised"); return; }
