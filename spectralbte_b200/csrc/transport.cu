@@ -77,6 +77,11 @@ __device__ __forceinline__ const double* cell_src(const double* __restrict__ f, 
 //   quiesce (first order only): wait until the neighbours' done reaches my epoch before the collision update
 //   overwrites f, which they read in the same pass.  At second order the update writes f_1 and f_conv, neither of
 //   which a neighbour reads before my next pass publishes ready, and the waits above cover every other overwrite.
+// Memory ordering: a pass has ONE system-scope fence on the publishing side (before `ready`, by block (0,0); before
+// `done`, by the last block, cumulative over the device-scope fence + counter every block leaves through) and
+// system-scope acquire loads on the waiting side.  A system-scope fence per block -- the first form of this protocol --
+// cost 0.05 ms per step with one neighbour: with peer mappings in place membar.sys takes microseconds
+// (profiles/r02_halo_cost_ab.txt).
 // Waits are bounded by `timeout` clock cycles (0 = wait for ever; the slab passes SBTE_HALO_TIMEOUT_S, default 120 s).
 // A rank may legitimately be late (writing files, instantiating a graph, stopped in a debugger), so running out of
 // time is NOT a trap: the waiting rank raises the error word flags[3], stops waiting -- every later wait of this slab
