@@ -127,7 +127,7 @@ __device__ __forceinline__ void red_add_f64(double* p, double v) {
 
 // ---------------------------------------------------------------- hand-over of a running sum between two CTAs of a launch
 // One word per (producer CTA, warp): the producer stores its data, fences, and publishes 1; the consumer waits for the 1
-// (bounded: a lost publication traps instead of hanging the GPU), reads the data past L1 and re-arms the word with 0 for
+// (bounded in wall time: a lost publication traps instead of hanging the GPU), reads the data past L1 and re-arms the word with 0 for
 // the next launch in the stream.  Used by the batched convolution where a stream-K cut falls inside a xi_x chunk.
 __device__ __forceinline__ void carry_publish(int* flag) {
   asm volatile("st.release.gpu.global.s32 [%0], %1;" ::"l"(flag), "r"(1) : "memory");
@@ -135,11 +135,20 @@ __device__ __forceinline__ void carry_publish(int* flag) {
 __device__ __forceinline__ void carry_await(const int* flag) {
   int v = 0;
   unsigned spins = 0;
+  unsigned long long t0 = 0;
   for (;;) {
     asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(v) : "l"(flag) : "memory");
     if (v != 0) break;
     __nanosleep(64);
-    if (++spins > (1u << 25)) __trap();   // seconds: the producer publishes at the very start of its range
+    // The producer publishes at the very start of its range and is dispatched before its consumer, so this wait is
+    // short unless the device is shared and the producer's CTA has to queue behind somebody else's kernel: two minutes
+    // of wall time (the halo waits' default bound) before a lost publication becomes a trap.
+    if ((++spins & 1023u) == 0) {
+      unsigned long long t;
+      asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+      if (t0 == 0) t0 = t;
+      else if (t - t0 > 120000000000ULL) __trap();
+    }
   }
 }
 __device__ __forceinline__ void carry_rearm(int* flag) { *reinterpret_cast<volatile int*>(flag) = 0; }
